@@ -1,0 +1,132 @@
+/* tokenpacker_b200 — C ABI of the B200-native TokenPacker hot path (libtokenpacker_b200.so).
+ *
+ * The reference (CircleRadon/TokenPacker) is pure Python and has no FFI of its own: its boundary for this path is
+ * the nn.Module ``TokenPacker`` (llava/model/multimodal_projector/builder.py:39-137) plus the HD front end
+ * (llava/patch_divide.py:71-105, llava/train/train.py:695-731, llava/model/llava_arch.py:139-155).  This header is
+ * the seam a maintainer binds instead (ctypes stub in INTEGRATION.md); each entry point cites what it replaces.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / C++ types cross the ABI
+ *   - every buffer is owned by the caller; the library allocates nothing that outlives a call
+ *   - device pointers unless the name says "host"; bf16 storage, fp32 accumulation
+ *   - every function returns a tp_status (0 = ok) and never throws, exits or synchronises the device
+ *     (except the *_host helpers, which synchronise their own stream before returning)
+ *   - work is enqueued on the ``stream`` argument (a cudaStream_t passed as void*); re-entrant, no global state
+ */
+#ifndef TOKENPACKER_B200_H_
+#define TOKENPACKER_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TP_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define TP_API __attribute__((visibility("default")))
+#else
+#define TP_API
+#endif
+
+typedef enum tp_status {
+  TP_OK = 0,
+  TP_ERR_INVALID_ARGUMENT = 1, /* null pointer, bad shape, hidden size not a multiple of 32 ... */
+  TP_ERR_BAD_SCALE_FACTOR = 2, /* 24 % scale_factor != 0  (reference: ValueError, builder.py:51-52) */
+  TP_ERR_WORKSPACE_TOO_SMALL = 3,
+  TP_ERR_CUDA = 4,             /* a CUDA runtime / driver call failed; see tp_last_cuda_error() */
+  TP_ERR_UNSUPPORTED_DEVICE = 5, /* not a compute-capability 10.x device */
+  TP_ERR_BAD_PATCH_NUM = 6     /* patch_num not in {9,16,25} (reference: NotImplementedError, patch_divide.py:79-80) */
+} tp_status;
+
+TP_API const char* tp_strerror(int status);
+TP_API int tp_abi_version(void);
+/* Name of the last failing CUDA call on this thread ("" if none); diagnostic only. */
+TP_API const char* tp_last_cuda_error(void);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Parameters.  Raw module parameters exactly as the reference state_dict holds them (builder.py:59-83), bf16,
+ * row-major [out, in], on the device.  Replaces: TokenPacker.__init__ / load_state_dict (llava_arch.py:78-83).
+ * ------------------------------------------------------------------------------------------------------------- */
+typedef struct tp_weights {
+  const void* q_proj_w;                        /* q_proj_1.weight            [1024,1024]  (no bias)            */
+  const void* k_proj_0_w; const void* k_proj_0_b; /* k_proj_1.0             [1024,4096], [1024]               */
+  const void* k_proj_2_w; const void* k_proj_2_b; /* k_proj_1.2             [1024,1024], [1024]               */
+  const void* v_proj_0_w; const void* v_proj_0_b; /* v_proj_1.0                                               */
+  const void* v_proj_2_w; const void* v_proj_2_b; /* v_proj_1.2                                               */
+  const void* ln_q_w; const void* ln_q_b;      /* ln_q_1  [1024] x2, eps 1e-6                                   */
+  const void* ln_k_w; const void* ln_k_b;
+  const void* ln_v_w; const void* ln_v_b;
+  const void* in_proj_w; const void* in_proj_b;   /* clip_attn.in_proj_{weight,bias}  [3072,1024], [3072]     */
+  const void* out_proj_w; const void* out_proj_b; /* clip_attn.out_proj               [1024,1024], [1024]     */
+  const void* mlp_0_w; const void* mlp_0_b;    /* mlp.0  [H,1024], [H]                                          */
+  const void* mlp_2_w; const void* mlp_2_b;    /* mlp.2  [H,H],    [H]                                          */
+} tp_weights;
+
+/* Size of the derived ("packed") weight cache for hidden size H: concatenated K/V first layers, LayerNorm affine
+ * folded into the MHA in-projections, fp32 biases.  The cache must be rebuilt whenever a parameter changes. */
+TP_API size_t tp_packed_bytes(int hidden);
+TP_API int tp_pack_weights(const tp_weights* w, int hidden, void* packed, size_t packed_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Projector forward.  Replaces TokenPacker.forward (builder.py:107-137).
+ *   x0  [n_crops, 576, 1024] bf16 — CLIP layer-23 patch features        (x[0] of the reference's input tuple)
+ *   xm  [n_crops, 576, 4096] bf16 — concatenated layers 12/16/22/23     (x[1])
+ *   x0_crop_stride / xm_crop_stride: elements between consecutive crops (576*1024 / 576*4096 when contiguous;
+ *        577*C for the [:,1:] views CLIPVisionTower.feature_select hands over, clip_encoder.py:37-38)
+ *   out [n_crops, M, H] bf16 contiguous, M = (24/scale_factor)^2 — or, when seg_row_offset != NULL, crop i's M
+ *        rows are written to rows seg_row_offset[i] .. +M-1 of ``out`` (row stride H): the packed HD layout
+ *        of llava_arch.py:139-155 without a second pass.  seg_row_offset is a DEVICE int64 array [n_crops].
+ * ------------------------------------------------------------------------------------------------------------- */
+TP_API size_t tp_workspace_bytes(int64_t n_crops, int scale_factor, int hidden);
+
+TP_API int tp_forward(const void* packed, const void* x0, const void* xm, int64_t n_crops, int64_t x0_crop_stride,
+               int64_t xm_crop_stride, int scale_factor, int hidden, void* out, const int64_t* seg_row_offset,
+               void* workspace, size_t workspace_bytes, void* stream);
+
+/* Same call with HOST buffers (pinned recommended): copies inputs in, runs, copies the result out, pipelined over
+ * chunks of crops on internal streams, and returns after the result is in ``out_host``.  d_* are caller-provided
+ * device staging buffers of at least the sizes tp_forward needs for n_crops.  This is the end-to-end entry point
+ * the benchmark times (host<->device traffic inside the call). */
+TP_API int tp_forward_host(const void* packed, const void* x0_host, const void* xm_host, int64_t n_crops, int scale_factor,
+                    int hidden, void* out_host, void* d_x0, void* d_xm, void* d_out, void* workspace,
+                    size_t workspace_bytes, int64_t chunk_crops, void* stream);
+
+/* A single fused-epilogue GEMM of the path, exposed for unit tests and microbenchmarks:
+ *   C[M,N] = alpha * act( A[M,K] . B[N,K]^T + bias ),  bf16 in/out, fp32 accumulate; bias fp32 [N] or NULL. */
+TP_API int tp_gemm_bf16(const void* a, int64_t lda, const void* b, int64_t ldb, void* c, int64_t ldc, int64_t m, int64_t n,
+                 int64_t k, const float* bias, int gelu, float alpha, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * TokenPacker-HD front end.
+ * ------------------------------------------------------------------------------------------------------------- */
+/* Image_Patch(image_size, patch_num).calculate(h, w)  (patch_divide.py:96-105).  Host function, no CUDA. */
+TP_API int tp_hd_grid(int64_t h, int64_t w, int patch_num, int image_size, int* h_block, int* w_block);
+
+/* Sizes produced by the tiling block for an h x w image on an hb x wb grid (train.py:701-708, :719-726):
+ * resized size of the main canvas content and of the thumbnail content.  Host function. */
+TP_API int tp_hd_fit(int64_t h, int64_t w, int h_block, int w_block, int* h_resized, int* w_resized, int* h_thumb, int* w_thumb);
+
+/* Tiling block (train.py:695-731): bilinear resize (align_corners=False, no antialias) of image[3,h,w] fp32 into a
+ * zero-padded 336*hb x 336*wb canvas, row-major 336x336 crops, plus — when hb*wb > 1 — the thumbnail resized
+ * from the PADDED canvas.  crops: [hb*wb (+1), 3, 336, 336] fp32.  All device pointers. */
+TP_API int tp_hd_tile(const float* image, int64_t h, int64_t w, int h_block, int w_block, float* crops, void* stream);
+
+/* Slice assembly (llava_arch.py:139-155).  Host helper: fills seg_row_offset_host[n_crops] (destination row of each
+ * crop's first token), sep_rows / ret_rows (destination rows of the ',' and '\n' embedding rows; capacities are the
+ * exact counts returned in *n_sep / *n_ret) and cu_seqlens_host[n_images+1].  Pass NULL outputs to only count. */
+TP_API int tp_hd_plan(const int* h_block, const int* w_block, int64_t n_images, int tokens_per_crop, int64_t* seg_row_offset_host,
+               int64_t* sep_rows_host, int64_t* ret_rows_host, int64_t* cu_seqlens_host, int64_t* n_crops, int64_t* n_sep,
+               int64_t* n_ret);
+
+/* Writes the separator rows of the packed output: out[sep_rows[i], :] = sep_row, out[ret_rows[i], :] = ret_row
+ * (bf16 vectors of length hidden).  Device pointers. */
+TP_API int tp_hd_fill_separators(void* out, int hidden, const int64_t* sep_rows, int64_t n_sep, const void* sep_row,
+                          const int64_t* ret_rows, int64_t n_ret, const void* ret_row, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TOKENPACKER_B200_H_ */

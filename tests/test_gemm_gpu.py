@@ -1,0 +1,61 @@
+"""tcgen05 GEMM (tp_gemm_bf16 through the C ABI) against a plain PyTorch fp32 reference of the same op."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref(a, b, bias, gelu, alpha):
+    y = a.float() @ b.float().t()
+    if bias is not None:
+        y = y + bias.float()
+    if gelu:
+        y = torch.nn.functional.gelu(y)          # exact erf form
+    return y * alpha
+
+
+@pytest.mark.parametrize("m,n,k", [(128, 128, 64), (128, 256, 64), (256, 256, 128), (128, 128, 1024), (384, 1024, 1024),
+                                   (576, 2048, 4096), (144, 4096, 1024), (64, 128, 128), (200, 160, 72), (1000, 5120, 1024),
+                                   (36864, 1024, 1024)])
+def test_gemm_shapes(m, n, k):
+    from tokenpacker_b200.kernels import gemm_bf16
+    g = torch.Generator(device="cuda").manual_seed(m * 7 + n * 3 + k)
+    a = torch.randn(m, k, device="cuda", generator=g).to(torch.bfloat16)
+    b = (torch.randn(n, k, device="cuda", generator=g) * 0.05).to(torch.bfloat16)
+    out = gemm_bf16(a, b)
+    ref = _ref(a, b, None, False, 1.0)
+    err = (out.float() - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    assert err <= 1e-2 * scale + 1e-3, (err, scale)     # bf16 output rounding: 2^-9 relative
+
+
+@pytest.mark.parametrize("gelu", [False, True])
+def test_gemm_epilogue_bias_gelu_alpha(gelu):
+    from tokenpacker_b200.kernels import gemm_bf16
+    g = torch.Generator(device="cuda").manual_seed(5)
+    a = torch.randn(300, 1024, device="cuda", generator=g).to(torch.bfloat16)
+    b = (torch.randn(512, 1024, device="cuda", generator=g) * 0.03).to(torch.bfloat16)
+    bias = torch.randn(512, device="cuda", generator=g)
+    out = gemm_bf16(a, b, bias=bias, gelu=gelu, alpha=0.5)
+    ref = _ref(a, b, bias, gelu, 0.5)
+    assert (out.float() - ref).abs().max().item() <= 1e-2 * ref.abs().max().item() + 1e-3
+
+
+def test_gemm_strided_operands_and_identity():
+    """A with a row stride larger than K (the h_kv[:, 1024:] view) and an exactly representable product."""
+    from tokenpacker_b200.kernels import gemm_bf16
+    big = torch.zeros(256, 2048, device="cuda", dtype=torch.bfloat16)
+    big[:, 1024:] = torch.randint(-4, 5, (256, 1024), device="cuda").to(torch.bfloat16)
+    eye = torch.eye(1024, device="cuda", dtype=torch.bfloat16)
+    out = gemm_bf16(big[:, 1024:], eye)
+    assert torch.equal(out, big[:, 1024:])            # A @ I^T == A, bit-exact
+
+
+def test_gemm_linearity():
+    from tokenpacker_b200.kernels import gemm_bf16
+    g = torch.Generator(device="cuda").manual_seed(9)
+    a = torch.randint(-3, 4, (512, 256), device="cuda", generator=g).to(torch.bfloat16)
+    b = torch.randint(-3, 4, (384, 256), device="cuda", generator=g).to(torch.bfloat16)
+    # small integers: every product and partial sum is exact in fp32, so the only rounding is the final fp32 -> bf16
+    out = gemm_bf16(a, b)
+    assert torch.equal(out, (a.float() @ b.float().t()).to(torch.bfloat16))

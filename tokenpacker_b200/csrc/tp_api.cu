@@ -1,0 +1,652 @@
+// C ABI of libtokenpacker_b200.so (see include/tokenpacker_b200.h).  Host-side orchestration only: tensor-map
+// encoding, workspace carving and kernel launches on the caller's stream.  No allocation, no synchronisation
+// (except tp_forward_host), no global mutable state.
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/tokenpacker_b200.h"
+#include "tp_gemm.cuh"
+#include "tp_kernels.cuh"
+
+namespace {
+
+using namespace tp;
+
+thread_local char g_last_cuda_error[256] = "";
+
+#define TP_CUDA(call)                                                                                        \
+  do {                                                                                                       \
+    cudaError_t err__ = (call);                                                                              \
+    if (err__ != cudaSuccess) {                                                                              \
+      snprintf(g_last_cuda_error, sizeof(g_last_cuda_error), "%s: %s", #call, cudaGetErrorString(err__));    \
+      return TP_ERR_CUDA;                                                                                    \
+    }                                                                                                        \
+  } while (0)
+
+#define TP_TRY(expr)                  \
+  do {                                \
+    int st__ = (expr);                \
+    if (st__ != TP_OK) return st__;   \
+  } while (0)
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// ------------------------------------------------------------------------------------------------
+// TMA tensor maps.  cuTensorMapEncodeTiled is resolved through the runtime so that the library has no link-time
+// dependency on libcuda.so (it must dlopen on a box without a driver for the CPU-side ABI test).
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+
+// bf16 matrix [rows, cols] with row stride ld (elements); box = 64 columns x box_rows rows, 128-byte swizzle.
+int make_map_2d(CUtensorMap* map, const void* ptr, long long rows, long long cols, long long ld, int box_rows) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (fn == nullptr) {
+    snprintf(g_last_cuda_error, sizeof(g_last_cuda_error), "cuTensorMapEncodeTiled entry point not found");
+    return TP_ERR_CUDA;
+  }
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0 || (ld * 2) % 16 != 0) return TP_ERR_INVALID_ARGUMENT;
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(kBlockK), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    snprintf(g_last_cuda_error, sizeof(g_last_cuda_error), "cuTensorMapEncodeTiled(2d) failed: %d", static_cast<int>(r));
+    return TP_ERR_CUDA;
+  }
+  return TP_OK;
+}
+
+// bf16 tensor [segs, seg_rows, cols] with row stride ld and segment stride seg_stride (elements); box 64 x 64 x 1.
+int make_map_3d(CUtensorMap* map, const void* ptr, long long segs, long long seg_rows, long long cols, long long ld,
+                long long seg_stride) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (fn == nullptr) {
+    snprintf(g_last_cuda_error, sizeof(g_last_cuda_error), "cuTensorMapEncodeTiled entry point not found");
+    return TP_ERR_CUDA;
+  }
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0 || (ld * 2) % 16 != 0 || (seg_stride * 2) % 16 != 0) return TP_ERR_INVALID_ARGUMENT;
+  cuuint64_t dims[3] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(seg_rows), static_cast<cuuint64_t>(segs)};
+  cuuint64_t strides[2] = {static_cast<cuuint64_t>(ld) * 2, static_cast<cuuint64_t>(seg_stride) * 2};
+  cuuint32_t box[3] = {static_cast<cuuint32_t>(kBlockK), 64, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    snprintf(g_last_cuda_error, sizeof(g_last_cuda_error), "cuTensorMapEncodeTiled(3d) failed: %d", static_cast<int>(r));
+    return TP_ERR_CUDA;
+  }
+  return TP_OK;
+}
+
+struct DeviceInfo {
+  int sms;
+};
+
+int device_info(DeviceInfo* info) {
+  int dev = 0, major = 0;
+  TP_CUDA(cudaGetDevice(&dev));
+  TP_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  if (major != 10) return TP_ERR_UNSUPPORTED_DEVICE;
+  TP_CUDA(cudaDeviceGetAttribute(&info->sms, cudaDevAttrMultiProcessorCount, dev));
+  return TP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// GEMM launch
+// ------------------------------------------------------------------------------------------------
+struct AOperand {
+  const void* ptr;
+  long long ld;          // row stride (elements)
+  long long seg_rows;    // 0: plain 2-D [M,K]; else rows per segment of a 3-D [M/seg_rows, seg_rows, K] tensor
+  long long seg_stride;  // elements between segments
+};
+
+template <int kBlockN>
+int launch_gemm_t(const AOperand& a, const void* b, long long ldb, long long M, long long N, long long K, const GemmEpilogue& ep,
+                  int sms, cudaStream_t stream) {
+  using Cfg = GemmConfig<kBlockN>;
+  CUtensorMap map_a, map_b;
+  if (a.seg_rows == 0) {
+    TP_TRY(make_map_2d(&map_a, a.ptr, M, K, a.ld, kBlockM));
+  } else {
+    if (a.seg_rows % 64 != 0 || M % a.seg_rows != 0) return TP_ERR_INVALID_ARGUMENT;
+    TP_TRY(make_map_3d(&map_a, a.ptr, M / a.seg_rows, a.seg_rows, K, a.ld, a.seg_stride));
+  }
+  TP_TRY(make_map_2d(&map_b, b, N, K, ldb, kBlockN));
+  TP_CUDA(cudaFuncSetAttribute(tp_gemm_kernel<kBlockN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+  const long long tiles = ((M + kBlockM - 1) / kBlockM) * ((N + kBlockN - 1) / kBlockN);
+  const int grid = static_cast<int>(tiles < sms ? tiles : sms);
+  tp_gemm_kernel<kBlockN><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(map_a, map_b, static_cast<int>(M), static_cast<int>(N),
+                                                                            static_cast<int>(K), static_cast<int>(a.seg_rows), ep);
+  TP_CUDA(cudaGetLastError());
+  return TP_OK;
+}
+
+int launch_gemm(const AOperand& a, const void* b, long long ldb, long long M, long long N, long long K, const GemmEpilogue& ep,
+                int sms, cudaStream_t stream) {
+  if (M <= 0 || N <= 0 || K <= 0 || N % 32 != 0 || K % 8 != 0 || M > 0x7fffff00ll) return TP_ERR_INVALID_ARGUMENT;
+  if ((reinterpret_cast<uintptr_t>(ep.c) & 15) != 0 || (ep.ldc * 2) % 16 != 0) return TP_ERR_INVALID_ARGUMENT;
+  if (N % 256 == 0) return launch_gemm_t<256>(a, b, ldb, M, N, K, ep, sms, stream);
+  return launch_gemm_t<128>(a, b, ldb, M, N, K, ep, sms, stream);
+}
+
+GemmEpilogue plain_epilogue(void* c, long long ldc, const float* bias, int gelu) {
+  GemmEpilogue ep;
+  memset(&ep, 0, sizeof(ep));
+  ep.c = static_cast<__nv_bfloat16*>(c);
+  ep.ldc = ldc;
+  ep.col_b = bias;
+  ep.gelu = gelu;
+  ep.alpha = 1.0f;
+  ep.ln_inv_dim = 1.0f / kC;
+  ep.ln_eps = 1e-6f;     // builder.py:48
+  return ep;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Packed weights layout
+// ------------------------------------------------------------------------------------------------
+struct PackedLayout {
+  size_t w_kv0, b_kv0;                 // [2048,4096] bf16 (k rows then v rows), [2048] f32
+  size_t w_k2, b_k2, w_v2, b_v2;       // [1024,1024] bf16, [1024] f32
+  size_t w_ik, wsum_k, c_k;            // gamma_k-folded in_proj K weight, its row sums, folded constant
+  size_t w_iv, wsum_v, c_v;
+  size_t w_q;                          // q_proj_1
+  size_t w_iq, wsum_q, c_q;
+  size_t w_o, b_o;
+  size_t w_m0, b_m0, w_m2, b_m2;
+  size_t total;
+};
+
+PackedLayout packed_layout(int H) {
+  PackedLayout L;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+  const size_t mat = static_cast<size_t>(kC) * kC * 2, vec = static_cast<size_t>(kC) * 4;
+  L.w_kv0 = take(2ull * kC * kCm * 2); L.b_kv0 = take(2 * vec);
+  L.w_k2 = take(mat); L.b_k2 = take(vec); L.w_v2 = take(mat); L.b_v2 = take(vec);
+  L.w_ik = take(mat); L.wsum_k = take(vec); L.c_k = take(vec);
+  L.w_iv = take(mat); L.wsum_v = take(vec); L.c_v = take(vec);
+  L.w_q = take(mat);
+  L.w_iq = take(mat); L.wsum_q = take(vec); L.c_q = take(vec);
+  L.w_o = take(mat); L.b_o = take(vec);
+  L.w_m0 = take(static_cast<size_t>(H) * kC * 2); L.b_m0 = take(static_cast<size_t>(H) * 4);
+  L.w_m2 = take(static_cast<size_t>(H) * H * 2); L.b_m2 = take(static_cast<size_t>(H) * 4);
+  L.total = off;
+  return L;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Workspace layout (per call; all intermediates bf16 unless noted)
+// ------------------------------------------------------------------------------------------------
+struct WorkLayout {
+  size_t h_kv;      // [R,2048]  GELU(W0 xm + b) for k|v ; reused as k' | v' ([R,1024] each) once consumed
+  size_t y_k, y_v;  // [R,1024]  second linear outputs (pre-LayerNorm)
+  size_t stats;     // f32 [2R + Q, 2]  per-row (sum, sumsq): k rows, v rows, q rows
+  size_t q, y_q, q_p, ctx, o, h_m;   // [Q,1024] x5, [Q,H]
+  size_t total;
+};
+
+WorkLayout work_layout(long long n_crops, int s, int H) {
+  const size_t R = static_cast<size_t>(n_crops) * kTokens;
+  const int g = kGrid / s;
+  const size_t Q = static_cast<size_t>(n_crops) * g * g;
+  WorkLayout L;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 1024); return o; };
+  L.h_kv = take(R * 2 * kC * 2);
+  L.y_k = take(R * kC * 2);
+  L.y_v = take(R * kC * 2);
+  L.stats = take((2 * R + Q) * 2 * 4);
+  L.q = take(Q * kC * 2); L.y_q = take(Q * kC * 2); L.q_p = take(Q * kC * 2); L.ctx = take(Q * kC * 2); L.o = take(Q * kC * 2);
+  L.h_m = take(Q * static_cast<size_t>(H) * 2);
+  L.total = off;
+  return L;
+}
+
+bool valid_hidden(int H) { return H >= 32 && H % 32 == 0 && H <= 65536; }
+
+template <int S>
+int launch_front(const __nv_bfloat16* x0, long long x0_stride, __nv_bfloat16* q, long long Q, cudaStream_t stream) {
+  const long long threads = Q * 128;
+  point_query_kernel<S><<<static_cast<unsigned>((threads + 255) / 256), 256, 0, stream>>>(x0, x0_stride, q, Q);
+  TP_CUDA(cudaGetLastError());
+  return TP_OK;
+}
+
+template <int S>
+int launch_attn(const __nv_bfloat16* qp, const __nv_bfloat16* kp, const __nv_bfloat16* vp, __nv_bfloat16* ctx, long long Q,
+                cudaStream_t stream) {
+  const long long threads = Q * 32;
+  window_attn_kernel<S><<<static_cast<unsigned>((threads + 255) / 256), 256, 0, stream>>>(qp, kp, vp, ctx, Q);
+  TP_CUDA(cudaGetLastError());
+  return TP_OK;
+}
+
+}  // namespace
+
+// ==================================================================================================
+// extern "C"
+// ==================================================================================================
+extern "C" {
+
+const char* tp_strerror(int status) {
+  switch (status) {
+    case TP_OK: return "ok";
+    case TP_ERR_INVALID_ARGUMENT: return "invalid argument";
+    case TP_ERR_BAD_SCALE_FACTOR: return "scale_factor must be divisible by grid size";   // builder.py:52 message
+    case TP_ERR_WORKSPACE_TOO_SMALL: return "workspace too small";
+    case TP_ERR_CUDA: return "CUDA error";
+    case TP_ERR_UNSUPPORTED_DEVICE: return "unsupported device: tokenpacker_b200 needs an sm_100a (B200) GPU";
+    case TP_ERR_BAD_PATCH_NUM: return "patch_num must be 9, 16 or 25";
+    default: return "unknown status";
+  }
+}
+
+int tp_abi_version(void) { return TP_ABI_VERSION; }
+
+const char* tp_last_cuda_error(void) { return g_last_cuda_error; }
+
+size_t tp_packed_bytes(int hidden) { return valid_hidden(hidden) ? packed_layout(hidden).total : 0; }
+
+int tp_pack_weights(const tp_weights* w, int hidden, void* packed, size_t packed_bytes, void* stream_) {
+  if (w == nullptr || packed == nullptr || !valid_hidden(hidden)) return TP_ERR_INVALID_ARGUMENT;
+  const void* const* fields = reinterpret_cast<const void* const*>(w);
+  for (size_t i = 0; i < sizeof(tp_weights) / sizeof(void*); ++i)
+    if (fields[i] == nullptr) return TP_ERR_INVALID_ARGUMENT;
+  const PackedLayout L = packed_layout(hidden);
+  if (packed_bytes < L.total) return TP_ERR_WORKSPACE_TOO_SMALL;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  uint8_t* P = static_cast<uint8_t*>(packed);
+  const size_t mat = static_cast<size_t>(kC) * kC * 2;
+  auto copy = [&](size_t off, const void* src, size_t bytes) { return cudaMemcpyAsync(P + off, src, bytes, cudaMemcpyDeviceToDevice, stream); };
+  auto bias = [&](size_t off, const void* src, int n) {
+    bf16_to_f32_kernel<<<(n + 255) / 256, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(src), reinterpret_cast<float*>(P + off), n);
+    return cudaGetLastError();
+  };
+  auto fold = [&](size_t w_off, size_t wsum_off, size_t c_off, const void* wsrc, const void* bsrc, const void* gamma, const void* beta) {
+    fold_layernorm_kernel<<<(kC * 32 + 255) / 256, 256, 0, stream>>>(
+        static_cast<const __nv_bfloat16*>(wsrc), static_cast<const __nv_bfloat16*>(bsrc), static_cast<const __nv_bfloat16*>(gamma),
+        static_cast<const __nv_bfloat16*>(beta), reinterpret_cast<__nv_bfloat16*>(P + w_off), reinterpret_cast<float*>(P + wsum_off),
+        reinterpret_cast<float*>(P + c_off), kC, kC);
+    return cudaGetLastError();
+  };
+  const size_t kv0 = static_cast<size_t>(kC) * kCm * 2;
+  TP_CUDA(copy(L.w_kv0, w->k_proj_0_w, kv0));
+  TP_CUDA(copy(L.w_kv0 + kv0, w->v_proj_0_w, kv0));
+  TP_CUDA(bias(L.b_kv0, w->k_proj_0_b, kC));
+  TP_CUDA(bias(L.b_kv0 + kC * 4, w->v_proj_0_b, kC));
+  TP_CUDA(copy(L.w_k2, w->k_proj_2_w, mat));
+  TP_CUDA(bias(L.b_k2, w->k_proj_2_b, kC));
+  TP_CUDA(copy(L.w_v2, w->v_proj_2_w, mat));
+  TP_CUDA(bias(L.b_v2, w->v_proj_2_b, kC));
+  const __nv_bfloat16* in_w = static_cast<const __nv_bfloat16*>(w->in_proj_w);
+  const __nv_bfloat16* in_b = static_cast<const __nv_bfloat16*>(w->in_proj_b);
+  // clip_attn.in_proj_weight rows [0,C) = q, [C,2C) = k, [2C,3C) = v   (torch MHA packed in-projection)
+  TP_CUDA(fold(L.w_iq, L.wsum_q, L.c_q, in_w, in_b, w->ln_q_w, w->ln_q_b));
+  TP_CUDA(fold(L.w_ik, L.wsum_k, L.c_k, in_w + static_cast<size_t>(kC) * kC, in_b + kC, w->ln_k_w, w->ln_k_b));
+  TP_CUDA(fold(L.w_iv, L.wsum_v, L.c_v, in_w + 2 * static_cast<size_t>(kC) * kC, in_b + 2 * kC, w->ln_v_w, w->ln_v_b));
+  TP_CUDA(copy(L.w_q, w->q_proj_w, mat));
+  TP_CUDA(copy(L.w_o, w->out_proj_w, mat));
+  TP_CUDA(bias(L.b_o, w->out_proj_b, kC));
+  TP_CUDA(copy(L.w_m0, w->mlp_0_w, static_cast<size_t>(hidden) * kC * 2));
+  TP_CUDA(bias(L.b_m0, w->mlp_0_b, hidden));
+  TP_CUDA(copy(L.w_m2, w->mlp_2_w, static_cast<size_t>(hidden) * hidden * 2));
+  TP_CUDA(bias(L.b_m2, w->mlp_2_b, hidden));
+  return TP_OK;
+}
+
+size_t tp_workspace_bytes(int64_t n_crops, int scale_factor, int hidden) {
+  if (n_crops <= 0 || scale_factor <= 0 || kGrid % scale_factor != 0 || !valid_hidden(hidden)) return 0;
+  return work_layout(n_crops, scale_factor, hidden).total;
+}
+
+int tp_forward(const void* packed, const void* x0, const void* xm, int64_t n_crops, int64_t x0_crop_stride, int64_t xm_crop_stride,
+               int scale_factor, int hidden, void* out, const int64_t* seg_row_offset, void* workspace, size_t workspace_bytes,
+               void* stream_) {
+  if (scale_factor <= 0 || kGrid % scale_factor != 0) return TP_ERR_BAD_SCALE_FACTOR;          // builder.py:51-52
+  if (scale_factor < 2 || scale_factor > 4) return TP_ERR_INVALID_ARGUMENT;   // released configurations: 144/64/36 tokens
+  if (packed == nullptr || x0 == nullptr || xm == nullptr || out == nullptr || workspace == nullptr || n_crops <= 0 ||
+      !valid_hidden(hidden))
+    return TP_ERR_INVALID_ARGUMENT;
+  if (x0_crop_stride < static_cast<int64_t>(kTokens) * kC || xm_crop_stride < static_cast<int64_t>(kTokens) * kCm ||
+      x0_crop_stride % 8 != 0 || xm_crop_stride % 8 != 0)
+    return TP_ERR_INVALID_ARGUMENT;
+  if (n_crops * kTokens > 0x7fff0000ll) return TP_ERR_INVALID_ARGUMENT;
+  DeviceInfo dev;
+  TP_TRY(device_info(&dev));
+  const int s = scale_factor, H = hidden;
+  const int g = kGrid / s, Mq = g * g;
+  const long long R = n_crops * kTokens, Q = n_crops * Mq;
+  const WorkLayout W = work_layout(n_crops, s, H);
+  if (workspace_bytes < W.total) return TP_ERR_WORKSPACE_TOO_SMALL;
+  const PackedLayout L = packed_layout(H);
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const uint8_t* P = static_cast<const uint8_t*>(packed);
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  auto wf = [&](size_t off) { return reinterpret_cast<const float*>(P + off); };
+  auto bf = [&](size_t off) { return reinterpret_cast<__nv_bfloat16*>(ws + off); };
+
+  float* stats_k = reinterpret_cast<float*>(ws + W.stats);
+  float* stats_v = stats_k + 2 * R;
+  float* stats_q = stats_v + 2 * R;
+  TP_CUDA(cudaMemsetAsync(stats_k, 0, static_cast<size_t>(2 * R + Q) * 2 * sizeof(float), stream));
+
+  // (1) builder.py:112-113, first linears + GELU of k_proj_1 / v_proj_1 as ONE GEMM over the concatenated weights:
+  //     h_kv[R, 0:1024] = GELU(W_k0 xm + b), h_kv[R, 1024:2048] = GELU(W_v0 xm + b)   (xm is read once)
+  {
+    AOperand a{xm, kCm, 0, 0};
+    if (xm_crop_stride != static_cast<int64_t>(kTokens) * kCm) a = AOperand{xm, kCm, kTokens, xm_crop_stride};
+    TP_TRY(launch_gemm(a, P + L.w_kv0, kCm, R, 2 * kC, kCm, plain_epilogue(bf(W.h_kv), 2 * kC, wf(L.b_kv0), 1), dev.sms, stream));
+  }
+  // (2) second linears; the epilogue also accumulates per-row (sum, sumsq) of the rounded outputs for LayerNorm
+  {
+    GemmEpilogue ep = plain_epilogue(bf(W.y_k), kC, wf(L.b_k2), 0);
+    ep.stats_out = stats_k;
+    TP_TRY(launch_gemm(AOperand{bf(W.h_kv), 2 * kC, 0, 0}, P + L.w_k2, kC, R, kC, kC, ep, dev.sms, stream));
+    ep = plain_epilogue(bf(W.y_v), kC, wf(L.b_v2), 0);
+    ep.stats_out = stats_v;
+    TP_TRY(launch_gemm(AOperand{bf(W.h_kv) + kC, 2 * kC, 0, 0}, P + L.w_v2, kC, R, kC, kC, ep, dev.sms, stream));
+  }
+  // (3) ln_k_1 / ln_v_1 folded into the MHA in-projections (builder.py:112-113 + torch MHA in_proj):
+  //     k' = rstd (y_k (gamma.W_ik)^T - mu rowsum) + (W_ik beta + b_ik)       -> written over the dead h_kv buffer
+  __nv_bfloat16* k_p = bf(W.h_kv);
+  __nv_bfloat16* v_p = bf(W.h_kv) + static_cast<size_t>(R) * kC;
+  {
+    GemmEpilogue ep = plain_epilogue(k_p, kC, wf(L.c_k), 0);
+    ep.col_a = wf(L.wsum_k);
+    ep.stats_in = stats_k;
+    TP_TRY(launch_gemm(AOperand{bf(W.y_k), kC, 0, 0}, P + L.w_ik, kC, R, kC, kC, ep, dev.sms, stream));
+    ep = plain_epilogue(v_p, kC, wf(L.c_v), 0);
+    ep.col_a = wf(L.wsum_v);
+    ep.stats_in = stats_v;
+    TP_TRY(launch_gemm(AOperand{bf(W.y_v), kC, 0, 0}, P + L.w_iv, kC, R, kC, kC, ep, dev.sms, stream));
+  }
+  // (4) point queries (builder.py:117-118) -> q_proj_1 (:120) -> ln_q_1 folded into in_proj_q, scaled by 1/sqrt(128)
+  {
+    const __nv_bfloat16* x0p = static_cast<const __nv_bfloat16*>(x0);
+    if (s == 2) TP_TRY(launch_front<2>(x0p, x0_crop_stride, bf(W.q), Q, stream));
+    else if (s == 3) TP_TRY(launch_front<3>(x0p, x0_crop_stride, bf(W.q), Q, stream));
+    else TP_TRY(launch_front<4>(x0p, x0_crop_stride, bf(W.q), Q, stream));
+    GemmEpilogue ep = plain_epilogue(bf(W.y_q), kC, nullptr, 0);
+    ep.stats_out = stats_q;
+    TP_TRY(launch_gemm(AOperand{bf(W.q), kC, 0, 0}, P + L.w_q, kC, Q, kC, kC, ep, dev.sms, stream));
+    ep = plain_epilogue(bf(W.q_p), kC, wf(L.c_q), 0);
+    ep.col_a = wf(L.wsum_q);
+    ep.stats_in = stats_q;
+    ep.alpha = 0.08838834764831845f;   // 1/sqrt(head_dim = 128): torch MHA scales q after the in-projection
+    TP_TRY(launch_gemm(AOperand{bf(W.y_q), kC, 0, 0}, P + L.w_iq, kC, Q, kC, kC, ep, dev.sms, stream));
+  }
+  // (5) window attention core (builder.py:122-130)
+  if (s == 2) TP_TRY(launch_attn<2>(bf(W.q_p), k_p, v_p, bf(W.ctx), Q, stream));
+  else if (s == 3) TP_TRY(launch_attn<3>(bf(W.q_p), k_p, v_p, bf(W.ctx), Q, stream));
+  else TP_TRY(launch_attn<4>(bf(W.q_p), k_p, v_p, bf(W.ctx), Q, stream));
+  // (6) out_proj, then the refinement MLP (builder.py:136); the last GEMM writes the final [N,M,H] (or packed HD) layout
+  TP_TRY(launch_gemm(AOperand{bf(W.ctx), kC, 0, 0}, P + L.w_o, kC, Q, kC, kC, plain_epilogue(bf(W.o), kC, wf(L.b_o), 0), dev.sms, stream));
+  TP_TRY(launch_gemm(AOperand{bf(W.o), kC, 0, 0}, P + L.w_m0, kC, Q, H, kC, plain_epilogue(bf(W.h_m), H, wf(L.b_m0), 1), dev.sms, stream));
+  {
+    GemmEpilogue ep = plain_epilogue(out, H, wf(L.b_m2), 0);
+    if (seg_row_offset != nullptr) {
+      ep.seg_row_offset = reinterpret_cast<const long long*>(seg_row_offset);
+      ep.seg_len = Mq;
+    }
+    TP_TRY(launch_gemm(AOperand{bf(W.h_m), H, 0, 0}, P + L.w_m2, H, Q, H, H, ep, dev.sms, stream));
+  }
+  return TP_OK;
+}
+
+int tp_forward_host(const void* packed, const void* x0_host, const void* xm_host, int64_t n_crops, int scale_factor, int hidden,
+                    void* out_host, void* d_x0, void* d_xm, void* d_out, void* workspace, size_t workspace_bytes, int64_t chunk_crops,
+                    void* stream_) {
+  if (x0_host == nullptr || xm_host == nullptr || out_host == nullptr || d_x0 == nullptr || d_xm == nullptr || d_out == nullptr ||
+      n_crops <= 0)
+    return TP_ERR_INVALID_ARGUMENT;
+  if (scale_factor <= 0 || kGrid % scale_factor != 0) return TP_ERR_BAD_SCALE_FACTOR;
+  if (chunk_crops <= 0 || chunk_crops > n_crops) chunk_crops = n_crops;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const int g = kGrid / scale_factor;
+  const size_t x0_b = static_cast<size_t>(kTokens) * kC * 2, xm_b = static_cast<size_t>(kTokens) * kCm * 2;
+  const size_t out_b = static_cast<size_t>(g) * g * hidden * 2;
+  cudaStream_t s_in = nullptr, s_out = nullptr;
+  TP_CUDA(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
+  TP_CUDA(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
+  int status = TP_OK;
+  cudaEvent_t ev_start = nullptr;
+  cudaEventCreateWithFlags(&ev_start, cudaEventDisableTiming);
+  cudaEventRecord(ev_start, stream);          // copies must not start before prior work on the caller's stream
+  cudaStreamWaitEvent(s_in, ev_start, 0);
+  cudaStreamWaitEvent(s_out, ev_start, 0);
+  const int64_t n_chunks = (n_crops + chunk_crops - 1) / chunk_crops;
+  for (int64_t c = 0; c < n_chunks && status == TP_OK; ++c) {
+    const int64_t c0 = c * chunk_crops;
+    const int64_t nc = (n_crops - c0) < chunk_crops ? (n_crops - c0) : chunk_crops;
+    cudaEvent_t ev_in = nullptr, ev_done = nullptr;
+    cudaEventCreateWithFlags(&ev_in, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ev_done, cudaEventDisableTiming);
+    cudaMemcpyAsync(static_cast<uint8_t*>(d_x0) + c0 * x0_b, static_cast<const uint8_t*>(x0_host) + c0 * x0_b, nc * x0_b,
+                    cudaMemcpyHostToDevice, s_in);
+    cudaMemcpyAsync(static_cast<uint8_t*>(d_xm) + c0 * xm_b, static_cast<const uint8_t*>(xm_host) + c0 * xm_b, nc * xm_b,
+                    cudaMemcpyHostToDevice, s_in);
+    cudaEventRecord(ev_in, s_in);
+    cudaStreamWaitEvent(stream, ev_in, 0);
+    status = tp_forward(packed, static_cast<uint8_t*>(d_x0) + c0 * x0_b, static_cast<uint8_t*>(d_xm) + c0 * xm_b, nc,
+                        static_cast<int64_t>(kTokens) * kC, static_cast<int64_t>(kTokens) * kCm, scale_factor, hidden,
+                        static_cast<uint8_t*>(d_out) + c0 * out_b, nullptr, workspace, workspace_bytes, stream);
+    cudaEventRecord(ev_done, stream);
+    cudaStreamWaitEvent(s_out, ev_done, 0);
+    cudaMemcpyAsync(static_cast<uint8_t*>(out_host) + c0 * out_b, static_cast<uint8_t*>(d_out) + c0 * out_b, nc * out_b,
+                    cudaMemcpyDeviceToHost, s_out);
+    cudaEventDestroy(ev_in);
+    cudaEventDestroy(ev_done);
+  }
+  cudaError_t e1 = cudaStreamSynchronize(s_out);
+  cudaError_t e2 = cudaStreamSynchronize(stream);
+  cudaError_t e3 = cudaStreamSynchronize(s_in);
+  cudaEventDestroy(ev_start);
+  cudaStreamDestroy(s_in);
+  cudaStreamDestroy(s_out);
+  if (status != TP_OK) return status;
+  TP_CUDA(e1);
+  TP_CUDA(e2);
+  TP_CUDA(e3);
+  return TP_OK;
+}
+
+int tp_gemm_bf16(const void* a, int64_t lda, const void* b, int64_t ldb, void* c, int64_t ldc, int64_t m, int64_t n, int64_t k,
+                 const float* bias, int gelu, float alpha, void* stream) {
+  if (a == nullptr || b == nullptr || c == nullptr) return TP_ERR_INVALID_ARGUMENT;
+  DeviceInfo dev;
+  TP_TRY(device_info(&dev));
+  GemmEpilogue ep = plain_epilogue(c, ldc, bias, gelu);
+  ep.alpha = alpha;
+  return launch_gemm(AOperand{a, lda, 0, 0}, b, ldb, m, n, k, ep, dev.sms, static_cast<cudaStream_t>(stream));
+}
+
+// ------------------------------------------------------------------------------------------------
+// HD front end
+// ------------------------------------------------------------------------------------------------
+namespace {
+struct GridPair { int h, w; };
+// Candidate tables: data of patch_divide.py:4-54 (argmax takes the FIRST maximum, so order is part of the contract;
+// the 25-table really lists (4,6),(6,4) twice).
+const GridPair kGrid9[] = {{1,1},{1,2},{2,1},{1,3},{3,1},{2,2},{1,4},{4,1},{1,5},{5,1},{1,6},{6,1},{2,3},{3,2},{1,7},{7,1},
+                           {4,2},{2,4},{1,8},{8,1},{3,3},{1,9},{9,1}};
+const GridPair kGrid16x[] = {{2,5},{5,2},{2,6},{6,2},{3,4},{4,3},{2,7},{7,2},{3,5},{5,3},{2,8},{8,2},{4,4}};
+const GridPair kGrid25x[] = {{3,6},{6,3},{2,9},{9,2},{4,5},{5,4},{2,10},{10,2},{3,7},{7,3},{11,2},{2,11},{4,6},{6,4},{12,2},{2,12},
+                             {3,8},{8,3},{4,6},{6,4},{5,5}};
+
+int grid_table(int patch_num, GridPair* out) {
+  int n = 0;
+  for (const GridPair& p : kGrid9) out[n++] = p;
+  if (patch_num == 9) return n;
+  for (const GridPair& p : kGrid16x) out[n++] = p;
+  if (patch_num == 16) return n;
+  for (const GridPair& p : kGrid25x) out[n++] = p;
+  return n;
+}
+
+// Python round(): round-half-to-even on doubles.
+long long py_round(double v) { return static_cast<long long>(nearbyint(v)); }
+}  // namespace
+
+int tp_hd_grid(int64_t h, int64_t w, int patch_num, int image_size, int* h_block, int* w_block) {
+  if (h_block == nullptr || w_block == nullptr || h <= 0 || w <= 0 || image_size <= 0) return TP_ERR_INVALID_ARGUMENT;
+  if (patch_num != 9 && patch_num != 16 && patch_num != 25) return TP_ERR_BAD_PATCH_NUM;
+  GridPair table[64];
+  const int n = grid_table(patch_num, table);
+  // float32 arithmetic op-for-op like the torch expression (patch_divide.py:96-105, box_iou :57-69); volatile keeps
+  // every intermediate rounded to float (no fused multiply-add, no excess precision).
+  const float fh = static_cast<float>(h), fw = static_cast<float>(w);
+  volatile float bh = fh * 1.4f, bw = fw * 1.4f;
+  volatile float area2 = bh * bw;
+  int best = 0;
+  float best_score = 0.f;
+  for (int i = 0; i < n; ++i) {
+    const long long ph = static_cast<long long>(table[i].h) * image_size, pw = static_cast<long long>(table[i].w) * image_size;
+    const float fph = static_cast<float>(ph), fpw = static_cast<float>(pw);
+    const float farea1 = static_cast<float>(ph * pw);
+    volatile float r0 = fph / fh, r1 = fpw / fw;
+    const float ratio = r0 < r1 ? r0 : r1;
+    volatile float hr = fh * ratio, wr = fw * ratio;
+    volatile float prod = nearbyintf(hr) * nearbyintf(wr);
+    volatile float score = prod / farea1;
+    const float wh0 = fph < bh ? fph : bh, wh1 = fpw < bw ? fpw : bw;
+    volatile float inter = wh0 * wh1;
+    volatile float uni = farea1 + area2;
+    uni = uni - inter;
+    volatile float den = uni + 1e-5f;
+    volatile float iou = inter / den;
+    volatile float iou01 = iou * 0.1f;
+    const float total = score + iou01;
+    if (i == 0 || total > best_score) { best_score = total; best = i; }
+  }
+  *h_block = table[best].h;
+  *w_block = table[best].w;
+  return TP_OK;
+}
+
+int tp_hd_fit(int64_t h, int64_t w, int h_block, int w_block, int* h_resized, int* w_resized, int* h_thumb, int* w_thumb) {
+  if (h <= 0 || w <= 0 || h_block <= 0 || w_block <= 0) return TP_ERR_INVALID_ARGUMENT;
+  auto fit = [&](int hb, int wb, int* oh, int* ow) {
+    // train.py:701-708 — Python float (double) ratios, round() half-to-even, min clamp
+    const double h_ratio = static_cast<double>(kBlockPx * hb) / static_cast<double>(h);
+    const double w_ratio = static_cast<double>(kBlockPx * wb) / static_cast<double>(w);
+    if (h_ratio <= w_ratio) {
+      *oh = kBlockPx * hb;
+      const long long r = py_round(static_cast<double>(w) * h_ratio);
+      *ow = static_cast<int>(r < kBlockPx * wb ? r : kBlockPx * wb);
+    } else {
+      *ow = kBlockPx * wb;
+      const long long r = py_round(static_cast<double>(h) * w_ratio);
+      *oh = static_cast<int>(r < kBlockPx * hb ? r : kBlockPx * hb);
+    }
+  };
+  int a, b;
+  fit(h_block, w_block, &a, &b);
+  if (h_resized) *h_resized = a;
+  if (w_resized) *w_resized = b;
+  fit(1, 1, &a, &b);
+  if (h_thumb) *h_thumb = a;
+  if (w_thumb) *w_thumb = b;
+  return TP_OK;
+}
+
+int tp_hd_tile(const float* image, int64_t h, int64_t w, int h_block, int w_block, float* crops, void* stream_) {
+  if (image == nullptr || crops == nullptr || h <= 0 || w <= 0 || h_block <= 0 || w_block <= 0 || h > 32768 || w > 32768)
+    return TP_ERR_INVALID_ARGUMENT;
+  int h_r, w_r, h_t, w_t;
+  TP_TRY(tp_hd_fit(h, w, h_block, w_block, &h_r, &w_r, &h_t, &w_t));
+  if (h_r <= 0 || w_r <= 0) return TP_ERR_INVALID_ARGUMENT;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const long long total = 3ll * h_block * kBlockPx * w_block * kBlockPx;
+  hd_tile_main_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(image, static_cast<int>(h), static_cast<int>(w),
+                                                                                      h_block, w_block, h_r, w_r, crops);
+  TP_CUDA(cudaGetLastError());
+  if (h_block * w_block > 1) {
+    if (h_t <= 0 || w_t <= 0) return TP_ERR_INVALID_ARGUMENT;
+    const int t = 3 * kBlockPx * kBlockPx;
+    hd_tile_thumb_kernel<<<(t + 255) / 256, 256, 0, stream>>>(h_block, w_block, h_t, w_t, crops);
+    TP_CUDA(cudaGetLastError());
+  }
+  return TP_OK;
+}
+
+int tp_hd_plan(const int* h_block, const int* w_block, int64_t n_images, int tokens_per_crop, int64_t* seg_row_offset_host,
+               int64_t* sep_rows_host, int64_t* ret_rows_host, int64_t* cu_seqlens_host, int64_t* n_crops, int64_t* n_sep, int64_t* n_ret) {
+  if (h_block == nullptr || w_block == nullptr || n_images < 0 || tokens_per_crop <= 0) return TP_ERR_INVALID_ARGUMENT;
+  int64_t row = 0, crop = 0, sep = 0, ret = 0;
+  if (cu_seqlens_host) cu_seqlens_host[0] = 0;
+  for (int64_t b = 0; b < n_images; ++b) {
+    const int hb = h_block[b], wb = w_block[b];
+    if (hb <= 0 || wb <= 0) return TP_ERR_INVALID_ARGUMENT;
+    // llava_arch.py:141-152
+    for (int i = 0; i < hb; ++i) {
+      for (int j = 0; j < wb; ++j) {
+        if (seg_row_offset_host) seg_row_offset_host[crop] = row;
+        ++crop;
+        row += tokens_per_crop;
+        if (j < wb - 1) {
+          if (sep_rows_host) sep_rows_host[sep] = row;
+          ++sep;
+          ++row;
+        }
+      }
+      if (ret_rows_host) ret_rows_host[ret] = row;
+      ++ret;
+      ++row;
+    }
+    if (hb * wb > 1) {
+      if (seg_row_offset_host) seg_row_offset_host[crop] = row;
+      ++crop;
+      row += tokens_per_crop;
+      if (ret_rows_host) ret_rows_host[ret] = row;
+      ++ret;
+      ++row;
+    }
+    if (cu_seqlens_host) cu_seqlens_host[b + 1] = row;
+  }
+  if (n_crops) *n_crops = crop;
+  if (n_sep) *n_sep = sep;
+  if (n_ret) *n_ret = ret;
+  return TP_OK;
+}
+
+int tp_hd_fill_separators(void* out, int hidden, const int64_t* sep_rows, int64_t n_sep, const void* sep_row, const int64_t* ret_rows,
+                          int64_t n_ret, const void* ret_row, void* stream_) {
+  if (out == nullptr || hidden <= 0 || hidden % 8 != 0 || n_sep < 0 || n_ret < 0) return TP_ERR_INVALID_ARGUMENT;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const int vecs = hidden / 8;
+  if (n_sep > 0) {
+    if (sep_rows == nullptr || sep_row == nullptr) return TP_ERR_INVALID_ARGUMENT;
+    fill_rows_kernel<<<static_cast<unsigned>((n_sep * vecs + 255) / 256), 256, 0, stream>>>(
+        static_cast<__nv_bfloat16*>(out), hidden, reinterpret_cast<const long long*>(sep_rows), n_sep, static_cast<const __nv_bfloat16*>(sep_row));
+    TP_CUDA(cudaGetLastError());
+  }
+  if (n_ret > 0) {
+    if (ret_rows == nullptr || ret_row == nullptr) return TP_ERR_INVALID_ARGUMENT;
+    fill_rows_kernel<<<static_cast<unsigned>((n_ret * vecs + 255) / 256), 256, 0, stream>>>(
+        static_cast<__nv_bfloat16*>(out), hidden, reinterpret_cast<const long long*>(ret_rows), n_ret, static_cast<const __nv_bfloat16*>(ret_row));
+    TP_CUDA(cudaGetLastError());
+  }
+  return TP_OK;
+}
+
+}  // extern "C"

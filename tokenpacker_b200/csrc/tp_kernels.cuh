@@ -1,0 +1,274 @@
+// Non-GEMM kernels of the TokenPacker path: point-query stencil, local-window attention, weight packing,
+// and the HD front end (tiling, separator rows).  All HBM-bound: 16-byte vector accesses along the channel dim.
+#pragma once
+
+#include "tp_ptx.cuh"
+
+namespace tp {
+
+constexpr int kGrid = 24;       // builder.py:42 raw_grid
+constexpr int kTokens = 576;    // 24*24
+constexpr int kC = 1024;        // embed_dim / kv_dim (builder.py:43,45)
+constexpr int kCm = 4096;       // multi-level stack width (builder.py:61,67)
+constexpr int kHeads = 8;       // builder.py:44
+constexpr int kHeadDim = 128;
+
+__device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
+  f[0] = bf16_lo(v.x); f[1] = bf16_hi(v.x); f[2] = bf16_lo(v.y); f[3] = bf16_hi(v.y);
+  f[4] = bf16_lo(v.z); f[5] = bf16_hi(v.z); f[6] = bf16_lo(v.w); f[7] = bf16_hi(v.w);
+}
+
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  return make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+}
+
+// ------------------------------------------------------------------------------------------------
+// Point queries (builder.py:117-118): bilinear 24x24 -> g x g with align_corners=False is a fixed stencil per
+// s x s window — s=2: mean of the 2x2; s=3: the centre token; s=4: mean of the centre 2x2 — computed in fp32
+// (the reference upcasts with .float()) and rounded once to bf16 (.to(x.dtype)).
+// One thread per 8 channels of one query.
+// ------------------------------------------------------------------------------------------------
+template <int S>
+__global__ void point_query_kernel(const __nv_bfloat16* __restrict__ x0, long long crop_stride, __nv_bfloat16* __restrict__ q,
+                                   long long n_queries) {
+  constexpr int G = kGrid / S;
+  constexpr int M = G * G;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long query = idx >> 7;          // 128 vectors of 8 channels per query
+  const int vec = static_cast<int>(idx & 127);
+  if (query >= n_queries) return;
+  const long long n = query / M;
+  const int m = static_cast<int>(query - n * M);
+  const int hb = m / G, wb = m - hb * G;
+  const __nv_bfloat16* base = x0 + n * crop_stride + vec * 8;
+  auto tok = [&](int r, int c) { return __ldg(reinterpret_cast<const uint4*>(base + static_cast<long long>(r * kGrid + c) * kC)); };
+  uint4 out;
+  if (S == 3) {
+    out = tok(hb * 3 + 1, wb * 3 + 1);
+  } else {
+    const int r0 = hb * S + (S == 2 ? 0 : 1);
+    const int c0 = wb * S + (S == 2 ? 0 : 1);
+    float a[8], b[8], c[8], d[8], o[8];
+    unpack8(tok(r0, c0), a);
+    unpack8(tok(r0, c0 + 1), b);
+    unpack8(tok(r0 + 1, c0), c);
+    unpack8(tok(r0 + 1, c0 + 1), d);
+    // 0.5*(0.5a+0.5b) + 0.5*(0.5c+0.5d): scaling by powers of two is exact, so this association is bit-identical
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = 0.25f * ((a[i] + b[i]) + (c[i] + d[i]));
+    out = pack8(o);
+  }
+  *reinterpret_cast<uint4*>(q + query * kC + vec * 8) = out;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Local-window cross attention core (builder.py:122-130 == nn.MultiheadAttention with L=1, S=s*s):
+//   per query (n, hb, wb) and head h:  p = softmax_j( q'_h . k'_{j,h} ),  ctx_h = sum_j p_j v'_{j,h}
+// q' is already scaled by 1/sqrt(128) (fused into the in_proj_q GEMM epilogue).  The window gather
+// (divide_feature, builder.py:96-105) is pure address arithmetic here: fine token (hb*s+hi, wb*s+wi).
+// One warp per query; lane l owns channels {256*i + 8*l .. +7 : i=0..3}; channel block i of lanes 0-15 is head 2i,
+// of lanes 16-31 head 2i+1, so a head's dot product is a 16-lane shuffle reduction.
+// ------------------------------------------------------------------------------------------------
+template <int S>
+__global__ void __launch_bounds__(256) window_attn_kernel(const __nv_bfloat16* __restrict__ qp, const __nv_bfloat16* __restrict__ kp,
+                                                          const __nv_bfloat16* __restrict__ vp, __nv_bfloat16* __restrict__ ctx,
+                                                          long long n_queries) {
+  constexpr int G = kGrid / S;
+  constexpr int M = G * G;
+  constexpr int W = S * S;
+  const long long query = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (query >= n_queries) return;
+  const long long n = query / M;
+  const int m = static_cast<int>(query - n * M);
+  const int hb = m / G, wb = m - hb * G;
+  const long long tok0 = n * kTokens + static_cast<long long>(hb * S) * kGrid + wb * S;
+
+  float qf[4][8];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) unpack8(__ldg(reinterpret_cast<const uint4*>(qp + query * kC + i * 256 + lane * 8)), qf[i]);
+
+  float sc[4][W];
+#pragma unroll
+  for (int j = 0; j < W; ++j) {
+    const long long tok = tok0 + (j / S) * kGrid + (j % S);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float kf[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(kp + tok * kC + i * 256 + lane * 8)), kf);
+      float d = 0.f;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) d = fmaf(qf[i][e], kf[e], d);
+      sc[i][j] = d;
+    }
+  }
+  // 16-lane reductions (lanes 0-15 and 16-31 hold different heads)
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < W; ++j) {
+      float d = sc[i][j];
+      d += __shfl_xor_sync(0xffffffffu, d, 8);
+      d += __shfl_xor_sync(0xffffffffu, d, 4);
+      d += __shfl_xor_sync(0xffffffffu, d, 2);
+      d += __shfl_xor_sync(0xffffffffu, d, 1);
+      sc[i][j] = d;
+    }
+  // softmax over the W keys, fp32
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float mx = sc[i][0];
+#pragma unroll
+    for (int j = 1; j < W; ++j) mx = fmaxf(mx, sc[i][j]);
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < W; ++j) {
+      sc[i][j] = __expf(sc[i][j] - mx);
+      sum += sc[i][j];
+    }
+    const float inv = 1.0f / sum;
+#pragma unroll
+    for (int j = 0; j < W; ++j) sc[i][j] *= inv;
+  }
+  float of[4][8];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) of[i][e] = 0.f;
+#pragma unroll
+  for (int j = 0; j < W; ++j) {
+    const long long tok = tok0 + (j / S) * kGrid + (j % S);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float vf[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(vp + tok * kC + i * 256 + lane * 8)), vf);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) of[i][e] = fmaf(sc[i][j], vf[e], of[i][e]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(ctx + query * kC + i * 256 + lane * 8) = pack8(of[i]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Weight packing
+// ------------------------------------------------------------------------------------------------
+__global__ void bf16_to_f32_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = __bfloat162float(src[i]);
+}
+
+// LayerNorm folded into the following linear (one warp per output feature o):
+//   LN(y) W^T + b = rstd * ( y (gamma.W)^T - mu * rowsum(gamma.W) ) + ( W beta + b )
+//   w_out[o,:] = bf16(W[o,:] * gamma),  wsum[o] = sum_i w_out[o,i] (of the ROUNDED values),  cst[o] = W[o,:].beta + b[o]
+__global__ void fold_layernorm_kernel(const __nv_bfloat16* __restrict__ w, const __nv_bfloat16* __restrict__ bias,
+                                      const __nv_bfloat16* __restrict__ gamma, const __nv_bfloat16* __restrict__ beta,
+                                      __nv_bfloat16* __restrict__ w_out, float* __restrict__ wsum, float* __restrict__ cst,
+                                      int out_dim, int in_dim) {
+  const int o = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (o >= out_dim) return;
+  float s = 0.f, c = 0.f;
+  for (int i = lane; i < in_dim; i += 32) {
+    const float wv = __bfloat162float(w[static_cast<long long>(o) * in_dim + i]);
+    const __nv_bfloat16 folded = __float2bfloat16_rn(wv * __bfloat162float(gamma[i]));
+    w_out[static_cast<long long>(o) * in_dim + i] = folded;
+    s += __bfloat162float(folded);
+    c = fmaf(wv, __bfloat162float(beta[i]), c);
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, off);
+    c += __shfl_xor_sync(0xffffffffu, c, off);
+  }
+  if (lane == 0) {
+    wsum[o] = s;
+    cst[o] = c + __bfloat162float(bias[o]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// HD front end
+// ------------------------------------------------------------------------------------------------
+constexpr int kBlockPx = 336;   // train.py:699 block_size
+
+struct LinearTap {
+  int i0, i1;
+  float w0, w1;
+};
+
+// ATen upsample_bilinear2d, align_corners=False, scales derived from sizes: src = (in/out)*(dst+0.5)-0.5 clamped at 0.
+__device__ __forceinline__ LinearTap linear_tap(int dst, int in_size, int out_size) {
+  const float scale = static_cast<float>(in_size) / static_cast<float>(out_size);
+  float src = __fmaf_rn(scale, static_cast<float>(dst) + 0.5f, 0.f) - 0.5f;   // keep mul and sub separately rounded
+  src = fmaxf(src, 0.f);
+  LinearTap t;
+  t.i0 = min(static_cast<int>(src), in_size - 1);
+  t.i1 = t.i0 + (t.i0 < in_size - 1 ? 1 : 0);
+  t.w1 = fminf(fmaxf(src - static_cast<float>(t.i0), 0.f), 1.f);
+  t.w0 = 1.f - t.w1;
+  return t;
+}
+
+__device__ __forceinline__ float bilerp(float a, float b, float c, float d, const LinearTap& ty, const LinearTap& tx) {
+  const float top = __fadd_rn(__fmul_rn(tx.w0, a), __fmul_rn(tx.w1, b));
+  const float bot = __fadd_rn(__fmul_rn(tx.w0, c), __fmul_rn(tx.w1, d));
+  return __fadd_rn(__fmul_rn(ty.w0, top), __fmul_rn(ty.w1, bot));
+}
+
+// Pass 1 (train.py:709-717): crops[(i*wb+j), ch, y, x] = canvas[ch, 336 i + y, 336 j + x], canvas = zero-padded
+// bilinear resize of image[3,h,w] to (h_r, w_r).
+__global__ void hd_tile_main_kernel(const float* __restrict__ image, int h, int w, int hb, int wb, int h_r, int w_r,
+                                    float* __restrict__ crops) {
+  const long long total = 3ll * hb * kBlockPx * wb * kBlockPx;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int cw = wb * kBlockPx, chh = hb * kBlockPx;
+  const int X = static_cast<int>(idx % cw);
+  const int Y = static_cast<int>((idx / cw) % chh);
+  const int ch = static_cast<int>(idx / (static_cast<long long>(cw) * chh));
+  float v = 0.f;
+  if (Y < h_r && X < w_r) {
+    const LinearTap ty = linear_tap(Y, h, h_r), tx = linear_tap(X, w, w_r);
+    const float* p = image + static_cast<long long>(ch) * h * w;
+    v = bilerp(p[static_cast<long long>(ty.i0) * w + tx.i0], p[static_cast<long long>(ty.i0) * w + tx.i1],
+               p[static_cast<long long>(ty.i1) * w + tx.i0], p[static_cast<long long>(ty.i1) * w + tx.i1], ty, tx);
+  }
+  const int ci = Y / kBlockPx, cj = X / kBlockPx;
+  const int y = Y - ci * kBlockPx, x = X - cj * kBlockPx;
+  crops[((static_cast<long long>(ci * wb + cj) * 3 + ch) * kBlockPx + y) * kBlockPx + x] = v;
+}
+
+// Pass 2 (train.py:718-730): thumbnail = zero-padded bilinear resize of the PADDED canvas (read back from the crop
+// layout written by pass 1) to (h_t, w_t); stored as crop index hb*wb.
+__global__ void hd_tile_thumb_kernel(int hb, int wb, int h_t, int w_t, float* __restrict__ crops) {
+  const int total = 3 * kBlockPx * kBlockPx;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int x = idx % kBlockPx;
+  const int y = (idx / kBlockPx) % kBlockPx;
+  const int ch = idx / (kBlockPx * kBlockPx);
+  float v = 0.f;
+  if (y < h_t && x < w_t) {
+    const LinearTap ty = linear_tap(y, hb * kBlockPx, h_t), tx = linear_tap(x, wb * kBlockPx, w_t);
+    auto canvas = [&](int Y, int X) {
+      const int ci = Y / kBlockPx, cj = X / kBlockPx;
+      return crops[((static_cast<long long>(ci * wb + cj) * 3 + ch) * kBlockPx + (Y - ci * kBlockPx)) * kBlockPx + (X - cj * kBlockPx)];
+    };
+    v = bilerp(canvas(ty.i0, tx.i0), canvas(ty.i0, tx.i1), canvas(ty.i1, tx.i0), canvas(ty.i1, tx.i1), ty, tx);
+  }
+  crops[((static_cast<long long>(hb * wb) * 3 + ch) * kBlockPx + y) * kBlockPx + x] = v;
+}
+
+// out[rows[i], :] = row (bf16 [hidden]); one thread per 8 channels.
+__global__ void fill_rows_kernel(__nv_bfloat16* __restrict__ out, int hidden, const long long* __restrict__ rows, long long n_rows,
+                                 const __nv_bfloat16* __restrict__ row) {
+  const int vecs = hidden / 8;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= n_rows * vecs) return;
+  const long long r = idx / vecs;
+  const int v = static_cast<int>(idx - r * vecs);
+  *reinterpret_cast<uint4*>(out + rows[r] * hidden + v * 8) = __ldg(reinterpret_cast<const uint4*>(row + v * 8));
+}
+
+}  // namespace tp

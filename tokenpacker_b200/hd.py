@@ -1,0 +1,132 @@
+"""TokenPacker-HD front end: grid selection, crop tiling and slice assembly, host side of the C ABI.
+
+Mirrors the reference seams:
+  * ``Image_Patch(image_size=336, patch_num).calculate(h, w)``        llava/patch_divide.py:71-105
+  * the inline resize -> pad -> split -> thumbnail block              llava/train/train.py:695-731 (9 pasted copies)
+  * the per-image interleaving of crop tokens with ',' / '\\n' rows   llava/model/llava_arch.py:139-155
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import torch
+
+from ._lib import lib, check
+
+BLOCK = 336
+
+
+def hd_grid(h: int, w: int, patch_num: int = 9, image_size: int = BLOCK):
+    hb, wb = C.c_int(0), C.c_int(0)
+    check(lib.tp_hd_grid(int(h), int(w), int(patch_num), int(image_size), C.byref(hb), C.byref(wb)), "tp_hd_grid")
+    return hb.value, wb.value
+
+
+class Image_Patch:
+    """Same constructor and ``calculate`` contract as patch_divide.py:71-105 (returns the (h_block, w_block) tuple)."""
+
+    def __init__(self, image_size=336, patch_num=9):
+        if patch_num not in (9, 16, 25):
+            raise NotImplementedError                                    # patch_divide.py:79-80
+        if isinstance(image_size, (tuple, list)):
+            if image_size[0] != image_size[1]:
+                raise NotImplementedError("square crops only (the reference always passes 336)")
+            image_size = image_size[0]
+        self.image_size = (image_size, image_size)
+        self.patch_num = patch_num
+
+    def calculate(self, h, w):
+        return hd_grid(h, w, self.patch_num, self.image_size[0])
+
+
+def hd_fit(h: int, w: int, hb: int, wb: int):
+    a, b, c, d = C.c_int(0), C.c_int(0), C.c_int(0), C.c_int(0)
+    check(lib.tp_hd_fit(int(h), int(w), hb, wb, C.byref(a), C.byref(b), C.byref(c), C.byref(d)), "tp_hd_fit")
+    return (a.value, b.value), (c.value, d.value)
+
+
+def n_crops(hb: int, wb: int) -> int:
+    return hb * wb + (1 if hb * wb > 1 else 0)
+
+
+def hd_tile(image: torch.Tensor, patch_num: int = 9):
+    """train.py:695-731 on the GPU.  image: float32 CUDA tensor [1,3,h,w] (or [3,h,w]), already normalised.
+    Returns (crops [hb*wb(+1), 3, 336, 336] float32, h_block, w_block)."""
+    if image.dim() == 4:
+        if image.shape[0] != 1:
+            raise ValueError("one image per call: [1,3,h,w]")
+        image = image[0]
+    if image.dim() != 3 or image.shape[0] != 3:
+        raise ValueError("image must be [1,3,h,w] or [3,h,w]")
+    if not image.is_cuda:
+        raise RuntimeError("tokenpacker_b200 has no CPU path: image must be a CUDA tensor")
+    image = image.to(torch.float32).contiguous()
+    h, w = int(image.shape[1]), int(image.shape[2])
+    hb, wb = hd_grid(h, w, patch_num)
+    with torch.cuda.device(image.device):
+        crops = torch.empty((n_crops(hb, wb), 3, BLOCK, BLOCK), dtype=torch.float32, device=image.device)
+        stream = torch.cuda.current_stream(image.device).cuda_stream
+        check(lib.tp_hd_tile(image.data_ptr(), h, w, hb, wb, crops.data_ptr(), stream), "tp_hd_tile")
+    return crops, hb, wb
+
+
+def hd_seq_len(hb: int, wb: int, m: int) -> int:
+    return hb * wb * m + hb * (wb - 1) + hb + ((m + 1) if hb * wb > 1 else 0)
+
+
+@dataclass
+class HdPlan:
+    n_crops: int
+    seg_row_offset: torch.Tensor   # int64 [n_crops]   destination row of each crop's first token
+    sep_rows: torch.Tensor         # int64 [n_sep]     rows holding the ',' embedding
+    ret_rows: torch.Tensor         # int64 [n_ret]     rows holding the '\n' embedding
+    cu_seqlens: torch.Tensor       # int64 [B+1]
+
+
+def hd_plan(h_block, w_block, tokens_per_crop: int) -> HdPlan:
+    hb = [int(v) for v in h_block]
+    wb = [int(v) for v in w_block]
+    if len(hb) != len(wb):
+        raise ValueError("h_block and w_block must have the same length")
+    b = len(hb)
+    arr = C.c_int * max(b, 1)
+    hb_c, wb_c = arr(*hb), arr(*wb)
+    nc, ns, nr = C.c_int64(0), C.c_int64(0), C.c_int64(0)
+    check(lib.tp_hd_plan(hb_c, wb_c, b, tokens_per_crop, None, None, None, None, C.byref(nc), C.byref(ns), C.byref(nr)), "tp_hd_plan")
+    seg = torch.empty(nc.value, dtype=torch.int64)
+    sep = torch.empty(ns.value, dtype=torch.int64)
+    ret = torch.empty(nr.value, dtype=torch.int64)
+    cu = torch.empty(b + 1, dtype=torch.int64)
+    p64 = C.POINTER(C.c_int64)
+    check(lib.tp_hd_plan(hb_c, wb_c, b, tokens_per_crop, C.cast(seg.data_ptr(), p64), C.cast(sep.data_ptr(), p64),
+                         C.cast(ret.data_ptr(), p64), C.cast(cu.data_ptr(), p64), C.byref(nc), C.byref(ns), C.byref(nr)), "tp_hd_plan")
+    return HdPlan(nc.value, seg, sep, ret, cu)
+
+
+def hd_assemble(feats: torch.Tensor, h_block, w_block, sep_row: torch.Tensor, ret_row: torch.Tensor):
+    """llava_arch.py:139-155 for already-projected crop features [sum(crops), M, H] (bf16, CUDA).
+
+    Standalone form of the assembly (used after the multi-GPU all-gather); ``TokenPackerB200.forward_packed`` fuses
+    the same scatter into the projector's last GEMM instead.  Returns (packed [sum(L_i), H], cu_seqlens)."""
+    if not feats.is_cuda:
+        raise RuntimeError("tokenpacker_b200 has no CPU path: feats must be a CUDA tensor")
+    m, hdim = int(feats.shape[1]), int(feats.shape[2])
+    plan = hd_plan(h_block, w_block, m)
+    if plan.n_crops != feats.shape[0]:
+        raise ValueError(f"grids describe {plan.n_crops} crops but {feats.shape[0]} were given")
+    device = feats.device
+    fb = feats.to(torch.bfloat16).contiguous()
+    with torch.cuda.device(device):
+        out = torch.empty((int(plan.cu_seqlens[-1]), hdim), dtype=torch.bfloat16, device=device)
+        seg = plan.seg_row_offset.to(device)
+        # crop tokens: a strided block copy per crop, expressed as one indexed copy (plumbing: torch device copy)
+        rows = (seg[:, None] + torch.arange(m, device=device)[None, :]).reshape(-1)
+        out.index_copy_(0, rows, fb.reshape(-1, hdim))
+        sep_rows, ret_rows = plan.sep_rows.to(device), plan.ret_rows.to(device)
+        sep_b = sep_row.to(device=device, dtype=torch.bfloat16).contiguous()
+        ret_b = ret_row.to(device=device, dtype=torch.bfloat16).contiguous()
+        stream = torch.cuda.current_stream(device).cuda_stream
+        check(lib.tp_hd_fill_separators(out.data_ptr(), hdim, sep_rows.data_ptr(), sep_rows.numel(), sep_b.data_ptr(),
+                                        ret_rows.data_ptr(), ret_rows.numel(), ret_b.data_ptr(), stream), "tp_hd_fill_separators")
+    return (out if feats.dtype == torch.bfloat16 else out.to(feats.dtype)), plan.cu_seqlens

@@ -1,0 +1,203 @@
+"""Host-side mirror of the reference projector interface (llava/model/multimodal_projector/builder.py).
+
+``TokenPackerB200`` keeps the reference module's constructor arguments (builder.py:40-49), its parameter names and
+shapes (so ``mm_projector.bin`` checkpoints load unchanged, llava_arch.py:78-83), its ``forward(x, attn_mask=None)``
+signature with ``x = (feat[N,576,1024], feat_multi[N,576,4096])`` as handed over by ``CLIPVisionTower.forward``
+(clip_encoder.py:62) and its ``[N, (24/s)^2, hidden]`` contiguous output (builder.py:136-137).  All arithmetic is
+done by libtokenpacker_b200.so; the ``nn.Linear`` / ``nn.LayerNorm`` / ``nn.MultiheadAttention`` children below are
+parameter containers only — their ``forward`` is never called.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from functools import partial
+
+import torch
+import torch.nn as nn
+from torch.nn.init import trunc_normal_
+
+from . import _lib
+from ._lib import lib, check
+
+_CLIP_LAYERS = 4          # builder.py:61,67: the multi-level stack is 4 CLIP layers x 1024 = 4096 (hard-coded upstream)
+
+
+class IdentityMap(nn.Module):
+    """builder.py:11-20 (unused upstream; kept so `from ... import IdentityMap` keeps working)."""
+
+    def forward(self, x, *args, **kwargs):
+        return x
+
+    @property
+    def config(self):
+        return {"mm_projector_type": "identity"}
+
+
+def _two_layer(in_dim: int, mid: int, out: int) -> nn.Sequential:
+    # index 0 and 2 carry parameters, index 1 is the GELU: gives the state_dict keys "<name>.0.*" / "<name>.2.*"
+    return nn.Sequential(nn.Linear(in_dim, mid), nn.GELU(), nn.Linear(mid, out))
+
+
+class TokenPackerB200(nn.Module):
+    def __init__(self, raw_grid=24, embed_dim=1024, num_heads=1024 // 128, kv_dim=1024, hidden_size=4096, scale_factor=2,
+                 norm_layer=partial(nn.LayerNorm, eps=1e-6)):
+        super().__init__()
+        if raw_grid % scale_factor != 0:
+            raise ValueError("scale_factor must be divisible by grid size")      # builder.py:51-52, same message
+        if (raw_grid, embed_dim, num_heads, kv_dim) != (24, 1024, 8, 1024):
+            raise NotImplementedError("the sm_100a kernels are specialised for CLIP-ViT-L/14-336: raw_grid=24, "
+                                      "embed_dim=kv_dim=1024, num_heads=8 (the only configuration the reference builds)")
+        if scale_factor not in (2, 3, 4):
+            raise NotImplementedError("scale_factor must be 2, 3 or 4 (144 / 64 / 36 tokens)")
+        if hidden_size % 32 != 0:
+            raise NotImplementedError("hidden_size must be a multiple of 32")
+        self.raw_grid = raw_grid
+        self.grid_size = raw_grid // scale_factor
+        self.num_queries = self.grid_size ** 2
+        self.embed_dim = embed_dim
+        self.num_heads = num_heads
+        self.scale_factor = scale_factor
+        self.hidden_size = hidden_size
+
+        self.q_proj_1 = nn.Linear(kv_dim, embed_dim, bias=False)
+        self.k_proj_1 = _two_layer(_CLIP_LAYERS * 1024, 1024, 1024)
+        self.v_proj_1 = _two_layer(_CLIP_LAYERS * 1024, 1024, 1024)
+        self.ln_q_1 = norm_layer(embed_dim)
+        self.ln_k_1 = norm_layer(embed_dim)
+        self.ln_v_1 = norm_layer(embed_dim)
+        self.clip_attn = nn.MultiheadAttention(embed_dim, num_heads)
+        self.mlp = _two_layer(1024, hidden_size, hidden_size)
+        for ln in (self.ln_q_1, self.ln_k_1, self.ln_v_1):
+            if abs(ln.eps - 1e-6) > 1e-12 or not ln.elementwise_affine:
+                raise NotImplementedError("norm_layer must be LayerNorm(eps=1e-6) with affine parameters")
+        self.apply(self._init_weights)
+        self._packed = None
+        self._packed_key = None
+
+    @staticmethod
+    def _init_weights(m):
+        # builder.py:87-94: trunc_normal(std=.02) Linear weights, zero biases, LayerNorm (1, 0).  Like upstream this
+        # leaves clip_attn.in_proj_weight at nn.MultiheadAttention's own xavier init (it is not an nn.Linear).
+        if isinstance(m, nn.Linear):
+            trunc_normal_(m.weight, std=.02)
+            if m.bias is not None:
+                nn.init.constant_(m.bias, 0)
+        elif isinstance(m, nn.LayerNorm):
+            nn.init.constant_(m.bias, 0)
+            nn.init.constant_(m.weight, 1.0)
+
+    # ------------------------------------------------------------------------------------------------------------
+    # derived weight cache
+    # ------------------------------------------------------------------------------------------------------------
+    def _raw_params(self):
+        sd = dict(self.named_parameters())
+        return [sd[key] for _, key in _lib.WEIGHT_FIELDS]
+
+    def _packed_weights(self, device):
+        params = self._raw_params()
+        key = (str(device),) + tuple((p.data_ptr(), p._version, p.dtype) for p in params)
+        if self._packed is not None and self._packed_key == key:
+            return self._packed
+        bf = [p.detach().to(device=device, dtype=torch.bfloat16).contiguous() for p in params]
+        w = _lib.TpWeights(*[t.data_ptr() for t in bf])
+        nbytes = lib.tp_packed_bytes(self.hidden_size)
+        packed = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        stream = torch.cuda.current_stream(device).cuda_stream
+        check(lib.tp_pack_weights(C.byref(w), self.hidden_size, packed.data_ptr(), nbytes, stream), "tp_pack_weights")
+        self._keepalive = bf     # sources must outlive the asynchronous packing kernels
+        self._packed, self._packed_key = packed, key
+        return packed
+
+    # ------------------------------------------------------------------------------------------------------------
+    # forward
+    # ------------------------------------------------------------------------------------------------------------
+    @staticmethod
+    def _as_crop_strided(t: torch.Tensor, width: int):
+        """Return (tensor, crop_stride) with unit channel stride and dense rows; [:,1:] CLIP views pass through."""
+        if t.stride(2) == 1 and t.stride(1) == width and t.stride(0) >= 576 * width and t.stride(0) % 8 == 0 \
+                and t.data_ptr() % 16 == 0:
+            return t, t.stride(0)
+        t = t.contiguous()
+        return t, t.stride(0)
+
+    def _check_inputs(self, x, attn_mask):
+        if attn_mask is not None:
+            raise NotImplementedError("attn_mask must be None (the reference's sole caller passes none, llava_arch.py:97)")
+        if not isinstance(x, (tuple, list)) or len(x) != 2:
+            raise TypeError("x must be the (feat, feat_multi) pair returned by CLIPVisionTower.forward")
+        x0, xm = x[0], x[1]
+        if x0.dim() != 3 or xm.dim() != 3 or x0.shape[1:] != (576, 1024) or xm.shape[1:] != (576, 4096) \
+                or x0.shape[0] != xm.shape[0]:
+            raise ValueError(f"expected feat [N,576,1024] and feat_multi [N,576,4096], got {tuple(x0.shape)} {tuple(xm.shape)}")
+        if not (x0.is_cuda and xm.is_cuda):
+            raise RuntimeError("tokenpacker_b200 has no CPU path: inputs must be CUDA tensors on a B200")
+        if torch.is_grad_enabled() and (x0.requires_grad or xm.requires_grad or any(p.requires_grad for p in self.parameters())):
+            raise NotImplementedError("backward is not implemented yet: call under torch.no_grad() / inference_mode()")
+        return x0, xm
+
+    def forward(self, x, attn_mask=None):
+        x0, xm = self._check_inputs(x, attn_mask)
+        out_dtype = x0.dtype
+        n = x0.shape[0]
+        device = x0.device
+        if n == 0:
+            return x0.new_empty((0, self.num_queries, self.hidden_size))
+        with torch.cuda.device(device):
+            x0b, s0 = self._as_crop_strided(x0.to(torch.bfloat16), 1024)
+            xmb, sm = self._as_crop_strided(xm.to(torch.bfloat16), 4096)
+            out = torch.empty((n, self.num_queries, self.hidden_size), dtype=torch.bfloat16, device=device)
+            self._launch(x0b, s0, xmb, sm, out, None)
+        return out if out_dtype == torch.bfloat16 else out.to(out_dtype)
+
+    def _launch(self, x0b, s0, xmb, sm, out, seg_row_offset):
+        device = x0b.device
+        n = x0b.shape[0]
+        packed = self._packed_weights(device)
+        ws_bytes = lib.tp_workspace_bytes(n, self.scale_factor, self.hidden_size)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=device)
+        stream = torch.cuda.current_stream(device).cuda_stream
+        seg_ptr = seg_row_offset.data_ptr() if seg_row_offset is not None else None
+        check(lib.tp_forward(packed.data_ptr(), x0b.data_ptr(), xmb.data_ptr(), n, s0, sm, self.scale_factor,
+                             self.hidden_size, out.data_ptr(), seg_ptr, ws.data_ptr(), ws_bytes, stream), "tp_forward")
+
+    def forward_packed(self, x, h_block, w_block, sep_row, ret_row):
+        """Projector + HD slice assembly (llava_arch.py:139-155) in one pass.
+
+        x as in forward(), crops ordered image by image (grid row-major, then the thumbnail); h_block / w_block:
+        per-image grids; sep_row / ret_row: the ',' and '\\n' embedding rows [hidden].  The last GEMM's epilogue writes
+        every crop's tokens straight to its place in the packed sequence; separator rows are filled by a tiny kernel.
+        Returns (packed [sum(L_i), hidden], cu_seqlens int64 [B+1] on the host)."""
+        from .hd import hd_plan
+        x0, xm = self._check_inputs(x, None)
+        device = x0.device
+        plan = hd_plan(h_block, w_block, self.num_queries)
+        if plan.n_crops != x0.shape[0]:
+            raise ValueError(f"grids describe {plan.n_crops} crops but {x0.shape[0]} were given")
+        with torch.cuda.device(device):
+            x0b, s0 = self._as_crop_strided(x0.to(torch.bfloat16), 1024)
+            xmb, sm = self._as_crop_strided(xm.to(torch.bfloat16), 4096)
+            total = int(plan.cu_seqlens[-1])
+            out = torch.empty((total, self.hidden_size), dtype=torch.bfloat16, device=device)
+            seg = plan.seg_row_offset.to(device, non_blocking=True)
+            self._launch(x0b, s0, xmb, sm, out, seg)
+            sep_rows = plan.sep_rows.to(device, non_blocking=True)
+            ret_rows = plan.ret_rows.to(device, non_blocking=True)
+            sep_b = sep_row.to(device=device, dtype=torch.bfloat16).contiguous()
+            ret_b = ret_row.to(device=device, dtype=torch.bfloat16).contiguous()
+            stream = torch.cuda.current_stream(device).cuda_stream
+            check(lib.tp_hd_fill_separators(out.data_ptr(), self.hidden_size, sep_rows.data_ptr(), sep_rows.numel(),
+                                            sep_b.data_ptr(), ret_rows.data_ptr(), ret_rows.numel(), ret_b.data_ptr(), stream),
+                  "tp_hd_fill_separators")
+        return (out if x0.dtype == torch.bfloat16 else out.to(x0.dtype)), plan.cu_seqlens
+
+    def extra_repr(self):
+        return f"scale_factor={self.scale_factor}, num_queries={self.num_queries}, hidden_size={self.hidden_size}, backend=sm_100a"
+
+
+# the reference's class name, so `from ...builder import TokenPacker` style imports can be redirected unchanged
+TokenPacker = TokenPackerB200
+
+
+def build_vision_projector(config):
+    """builder.py:144-145 — ignores mm_projector_type exactly like upstream."""
+    return TokenPackerB200(hidden_size=config.hidden_size, scale_factor=config.scale_factor)
