@@ -1,0 +1,293 @@
+#!/usr/bin/env python
+"""Benchmark of the TokenPacker projector hot path on B200 (contract: see the task brief / DESIGN.md §Measurement).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+One "step" = one TokenPacker.forward over one batch of synthetic CLIP features per GPU.  Workload at every N:
+BASELINE.json configs[1] per GPU — batch=64 crops of 576x1024 (+576x4096 multi-level) bf16 features, scale_factor=2,
+hidden=4096 -> 9,216 compressed tokens per GPU per step (weak scaling: crops shard across ranks, no data-path
+collective; weights replicated).  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = "compressed_visual_tokens_per_sec"
+UNIT = "tokens/s"
+N_CROPS, SCALE, HIDDEN = 64, 2, 4096
+TOKENS_PER_CROP = (24 // SCALE) ** 2
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_burst": p["bf16_tflops"], "bf16_sustained": p.get("bf16_tflops_sustained", p["bf16_tflops"]),
+                "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "bf16_burst": 1590.0, "bf16_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle sampling during the timed region (B200_PROFILING.md recipe)."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index: int):
+        self.rows, self.proc, self.thread = [], None, None
+        self.gpu_index = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu_index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t0=None, t1=None):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        rows = [r for t, r in self.rows if (t0 is None or t >= t0) and (t1 is None or t <= t1)] or [r for _, r in self.rows]
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            f = [v.strip() for v in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)), "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+def cpu_reference_run(steps: int, warmup: int, crops: int):
+    """The reference's own algorithm as PyTorch-CPU ops (oracle/torch_port.py, pinned to the reference fixtures) on all
+    host threads, fp32 (the reference's CPU dtype).  One step = one forward over a bounded sample of ``crops`` crops of the
+    configs[1] workload; exactly ``steps`` steps are timed after ``warmup`` untimed ones."""
+    from oracle import tokenpacker_oracle as tpo
+    from oracle import torch_port
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    params = {k: torch.from_numpy(v) for k, v in tpo.make_params(HIDDEN, seed=0).items()}
+    x0, xm = tpo.make_inputs(crops, seed=1234)
+    x0, xm = torch.from_numpy(x0), torch.from_numpy(xm)
+    with torch.no_grad():
+        for _ in range(warmup):
+            torch_port.forward(params, x0, xm, SCALE)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            torch_port.forward(params, x0, xm, SCALE)
+        dt = (time.perf_counter() - t0) / steps
+    return {"value": crops * TOKENS_PER_CROP / dt, "unit": UNIT, "cores": int(torch.get_num_threads()), "kind": "port",
+            "sample": f"{crops} crops/step x {steps} steps of the configs[1] workload (fp32, torch {torch.__version__} CPU ops, "
+                      f"oracle/torch_port.py restatement of builder.py:107-137), {dt * 1e3:.1f} ms/step"}, dt
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path (the pinned PyTorch-CPU port; /root/reference is
+    not present on the GPU box and the reference is pure Python) on the host cores, same metric/config."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    crops = 8
+    cb, dt = cpu_reference_run(args.steps, args.warmup, crops)
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"BASELINE configs[1] bounded sample: {crops} crops/step of CLIP-ViT-L/14-336 feats 576x1024 + "
+                                   "576x4096, scale_factor=2, hidden=4096, reference algorithm on the host CPU"},
+            "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU baseline leg (profiling runs)")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg (profiling runs)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch multi-GPU runs with torch.distributed.run (one process per GPU)")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl ours needs a B200: tokenpacker_b200 has no CPU path")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    from tokenpacker_b200 import TokenPackerB200
+    from tokenpacker_b200 import synthetic as syn       # seeded synthetic weights + algorithmic FLOP/byte model
+
+    peaks = load_peaks()
+    torch.manual_seed(0)
+    model = TokenPackerB200(hidden_size=HIDDEN, scale_factor=SCALE)
+    model.load_state_dict({k: torch.from_numpy(v) for k, v in syn.synthetic_state_dict(HIDDEN, seed=0).items()})
+    model = model.to(dev, torch.bfloat16).eval()
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    x0 = torch.randn(N_CROPS, 576, 1024, device=dev, generator=g).to(torch.bfloat16)
+    xm = torch.randn(N_CROPS, 576, 4096, device=dev, generator=g).to(torch.bfloat16)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ------------------------------------------------------------------ device-resident throughput ("value")
+    with torch.no_grad():
+        for _ in range(args.warmup):
+            out = model((x0, xm))
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+            time.sleep(0.3)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t_wall0 = time.perf_counter()
+        e0.record()
+        for _ in range(args.steps):
+            out = model((x0, xm))
+        e1.record()
+        barrier()
+        t_wall1 = time.perf_counter()
+        elapsed_ms = e0.elapsed_time(e1)
+    if dist is not None:
+        t = torch.tensor([elapsed_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(t.item())
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+    ms_per_step = elapsed_ms / args.steps
+    tokens_per_step = N_CROPS * TOKENS_PER_CROP * world
+    value = tokens_per_step / (ms_per_step * 1e-3)
+    assert torch.isfinite(out.float()).all()
+
+    # ------------------------------------------------------------------ end to end through the public API, HOST buffers
+    e2e = None
+    if not args.no_e2e:
+        hx0 = x0.cpu().pin_memory()
+        hxm = xm.cpu().pin_memory()
+        hout = torch.empty((N_CROPS, TOKENS_PER_CROP, HIDDEN), dtype=torch.bfloat16).pin_memory()
+        with torch.no_grad():
+            for _ in range(2):
+                model.forward_host((hx0, hxm), out=hout, chunk_crops=8)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                model.forward_host((hx0, hxm), out=hout, chunk_crops=8)      # synchronous: result is in hout on return
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+        if dist is not None:
+            t = torch.tensor([dt], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        assert torch.equal(hout, out.cpu()), "host-buffer path and device path disagree"
+        e2e = {"value": tokens_per_step / (dt / args.steps), "unit": UNIT,
+               "h2d_bytes_per_step": int(hx0.numel() * 2 + hxm.numel() * 2), "d2h_bytes_per_step": int(hout.numel() * 2),
+               "ms_per_step": dt / args.steps * 1e3, "api": "TokenPackerB200.forward_host -> tp_forward_host (pinned host buffers, 8-crop chunks)"}
+
+    # ------------------------------------------------------------------ roofline of the dominant kernel
+    # tp_gemm_kernel<256> on its largest launch: h_kv = GELU(xm . [W_k0;W_v0]^T + b)  (M=36864, N=2048, K=4096), 56% of the
+    # step's FLOPs.  Timed live with CUDA events on the launching stream, 10 back-to-back launches after 3 warm-ups.
+    roofline = None
+    if rank == 0:
+        from tokenpacker_b200.kernels import gemm_bf16
+        m_, n_, k_ = N_CROPS * 576, 2048, 4096
+        wkv = torch.cat([model.k_proj_1[0].weight, model.v_proj_1[0].weight], 0).detach().contiguous()
+        bkv = torch.cat([model.k_proj_1[0].bias, model.v_proj_1[0].bias], 0).detach().float()
+        a2 = xm.reshape(m_, k_)
+        c2 = torch.empty((m_, n_), dtype=torch.bfloat16, device=dev)
+        for _ in range(3):
+            gemm_bf16(a2, wkv, bias=bkv, gelu=True, out=c2)
+        torch.cuda.synchronize()
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 10
+        r0.record()
+        for _ in range(reps):
+            gemm_bf16(a2, wkv, bias=bkv, gelu=True, out=c2)
+        r1.record()
+        torch.cuda.synchronize()
+        k_ms = r0.elapsed_time(r1) / reps
+        flops = 2.0 * m_ * n_ * k_
+        achieved = flops / (k_ms * 1e-3) / 1e12
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+        roofline = {"bound": "tensor", "kernel": "tp_gemm_kernel<256> (k/v_proj.0 GEMM, M=36864 N=2048 K=4096, bias+GELU epilogue)",
+                    "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_sustained"],
+                    "frac_of_burst": achieved / peaks["bf16_burst"], "peak_source": peaks["source"] + ", sustained (back-to-back launches)",
+                    "traffic": traffic, "ms_per_launch": k_ms, "flops_per_launch": flops,
+                    "step": {"achieved_tflops": syn.flops_per_crop(SCALE, HIDDEN) * N_CROPS / (ms_per_step * 1e-3) / 1e12,
+                             "frac_of_sustained": syn.flops_per_crop(SCALE, HIDDEN) * N_CROPS / (ms_per_step * 1e-3) / 1e12 / peaks["bf16_sustained"],
+                             "hbm_gbs": (syn.bytes_per_crop(SCALE, HIDDEN) * N_CROPS + syn.weight_bytes(HIDDEN)) / (ms_per_step * 1e-3) / 1e9,
+                             "hbm_frac": (syn.bytes_per_crop(SCALE, HIDDEN) * N_CROPS + syn.weight_bytes(HIDDEN)) / (ms_per_step * 1e-3) / 1e9 / peaks["hbm_gbs"]}}
+
+    # ------------------------------------------------------------------ CPU baseline (rank 0, N=1 only)
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu_baseline, _ = cpu_reference_run(steps=20, warmup=2, crops=8)
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+                "data": "synthetic",
+                "config": {"workload": "BASELINE configs[1] per GPU: batch=64 crops, CLIP-ViT-L/14-336 feats 576x1024 + 576x4096, "
+                                       "scale_factor=2 (144 tok/crop), hidden=4096, bf16, seeded random weights",
+                           "crops_per_gpu": N_CROPS, "tokens_per_step": tokens_per_step,
+                           "l2": "inputs 377 MB/step per GPU exceed the 126 MB L2 (no explicit flush needed)",
+                           "parallelism": f"dp{world} (crops sharded, weights replicated, no data-path collective)"},
+                "e2e": e2e, "gpu_launches": 13 * args.steps, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline}
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

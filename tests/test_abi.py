@@ -81,3 +81,13 @@ def test_init_statistics():
     m = TokenPackerB200(hidden_size=128)
     assert float(m.mlp[0].bias.abs().max()) == 0.0 and float(m.ln_k_1.weight.min()) == 1.0
     assert abs(float(m.k_proj_1[0].weight.std()) - 0.02) < 5e-4
+
+
+def test_synthetic_generators_agree_with_oracle_copy():
+    from oracle import tokenpacker_oracle as tpo
+    from tokenpacker_b200 import synthetic as syn
+    a, b = syn.synthetic_state_dict(128, 3), tpo.make_params(128, 3)
+    assert list(a) == list(b) and all(np.array_equal(a[k], b[k]) for k in a)
+    for s in (2, 3, 4):
+        assert syn.flops_per_crop(s) == tpo.flops_per_crop(s) and syn.bytes_per_crop(s) == tpo.bytes_per_crop(s)
+    assert syn.weight_bytes(4096) == 2 * 36_722_688

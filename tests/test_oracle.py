@@ -117,3 +117,16 @@ def test_hd_assemble(golden_dir):
     np.testing.assert_array_equal(cu, g["cu"])
     np.testing.assert_array_equal(packed, g["packed"])
     assert hdo.hd_seq_len(3, 3, 144) == 1450 and hdo.hd_seq_len(1, 1, 144) == 145 and hdo.hd_seq_len(5, 5, 36) == 962
+
+
+@pytest.mark.parametrize("s", [2, 3, 4])
+def test_torch_port_matches_reference(golden_dir, s):
+    """The PyTorch-CPU port that bench.py times as the CPU baseline reproduces the reference's own output."""
+    import torch
+    from oracle import torch_port
+    g = np.load(os.path.join(golden_dir, f"projector_s{s}_h128.npz"))
+    params = {k: torch.from_numpy(v) for k, v in tpo.make_params(int(g["hidden"]), seed=int(g["param_seed"])).items()}
+    x0, xm = tpo.make_inputs(int(g["n"]), seed=int(g["input_seed"]))
+    with torch.no_grad():
+        out = torch_port.forward(params, torch.from_numpy(x0), torch.from_numpy(xm), s).numpy()
+    assert np.abs(out - g["out"]).max() < 1e-6

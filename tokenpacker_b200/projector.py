@@ -160,6 +160,36 @@ class TokenPackerB200(nn.Module):
         check(lib.tp_forward(packed.data_ptr(), x0b.data_ptr(), xmb.data_ptr(), n, s0, sm, self.scale_factor,
                              self.hidden_size, out.data_ptr(), seg_ptr, ws.data_ptr(), ws_bytes, stream), "tp_forward")
 
+    def forward_host(self, x, out: torch.Tensor | None = None, chunk_crops: int = 8, device=None):
+        """End-to-end call with HOST tensors (pinned recommended): (feat, feat_multi) bf16 CPU tensors in, [N,M,H] bf16 CPU
+        tensor out.  Host->device copies, the kernels and the device->host copy are pipelined over chunks of crops inside
+        tp_forward_host; the call returns when ``out`` is complete."""
+        x0, xm = x[0], x[1]
+        if x0.is_cuda or xm.is_cuda or x0.dtype != torch.bfloat16 or xm.dtype != torch.bfloat16:
+            raise TypeError("forward_host takes bf16 CPU tensors")
+        if x0.shape[1:] != (576, 1024) or xm.shape[1:] != (576, 4096) or x0.shape[0] != xm.shape[0]:
+            raise ValueError("expected feat [N,576,1024] and feat_multi [N,576,4096]")
+        x0, xm = x0.contiguous(), xm.contiguous()
+        n = x0.shape[0]
+        device = torch.device(device if device is not None else next(self.parameters()).device)
+        if device.type != "cuda":
+            raise RuntimeError("tokenpacker_b200 has no CPU path: move the module to a B200 first")
+        if out is None:
+            out = torch.empty((n, self.num_queries, self.hidden_size), dtype=torch.bfloat16).pin_memory()
+        with torch.cuda.device(device):
+            packed = self._packed_weights(device)
+            chunk = max(1, min(int(chunk_crops), n))
+            d_x0 = torch.empty((n, 576, 1024), dtype=torch.bfloat16, device=device)
+            d_xm = torch.empty((n, 576, 4096), dtype=torch.bfloat16, device=device)
+            d_out = torch.empty((n, self.num_queries, self.hidden_size), dtype=torch.bfloat16, device=device)
+            ws_bytes = lib.tp_workspace_bytes(chunk, self.scale_factor, self.hidden_size)
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=device)
+            stream = torch.cuda.current_stream(device).cuda_stream
+            check(lib.tp_forward_host(packed.data_ptr(), x0.data_ptr(), xm.data_ptr(), n, self.scale_factor, self.hidden_size,
+                                      out.data_ptr(), d_x0.data_ptr(), d_xm.data_ptr(), d_out.data_ptr(), ws.data_ptr(), ws_bytes,
+                                      chunk, stream), "tp_forward_host")
+        return out
+
     def forward_packed(self, x, h_block, w_block, sep_row, ret_row):
         """Projector + HD slice assembly (llava_arch.py:139-155) in one pass.
 
