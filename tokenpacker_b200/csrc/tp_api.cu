@@ -3,6 +3,7 @@
 // (except tp_forward_host), no global mutable state.
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/tokenpacker_b200.h"
@@ -140,10 +141,40 @@ int launch_gemm_t(const AOperand& a, const void* b, long long ldb, long long M, 
   return TP_OK;
 }
 
+int launch_gemm_pair(const AOperand& a, const void* b, long long ldb, long long M, long long N, long long K, const GemmEpilogue& ep,
+                     int sms, cudaStream_t stream) {
+  using Cfg = Gemm2Config;
+  CUtensorMap map_a, map_b;
+  if (a.seg_rows == 0) {
+    TP_TRY(make_map_2d(&map_a, a.ptr, M, K, a.ld, kBlockM));
+  } else {
+    if (a.seg_rows % 64 != 0 || M % a.seg_rows != 0) return TP_ERR_INVALID_ARGUMENT;
+    TP_TRY(make_map_3d(&map_a, a.ptr, M / a.seg_rows, a.seg_rows, K, a.ld, a.seg_stride));
+  }
+  TP_TRY(make_map_2d(&map_b, b, N, K, ldb, Cfg::kTileN / 2));
+  TP_CUDA(cudaFuncSetAttribute(tp_gemm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+  const long long tiles = ((M + Cfg::kTileM - 1) / Cfg::kTileM) * ((N + Cfg::kTileN - 1) / Cfg::kTileN);
+  const long long max_pairs = sms / 2;
+  const int grid = 2 * static_cast<int>(tiles < max_pairs ? tiles : max_pairs);
+  tp_gemm2_kernel<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(map_a, map_b, static_cast<int>(M), static_cast<int>(N),
+                                                                    static_cast<int>(K), static_cast<int>(a.seg_rows), ep);
+  TP_CUDA(cudaGetLastError());
+  return TP_OK;
+}
+
+// Kernel selection: CTA-pair 256x256 tiles whenever the problem fills them, else one-CTA 128 x {256,128} tiles.
+// TP_GEMM_MODE=1 forces the one-CTA kernels, =2 forces the pair kernel (A/B experiments; read per call, no caching).
 int launch_gemm(const AOperand& a, const void* b, long long ldb, long long M, long long N, long long K, const GemmEpilogue& ep,
                 int sms, cudaStream_t stream) {
   if (M <= 0 || N <= 0 || K <= 0 || N % 32 != 0 || K % 8 != 0 || M > 0x7fffff00ll) return TP_ERR_INVALID_ARGUMENT;
   if ((reinterpret_cast<uintptr_t>(ep.c) & 15) != 0 || (ep.ldc * 2) % 16 != 0) return TP_ERR_INVALID_ARGUMENT;
+  if (ep.stats_out != nullptr && (N % 256 != 0 || ep.stats_out_slots != N / 128)) return TP_ERR_INVALID_ARGUMENT;
+  if (ep.col_a != nullptr && (ep.stats_in == nullptr || ep.stats_in_slots <= 0)) return TP_ERR_INVALID_ARGUMENT;
+  const char* mode_env = getenv("TP_GEMM_MODE");
+  const int mode = mode_env != nullptr ? atoi(mode_env) : 0;
+  const bool pair_ok = (N % 256 == 0) && sms >= 2;
+  const bool want_pair = mode == 2 || (mode == 0 && M >= 256);
+  if (pair_ok && want_pair) return launch_gemm_pair(a, b, ldb, M, N, K, ep, sms, stream);
   if (N % 256 == 0) return launch_gemm_t<256>(a, b, ldb, M, N, K, ep, sms, stream);
   return launch_gemm_t<128>(a, b, ldb, M, N, K, ep, sms, stream);
 }
@@ -197,10 +228,12 @@ PackedLayout packed_layout(int H) {
 // ------------------------------------------------------------------------------------------------
 // Workspace layout (per call; all intermediates bf16 unless noted)
 // ------------------------------------------------------------------------------------------------
+constexpr int kStatSlots = kC / 128;   // one (sum, sumsq) slot per 128 output columns of a 1024-wide linear
+
 struct WorkLayout {
   size_t h_kv;      // [R,2048]  GELU(W0 xm + b) for k|v ; reused as k' | v' ([R,1024] each) once consumed
   size_t y_k, y_v;  // [R,1024]  second linear outputs (pre-LayerNorm)
-  size_t stats;     // f32 [2R + Q, 2]  per-row (sum, sumsq): k rows, v rows, q rows
+  size_t stats;     // f32 [2R + Q, 8, 2]  per-row partial (sum, sumsq) per 128-column block: k rows, v rows, q rows
   size_t q, y_q, q_p, ctx, o, h_m;   // [Q,1024] x5, [Q,H]
   size_t total;
 };
@@ -215,7 +248,7 @@ WorkLayout work_layout(long long n_crops, int s, int H) {
   L.h_kv = take(R * 2 * kC * 2);
   L.y_k = take(R * kC * 2);
   L.y_v = take(R * kC * 2);
-  L.stats = take((2 * R + Q) * 2 * 4);
+  L.stats = take((2 * R + Q) * kStatSlots * 2 * 4);
   L.q = take(Q * kC * 2); L.y_q = take(Q * kC * 2); L.q_p = take(Q * kC * 2); L.ctx = take(Q * kC * 2); L.o = take(Q * kC * 2);
   L.h_m = take(Q * static_cast<size_t>(H) * 2);
   L.total = off;
@@ -346,9 +379,8 @@ int tp_forward(const void* packed, const void* x0, const void* xm, int64_t n_cro
   auto bf = [&](size_t off) { return reinterpret_cast<__nv_bfloat16*>(ws + off); };
 
   float* stats_k = reinterpret_cast<float*>(ws + W.stats);
-  float* stats_v = stats_k + 2 * R;
-  float* stats_q = stats_v + 2 * R;
-  TP_CUDA(cudaMemsetAsync(stats_k, 0, static_cast<size_t>(2 * R + Q) * 2 * sizeof(float), stream));
+  float* stats_v = stats_k + 2 * kStatSlots * R;
+  float* stats_q = stats_v + 2 * kStatSlots * R;     // every slot is written by the producing GEMM: no memset needed
 
   // (1) builder.py:112-113, first linears + GELU of k_proj_1 / v_proj_1 as ONE GEMM over the concatenated weights:
   //     h_kv[R, 0:1024] = GELU(W_k0 xm + b), h_kv[R, 1024:2048] = GELU(W_v0 xm + b)   (xm is read once)
@@ -361,9 +393,11 @@ int tp_forward(const void* packed, const void* x0, const void* xm, int64_t n_cro
   {
     GemmEpilogue ep = plain_epilogue(bf(W.y_k), kC, wf(L.b_k2), 0);
     ep.stats_out = stats_k;
+    ep.stats_out_slots = kStatSlots;
     TP_TRY(launch_gemm(AOperand{bf(W.h_kv), 2 * kC, 0, 0}, P + L.w_k2, kC, R, kC, kC, ep, dev.sms, stream));
     ep = plain_epilogue(bf(W.y_v), kC, wf(L.b_v2), 0);
     ep.stats_out = stats_v;
+    ep.stats_out_slots = kStatSlots;
     TP_TRY(launch_gemm(AOperand{bf(W.h_kv) + kC, 2 * kC, 0, 0}, P + L.w_v2, kC, R, kC, kC, ep, dev.sms, stream));
   }
   // (3) ln_k_1 / ln_v_1 folded into the MHA in-projections (builder.py:112-113 + torch MHA in_proj):
@@ -374,10 +408,12 @@ int tp_forward(const void* packed, const void* x0, const void* xm, int64_t n_cro
     GemmEpilogue ep = plain_epilogue(k_p, kC, wf(L.c_k), 0);
     ep.col_a = wf(L.wsum_k);
     ep.stats_in = stats_k;
+    ep.stats_in_slots = kStatSlots;
     TP_TRY(launch_gemm(AOperand{bf(W.y_k), kC, 0, 0}, P + L.w_ik, kC, R, kC, kC, ep, dev.sms, stream));
     ep = plain_epilogue(v_p, kC, wf(L.c_v), 0);
     ep.col_a = wf(L.wsum_v);
     ep.stats_in = stats_v;
+    ep.stats_in_slots = kStatSlots;
     TP_TRY(launch_gemm(AOperand{bf(W.y_v), kC, 0, 0}, P + L.w_iv, kC, R, kC, kC, ep, dev.sms, stream));
   }
   // (4) point queries (builder.py:117-118) -> q_proj_1 (:120) -> ln_q_1 folded into in_proj_q, scaled by 1/sqrt(128)
@@ -388,10 +424,12 @@ int tp_forward(const void* packed, const void* x0, const void* xm, int64_t n_cro
     else TP_TRY(launch_front<4>(x0p, x0_crop_stride, bf(W.q), Q, stream));
     GemmEpilogue ep = plain_epilogue(bf(W.y_q), kC, nullptr, 0);
     ep.stats_out = stats_q;
+    ep.stats_out_slots = kStatSlots;
     TP_TRY(launch_gemm(AOperand{bf(W.q), kC, 0, 0}, P + L.w_q, kC, Q, kC, kC, ep, dev.sms, stream));
     ep = plain_epilogue(bf(W.q_p), kC, wf(L.c_q), 0);
     ep.col_a = wf(L.wsum_q);
     ep.stats_in = stats_q;
+    ep.stats_in_slots = kStatSlots;
     ep.alpha = 0.08838834764831845f;   // 1/sqrt(head_dim = 128): torch MHA scales q after the in-projection
     TP_TRY(launch_gemm(AOperand{bf(W.y_q), kC, 0, 0}, P + L.w_iq, kC, Q, kC, kC, ep, dev.sms, stream));
   }

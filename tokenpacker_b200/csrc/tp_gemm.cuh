@@ -1,15 +1,21 @@
-// Persistent warp-specialised tcgen05 GEMM for sm_100a with the fused epilogues the TokenPacker path needs.
+// Persistent warp-specialised tcgen05 GEMMs for sm_100a with the fused epilogues the TokenPacker path needs.
 //
 //   C[M,N] (bf16) = epilogue( A[M,K] (bf16, K-major) . B[N,K]^T (bf16, K-major) ),  fp32 accumulation in TMEM.
 //
 // Every nn.Linear on the reference hot path (builder.py:59-83; MHA in/out projections builder.py:77) is an
-// instance of this kernel: activations are [rows, in] and weights are [out, in], both K-major, which is exactly the
+// instance of these kernels: activations are [rows, in] and weights are [out, in], both K-major, which is exactly the
 // operand form tcgen05.mma takes from shared memory, so no transposes exist anywhere.
 //
-// CTA = 384 threads, one CTA per SM, persistent over 128 x BLOCK_N output tiles:
-//   warp 0      TMA producer   (one lane): cp.async.bulk.tensor 2-D boxes, 128B swizzle, kStages-deep mbarrier ring
-//   warp 1      MMA issuer     (one lane): tcgen05.mma cta_group::1 kind::f16, 128 x BLOCK_N x 16, fp32 accum in TMEM
-//   warp 2      TMEM allocator (2 accumulator buffers of BLOCK_N columns: the epilogue of tile i overlaps tile i+1's MMAs)
+// Two kernels share one epilogue:
+//   tp_gemm_kernel<BN>   one CTA per SM, 128 x BN tiles,  tcgen05.mma cta_group::1 (small problems, BN = 128 | 256)
+//   tp_gemm2_kernel      CTA pairs (cluster 2x1x1) on the two SMs of a TPC, 256 x 256 tiles, cta_group::2: each CTA
+//                        stages its own 128 rows of A and HALF of the B tile, so shared-memory fill traffic per FLOP
+//                        drops by a third and the mbarrier ring gets 6 stages deep instead of 4.
+//
+// CTA = 384 threads, persistent over output tiles:
+//   warp 0      TMA producer   (one lane): cp.async.bulk.tensor boxes, 128B swizzle, mbarrier ring
+//   warp 1      MMA issuer     (one lane, leader CTA only in pair mode): fp32 accumulators in TMEM
+//   warp 2      TMEM allocator (2 accumulator buffers: the epilogue of tile i overlaps tile i+1's MMAs)
 //   warps 4-11  epilogue: tcgen05.ld 32x32b (thread == output row), fused per-row / per-column math, 16-byte stores
 //
 // Fused epilogue (all optional, selected at run time, warp-uniform branches):
@@ -18,7 +24,8 @@
 //   v = v + col_b[c]                             bias (or the folded constant W.beta + b)
 //   v = gelu_erf(v)                              exact erf GELU (nn.GELU default)
 //   v = alpha * v                                1/sqrt(head_dim) query scaling
-//   y = bf16(v);  stats_out[r] += (y, y*y)       per-row sums of the ROUNDED values for the next LayerNorm fold
+//   y = bf16(v);  stats_out[r][slot] = (sum y, sum y*y) over this warp's columns  -> next LayerNorm fold (deterministic:
+//                                                one slot per 128-column block, summed in fixed order by the consumer)
 //   C[dst_row(r), c] = y                         optional segment scatter (HD packed output)
 #pragma once
 
@@ -31,10 +38,12 @@ struct GemmEpilogue {
   long long ldc;           // elements between output rows
   const float* col_a;      // [N]  LN fold: row-sum of the gamma-folded weight      (nullptr: no LN fold)
   const float* col_b;      // [N]  bias                                             (nullptr: none)
-  const float* stats_in;   // [M,2] (sum, sum of squares) of the A rows over ln_dim (required with col_a)
-  float* stats_out;        // [M,2] accumulated with atomics                        (nullptr: none)
+  const float* stats_in;   // [M, stats_in_slots, 2] partial (sum, sumsq) of the A rows (required with col_a)
+  float* stats_out;        // [M, stats_out_slots, 2]                               (nullptr: none)
   const long long* seg_row_offset;  // [M / seg_len] destination row of each segment's first row (nullptr: identity)
   int seg_len;
+  int stats_in_slots;
+  int stats_out_slots;     // = N / 128 (host-checked; statistics need 256-column tiles): slot = col / 128
   float ln_inv_dim;        // 1 / ln_dim
   float ln_eps;
   float alpha;
@@ -47,7 +56,116 @@ constexpr int kUmmaK = 16;
 constexpr int kGemmThreads = 384;
 constexpr int kEpiWarp0 = 4;
 constexpr int kNumEpiWarps = 8;
+constexpr int kEpiThreads = kNumEpiWarps * 32;
+constexpr int kEpiBarrierId = 1;
 
+// ------------------------------------------------------------------------------------------------
+// Shared epilogue for one 128-row x kTileN-column accumulator tile held in this CTA's TMEM.
+//   tmem_acc : TMEM address of the accumulator buffer (column offset applied, lane 0)
+//   row      : global output row of this thread (lane of TMEM == row inside the tile)
+//   col_tile0: global column of the tile's first column
+//   s_col    : shared staging for this tile's col_a / col_b slices, [2][kTileN] floats (already filled + synced)
+// `release()` is invoked as soon as the last tcgen05.ld of this warp has landed in registers, so the MMA warp gets
+// the TMEM buffer back before the math / stores of the final chunk.
+// ------------------------------------------------------------------------------------------------
+template <int kTileN, typename ReleaseFn>
+__device__ __forceinline__ void epilogue_tile(const GemmEpilogue& ep, int M, int N, uint32_t tmem_acc, int row, int col_tile0,
+                                              int quarter, int half, const float* s_col, ReleaseFn release) {
+  constexpr int kColsPerWarp = kTileN / 2;
+  constexpr int kChunks = kColsPerWarp / 32;
+  const bool ln_fold = ep.col_a != nullptr;
+  const bool row_ok = row < M;
+  float mu = 0.f, rstd = 1.f;
+  if (ln_fold && row_ok) {
+    float t1 = 0.f, t2 = 0.f;
+    const float2* st = reinterpret_cast<const float2*>(ep.stats_in) + static_cast<long long>(row) * ep.stats_in_slots;
+    for (int i = 0; i < ep.stats_in_slots; ++i) {     // fixed order -> bitwise reproducible LayerNorm statistics
+      const float2 v = st[i];
+      t1 += v.x;
+      t2 += v.y;
+    }
+    mu = t1 * ep.ln_inv_dim;
+    const float var = fmaxf(t2 * ep.ln_inv_dim - mu * mu, 0.f);
+    rstd = rsqrtf(var + ep.ln_eps);
+  }
+  long long dst_row = row;
+  if (ep.seg_row_offset != nullptr && row_ok) {
+    const int seg = row / ep.seg_len;
+    dst_row = ep.seg_row_offset[seg] + (row - seg * ep.seg_len);
+  }
+  __nv_bfloat16* c_row = ep.c + dst_row * ep.ldc;
+  const uint32_t taddr = tmem_acc + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(half * kColsPerWarp);
+  const float* sa = s_col + half * kColsPerWarp;
+  const float* sb = s_col + kTileN + half * kColsPerWarp;
+
+  float s1 = 0.f, s2 = 0.f;
+  uint32_t r[2][32];
+  tmem_ld_32x32b_x32(taddr, r[0]);
+#pragma unroll
+  for (int chunk = 0; chunk < kChunks; ++chunk) {
+    tmem_ld_wait();
+    if (chunk + 1 < kChunks) tmem_ld_32x32b_x32(taddr + static_cast<uint32_t>((chunk + 1) * 32), r[(chunk + 1) & 1]);
+    else release();                                   // every TMEM read of this warp has landed in registers
+    const int col0 = col_tile0 + half * kColsPerWarp + chunk * 32;
+    if (col0 < N) {        // N is a multiple of 32 (checked on the host) -> whole chunk in or out
+#pragma unroll
+      for (int g8 = 0; g8 < 4; ++g8) {     // 8 columns = one 16-byte store
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[chunk & 1][g8 * 8 + j]);
+        const int lc = chunk * 32 + g8 * 8;
+        if (ln_fold) {
+          const float4 a0 = *reinterpret_cast<const float4*>(sa + lc);
+          const float4 a1 = *reinterpret_cast<const float4*>(sa + lc + 4);
+          const float ca[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = rstd * (v[j] - mu * ca[j]);
+        }
+        {
+          const float4 b0 = *reinterpret_cast<const float4*>(sb + lc);
+          const float4 b1 = *reinterpret_cast<const float4*>(sb + lc + 4);
+          const float cb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] += cb[j];
+        }
+        if (ep.gelu) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = gelu_erf(v[j]);
+        }
+        uint32_t pk[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          pk[j] = pack_bf16x2(v[2 * j] * ep.alpha, v[2 * j + 1] * ep.alpha);
+          const float y0 = bf16_lo(pk[j]), y1 = bf16_hi(pk[j]);
+          s1 += y0 + y1;
+          s2 = fmaf(y0, y0, fmaf(y1, y1, s2));
+        }
+        if (row_ok) *reinterpret_cast<uint4*>(c_row + col0 + g8 * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      }
+    }
+  }
+  if (ep.stats_out != nullptr && row_ok) {
+    const int slot = (col_tile0 + half * kColsPerWarp) / kColsPerWarp;
+    if (slot < ep.stats_out_slots)
+      reinterpret_cast<float2*>(ep.stats_out)[static_cast<long long>(row) * ep.stats_out_slots + slot] = make_float2(s1, s2);
+  }
+}
+
+// Stage this tile's slices of col_a / col_b into shared memory (coalesced), then sync the 256 epilogue threads.
+template <int kTileN>
+__device__ __forceinline__ void stage_col_vectors(const GemmEpilogue& ep, int N, int col_tile0, float* s_col, int epi_tid) {
+  for (int c = epi_tid; c < kTileN; c += kEpiThreads) {
+    const int col = col_tile0 + c;
+    const bool ok = col < N;
+    s_col[c] = (ok && ep.col_a != nullptr) ? __ldg(ep.col_a + col) : 0.f;
+    s_col[kTileN + c] = (ok && ep.col_b != nullptr) ? __ldg(ep.col_b + col) : 0.f;
+  }
+  named_bar_sync(kEpiBarrierId, kEpiThreads);
+}
+
+// ================================================================================================
+// One-CTA kernel: 128 x kBlockN tiles
+// ================================================================================================
 template <int kBlockN>
 struct GemmConfig {
   static constexpr int kStages = (kBlockN == 256) ? 4 : 6;
@@ -55,8 +173,9 @@ struct GemmConfig {
   static constexpr int kBBytes = kBlockN * kBlockK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kTmemCols = 2 * kBlockN;  // double-buffered accumulator
+  static constexpr int kColStageBytes = 2 * 2 * kBlockN * 4;   // [2 buffers][col_a | col_b][kBlockN] floats
   static constexpr int kBarrierBytes = (2 * kStages + 4) * 8 + 16;
-  static constexpr int kSmemBytes = kStages * kStageBytes + kBarrierBytes + 1024;  // +1024: manual 1 KiB alignment
+  static constexpr int kSmemBytes = kStages * kStageBytes + kColStageBytes + kBarrierBytes + 1024;  // +1024: manual alignment
 };
 
 template <int kBlockN>
@@ -69,7 +188,8 @@ tp_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
+  float* s_col_base = reinterpret_cast<float*>(smem + kStages * Cfg::kStageBytes);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes + Cfg::kColStageBytes);
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tmem_full_bar = empty_bar + kStages;
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;
@@ -171,84 +291,23 @@ tp_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const int e = warp_idx - kEpiWarp0;
     const int quarter = warp_idx & 3;            // TMEM lane quarter this warp may access
     const int half = e >> 2;                     // which half of the tile's columns
-    constexpr int kColsPerWarp = kBlockN / 2;
-    const bool ln_fold = ep.col_a != nullptr;
+    const int epi_tid = e * 32 + static_cast<int>(lane);
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_blk = tile / num_n_blocks;
       const int n_blk = tile - m_blk * num_n_blocks;
-      const int row = m_blk * kBlockM + quarter * 32 + static_cast<int>(lane);
-      const bool row_ok = row < M;
-      float mu = 0.f, rstd = 1.f;
-      if (ln_fold && row_ok) {
-        const float2 st = *reinterpret_cast<const float2*>(ep.stats_in + 2ll * row);
-        mu = st.x * ep.ln_inv_dim;
-        const float var = fmaxf(st.y * ep.ln_inv_dim - mu * mu, 0.f);
-        rstd = rsqrtf(var + ep.ln_eps);
-      }
-      long long dst_row = row;
-      if (ep.seg_row_offset != nullptr && row_ok) {
-        const int seg = row / ep.seg_len;
-        dst_row = ep.seg_row_offset[seg] + (row - seg * ep.seg_len);
-      }
-      __nv_bfloat16* c_row = ep.c + dst_row * ep.ldc;
-
+      float* s_col = s_col_base + acc * 2 * kBlockN;
+      stage_col_vectors<kBlockN>(ep, N, n_blk * kBlockN, s_col, epi_tid);
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tcgen05_fence_after();
-      float s1 = 0.f, s2 = 0.f;
-#pragma unroll 1
-      for (int chunk = 0; chunk < kColsPerWarp / 32; ++chunk) {
-        const int col_in_tile = half * kColsPerWarp + chunk * 32;
-        const int col0 = n_blk * kBlockN + col_in_tile;
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * kBlockN + col_in_tile), r);
-        tmem_ld_wait();
-        if (col0 < N) {        // N is a multiple of 32 (checked on the host) -> whole chunk in or out
-#pragma unroll
-          for (int g8 = 0; g8 < 4; ++g8) {     // 8 columns = one 16-byte store
-            float v[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g8 * 8 + j]);
-            const int c8 = col0 + g8 * 8;
-            if (ln_fold) {
-              const float4 a0 = __ldg(reinterpret_cast<const float4*>(ep.col_a + c8));
-              const float4 a1 = __ldg(reinterpret_cast<const float4*>(ep.col_a + c8 + 4));
-              const float ca[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-#pragma unroll
-              for (int j = 0; j < 8; ++j) v[j] = rstd * (v[j] - mu * ca[j]);
-            }
-            if (ep.col_b != nullptr) {
-              const float4 b0 = __ldg(reinterpret_cast<const float4*>(ep.col_b + c8));
-              const float4 b1 = __ldg(reinterpret_cast<const float4*>(ep.col_b + c8 + 4));
-              const float cb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-              for (int j = 0; j < 8; ++j) v[j] += cb[j];
-            }
-            if (ep.gelu) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) v[j] = gelu_erf(v[j]);
-            }
-            uint32_t pk[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              pk[j] = pack_bf16x2(v[2 * j] * ep.alpha, v[2 * j + 1] * ep.alpha);
-              const float y0 = bf16_lo(pk[j]), y1 = bf16_hi(pk[j]);
-              s1 += y0 + y1;
-              s2 = fmaf(y0, y0, fmaf(y1, y1, s2));
-            }
-            if (row_ok) *reinterpret_cast<uint4*>(c_row + c8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-          }
-        }
-      }
-      // all TMEM reads of this warp for this accumulator are complete -> hand the buffer back to the MMA warp
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
-      if (ep.stats_out != nullptr && row_ok) {
-        atomicAdd(ep.stats_out + 2ll * row, s1);
-        atomicAdd(ep.stats_out + 2ll * row + 1, s2);
-      }
+      uint64_t* release_bar = &tmem_empty_bar[acc];
+      epilogue_tile<kBlockN>(ep, M, N, tmem_base + static_cast<uint32_t>(acc * kBlockN),
+                             m_blk * kBlockM + quarter * 32 + static_cast<int>(lane), n_blk * kBlockN, quarter, half, s_col, [&]() {
+                               tcgen05_fence_before();
+                               __syncwarp();
+                               if (lane == 0) mbar_arrive(release_bar);
+                             });
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
   }
@@ -258,6 +317,172 @@ tp_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   if (warp_idx == 2) {
     tcgen05_fence_after();
     tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+  }
+}
+
+// ================================================================================================
+// CTA-pair kernel: 256 x 256 tiles, cta_group::2
+// ================================================================================================
+struct Gemm2Config {
+  static constexpr int kTileM = 256;
+  static constexpr int kTileN = 256;
+  static constexpr int kStages = 6;
+  static constexpr int kABytes = kBlockM * kBlockK * 2;          // this CTA's 128 rows of A
+  static constexpr int kBBytes = (kTileN / 2) * kBlockK * 2;     // this CTA's half of the B tile
+  static constexpr int kStageBytes = kABytes + kBBytes;          // 32 KiB
+  static constexpr int kTmemCols = 2 * kTileN;
+  static constexpr int kColStageBytes = 2 * 2 * kTileN * 4;
+  static constexpr int kBarrierBytes = (2 * kStages + 4) * 8 + 16;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kColStageBytes + kBarrierBytes + 1024;
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+tp_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, int M, int N, int K,
+                int a_seg_rows, GemmEpilogue ep) {
+  using Cfg = Gemm2Config;
+  constexpr int kStages = Cfg::kStages;
+  constexpr int kTileN = Cfg::kTileN;
+
+  extern __shared__ uint8_t smem_raw[];
+  // the dynamic smem base has the same offset in both CTAs of the pair, so this alignment fix-up is identical too
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  float* s_col_base = reinterpret_cast<float*>(smem + kStages * Cfg::kStageBytes);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes + Cfg::kColStageBytes);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tmem_full_bar = empty_bar + kStages;
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;
+  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp_idx = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
+  const uint32_t lane = lane_id();
+  const uint32_t cta_rank = cluster_ctarank();
+  const bool is_leader = cta_rank == 0;
+
+  const int num_m_blocks = (M + Cfg::kTileM - 1) / Cfg::kTileM;
+  const int num_n_blocks = (N + kTileN - 1) / kTileN;
+  const int num_tiles = num_m_blocks * num_n_blocks;
+  const int num_k_blocks = (K + kBlockK - 1) / kBlockK;
+  const int pair_idx = static_cast<int>(blockIdx.x >> 1);
+  const int num_pairs = static_cast<int>(gridDim.x >> 1);
+
+  if (warp_idx == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+  } else if (warp_idx == 1 && lane == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&full_bar[i], 2);          // one arrival per CTA's producer (the leader's carries the expected bytes of both)
+      mbar_init(&empty_bar[i], 1);         // multicast tcgen05.commit from the leader
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full_bar[i], 1);                   // multicast tcgen05.commit from the leader
+      mbar_init(&tmem_empty_bar[i], 2 * kNumEpiWarps);   // epilogue warps of BOTH CTAs (waited on in the leader only)
+    }
+    fence_barrier_init();
+  } else if (warp_idx == 2) {
+    tmem_alloc_pair<Cfg::kTmemCols>(tmem_base_smem);
+  }
+  tcgen05_fence_before();
+  cluster_sync_all();                      // barriers of both CTAs initialised before any remote arrive / multicast commit
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_base_smem;
+
+  if (warp_idx == 0) {
+    // ======================================= TMA producer (both CTAs) ============================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = pair_idx; tile < num_tiles; tile += num_pairs) {
+        const int m_blk = tile / num_n_blocks;
+        const int n_blk = tile - m_blk * num_n_blocks;
+        const int row0 = m_blk * Cfg::kTileM + static_cast<int>(cta_rank) * kBlockM;          // my 128 rows of A
+        const int brow0 = n_blk * kTileN + static_cast<int>(cta_rank) * (kTileN / 2);        // my half of the B tile
+        for (int kb = 0; kb < num_k_blocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          uint8_t* sa = smem + stage * Cfg::kStageBytes;
+          uint8_t* sb = sa + Cfg::kABytes;
+          if (is_leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
+          else mbar_arrive_cluster(&full_bar[stage], 0);
+          if (a_seg_rows == 0) {
+            tma_load_2d_pair(sa, &tmap_a, &full_bar[stage], kb * kBlockK, row0);
+          } else {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const int g = row0 + h * 64;
+              const int seg = g / a_seg_rows;
+              tma_load_3d_pair(sa + h * (Cfg::kABytes / 2), &tmap_a, &full_bar[stage], kb * kBlockK, g - seg * a_seg_rows, seg);
+            }
+          }
+          tma_load_2d_pair(sb, &tmap_b, &full_bar[stage], kb * kBlockK, brow0);
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp_idx == 1) {
+    // ======================================= MMA issuer (leader CTA only) ========================
+    if (is_leader && lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16_f32(Cfg::kTileM, kTileN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = pair_idx; tile < num_tiles; tile += num_pairs) {
+        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1u);
+        tcgen05_fence_after();
+        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * kTileN);
+        for (int kb = 0; kb < num_k_blocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);                // both CTAs' boxes have landed
+          tcgen05_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
+          const uint64_t desc_a = make_smem_desc_kmajor_sw128(sa);
+          const uint64_t desc_b = make_smem_desc_kmajor_sw128(sa + Cfg::kABytes);
+#pragma unroll
+          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+            umma_bf16_pair(tmem_d, desc_a + static_cast<uint64_t>(k * 2), desc_b + static_cast<uint64_t>(k * 2), idesc,
+                           static_cast<uint32_t>((kb | k) != 0));
+          }
+          umma_commit_pair(&empty_bar[stage], 0x3);          // frees the slot in BOTH CTAs
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit_pair(&tmem_full_bar[acc], 0x3);          // accumulator complete -> both epilogues
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+    __syncwarp();
+  } else if (warp_idx >= kEpiWarp0) {
+    // ======================================= epilogue (both CTAs, own 128 rows) ==================
+    const int e = warp_idx - kEpiWarp0;
+    const int quarter = warp_idx & 3;
+    const int half = e >> 2;
+    const int epi_tid = e * 32 + static_cast<int>(lane);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = pair_idx; tile < num_tiles; tile += num_pairs) {
+      const int m_blk = tile / num_n_blocks;
+      const int n_blk = tile - m_blk * num_n_blocks;
+      float* s_col = s_col_base + acc * 2 * kTileN;
+      stage_col_vectors<kTileN>(ep, N, n_blk * kTileN, s_col, epi_tid);
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      tcgen05_fence_after();
+      uint64_t* release_bar = &tmem_empty_bar[acc];
+      const int row = m_blk * Cfg::kTileM + static_cast<int>(cta_rank) * kBlockM + quarter * 32 + static_cast<int>(lane);
+      epilogue_tile<kTileN>(ep, M, N, tmem_base + static_cast<uint32_t>(acc * kTileN), row, n_blk * kTileN, quarter, half, s_col, [&]() {
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (is_leader) mbar_arrive(release_bar);
+          else mbar_arrive_cluster(release_bar, 0);
+        }
+      });
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+
+  tcgen05_fence_before();
+  cluster_sync_all();                      // the peer may read my smem / signal my barriers until here
+  if (warp_idx == 2) {
+    tcgen05_fence_after();
+    tmem_dealloc_pair<Cfg::kTmemCols>(tmem_base);
   }
 }
 

@@ -197,9 +197,109 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ------------------------------------------------------------------------------------------------
+// CTA-pair (cta_group::2) variants: two CTAs of a cluster on the two SMs of a TPC act as one 256-row MMA.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+// In the shared::cluster window a CTA's own shared memory sits at (cta rank in pair) << 24 | offset: clearing bit 24
+// turns a local barrier address into the address of the SAME barrier in the pair's leader (even) CTA.
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;
+
+// Arrive (count 1) on the mbarrier at the same offset in CTA `target_cta` of the cluster.
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t target_cta) {
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(target_cta)
+      : "memory");
+}
+
+// TMA loads issued by either CTA of a pair; completion bytes are signalled on the LEADER CTA's mbarrier.
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int32_t c0, int32_t c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+__device__ __forceinline__ void tma_load_3d_pair(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int32_t c0, int32_t c1, int32_t c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
+template <uint32_t kCols>
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_result) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)), "n"(kCols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+
+template <uint32_t kCols>
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t tmem_addr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_addr), "n"(kCols) : "memory");
+}
+
+// D[tmem of both CTAs] (+)= A (256 rows: 128 from each CTA's smem) * B^T (N columns: N/2 from each CTA's smem).
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// Commit: arrive on the mbarrier at this offset in every CTA of `cta_mask` once the pair's MMAs so far have retired.
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"(cta_mask)
+               : "memory");
+}
+
+__device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
 // small math / packing helpers
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+// Exact-erf GELU (nn.GELU default, builder.py:63,69,81).  erf by Abramowitz & Stegun 7.1.28,
+//   erf(t) = 1 - (1 + a1 t + ... + a6 t^6)^-16,  |error| <= 3e-7 analytically, <= 2e-6 evaluated in fp32,
+// i.e. a GELU error below 1e-6 absolute — three orders of magnitude under the bf16 rounding of the stored result —
+// at ~17 instructions instead of libdevice erff's two divergent branches (~40): the epilogue of the K=1024 GEMMs
+// is instruction-bound, so this is on the critical path.
+__device__ __forceinline__ float gelu_erf(float x) {
+  const float t = fabsf(x) * 0.70710678118654752440f;
+  float p = 0.0000430638f;
+  p = fmaf(p, t, 0.0002765672f);
+  p = fmaf(p, t, 0.0001520143f);
+  p = fmaf(p, t, 0.0092705272f);
+  p = fmaf(p, t, 0.0422820123f);
+  p = fmaf(p, t, 0.0705230784f);
+  p = fmaf(p, t, 1.0f);
+  p *= p; p *= p; p *= p; p *= p;                      // ^16 (overflows to +inf for |x| > ~24 -> erf = 1, exact)
+  const float e = 1.0f - __fdividef(1.0f, p);          // erf(|x| / sqrt 2)
+  const float hx = 0.5f * x;
+  return fmaf(fabsf(hx), e, hx);                        // 0.5 x (1 + sign(x) erf(|x|/sqrt 2)) = hx + |hx| e
+}
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);

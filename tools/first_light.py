@@ -67,6 +67,76 @@ def gemm_big():
 
 
 @stage
+def pair_tiny():
+    os.environ["TP_GEMM_MODE"] = "2"
+    _gemm_case(256, 256, 64)
+
+
+@stage
+def pair_k1024():
+    os.environ["TP_GEMM_MODE"] = "2"
+    _gemm_case(256, 256, 1024)
+
+
+@stage
+def pair_multi():
+    os.environ["TP_GEMM_MODE"] = "2"
+    _gemm_case(2048, 1024, 1024)
+
+
+@stage
+def pair_tails():
+    os.environ["TP_GEMM_MODE"] = "2"
+    _gemm_case(1000, 512, 200)
+
+
+@stage
+def pair_big():
+    os.environ["TP_GEMM_MODE"] = "2"
+    _gemm_case(36864, 2048, 4096)
+
+
+@stage
+def gemm_shapes_bench():
+    """Per-shape throughput of every GEMM of the N=64, s=2, H=4096 forward, one-CTA vs CTA-pair kernels."""
+    import torch
+    from tokenpacker_b200.kernels import gemm_bf16
+    shapes = [("kv_proj.0  ", 36864, 2048, 4096, True), ("kv_proj.2  ", 36864, 1024, 1024, False), ("q-side 1024", 9216, 1024, 1024, False),
+              ("mlp.0      ", 9216, 4096, 1024, True), ("mlp.2      ", 9216, 4096, 4096, False)]
+    for name, m, n, k, gelu in shapes:
+        a = torch.randn(m, k, device="cuda").bfloat16()
+        b = (torch.randn(n, k, device="cuda") * 0.02).bfloat16()
+        bias = torch.randn(n, device="cuda")
+        c = torch.empty(m, n, device="cuda", dtype=torch.bfloat16)
+        res = []
+        for mode in ("1", "2"):
+            os.environ["TP_GEMM_MODE"] = mode
+            for _ in range(3):
+                gemm_bf16(a, b, bias=bias, gelu=gelu, out=c)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(20):
+                gemm_bf16(a, b, bias=bias, gelu=gelu, out=c)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 20
+            res.append(f"mode{mode}: {ms * 1e3:8.1f} us {2.0 * m * n * k / ms / 1e9:7.1f} TF/s")
+        # cuBLAS reference point for the same shape (torch.matmul, no epilogue)
+        for _ in range(3):
+            torch.matmul(a, b.t())
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(20):
+            torch.matmul(a, b.t())
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 20
+        print(f"{name} M={m} N={n} K={k}: " + " | ".join(res) + f" | cuBLAS(no epilogue): {ms * 1e3:8.1f} us {2.0 * m * n * k / ms / 1e9:7.1f} TF/s", flush=True)
+
+
+@stage
 def projector_small():
     import numpy as np
     import torch
