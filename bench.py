@@ -283,7 +283,7 @@ def main():
                            "crops_per_gpu": N_CROPS, "tokens_per_step": tokens_per_step,
                            "l2": "inputs 377 MB/step per GPU exceed the 126 MB L2 (no explicit flush needed)",
                            "parallelism": f"dp{world} (crops sharded, weights replicated, no data-path collective)"},
-                "e2e": e2e, "gpu_launches": 13 * args.steps, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline}
+                "e2e": e2e, "gpu_launches": 7 * args.steps, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline}
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()

@@ -120,63 +120,126 @@ struct AOperand {
   long long seg_stride;  // elements between segments
 };
 
+// Every kernel of the path is launched with the programmatic-stream-serialization attribute (PDL): its CTAs may be
+// scheduled while the previous kernel on the stream drains, run their prologue (barrier init, TMEM allocation, tensor-map
+// prefetch) and then block in griddepcontrol.wait until the previous kernel's memory is visible.
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
+struct GemmItem {
+  AOperand a;
+  const void* b;
+  long long ldb;
+  long long M, N, K;
+  GemmEpilogue ep;
+};
+
+int check_item(const GemmItem& it) {
+  if (it.M <= 0 || it.N <= 0 || it.K <= 0 || it.N % 32 != 0 || it.K % 8 != 0 || it.M > 0x7fffff00ll) return TP_ERR_INVALID_ARGUMENT;
+  if ((reinterpret_cast<uintptr_t>(it.ep.c) & 15) != 0 || (it.ep.ldc * 2) % 16 != 0) return TP_ERR_INVALID_ARGUMENT;
+  if (it.ep.stats_out != nullptr && (it.N % 256 != 0 || it.ep.stats_out_slots != it.N / 128)) return TP_ERR_INVALID_ARGUMENT;
+  if (it.ep.col_a != nullptr && (it.ep.stats_in == nullptr || it.ep.stats_in_slots <= 0)) return TP_ERR_INVALID_ARGUMENT;
+  return TP_OK;
+}
+
+int make_a_map(CUtensorMap* map, const AOperand& a, long long M, long long K) {
+  if (a.seg_rows == 0) return make_map_2d(map, a.ptr, M, K, a.ld, kBlockM);
+  if (a.seg_rows % 64 != 0 || M % a.seg_rows != 0) return TP_ERR_INVALID_ARGUMENT;
+  return make_map_3d(map, a.ptr, M / a.seg_rows, a.seg_rows, K, a.ld, a.seg_stride);
+}
+
 template <int kBlockN>
-int launch_gemm_t(const AOperand& a, const void* b, long long ldb, long long M, long long N, long long K, const GemmEpilogue& ep,
-                  int sms, cudaStream_t stream) {
+int launch_gemm_t(const GemmItem& it, int sms, cudaStream_t stream) {
   using Cfg = GemmConfig<kBlockN>;
   CUtensorMap map_a, map_b;
-  if (a.seg_rows == 0) {
-    TP_TRY(make_map_2d(&map_a, a.ptr, M, K, a.ld, kBlockM));
-  } else {
-    if (a.seg_rows % 64 != 0 || M % a.seg_rows != 0) return TP_ERR_INVALID_ARGUMENT;
-    TP_TRY(make_map_3d(&map_a, a.ptr, M / a.seg_rows, a.seg_rows, K, a.ld, a.seg_stride));
-  }
-  TP_TRY(make_map_2d(&map_b, b, N, K, ldb, kBlockN));
+  TP_TRY(make_a_map(&map_a, it.a, it.M, it.K));
+  TP_TRY(make_map_2d(&map_b, it.b, it.N, it.K, it.ldb, kBlockN));
   TP_CUDA(cudaFuncSetAttribute(tp_gemm_kernel<kBlockN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-  const long long tiles = ((M + kBlockM - 1) / kBlockM) * ((N + kBlockN - 1) / kBlockN);
+  const long long tiles = ((it.M + kBlockM - 1) / kBlockM) * ((it.N + kBlockN - 1) / kBlockN);
   const int grid = static_cast<int>(tiles < sms ? tiles : sms);
-  tp_gemm_kernel<kBlockN><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(map_a, map_b, static_cast<int>(M), static_cast<int>(N),
-                                                                            static_cast<int>(K), static_cast<int>(a.seg_rows), ep);
-  TP_CUDA(cudaGetLastError());
+  TP_CUDA(launch_pdl(tp_gemm_kernel<kBlockN>, dim3(grid), dim3(kGemmThreads), Cfg::kSmemBytes, stream, map_a, map_b, static_cast<int>(it.M),
+                     static_cast<int>(it.N), static_cast<int>(it.K), static_cast<int>(it.a.seg_rows), it.ep));
   return TP_OK;
 }
 
-int launch_gemm_pair(const AOperand& a, const void* b, long long ldb, long long M, long long N, long long K, const GemmEpilogue& ep,
-                     int sms, cudaStream_t stream) {
+// Up to kMaxGroup independent problems in ONE launch of the CTA-pair kernel.
+int launch_gemm_pair_group(const GemmItem* items, int count, int sms, cudaStream_t stream) {
   using Cfg = Gemm2Config;
-  CUtensorMap map_a, map_b;
-  if (a.seg_rows == 0) {
-    TP_TRY(make_map_2d(&map_a, a.ptr, M, K, a.ld, kBlockM));
-  } else {
-    if (a.seg_rows % 64 != 0 || M % a.seg_rows != 0) return TP_ERR_INVALID_ARGUMENT;
-    TP_TRY(make_map_3d(&map_a, a.ptr, M / a.seg_rows, a.seg_rows, K, a.ld, a.seg_stride));
+  GemmGroup g;
+  memset(&g, 0, sizeof(g));
+  g.count = count;
+  long long total = 0;
+  for (int i = 0; i < count; ++i) {
+    const GemmItem& it = items[i];
+    GemmProblem& p = g.p[i];
+    TP_TRY(make_a_map(&p.tmap_a, it.a, it.M, it.K));
+    TP_TRY(make_map_2d(&p.tmap_b, it.b, it.N, it.K, it.ldb, Cfg::kTileN / 2));
+    // C goes out through TMA stores (64-col x 128-row swizzled slabs) unless rows are scattered to segment offsets
+    TP_TRY(make_map_2d(&p.tmap_c, it.ep.c, it.M, it.N, it.ep.ldc, kBlockM));
+    p.use_tma_store = it.ep.seg_row_offset == nullptr ? 1 : 0;
+    p.M = static_cast<int>(it.M);
+    p.N = static_cast<int>(it.N);
+    p.K = static_cast<int>(it.K);
+    p.a_seg_rows = static_cast<int>(it.a.seg_rows);
+    p.num_n_blocks = static_cast<int>((it.N + Cfg::kTileN - 1) / Cfg::kTileN);
+    p.num_tiles = static_cast<int>((it.M + Cfg::kTileM - 1) / Cfg::kTileM) * p.num_n_blocks;
+    p.num_k_blocks = static_cast<int>((it.K + kBlockK - 1) / kBlockK);
+    p.ep = it.ep;
+    total += p.num_tiles;
   }
-  TP_TRY(make_map_2d(&map_b, b, N, K, ldb, Cfg::kTileN / 2));
+  if (total > 0x7fffffffll) return TP_ERR_INVALID_ARGUMENT;
+  g.total_tiles = static_cast<int>(total);
   TP_CUDA(cudaFuncSetAttribute(tp_gemm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-  const long long tiles = ((M + Cfg::kTileM - 1) / Cfg::kTileM) * ((N + Cfg::kTileN - 1) / Cfg::kTileN);
   const long long max_pairs = sms / 2;
-  const int grid = 2 * static_cast<int>(tiles < max_pairs ? tiles : max_pairs);
-  tp_gemm2_kernel<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(map_a, map_b, static_cast<int>(M), static_cast<int>(N),
-                                                                    static_cast<int>(K), static_cast<int>(a.seg_rows), ep);
-  TP_CUDA(cudaGetLastError());
+  const int grid = 2 * static_cast<int>(total < max_pairs ? total : max_pairs);
+  TP_CUDA(launch_pdl(tp_gemm2_kernel, dim3(grid), dim3(kGemmThreads), Cfg::kSmemBytes, stream, g));
   return TP_OK;
 }
 
-// Kernel selection: CTA-pair 256x256 tiles whenever the problem fills them, else one-CTA 128 x {256,128} tiles.
-// TP_GEMM_MODE=1 forces the one-CTA kernels, =2 forces the pair kernel (A/B experiments; read per call, no caching).
-int launch_gemm(const AOperand& a, const void* b, long long ldb, long long M, long long N, long long K, const GemmEpilogue& ep,
-                int sms, cudaStream_t stream) {
-  if (M <= 0 || N <= 0 || K <= 0 || N % 32 != 0 || K % 8 != 0 || M > 0x7fffff00ll) return TP_ERR_INVALID_ARGUMENT;
-  if ((reinterpret_cast<uintptr_t>(ep.c) & 15) != 0 || (ep.ldc * 2) % 16 != 0) return TP_ERR_INVALID_ARGUMENT;
-  if (ep.stats_out != nullptr && (N % 256 != 0 || ep.stats_out_slots != N / 128)) return TP_ERR_INVALID_ARGUMENT;
-  if (ep.col_a != nullptr && (ep.stats_in == nullptr || ep.stats_in_slots <= 0)) return TP_ERR_INVALID_ARGUMENT;
+// Kernel selection: CTA-pair 256x256 tiles whenever the problem fills them (independent problems of one stage share a
+// launch), else one-CTA 128 x {256,128} tiles.  TP_GEMM_MODE=1 forces the one-CTA kernels, =2 forces the pair kernel,
+// =3 pair kernel without grouping (A/B experiments; read per call, no caching).
+int launch_gemms(const GemmItem* items, int count, int sms, cudaStream_t stream) {
+  if (count <= 0 || count > kMaxGroup) return TP_ERR_INVALID_ARGUMENT;
   const char* mode_env = getenv("TP_GEMM_MODE");
   const int mode = mode_env != nullptr ? atoi(mode_env) : 0;
-  const bool pair_ok = (N % 256 == 0) && sms >= 2;
-  const bool want_pair = mode == 2 || (mode == 0 && M >= 256);
-  if (pair_ok && want_pair) return launch_gemm_pair(a, b, ldb, M, N, K, ep, sms, stream);
-  if (N % 256 == 0) return launch_gemm_t<256>(a, b, ldb, M, N, K, ep, sms, stream);
-  return launch_gemm_t<128>(a, b, ldb, M, N, K, ep, sms, stream);
+  GemmItem grouped[kMaxGroup];
+  int n_grouped = 0;
+  for (int i = 0; i < count; ++i) {
+    TP_TRY(check_item(items[i]));
+    const GemmItem& it = items[i];
+    const bool pair_ok = (it.N % 256 == 0) && sms >= 2;
+    const bool want_pair = mode == 2 || mode == 3 || (mode == 0 && it.M >= 256);
+    if (pair_ok && want_pair) {
+      if (mode == 3) TP_TRY(launch_gemm_pair_group(&it, 1, sms, stream));
+      else grouped[n_grouped++] = it;
+    } else if (it.N % 256 == 0) {
+      TP_TRY(launch_gemm_t<256>(it, sms, stream));
+    } else {
+      TP_TRY(launch_gemm_t<128>(it, sms, stream));
+    }
+  }
+  if (n_grouped > 0) TP_TRY(launch_gemm_pair_group(grouped, n_grouped, sms, stream));
+  return TP_OK;
+}
+
+int launch_gemm(const AOperand& a, const void* b, long long ldb, long long M, long long N, long long K, const GemmEpilogue& ep,
+                int sms, cudaStream_t stream) {
+  const GemmItem it{a, b, ldb, M, N, K, ep};
+  return launch_gemms(&it, 1, sms, stream);
 }
 
 GemmEpilogue plain_epilogue(void* c, long long ldc, const float* bias, int gelu) {
@@ -202,8 +265,9 @@ struct PackedLayout {
   size_t w_iv, wsum_v, c_v;
   size_t w_q;                          // q_proj_1
   size_t w_iq, wsum_q, c_q;
-  size_t w_o, b_o;
-  size_t w_m0, b_m0, w_m2, b_m2;
+  size_t w_ot;                         // W_o^T scratch (pack time only)
+  size_t w_om, b_om;                   // out_proj folded into mlp.0: W_m0 W_o [H,1024] bf16, W_m0 b_o + b_m0 [H] f32
+  size_t w_m2, b_m2;
   size_t total;
 };
 
@@ -218,8 +282,8 @@ PackedLayout packed_layout(int H) {
   L.w_iv = take(mat); L.wsum_v = take(vec); L.c_v = take(vec);
   L.w_q = take(mat);
   L.w_iq = take(mat); L.wsum_q = take(vec); L.c_q = take(vec);
-  L.w_o = take(mat); L.b_o = take(vec);
-  L.w_m0 = take(static_cast<size_t>(H) * kC * 2); L.b_m0 = take(static_cast<size_t>(H) * 4);
+  L.w_ot = take(mat);
+  L.w_om = take(static_cast<size_t>(H) * kC * 2); L.b_om = take(static_cast<size_t>(H) * 4);
   L.w_m2 = take(static_cast<size_t>(H) * H * 2); L.b_m2 = take(static_cast<size_t>(H) * 4);
   L.total = off;
   return L;
@@ -234,7 +298,7 @@ struct WorkLayout {
   size_t h_kv;      // [R,2048]  GELU(W0 xm + b) for k|v ; reused as k' | v' ([R,1024] each) once consumed
   size_t y_k, y_v;  // [R,1024]  second linear outputs (pre-LayerNorm)
   size_t stats;     // f32 [2R + Q, 8, 2]  per-row partial (sum, sumsq) per 128-column block: k rows, v rows, q rows
-  size_t q, y_q, q_p, ctx, o, h_m;   // [Q,1024] x5, [Q,H]
+  size_t q, y_q, q_p, ctx, h_m;      // [Q,1024] x4, [Q,H]
   size_t total;
 };
 
@@ -249,7 +313,7 @@ WorkLayout work_layout(long long n_crops, int s, int H) {
   L.y_k = take(R * kC * 2);
   L.y_v = take(R * kC * 2);
   L.stats = take((2 * R + Q) * kStatSlots * 2 * 4);
-  L.q = take(Q * kC * 2); L.y_q = take(Q * kC * 2); L.q_p = take(Q * kC * 2); L.ctx = take(Q * kC * 2); L.o = take(Q * kC * 2);
+  L.q = take(Q * kC * 2); L.y_q = take(Q * kC * 2); L.q_p = take(Q * kC * 2); L.ctx = take(Q * kC * 2);
   L.h_m = take(Q * static_cast<size_t>(H) * 2);
   L.total = off;
   return L;
@@ -260,8 +324,7 @@ bool valid_hidden(int H) { return H >= 32 && H % 32 == 0 && H <= 65536; }
 template <int S>
 int launch_front(const __nv_bfloat16* x0, long long x0_stride, __nv_bfloat16* q, long long Q, cudaStream_t stream) {
   const long long threads = Q * 128;
-  point_query_kernel<S><<<static_cast<unsigned>((threads + 255) / 256), 256, 0, stream>>>(x0, x0_stride, q, Q);
-  TP_CUDA(cudaGetLastError());
+  TP_CUDA(launch_pdl(point_query_kernel<S>, dim3(static_cast<unsigned>((threads + 255) / 256)), dim3(256), 0, stream, x0, x0_stride, q, Q));
   return TP_OK;
 }
 
@@ -269,8 +332,7 @@ template <int S>
 int launch_attn(const __nv_bfloat16* qp, const __nv_bfloat16* kp, const __nv_bfloat16* vp, __nv_bfloat16* ctx, long long Q,
                 cudaStream_t stream) {
   const long long threads = Q * 32;
-  window_attn_kernel<S><<<static_cast<unsigned>((threads + 255) / 256), 256, 0, stream>>>(qp, kp, vp, ctx, Q);
-  TP_CUDA(cudaGetLastError());
+  TP_CUDA(launch_pdl(window_attn_kernel<S>, dim3(static_cast<unsigned>((threads + 255) / 256)), dim3(256), 0, stream, qp, kp, vp, ctx, Q));
   return TP_OK;
 }
 
@@ -338,10 +400,21 @@ int tp_pack_weights(const tp_weights* w, int hidden, void* packed, size_t packed
   TP_CUDA(fold(L.w_ik, L.wsum_k, L.c_k, in_w + static_cast<size_t>(kC) * kC, in_b + kC, w->ln_k_w, w->ln_k_b));
   TP_CUDA(fold(L.w_iv, L.wsum_v, L.c_v, in_w + 2 * static_cast<size_t>(kC) * kC, in_b + 2 * kC, w->ln_v_w, w->ln_v_b));
   TP_CUDA(copy(L.w_q, w->q_proj_w, mat));
-  TP_CUDA(copy(L.w_o, w->out_proj_w, mat));
-  TP_CUDA(bias(L.b_o, w->out_proj_b, kC));
-  TP_CUDA(copy(L.w_m0, w->mlp_0_w, static_cast<size_t>(hidden) * kC * 2));
-  TP_CUDA(bias(L.b_m0, w->mlp_0_b, hidden));
+  // out_proj folded into mlp.0 (exact re-association, no nonlinearity in between):
+  //   mlp.0(out_proj(x)) = (W_m0 W_o) x + (W_m0 b_o + b_m0);  W_m0 W_o computed by our own GEMM with B = W_o^T (K-major)
+  {
+    DeviceInfo dev;
+    TP_TRY(device_info(&dev));
+    transpose_bf16_kernel<<<dim3(kC / 32, kC / 32), dim3(32, 8), 0, stream>>>(static_cast<const __nv_bfloat16*>(w->out_proj_w),
+                                                                              reinterpret_cast<__nv_bfloat16*>(P + L.w_ot), kC);
+    TP_CUDA(cudaGetLastError());
+    TP_TRY(launch_gemm(AOperand{w->mlp_0_w, kC, 0, 0}, P + L.w_ot, kC, hidden, kC, kC, plain_epilogue(P + L.w_om, kC, nullptr, 0), dev.sms, stream));
+    matvec_bias_kernel<<<(hidden * 32 + 255) / 256, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(w->mlp_0_w),
+                                                                      static_cast<const __nv_bfloat16*>(w->out_proj_b),
+                                                                      static_cast<const __nv_bfloat16*>(w->mlp_0_b),
+                                                                      reinterpret_cast<float*>(P + L.b_om), hidden, kC);
+    TP_CUDA(cudaGetLastError());
+  }
   TP_CUDA(copy(L.w_m2, w->mlp_2_w, static_cast<size_t>(hidden) * hidden * 2));
   TP_CUDA(bias(L.b_m2, w->mlp_2_b, hidden));
   return TP_OK;
@@ -382,64 +455,62 @@ int tp_forward(const void* packed, const void* x0, const void* xm, int64_t n_cro
   float* stats_v = stats_k + 2 * kStatSlots * R;
   float* stats_q = stats_v + 2 * kStatSlots * R;     // every slot is written by the producing GEMM: no memset needed
 
-  // (1) builder.py:112-113, first linears + GELU of k_proj_1 / v_proj_1 as ONE GEMM over the concatenated weights:
-  //     h_kv[R, 0:1024] = GELU(W_k0 xm + b), h_kv[R, 1024:2048] = GELU(W_v0 xm + b)   (xm is read once)
-  {
-    AOperand a{xm, kCm, 0, 0};
-    if (xm_crop_stride != static_cast<int64_t>(kTokens) * kCm) a = AOperand{xm, kCm, kTokens, xm_crop_stride};
-    TP_TRY(launch_gemm(a, P + L.w_kv0, kCm, R, 2 * kC, kCm, plain_epilogue(bf(W.h_kv), 2 * kC, wf(L.b_kv0), 1), dev.sms, stream));
-  }
-  // (2) second linears; the epilogue also accumulates per-row (sum, sumsq) of the rounded outputs for LayerNorm
-  {
-    GemmEpilogue ep = plain_epilogue(bf(W.y_k), kC, wf(L.b_k2), 0);
-    ep.stats_out = stats_k;
-    ep.stats_out_slots = kStatSlots;
-    TP_TRY(launch_gemm(AOperand{bf(W.h_kv), 2 * kC, 0, 0}, P + L.w_k2, kC, R, kC, kC, ep, dev.sms, stream));
-    ep = plain_epilogue(bf(W.y_v), kC, wf(L.b_v2), 0);
-    ep.stats_out = stats_v;
-    ep.stats_out_slots = kStatSlots;
-    TP_TRY(launch_gemm(AOperand{bf(W.h_kv) + kC, 2 * kC, 0, 0}, P + L.w_v2, kC, R, kC, kC, ep, dev.sms, stream));
-  }
-  // (3) ln_k_1 / ln_v_1 folded into the MHA in-projections (builder.py:112-113 + torch MHA in_proj):
-  //     k' = rstd (y_k (gamma.W_ik)^T - mu rowsum) + (W_ik beta + b_ik)       -> written over the dead h_kv buffer
-  __nv_bfloat16* k_p = bf(W.h_kv);
-  __nv_bfloat16* v_p = bf(W.h_kv) + static_cast<size_t>(R) * kC;
-  {
-    GemmEpilogue ep = plain_epilogue(k_p, kC, wf(L.c_k), 0);
-    ep.col_a = wf(L.wsum_k);
-    ep.stats_in = stats_k;
-    ep.stats_in_slots = kStatSlots;
-    TP_TRY(launch_gemm(AOperand{bf(W.y_k), kC, 0, 0}, P + L.w_ik, kC, R, kC, kC, ep, dev.sms, stream));
-    ep = plain_epilogue(v_p, kC, wf(L.c_v), 0);
-    ep.col_a = wf(L.wsum_v);
-    ep.stats_in = stats_v;
-    ep.stats_in_slots = kStatSlots;
-    TP_TRY(launch_gemm(AOperand{bf(W.y_v), kC, 0, 0}, P + L.w_iv, kC, R, kC, kC, ep, dev.sms, stream));
-  }
-  // (4) point queries (builder.py:117-118) -> q_proj_1 (:120) -> ln_q_1 folded into in_proj_q, scaled by 1/sqrt(128)
+  // Launch plan (7 kernels; independent GEMMs of a stage share one grouped launch of the CTA-pair kernel):
+  //   [S] point queries            builder.py:117-118
+  //   [1] h_kv = GELU(xm [W_k0;W_v0]^T + b)                                 :112-113 first linears, xm read once
+  //   [2] y_k | y_v | y_q   = second linears k/v + q_proj_1 (+ row sums for the LayerNorms)   :112-113, :120
+  //   [3] k'  | v'  | q'    = LayerNorm folded into the MHA in-projections (q' scaled by 1/sqrt 128)   MHA in_proj
+  //   [A] window attention core                                              :122-130
+  //   [4] h_m = GELU(ctx (W_m0 W_o)^T + (W_m0 b_o + b_m0))                   out_proj folded into mlp.0  (:130,:136)
+  //   [5] out = h_m W_m2^T + b_m2  -> final [N,M,H] (or packed HD) layout    :136
   {
     const __nv_bfloat16* x0p = static_cast<const __nv_bfloat16*>(x0);
     if (s == 2) TP_TRY(launch_front<2>(x0p, x0_crop_stride, bf(W.q), Q, stream));
     else if (s == 3) TP_TRY(launch_front<3>(x0p, x0_crop_stride, bf(W.q), Q, stream));
     else TP_TRY(launch_front<4>(x0p, x0_crop_stride, bf(W.q), Q, stream));
-    GemmEpilogue ep = plain_epilogue(bf(W.y_q), kC, nullptr, 0);
-    ep.stats_out = stats_q;
-    ep.stats_out_slots = kStatSlots;
-    TP_TRY(launch_gemm(AOperand{bf(W.q), kC, 0, 0}, P + L.w_q, kC, Q, kC, kC, ep, dev.sms, stream));
-    ep = plain_epilogue(bf(W.q_p), kC, wf(L.c_q), 0);
-    ep.col_a = wf(L.wsum_q);
-    ep.stats_in = stats_q;
-    ep.stats_in_slots = kStatSlots;
-    ep.alpha = 0.08838834764831845f;   // 1/sqrt(head_dim = 128): torch MHA scales q after the in-projection
-    TP_TRY(launch_gemm(AOperand{bf(W.y_q), kC, 0, 0}, P + L.w_iq, kC, Q, kC, kC, ep, dev.sms, stream));
   }
-  // (5) window attention core (builder.py:122-130)
+  {
+    AOperand a{xm, kCm, 0, 0};
+    if (xm_crop_stride != static_cast<int64_t>(kTokens) * kCm) a = AOperand{xm, kCm, kTokens, xm_crop_stride};
+    TP_TRY(launch_gemm(a, P + L.w_kv0, kCm, R, 2 * kC, kCm, plain_epilogue(bf(W.h_kv), 2 * kC, wf(L.b_kv0), 1), dev.sms, stream));
+  }
+  {
+    GemmItem g[3];
+    g[0] = GemmItem{AOperand{bf(W.h_kv), 2 * kC, 0, 0}, P + L.w_k2, kC, R, kC, kC, plain_epilogue(bf(W.y_k), kC, wf(L.b_k2), 0)};
+    g[0].ep.stats_out = stats_k;
+    g[0].ep.stats_out_slots = kStatSlots;
+    g[1] = GemmItem{AOperand{bf(W.h_kv) + kC, 2 * kC, 0, 0}, P + L.w_v2, kC, R, kC, kC, plain_epilogue(bf(W.y_v), kC, wf(L.b_v2), 0)};
+    g[1].ep.stats_out = stats_v;
+    g[1].ep.stats_out_slots = kStatSlots;
+    g[2] = GemmItem{AOperand{bf(W.q), kC, 0, 0}, P + L.w_q, kC, Q, kC, kC, plain_epilogue(bf(W.y_q), kC, nullptr, 0)};
+    g[2].ep.stats_out = stats_q;
+    g[2].ep.stats_out_slots = kStatSlots;
+    TP_TRY(launch_gemms(g, 3, dev.sms, stream));
+  }
+  // k' / v' are written over the dead h_kv buffer
+  __nv_bfloat16* k_p = bf(W.h_kv);
+  __nv_bfloat16* v_p = bf(W.h_kv) + static_cast<size_t>(R) * kC;
+  {
+    GemmItem g[3];
+    g[0] = GemmItem{AOperand{bf(W.y_k), kC, 0, 0}, P + L.w_ik, kC, R, kC, kC, plain_epilogue(k_p, kC, wf(L.c_k), 0)};
+    g[0].ep.col_a = wf(L.wsum_k);
+    g[0].ep.stats_in = stats_k;
+    g[0].ep.stats_in_slots = kStatSlots;
+    g[1] = GemmItem{AOperand{bf(W.y_v), kC, 0, 0}, P + L.w_iv, kC, R, kC, kC, plain_epilogue(v_p, kC, wf(L.c_v), 0)};
+    g[1].ep.col_a = wf(L.wsum_v);
+    g[1].ep.stats_in = stats_v;
+    g[1].ep.stats_in_slots = kStatSlots;
+    g[2] = GemmItem{AOperand{bf(W.y_q), kC, 0, 0}, P + L.w_iq, kC, Q, kC, kC, plain_epilogue(bf(W.q_p), kC, wf(L.c_q), 0)};
+    g[2].ep.col_a = wf(L.wsum_q);
+    g[2].ep.stats_in = stats_q;
+    g[2].ep.stats_in_slots = kStatSlots;
+    g[2].ep.alpha = 0.08838834764831845f;   // 1/sqrt(head_dim = 128): torch MHA scales q after the in-projection
+    TP_TRY(launch_gemms(g, 3, dev.sms, stream));
+  }
   if (s == 2) TP_TRY(launch_attn<2>(bf(W.q_p), k_p, v_p, bf(W.ctx), Q, stream));
   else if (s == 3) TP_TRY(launch_attn<3>(bf(W.q_p), k_p, v_p, bf(W.ctx), Q, stream));
   else TP_TRY(launch_attn<4>(bf(W.q_p), k_p, v_p, bf(W.ctx), Q, stream));
-  // (6) out_proj, then the refinement MLP (builder.py:136); the last GEMM writes the final [N,M,H] (or packed HD) layout
-  TP_TRY(launch_gemm(AOperand{bf(W.ctx), kC, 0, 0}, P + L.w_o, kC, Q, kC, kC, plain_epilogue(bf(W.o), kC, wf(L.b_o), 0), dev.sms, stream));
-  TP_TRY(launch_gemm(AOperand{bf(W.o), kC, 0, 0}, P + L.w_m0, kC, Q, H, kC, plain_epilogue(bf(W.h_m), H, wf(L.b_m0), 1), dev.sms, stream));
+  TP_TRY(launch_gemm(AOperand{bf(W.ctx), kC, 0, 0}, P + L.w_om, kC, Q, H, kC, plain_epilogue(bf(W.h_m), H, wf(L.b_om), 1), dev.sms, stream));
   {
     GemmEpilogue ep = plain_epilogue(out, H, wf(L.b_m2), 0);
     if (seg_row_offset != nullptr) {
@@ -507,6 +578,21 @@ int tp_forward_host(const void* packed, const void* x0_host, const void* xm_host
   TP_CUDA(e3);
   return TP_OK;
 }
+
+#ifdef TP_GEMM_PROFILE
+// Profile builds only (libtokenpacker_b200_prof.so, not part of the public ABI): same as tp_gemm_bf16 plus a device
+// buffer [grid][8] of cycle counters: {producer wait-empty, producer total, mma wait-full, mma wait-tmem, mma total,
+// epilogue wait-accumulator, epilogue busy, -}.
+TP_API int tp_gemm_bf16_prof(const void* a, int64_t lda, const void* b, int64_t ldb, void* c, int64_t ldc, int64_t m, int64_t n, int64_t k,
+                             const float* bias, int gelu, float alpha, long long* prof, void* stream) {
+  DeviceInfo dev;
+  TP_TRY(device_info(&dev));
+  GemmEpilogue ep = plain_epilogue(c, ldc, bias, gelu);
+  ep.alpha = alpha;
+  ep.prof = prof;
+  return launch_gemm(AOperand{a, lda, 0, 0}, b, ldb, m, n, k, ep, dev.sms, static_cast<cudaStream_t>(stream));
+}
+#endif
 
 int tp_gemm_bf16(const void* a, int64_t lda, const void* b, int64_t ldb, void* c, int64_t ldc, int64_t m, int64_t n, int64_t k,
                  const float* bias, int gelu, float alpha, void* stream) {

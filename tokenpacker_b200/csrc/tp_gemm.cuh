@@ -48,13 +48,39 @@ struct GemmEpilogue {
   float ln_eps;
   float alpha;
   int gelu;
+  long long* prof;         // TP_GEMM_PROFILE builds only: [grid][8] cycle counters (nullptr otherwise)
 };
+
+#ifdef TP_GEMM_PROFILE
+#define TP_PROF_T0() const long long prof_t0__ = clock64()
+#define TP_PROF_ADD(var) (var) += clock64() - prof_t0__
+#else
+#define TP_PROF_T0() do {} while (0)
+#define TP_PROF_ADD(var) do {} while (0)
+#endif
 
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;     // 64 bf16 = 128 bytes = one swizzle-128B row
 constexpr int kUmmaK = 16;
 constexpr int kGemmThreads = 384;
+// Warp roles.  The warp scheduler favours higher warp ids when several warps of an SM sub-partition are eligible, and
+// the single-lane TMA / MMA warps must never lose an issue slot to the (instruction-heavy) epilogue warps: they get
+// the HIGHEST ids.  Epilogue warp w reads TMEM lanes 32*(w % 4)..+31 (hardware restriction), so 8 epilogue warps =
+// 4 lane quarters x 2 column halves.
+#ifndef TP_ROLE_LAYOUT
+#define TP_ROLE_LAYOUT 1
+#endif
+#if TP_ROLE_LAYOUT == 1
+constexpr int kEpiWarp0 = 0;
+constexpr int kTmaWarp = 10;
+constexpr int kMmaWarp = 11;
+constexpr int kAllocWarp = 9;
+#else
 constexpr int kEpiWarp0 = 4;
+constexpr int kTmaWarp = 0;
+constexpr int kMmaWarp = 1;
+constexpr int kAllocWarp = 2;
+#endif
 constexpr int kNumEpiWarps = 8;
 constexpr int kEpiThreads = kNumEpiWarps * 32;
 constexpr int kEpiBarrierId = 1;
@@ -68,9 +94,21 @@ constexpr int kEpiBarrierId = 1;
 // `release()` is invoked as soon as the last tcgen05.ld of this warp has landed in registers, so the MMA warp gets
 // the TMEM buffer back before the math / stores of the final chunk.
 // ------------------------------------------------------------------------------------------------
+// Output staging for TMA stores: each column half of the tile (4 warps) owns two 16 KiB buffers holding a 128-row x 64-col
+// slab in the 128B-swizzled layout; a slab is written with conflict-free 16-byte st.shared, then ONE thread hands it
+// to the TMA unit (full 128-byte row segments instead of 16-byte scattered stores: less L1/L2 work and less power).
+struct OutStage {
+  uint8_t* buf;              // this half's 2 x 16 KiB staging buffers (nullptr: direct 16-byte global stores)
+  const CUtensorMap* tmap;   // C tensor map, box = 64 cols x 128 rows, SWIZZLE_128B
+  int row_tile0;             // first global row of this CTA's 128-row tile
+  uint32_t barrier_id;       // named barrier shared by the 4 warps (128 threads) of this half
+  bool issuer;               // this thread issues (and tracks) the half's TMA stores
+};
+constexpr int kOutSlabBytes = 128 * 128;   // 128 rows x 64 bf16
+
 template <int kTileN, typename ReleaseFn>
 __device__ __forceinline__ void epilogue_tile(const GemmEpilogue& ep, int M, int N, uint32_t tmem_acc, int row, int col_tile0,
-                                              int quarter, int half, const float* s_col, ReleaseFn release) {
+                                              int quarter, int half, const float* s_col, const OutStage& out, ReleaseFn release) {
   constexpr int kColsPerWarp = kTileN / 2;
   constexpr int kChunks = kColsPerWarp / 32;
   const bool ln_fold = ep.col_a != nullptr;
@@ -140,7 +178,27 @@ __device__ __forceinline__ void epilogue_tile(const GemmEpilogue& ep, int M, int
           s1 += y0 + y1;
           s2 = fmaf(y0, y0, fmaf(y1, y1, s2));
         }
-        if (row_ok) *reinterpret_cast<uint4*>(c_row + col0 + g8 * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        if (out.buf != nullptr) {
+          // slab = 2 chunks; 16-byte chunk index inside the 128-byte row, XOR-swizzled with (row & 7) like TMA's SWIZZLE_128B
+          const int rloc = quarter * 32 + static_cast<int>(lane_id());
+          const int ci = (chunk & 1) * 4 + g8;
+          uint8_t* dst = out.buf + ((chunk >> 1) & 1) * kOutSlabBytes + rloc * 128 + ((ci ^ (rloc & 7)) << 4);
+          *reinterpret_cast<uint4*>(dst) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        } else if (row_ok) {
+          *reinterpret_cast<uint4*>(c_row + col0 + g8 * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
+      }
+    }
+    if (out.buf != nullptr && (chunk & 1) == 1) {
+      // slab complete: publish to the async proxy, make sure the previous store of this half has drained its buffer
+      // (so the NEXT slab may overwrite it), then one thread issues the TMA store
+      fence_proxy_async_smem();
+      if (out.issuer) bulk_wait_group_read<0>();
+      named_bar_sync(out.barrier_id, 128);
+      if (out.issuer) {
+        const int slab = chunk >> 1;
+        tma_store_2d(out.tmap, out.buf + (slab & 1) * kOutSlabBytes, col_tile0 + half * kColsPerWarp + slab * 64, out.row_tile0);
+        bulk_commit_group();
       }
     }
   }
@@ -203,10 +261,10 @@ tp_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   const int num_tiles = num_m_blocks * num_n_blocks;
   const int num_k_blocks = (K + kBlockK - 1) / kBlockK;
 
-  if (warp_idx == 0 && lane == 0) {
+  if (warp_idx == kTmaWarp && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
-  } else if (warp_idx == 1 && lane == 0) {
+  } else if (warp_idx == kMmaWarp && lane == 0) {
     for (int i = 0; i < kStages; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
@@ -216,15 +274,17 @@ tp_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       mbar_init(&tmem_empty_bar[i], kNumEpiWarps);
     }
     fence_barrier_init();
-  } else if (warp_idx == 2) {
+  } else if (warp_idx == kAllocWarp) {
     tmem_alloc<Cfg::kTmemCols>(tmem_base_smem);
   }
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_base_smem;
+  grid_dependency_wait();                  // PDL: the prologue above overlapped the previous kernel's tail
+  grid_launch_dependents();
 
-  if (warp_idx == 0) {
+  if (warp_idx == kTmaWarp) {
     // ======================================= TMA producer =======================================
     if (lane == 0) {
       int stage = 0;
@@ -254,7 +314,7 @@ tp_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       }
     }
     __syncwarp();
-  } else if (warp_idx == 1) {
+  } else if (warp_idx == kMmaWarp) {
     // ======================================= MMA issuer =========================================
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_bf16_f32(kBlockM, kBlockN);
@@ -286,7 +346,7 @@ tp_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       }
     }
     __syncwarp();
-  } else if (warp_idx >= kEpiWarp0) {
+  } else if (warp_idx >= kEpiWarp0 && warp_idx < kEpiWarp0 + kNumEpiWarps) {
     // ======================================= epilogue ===========================================
     const int e = warp_idx - kEpiWarp0;
     const int quarter = warp_idx & 3;            // TMEM lane quarter this warp may access
@@ -302,8 +362,9 @@ tp_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tcgen05_fence_after();
       uint64_t* release_bar = &tmem_empty_bar[acc];
+      const OutStage no_stage{nullptr, nullptr, 0, 0, false};
       epilogue_tile<kBlockN>(ep, M, N, tmem_base + static_cast<uint32_t>(acc * kBlockN),
-                             m_blk * kBlockM + quarter * 32 + static_cast<int>(lane), n_blk * kBlockN, quarter, half, s_col, [&]() {
+                             m_blk * kBlockM + quarter * 32 + static_cast<int>(lane), n_blk * kBlockN, quarter, half, s_col, no_stage, [&]() {
                                tcgen05_fence_before();
                                __syncwarp();
                                if (lane == 0) mbar_arrive(release_bar);
@@ -314,31 +375,71 @@ tp_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 
   tcgen05_fence_before();
   __syncthreads();
-  if (warp_idx == 2) {
+  if (warp_idx == kAllocWarp) {
     tcgen05_fence_after();
     tmem_dealloc<Cfg::kTmemCols>(tmem_base);
   }
 }
 
 // ================================================================================================
-// CTA-pair kernel: 256 x 256 tiles, cta_group::2
+// CTA-pair kernel: 256 x 256 tiles, cta_group::2, GROUPED: one launch runs up to kMaxGroup independent GEMM problems
+// (e.g. k_proj_1.2 | v_proj_1.2 | q_proj_1, which share no data but would each leave the machine with a partial last
+// wave and pay launch + prologue + drain on their own).  Tiles are numbered across the problems of the group; every warp
+// role walks the same sequence.
 // ================================================================================================
 struct Gemm2Config {
   static constexpr int kTileM = 256;
   static constexpr int kTileN = 256;
-  static constexpr int kStages = 6;
+  static constexpr int kStages = 4;
   static constexpr int kABytes = kBlockM * kBlockK * 2;          // this CTA's 128 rows of A
   static constexpr int kBBytes = (kTileN / 2) * kBlockK * 2;     // this CTA's half of the B tile
   static constexpr int kStageBytes = kABytes + kBBytes;          // 32 KiB
   static constexpr int kTmemCols = 2 * kTileN;
+  static constexpr int kOutBytes = 2 * 2 * kOutSlabBytes;        // [2 column halves][2 buffers] output slabs for TMA stores
   static constexpr int kColStageBytes = 2 * 2 * kTileN * 4;
   static constexpr int kBarrierBytes = (2 * kStages + 4) * 8 + 16;
-  static constexpr int kSmemBytes = kStages * kStageBytes + kColStageBytes + kBarrierBytes + 1024;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kOutBytes + kColStageBytes + kBarrierBytes + 1024;
 };
 
+constexpr int kMaxGroup = 3;
+
+struct GemmProblem {
+  CUtensorMap tmap_a, tmap_b, tmap_c;
+  int M, N, K;
+  int a_seg_rows;        // 0: plain 2-D A; else rows per segment of the 3-D (crop-strided) A map
+  int use_tma_store;     // C through TMA stores (0 when rows are scattered to segment offsets)
+  int num_n_blocks;
+  int num_tiles;
+  int num_k_blocks;
+  GemmEpilogue ep;
+};
+
+struct GemmGroup {
+  GemmProblem p[kMaxGroup];
+  int count;
+  int total_tiles;
+};
+
+struct TileRef {
+  const GemmProblem* pr;
+  int m_blk, n_blk;
+};
+
+__device__ __forceinline__ TileRef decode_tile(const GemmGroup& g, int tile) {
+  int p = 0;
+  while (p + 1 < g.count && tile >= g.p[p].num_tiles) {
+    tile -= g.p[p].num_tiles;
+    ++p;
+  }
+  TileRef t;
+  t.pr = &g.p[p];
+  t.m_blk = tile / t.pr->num_n_blocks;
+  t.n_blk = tile - t.m_blk * t.pr->num_n_blocks;
+  return t;
+}
+
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
-tp_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, int M, int N, int K,
-                int a_seg_rows, GemmEpilogue ep) {
+tp_gemm2_kernel(const __grid_constant__ GemmGroup grp) {
   using Cfg = Gemm2Config;
   constexpr int kStages = Cfg::kStages;
   constexpr int kTileN = Cfg::kTileN;
@@ -346,8 +447,9 @@ tp_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   extern __shared__ uint8_t smem_raw[];
   // the dynamic smem base has the same offset in both CTAs of the pair, so this alignment fix-up is identical too
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  float* s_col_base = reinterpret_cast<float*>(smem + kStages * Cfg::kStageBytes);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes + Cfg::kColStageBytes);
+  uint8_t* s_out = smem + kStages * Cfg::kStageBytes;                                  // 1 KiB aligned (swizzle atoms)
+  float* s_col_base = reinterpret_cast<float*>(s_out + Cfg::kOutBytes);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_out + Cfg::kOutBytes + Cfg::kColStageBytes);
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tmem_full_bar = empty_bar + kStages;
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;
@@ -357,18 +459,17 @@ tp_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   const uint32_t lane = lane_id();
   const uint32_t cta_rank = cluster_ctarank();
   const bool is_leader = cta_rank == 0;
-
-  const int num_m_blocks = (M + Cfg::kTileM - 1) / Cfg::kTileM;
-  const int num_n_blocks = (N + kTileN - 1) / kTileN;
-  const int num_tiles = num_m_blocks * num_n_blocks;
-  const int num_k_blocks = (K + kBlockK - 1) / kBlockK;
+  const int num_tiles = grp.total_tiles;
   const int pair_idx = static_cast<int>(blockIdx.x >> 1);
   const int num_pairs = static_cast<int>(gridDim.x >> 1);
 
-  if (warp_idx == 0 && lane == 0) {
-    tma_prefetch_desc(&tmap_a);
-    tma_prefetch_desc(&tmap_b);
-  } else if (warp_idx == 1 && lane == 0) {
+  if (warp_idx == kTmaWarp && lane == 0) {
+    for (int i = 0; i < grp.count; ++i) {
+      tma_prefetch_desc(&grp.p[i].tmap_a);
+      tma_prefetch_desc(&grp.p[i].tmap_b);
+      if (grp.p[i].use_tma_store) tma_prefetch_desc(&grp.p[i].tmap_c);
+    }
+  } else if (warp_idx == kMmaWarp && lane == 0) {
     for (int i = 0; i < kStages; ++i) {
       mbar_init(&full_bar[i], 2);          // one arrival per CTA's producer (the leader's carries the expected bytes of both)
       mbar_init(&empty_bar[i], 1);         // multicast tcgen05.commit from the leader
@@ -378,78 +479,119 @@ tp_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       mbar_init(&tmem_empty_bar[i], 2 * kNumEpiWarps);   // epilogue warps of BOTH CTAs (waited on in the leader only)
     }
     fence_barrier_init();
-  } else if (warp_idx == 2) {
+  } else if (warp_idx == kAllocWarp) {
     tmem_alloc_pair<Cfg::kTmemCols>(tmem_base_smem);
   }
   tcgen05_fence_before();
   cluster_sync_all();                      // barriers of both CTAs initialised before any remote arrive / multicast commit
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_base_smem;
+  // Programmatic dependent launch: everything above overlapped the tail of the previous kernel on the stream; from here
+  // on we read what it wrote.  (No-op when the launch carries no PDL attribute.)
+  grid_dependency_wait();
+  grid_launch_dependents();                // the next kernel's CTAs may take over SMs as ours exit (they block in their own wait)
 
-  if (warp_idx == 0) {
+  if (warp_idx == kTmaWarp) {
     // ======================================= TMA producer (both CTAs) ============================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = pair_idx; tile < num_tiles; tile += num_pairs) {
-        const int m_blk = tile / num_n_blocks;
-        const int n_blk = tile - m_blk * num_n_blocks;
-        const int row0 = m_blk * Cfg::kTileM + static_cast<int>(cta_rank) * kBlockM;          // my 128 rows of A
-        const int brow0 = n_blk * kTileN + static_cast<int>(cta_rank) * (kTileN / 2);        // my half of the B tile
-        for (int kb = 0; kb < num_k_blocks; ++kb) {
+    // Whole warp runs the loop (uniform control flow); one elected lane issues the arrive + TMA instructions.
+    int stage = 0;
+    uint32_t phase = 0;
+    [[maybe_unused]] long long w_empty = 0;
+    [[maybe_unused]] const long long t_begin = clock64();
+    for (int tile = pair_idx; tile < num_tiles; tile += num_pairs) {
+      const TileRef t = decode_tile(grp, tile);
+      const GemmProblem& pr = *t.pr;
+      const int row0 = t.m_blk * Cfg::kTileM + static_cast<int>(cta_rank) * kBlockM;          // my 128 rows of A
+      const int brow0 = t.n_blk * kTileN + static_cast<int>(cta_rank) * (kTileN / 2);        // my half of the B tile
+      // segmented A (3-D map, 64-row boxes): global row g -> (segment g / seg_rows, row g % seg_rows); hoisted per tile
+      int seg0 = 0, srow0 = 0, seg1 = 0, srow1 = 0;
+      if (pr.a_seg_rows != 0) {
+        seg0 = row0 / pr.a_seg_rows;
+        srow0 = row0 - seg0 * pr.a_seg_rows;
+        seg1 = (row0 + 64) / pr.a_seg_rows;
+        srow1 = row0 + 64 - seg1 * pr.a_seg_rows;
+      }
+      for (int kb = 0; kb < pr.num_k_blocks; ++kb) {
+        {
+          TP_PROF_T0();
           mbar_wait(&empty_bar[stage], phase ^ 1u);
+          TP_PROF_ADD(w_empty);
+        }
+        if (elect_one()) {
           uint8_t* sa = smem + stage * Cfg::kStageBytes;
           uint8_t* sb = sa + Cfg::kABytes;
           if (is_leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
           else mbar_arrive_cluster(&full_bar[stage], 0);
-          if (a_seg_rows == 0) {
-            tma_load_2d_pair(sa, &tmap_a, &full_bar[stage], kb * kBlockK, row0);
+          if (pr.a_seg_rows == 0) {
+            tma_load_2d_pair(sa, &pr.tmap_a, &full_bar[stage], kb * kBlockK, row0);
           } else {
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              const int g = row0 + h * 64;
-              const int seg = g / a_seg_rows;
-              tma_load_3d_pair(sa + h * (Cfg::kABytes / 2), &tmap_a, &full_bar[stage], kb * kBlockK, g - seg * a_seg_rows, seg);
-            }
+            tma_load_3d_pair(sa, &pr.tmap_a, &full_bar[stage], kb * kBlockK, srow0, seg0);
+            tma_load_3d_pair(sa + Cfg::kABytes / 2, &pr.tmap_a, &full_bar[stage], kb * kBlockK, srow1, seg1);
           }
-          tma_load_2d_pair(sb, &tmap_b, &full_bar[stage], kb * kBlockK, brow0);
-          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+          tma_load_2d_pair(sb, &pr.tmap_b, &full_bar[stage], kb * kBlockK, brow0);
         }
+        __syncwarp();
+        if (++stage == kStages) { stage = 0; phase ^= 1u; }
       }
     }
-    __syncwarp();
-  } else if (warp_idx == 1) {
+#ifdef TP_GEMM_PROFILE
+    if (grp.p[0].ep.prof != nullptr && lane == 0) {
+      grp.p[0].ep.prof[blockIdx.x * 8 + 0] = w_empty;
+      grp.p[0].ep.prof[blockIdx.x * 8 + 1] = clock64() - t_begin;
+    }
+#endif
+  } else if (warp_idx == kMmaWarp) {
     // ======================================= MMA issuer (leader CTA only) ========================
-    if (is_leader && lane == 0) {
+    if (is_leader) {
       constexpr uint32_t idesc = make_idesc_bf16_f32(Cfg::kTileM, kTileN);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      [[maybe_unused]] long long w_full = 0, w_tmem = 0;
+      [[maybe_unused]] const long long t_begin = clock64();
       for (int tile = pair_idx; tile < num_tiles; tile += num_pairs) {
-        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1u);
+        const int num_k_blocks = decode_tile(grp, tile).pr->num_k_blocks;
+        {
+          TP_PROF_T0();
+          mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1u);   // both epilogues have drained this accumulator buffer
+          TP_PROF_ADD(w_tmem);
+        }
         tcgen05_fence_after();
         const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * kTileN);
         for (int kb = 0; kb < num_k_blocks; ++kb) {
-          mbar_wait(&full_bar[stage], phase);                // both CTAs' boxes have landed
-          tcgen05_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
-          const uint64_t desc_a = make_smem_desc_kmajor_sw128(sa);
-          const uint64_t desc_b = make_smem_desc_kmajor_sw128(sa + Cfg::kABytes);
-#pragma unroll
-          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-            umma_bf16_pair(tmem_d, desc_a + static_cast<uint64_t>(k * 2), desc_b + static_cast<uint64_t>(k * 2), idesc,
-                           static_cast<uint32_t>((kb | k) != 0));
+          {
+            TP_PROF_T0();
+            mbar_wait(&full_bar[stage], phase);              // both CTAs' boxes have landed
+            TP_PROF_ADD(w_full);
           }
-          umma_commit_pair(&empty_bar[stage], 0x3);          // frees the slot in BOTH CTAs
+          tcgen05_fence_after();
+          if (elect_one()) {
+            const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
+            const uint64_t desc_a = make_smem_desc_kmajor_sw128(sa);
+            const uint64_t desc_b = make_smem_desc_kmajor_sw128(sa + Cfg::kABytes);
+#pragma unroll
+            for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+              umma_bf16_pair(tmem_d, desc_a + static_cast<uint64_t>(k * 2), desc_b + static_cast<uint64_t>(k * 2), idesc,
+                             static_cast<uint32_t>((kb | k) != 0));
+            }
+            umma_commit_pair(&empty_bar[stage], 0x3);        // frees the slot in BOTH CTAs
+            if (kb == num_k_blocks - 1) umma_commit_pair(&tmem_full_bar[acc], 0x3);   // accumulator complete -> both epilogues
+          }
+          __syncwarp();
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
-        umma_commit_pair(&tmem_full_bar[acc], 0x3);          // accumulator complete -> both epilogues
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
       }
+#ifdef TP_GEMM_PROFILE
+      if (grp.p[0].ep.prof != nullptr && lane == 0) {
+        grp.p[0].ep.prof[blockIdx.x * 8 + 2] = w_full;
+        grp.p[0].ep.prof[blockIdx.x * 8 + 3] = w_tmem;
+        grp.p[0].ep.prof[blockIdx.x * 8 + 4] = clock64() - t_begin;
+      }
+#endif
     }
-    __syncwarp();
-  } else if (warp_idx >= kEpiWarp0) {
+  } else if (warp_idx >= kEpiWarp0 && warp_idx < kEpiWarp0 + kNumEpiWarps) {
     // ======================================= epilogue (both CTAs, own 128 rows) ==================
     const int e = warp_idx - kEpiWarp0;
     const int quarter = warp_idx & 3;
@@ -457,30 +599,50 @@ tp_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     const int epi_tid = e * 32 + static_cast<int>(lane);
     int acc = 0;
     uint32_t acc_phase = 0;
+    bool stored = false;
+    [[maybe_unused]] long long w_acc = 0, t_work = 0;
     for (int tile = pair_idx; tile < num_tiles; tile += num_pairs) {
-      const int m_blk = tile / num_n_blocks;
-      const int n_blk = tile - m_blk * num_n_blocks;
+      const TileRef t = decode_tile(grp, tile);
+      const GemmProblem& pr = *t.pr;
       float* s_col = s_col_base + acc * 2 * kTileN;
-      stage_col_vectors<kTileN>(ep, N, n_blk * kTileN, s_col, epi_tid);
-      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      stage_col_vectors<kTileN>(pr.ep, pr.N, t.n_blk * kTileN, s_col, epi_tid);
+      {
+        TP_PROF_T0();
+        mbar_wait(&tmem_full_bar[acc], acc_phase);
+        TP_PROF_ADD(w_acc);
+      }
+      TP_PROF_T0();
       tcgen05_fence_after();
       uint64_t* release_bar = &tmem_empty_bar[acc];
-      const int row = m_blk * Cfg::kTileM + static_cast<int>(cta_rank) * kBlockM + quarter * 32 + static_cast<int>(lane);
-      epilogue_tile<kTileN>(ep, M, N, tmem_base + static_cast<uint32_t>(acc * kTileN), row, n_blk * kTileN, quarter, half, s_col, [&]() {
-        tcgen05_fence_before();
-        __syncwarp();
-        if (lane == 0) {
-          if (is_leader) mbar_arrive(release_bar);
-          else mbar_arrive_cluster(release_bar, 0);
-        }
-      });
+      const int row_tile0 = t.m_blk * Cfg::kTileM + static_cast<int>(cta_rank) * kBlockM;
+      const int row = row_tile0 + quarter * 32 + static_cast<int>(lane);
+      const OutStage out{pr.use_tma_store ? s_out + half * 2 * kOutSlabBytes : nullptr, &pr.tmap_c, row_tile0, static_cast<uint32_t>(2 + half),
+                         quarter == 0 && lane == 0};
+      stored = stored || pr.use_tma_store;
+      epilogue_tile<kTileN>(pr.ep, pr.M, pr.N, tmem_base + static_cast<uint32_t>(acc * kTileN), row, t.n_blk * kTileN, quarter, half, s_col,
+                            out, [&]() {
+                              tcgen05_fence_before();
+                              __syncwarp();
+                              if (lane == 0) {
+                                if (is_leader) mbar_arrive(release_bar);
+                                else mbar_arrive_cluster(release_bar, 0);
+                              }
+                            });
+      TP_PROF_ADD(t_work);
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
+    if (stored && quarter == 0 && lane == 0) bulk_wait_group<0>();   // my half's last TMA stores have been performed
+#ifdef TP_GEMM_PROFILE
+    if (grp.p[0].ep.prof != nullptr && e == 0 && lane == 0) {
+      grp.p[0].ep.prof[blockIdx.x * 8 + 5] = w_acc;
+      grp.p[0].ep.prof[blockIdx.x * 8 + 6] = t_work;
+    }
+#endif
   }
 
   tcgen05_fence_before();
   cluster_sync_all();                      // the peer may read my smem / signal my barriers until here
-  if (warp_idx == 2) {
+  if (warp_idx == kAllocWarp) {
     tcgen05_fence_after();
     tmem_dealloc_pair<Cfg::kTmemCols>(tmem_base);
   }

@@ -33,6 +33,8 @@ __global__ void point_query_kernel(const __nv_bfloat16* __restrict__ x0, long lo
                                    long long n_queries) {
   constexpr int G = kGrid / S;
   constexpr int M = G * G;
+  grid_dependency_wait();        // PDL: inputs may come from the previous kernel on the stream
+  grid_launch_dependents();
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long long query = idx >> 7;          // 128 vectors of 8 channels per query
   const int vec = static_cast<int>(idx & 127);
@@ -76,6 +78,8 @@ __global__ void __launch_bounds__(256) window_attn_kernel(const __nv_bfloat16* _
   constexpr int G = kGrid / S;
   constexpr int M = G * G;
   constexpr int W = S * S;
+  grid_dependency_wait();        // PDL: q', k', v' come from the previous GEMM launch
+  grid_launch_dependents();
   const long long query = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (query >= n_queries) return;
@@ -185,6 +189,28 @@ __global__ void fold_layernorm_kernel(const __nv_bfloat16* __restrict__ w, const
     wsum[o] = s;
     cst[o] = c + __bfloat162float(bias[o]);
   }
+}
+
+// out[c, r] = in[r, c] for a square bf16 matrix (pack time only: W_o^T as the K-major B operand of the fold GEMM)
+__global__ void transpose_bf16_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int n) {
+  __shared__ __nv_bfloat16 tile[32][33];
+  const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) tile[i][threadIdx.x] = in[static_cast<long long>(by + i) * n + bx + threadIdx.x];
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) out[static_cast<long long>(bx + i) * n + by + threadIdx.x] = tile[threadIdx.x][i];
+}
+
+// out[o] = sum_i w[o, i] * x[i] + b[o]   (fp32 out; one warp per output; pack time only)
+__global__ void matvec_bias_kernel(const __nv_bfloat16* __restrict__ w, const __nv_bfloat16* __restrict__ x,
+                                   const __nv_bfloat16* __restrict__ b, float* __restrict__ out, int out_dim, int in_dim) {
+  const int o = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (o >= out_dim) return;
+  float acc = 0.f;
+  for (int i = lane; i < in_dim; i += 32) acc = fmaf(__bfloat162float(w[static_cast<long long>(o) * in_dim + i]), __bfloat162float(x[i]), acc);
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+  if (lane == 0) out[o] = acc + __bfloat162float(b[o]);
 }
 
 // ------------------------------------------------------------------------------------------------

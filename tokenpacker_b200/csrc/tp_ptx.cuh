@@ -19,6 +19,21 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
 
+// One lane of a fully converged warp (the same lane every time).  Keeping the surrounding loop warp-uniform and
+// electing only around the single-thread instructions (TMA, tcgen05.mma, commits) lets ptxas keep loop state in uniform
+// registers instead of wrapping every UTMALDG / UTCHMMA in an R2UR "waterfall" loop.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // Every spin on an mbarrier is bounded: a protocol bug must trap (visible error), never hang the GPU.
 #ifndef TP_SPIN_LIMIT_CYCLES
 #define TP_SPIN_LIMIT_CYCLES (4000000000ll)   // ~2 s at 1.9 GHz
@@ -97,6 +112,37 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m
           smem_u32(smem_dst)),
       "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
+}
+
+// L2 prefetch of a box (no shared-memory destination, no barrier): lets the producer run further ahead of the
+// shared-memory ring than its capacity allows, hiding HBM latency of first-touch activation tiles.
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* m, int32_t c0, int32_t c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1)
+               : "memory");
+}
+
+__device__ __forceinline__ void tma_prefetch_l2_3d(const CUtensorMap* m, int32_t c0, int32_t c1, int32_t c2) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0),
+               "r"(c1), "r"(c2)
+               : "memory");
+}
+
+// TMA store of a shared-memory box to global memory (bulk async group semantics, tracked per issuing thread).
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem_src, int32_t c0, int32_t c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// wait until at most kPending of this thread's bulk groups still READ their shared-memory source
+template <int kPending>
+__device__ __forceinline__ void bulk_wait_group_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kPending) : "memory");
+}
+// wait until at most kPending of this thread's bulk groups are incomplete (writes performed)
+template <int kPending>
+__device__ __forceinline__ void bulk_wait_group() {
+  asm volatile("cp.async.bulk.wait_group %0;" ::"n"(kPending) : "memory");
 }
 
 // Same with an L2 cache-policy hint (createpolicy-style 64-bit immediate policies below).
@@ -273,6 +319,12 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar, uint16_t cta_mas
                "h"(cta_mask)
                : "memory");
 }
+
+// Programmatic dependent launch (PDL).  wait: block until the preceding kernel on the stream has completed and its
+// memory is visible (returns immediately if this launch has no programmatic dependency).  launch_dependents: allow the
+// NEXT kernel's CTAs to be scheduled (they run their prologue, then block in their own wait).
+__device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void grid_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
