@@ -52,7 +52,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu_index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
             return
@@ -97,11 +97,25 @@ def cpu_reference_run(steps: int, warmup: int, crops: int):
     configs[1] workload; exactly ``steps`` steps are timed after ``warmup`` untimed ones."""
     from oracle import tokenpacker_oracle as tpo
     from oracle import torch_port
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
+    avail = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     params = {k: torch.from_numpy(v) for k, v in tpo.make_params(HIDDEN, seed=0).items()}
     x0, xm = tpo.make_inputs(crops, seed=1234)
     x0, xm = torch.from_numpy(x0), torch.from_numpy(xm)
+    # "all the host threads it can use": torch's intra-op pool degrades badly past the point where GEMM panels get too
+    # thin (and on boxes whose cgroup quota is below the visible core count), so probe a few pool sizes up to every
+    # visible core and keep the FASTEST — the baseline is the best the reference's CPU path does on this host.
+    cands = sorted({c for c in (avail, avail // 2, avail // 4, 32, 16, 8) if 1 <= c <= avail}, reverse=True)
+    best_t, best_c = None, avail
+    with torch.no_grad():
+        for c in cands:
+            torch.set_num_threads(c)
+            torch_port.forward(params, x0, xm, SCALE)
+            t0 = time.perf_counter()
+            torch_port.forward(params, x0, xm, SCALE)
+            dt = time.perf_counter() - t0
+            if best_t is None or dt < best_t:
+                best_t, best_c = dt, c
+    torch.set_num_threads(best_c)
     with torch.no_grad():
         for _ in range(warmup):
             torch_port.forward(params, x0, xm, SCALE)
@@ -111,7 +125,7 @@ def cpu_reference_run(steps: int, warmup: int, crops: int):
         dt = (time.perf_counter() - t0) / steps
     return {"value": crops * TOKENS_PER_CROP / dt, "unit": UNIT, "cores": int(torch.get_num_threads()), "kind": "port",
             "sample": f"{crops} crops/step x {steps} steps of the configs[1] workload (fp32, torch {torch.__version__} CPU ops, "
-                      f"oracle/torch_port.py restatement of builder.py:107-137), {dt * 1e3:.1f} ms/step"}, dt
+                      f"oracle/torch_port.py restatement of builder.py:107-137; best of pool sizes {cands} on {avail} visible cores), {dt * 1e3:.1f} ms/step"}, dt
 
 
 def run_reference(args):
@@ -135,8 +149,8 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU baseline leg (profiling runs)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg (profiling runs)")
@@ -233,7 +247,7 @@ def main():
                "ms_per_step": dt / args.steps * 1e3, "api": "TokenPackerB200.forward_host -> tp_forward_host (pinned host buffers, 8-crop chunks)"}
 
     # ------------------------------------------------------------------ roofline of the dominant kernel
-    # tp_gemm_kernel<256> on its largest launch: h_kv = GELU(xm . [W_k0;W_v0]^T + b)  (M=36864, N=2048, K=4096), 56% of the
+    # tp_gemm2_kernel on its largest launch: h_kv = GELU(xm . [W_k0;W_v0]^T + b)  (M=36864, N=2048, K=4096), 56% of the
     # step's FLOPs.  Timed live with CUDA events on the launching stream, 10 back-to-back launches after 3 warm-ups.
     roofline = None
     if rank == 0:
@@ -260,7 +274,7 @@ def main():
         tpath = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")
         if os.path.exists(tpath):
             traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
-        roofline = {"bound": "tensor", "kernel": "tp_gemm_kernel<256> (k/v_proj.0 GEMM, M=36864 N=2048 K=4096, bias+GELU epilogue)",
+        roofline = {"bound": "tensor", "kernel": "tp_gemm2_kernel (CTA-pair tcgen05 GEMM; largest launch: k/v_proj.0, M=36864 N=2048 K=4096, bias+GELU epilogue)",
                     "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_sustained"],
                     "frac_of_burst": achieved / peaks["bf16_burst"], "peak_source": peaks["source"] + ", sustained (back-to-back launches)",
                     "traffic": traffic, "ms_per_launch": k_ms, "flops_per_launch": flops,

@@ -121,6 +121,11 @@ TP_API int tp_hd_plan(const int* h_block, const int* w_block, int64_t n_images, 
                int64_t* sep_rows_host, int64_t* ret_rows_host, int64_t* cu_seqlens_host, int64_t* n_crops, int64_t* n_sep,
                int64_t* n_ret);
 
+/* Stand-alone form of the crop scatter (used after the multi-GPU all-gather, where the projector's own scatter epilogue
+ * cannot be used): out[seg_row_offset[c] + m, :] = feats[c, m, :].  Device pointers, bf16. */
+TP_API int tp_hd_scatter_crops(const void* feats, int64_t n_crops, int tokens_per_crop, int hidden, const int64_t* seg_row_offset,
+                               void* out, void* stream);
+
 /* Writes the separator rows of the packed output: out[sep_rows[i], :] = sep_row, out[ret_rows[i], :] = ret_row
  * (bf16 vectors of length hidden).  Device pointers. */
 TP_API int tp_hd_fill_separators(void* out, int hidden, const int64_t* sep_rows, int64_t n_sep, const void* sep_row,

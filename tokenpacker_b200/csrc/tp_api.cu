@@ -753,6 +753,20 @@ int tp_hd_plan(const int* h_block, const int* w_block, int64_t n_images, int tok
   return TP_OK;
 }
 
+int tp_hd_scatter_crops(const void* feats, int64_t n_crops, int tokens_per_crop, int hidden, const int64_t* seg_row_offset, void* out,
+                        void* stream_) {
+  if (feats == nullptr || out == nullptr || seg_row_offset == nullptr || n_crops <= 0 || tokens_per_crop <= 0 || hidden <= 0 ||
+      hidden % 8 != 0)
+    return TP_ERR_INVALID_ARGUMENT;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const long long threads = n_crops * tokens_per_crop * (hidden / 8);
+  scatter_crops_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, stream>>>(
+      static_cast<const __nv_bfloat16*>(feats), n_crops, tokens_per_crop, hidden, reinterpret_cast<const long long*>(seg_row_offset),
+      static_cast<__nv_bfloat16*>(out));
+  TP_CUDA(cudaGetLastError());
+  return TP_OK;
+}
+
 int tp_hd_fill_separators(void* out, int hidden, const int64_t* sep_rows, int64_t n_sep, const void* sep_row, const int64_t* ret_rows,
                           int64_t n_ret, const void* ret_row, void* stream_) {
   if (out == nullptr || hidden <= 0 || hidden % 8 != 0 || n_sep < 0 || n_ret < 0) return TP_ERR_INVALID_ARGUMENT;

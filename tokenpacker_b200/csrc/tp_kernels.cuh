@@ -286,6 +286,20 @@ __global__ void hd_tile_thumb_kernel(int hb, int wb, int h_t, int w_t, float* __
   crops[((static_cast<long long>(hb * wb) * 3 + ch) * kBlockPx + y) * kBlockPx + x] = v;
 }
 
+// out[seg_row_offset[c] + m, :] = feats[c, m, :]  (bf16; one thread per 8 channels): crop token blocks -> packed rows.
+__global__ void scatter_crops_kernel(const __nv_bfloat16* __restrict__ feats, long long n_crops, int tokens, int hidden,
+                                     const long long* __restrict__ seg_row_offset, __nv_bfloat16* __restrict__ out) {
+  const int vecs = hidden / 8;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long rows = n_crops * tokens;
+  if (idx >= rows * vecs) return;
+  const long long r = idx / vecs;
+  const int v = static_cast<int>(idx - r * vecs);
+  const long long c = r / tokens;
+  const long long dst = seg_row_offset[c] + (r - c * tokens);
+  *reinterpret_cast<uint4*>(out + dst * hidden + v * 8) = __ldg(reinterpret_cast<const uint4*>(feats + r * hidden + v * 8));
+}
+
 // out[rows[i], :] = row (bf16 [hidden]); one thread per 8 channels.
 __global__ void fill_rows_kernel(__nv_bfloat16* __restrict__ out, int hidden, const long long* __restrict__ rows, long long n_rows,
                                  const __nv_bfloat16* __restrict__ row) {

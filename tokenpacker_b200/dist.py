@@ -1,0 +1,71 @@
+"""Multi-GPU use of the projector: one process per GPU, crops sharded across ranks, weights replicated.
+
+The projector itself needs no collective (every crop is independent, builder.py:107-137 has no cross-crop op), and the
+crops normally arrive already sharded because the CLIP tower upstream is data parallel.  The only exchange step of the
+path is the reassembly of per-image HD token sequences (llava_arch.py:139-155) when an image's crops live on different
+ranks: one all-gather of the projected crop blocks over NVLink (NCCL), then the packed assembly on every rank.
+Host logic only — works with the gloo backend on CPU tensors for tests; device work goes through the C ABI.
+"""
+from __future__ import annotations
+
+from typing import Sequence
+
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(n_items: int, world: int, rank: int):
+    """Contiguous block partition [lo, hi) of n_items over world ranks (sizes differ by at most one)."""
+    base, rem = divmod(n_items, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def shard_counts(n_items: int, world: int):
+    return [shard_bounds(n_items, world, r)[1] - shard_bounds(n_items, world, r)[0] for r in range(world)]
+
+
+def all_gather_crops(local: torch.Tensor, counts: Sequence[int], group=None) -> torch.Tensor:
+    """All-gather per-rank crop blocks [n_r, M, H] (n_r = counts[r]) into [sum(counts), M, H] on every rank.
+
+    Equal counts take the single-buffer NCCL path (all_gather_into_tensor); ragged counts are padded to the maximum."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    if len(counts) != world or local.shape[0] != counts[rank]:
+        raise ValueError(f"rank {rank}: local block has {local.shape[0]} crops, counts say {list(counts)}")
+    local = local.contiguous()
+    tail = tuple(local.shape[1:])
+    if len(set(counts)) == 1 and dist.get_backend(group) == "nccl":
+        out = local.new_empty((sum(counts),) + tail)
+        dist.all_gather_into_tensor(out, local, group=group)
+        return out
+    mx = max(counts)
+    padded = local
+    if local.shape[0] != mx:
+        padded = local.new_zeros((mx,) + tail)
+        padded[: local.shape[0]] = local
+    bufs = [local.new_empty((mx,) + tail) for _ in range(world)]
+    dist.all_gather(bufs, padded, group=group)
+    return torch.cat([b[:c] for b, c in zip(bufs, counts)], dim=0)
+
+
+class ShardedTokenPacker:
+    """Data-parallel wrapper: ``projector`` is a (replicated) TokenPackerB200 on this rank's GPU."""
+
+    def __init__(self, projector, group=None):
+        self.projector = projector
+        self.group = group
+
+    def forward_local(self, x_local):
+        """This rank's crops only — no communication."""
+        return self.projector(x_local)
+
+    def forward_gathered(self, x_local, counts: Sequence[int]):
+        """Project this rank's crops, then all-gather so every rank holds all [N, M, H] crop blocks."""
+        return all_gather_crops(self.forward_local(x_local), counts, self.group)
+
+    def forward_hd(self, x_local, counts: Sequence[int], h_block, w_block, sep_row, ret_row):
+        """HD path across ranks: local projection -> all-gather -> per-image packed assembly (every rank gets all images)."""
+        from .hd import hd_assemble
+        feats = self.forward_gathered(x_local, counts)
+        return hd_assemble(feats, h_block, w_block, sep_row, ret_row)

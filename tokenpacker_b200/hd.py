@@ -120,13 +120,11 @@ def hd_assemble(feats: torch.Tensor, h_block, w_block, sep_row: torch.Tensor, re
     with torch.cuda.device(device):
         out = torch.empty((int(plan.cu_seqlens[-1]), hdim), dtype=torch.bfloat16, device=device)
         seg = plan.seg_row_offset.to(device)
-        # crop tokens: a strided block copy per crop, expressed as one indexed copy (plumbing: torch device copy)
-        rows = (seg[:, None] + torch.arange(m, device=device)[None, :]).reshape(-1)
-        out.index_copy_(0, rows, fb.reshape(-1, hdim))
+        stream = torch.cuda.current_stream(device).cuda_stream
+        check(lib.tp_hd_scatter_crops(fb.data_ptr(), plan.n_crops, m, hdim, seg.data_ptr(), out.data_ptr(), stream), "tp_hd_scatter_crops")
         sep_rows, ret_rows = plan.sep_rows.to(device), plan.ret_rows.to(device)
         sep_b = sep_row.to(device=device, dtype=torch.bfloat16).contiguous()
         ret_b = ret_row.to(device=device, dtype=torch.bfloat16).contiguous()
-        stream = torch.cuda.current_stream(device).cuda_stream
         check(lib.tp_hd_fill_separators(out.data_ptr(), hdim, sep_rows.data_ptr(), sep_rows.numel(), sep_b.data_ptr(),
                                         ret_rows.data_ptr(), ret_rows.numel(), ret_b.data_ptr(), stream), "tp_hd_fill_separators")
     return (out if feats.dtype == torch.bfloat16 else out.to(feats.dtype)), plan.cu_seqlens
