@@ -130,3 +130,24 @@ def test_dtype_roundtrip_and_errors():
         m((x0[:, :100].bfloat16(), xm.bfloat16()))
     with pytest.raises(NotImplementedError):
         m((x0.bfloat16(), xm.bfloat16()))              # grad enabled + trainable params: backward not implemented
+
+
+def test_kernel_variants_agree_bitwise(monkeypatch):
+    """The one-CTA (cta_group::1) and CTA-pair (cta_group::2, grouped or not) GEMM kernels are interchangeable bit for bit
+    through the whole forward (explicit-intrinsic epilogue math), so the automatic size-based selection cannot make a
+    crop's result depend on how many crops share its call."""
+    s, hidden, n = 4, 256, 10
+    m, _ = make_module(hidden, s, seed=3)
+    g = torch.Generator(device="cuda").manual_seed(7)
+    x0 = torch.randn(n, 576, 1024, device="cuda", generator=g).bfloat16()
+    xm = torch.randn(n, 576, 4096, device="cuda", generator=g).bfloat16()
+    outs = {}
+    with torch.no_grad():
+        for mode in ("0", "1", "2", "3"):
+            monkeypatch.setenv("TP_GEMM_MODE", mode)
+            outs[mode] = m((x0, xm)).clone()
+            outs["half" + mode] = m((x0[5:], xm[5:])).clone()
+    for mode in ("1", "2", "3"):
+        assert torch.equal(outs["0"], outs[mode]), mode
+        assert torch.equal(outs["0"][5:], outs["half" + mode]), mode
+    assert torch.equal(outs["0"][5:], outs["half0"])       # Q=180 (one-CTA kernels) vs Q=360 (pair kernels) under auto selection

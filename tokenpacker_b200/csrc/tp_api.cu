@@ -135,7 +135,7 @@ cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t s
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = getenv("TP_NO_PDL") != nullptr ? 0 : 1;   // debugging aid: plain stream serialization
   return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 

@@ -119,12 +119,14 @@ __device__ __forceinline__ void epilogue_tile(const GemmEpilogue& ep, int M, int
     const float2* st = reinterpret_cast<const float2*>(ep.stats_in) + static_cast<long long>(row) * ep.stats_in_slots;
     for (int i = 0; i < ep.stats_in_slots; ++i) {     // fixed order -> bitwise reproducible LayerNorm statistics
       const float2 v = st[i];
-      t1 += v.x;
-      t2 += v.y;
+      t1 = __fadd_rn(t1, v.x);
+      t2 = __fadd_rn(t2, v.y);
     }
-    mu = t1 * ep.ln_inv_dim;
-    const float var = fmaxf(t2 * ep.ln_inv_dim - mu * mu, 0.f);
-    rstd = rsqrtf(var + ep.ln_eps);
+    // explicit intrinsics throughout the epilogue math: no FMA-contraction freedom for the compiler, so the one-CTA and
+    // CTA-pair instantiations (and any future one) produce the same bits for the same row
+    mu = __fmul_rn(t1, ep.ln_inv_dim);
+    const float var = fmaxf(fmaf(-mu, mu, __fmul_rn(t2, ep.ln_inv_dim)), 0.f);
+    rstd = rsqrtf(__fadd_rn(var, ep.ln_eps));
   }
   long long dst_row = row;
   if (ep.seg_row_offset != nullptr && row_ok) {
@@ -157,14 +159,14 @@ __device__ __forceinline__ void epilogue_tile(const GemmEpilogue& ep, int M, int
           const float4 a1 = *reinterpret_cast<const float4*>(sa + lc + 4);
           const float ca[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
 #pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] = rstd * (v[j] - mu * ca[j]);
+          for (int j = 0; j < 8; ++j) v[j] = __fmul_rn(rstd, fmaf(-mu, ca[j], v[j]));
         }
         {
           const float4 b0 = *reinterpret_cast<const float4*>(sb + lc);
           const float4 b1 = *reinterpret_cast<const float4*>(sb + lc + 4);
           const float cb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] += cb[j];
+          for (int j = 0; j < 8; ++j) v[j] = __fadd_rn(v[j], cb[j]);
         }
         if (ep.gelu) {
 #pragma unroll
@@ -173,9 +175,9 @@ __device__ __forceinline__ void epilogue_tile(const GemmEpilogue& ep, int M, int
         uint32_t pk[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          pk[j] = pack_bf16x2(v[2 * j] * ep.alpha, v[2 * j + 1] * ep.alpha);
+          pk[j] = pack_bf16x2(__fmul_rn(v[2 * j], ep.alpha), __fmul_rn(v[2 * j + 1], ep.alpha));
           const float y0 = bf16_lo(pk[j]), y1 = bf16_hi(pk[j]);
-          s1 += y0 + y1;
+          s1 = __fadd_rn(s1, __fadd_rn(y0, y1));
           s2 = fmaf(y0, y0, fmaf(y1, y1, s2));
         }
         if (out.buf != nullptr) {

@@ -339,7 +339,7 @@ __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t threads) {
 // at ~17 instructions instead of libdevice erff's two divergent branches (~40): the epilogue of the K=1024 GEMMs
 // is instruction-bound, so this is on the critical path.
 __device__ __forceinline__ float gelu_erf(float x) {
-  const float t = fabsf(x) * 0.70710678118654752440f;
+  const float t = __fmul_rn(fabsf(x), 0.70710678118654752440f);
   float p = 0.0000430638f;
   p = fmaf(p, t, 0.0002765672f);
   p = fmaf(p, t, 0.0001520143f);
@@ -347,9 +347,9 @@ __device__ __forceinline__ float gelu_erf(float x) {
   p = fmaf(p, t, 0.0422820123f);
   p = fmaf(p, t, 0.0705230784f);
   p = fmaf(p, t, 1.0f);
-  p *= p; p *= p; p *= p; p *= p;                      // ^16 (overflows to +inf for |x| > ~24 -> erf = 1, exact)
-  const float e = 1.0f - __fdividef(1.0f, p);          // erf(|x| / sqrt 2)
-  const float hx = 0.5f * x;
+  p = __fmul_rn(p, p); p = __fmul_rn(p, p); p = __fmul_rn(p, p); p = __fmul_rn(p, p);   // ^16 (+inf for |x| > ~24 -> erf = 1)
+  const float e = __fsub_rn(1.0f, __fdividef(1.0f, p));   // erf(|x| / sqrt 2)
+  const float hx = __fmul_rn(0.5f, x);
   return fmaf(fabsf(hx), e, hx);                        // 0.5 x (1 + sign(x) erf(|x|/sqrt 2)) = hx + |hx| e
 }
 
