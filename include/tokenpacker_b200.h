@@ -86,6 +86,16 @@ TP_API int tp_forward(const void* packed, const void* x0, const void* xm, int64_
                int64_t xm_crop_stride, int scale_factor, int hidden, void* out, const int64_t* seg_row_offset,
                void* workspace, size_t workspace_bytes, void* stream);
 
+/* Multi-GPU form with the all-gather FUSED into the last GEMM's epilogue.  peer_out[p] (p < n_peers <= 8) is the base of a
+ * gathered buffer [total_crops, M, H] bf16 on GPU p, mapped into this process (CUDA IPC / symmetric memory; own buffer
+ * included).  This rank's n_crops crops are written to rows [crop_offset*M, (crop_offset+n_crops)*M) of EVERY peer buffer by
+ * TMA stores over NVLink, tile by tile as the GEMM produces them — no separate collective kernel and no staging copy.
+ * The caller must run a cross-rank barrier after the stream reaches this call before any rank reads its gathered buffer.
+ * Needs hidden % 256 == 0.  Replaces: encode_images on sharded crops + the cross-rank reassembly of llava_arch.py:139-155. */
+TP_API int tp_forward_allgather(const void* packed, const void* x0, const void* xm, int64_t n_crops, int64_t x0_crop_stride,
+                                int64_t xm_crop_stride, int scale_factor, int hidden, void* const* peer_out, int n_peers,
+                                int64_t crop_offset, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Same call with HOST buffers (pinned recommended): copies inputs in, runs, copies the result out, pipelined over
  * chunks of crops on internal streams, and returns after the result is in ``out_host``.  d_* are caller-provided
  * device staging buffers of at least the sizes tp_forward needs for n_crops.  This is the end-to-end entry point

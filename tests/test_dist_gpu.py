@@ -19,7 +19,7 @@ def _worker(rank, world, port, tmp):
     import torch.distributed as dist
     from tokenpacker_b200 import TokenPackerB200
     from tokenpacker_b200 import synthetic as syn
-    from tokenpacker_b200.dist import ShardedTokenPacker, shard_bounds, shard_counts
+    from tokenpacker_b200.dist import FusedGatherTokenPacker, ShardedTokenPacker, shard_bounds, shard_counts
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
@@ -42,6 +42,13 @@ def _worker(rank, world, port, tmp):
             ref, ref_cu = m.forward_packed((x0, xm), hb, wb, sep, ret)
         assert torch.equal(cu, ref_cu)
         assert torch.equal(packed, ref), "sharded + all-gather + assembly differs from the single-GPU packed forward"
+        # fused path: the last GEMM's TMA stores write into every rank's gathered buffer over NVLink (no NCCL all-gather)
+        fused = FusedGatherTokenPacker(m)
+        with torch.no_grad():
+            for _ in range(3):                    # repeated use of the same symmetric buffer
+                packed_f, cu_f = fused.forward_hd((x0[lo:hi], xm[lo:hi]), shard_counts(n, world), hb, wb, sep, ret)
+                assert torch.equal(cu_f, ref_cu)
+                assert torch.equal(packed_f, ref), "fused peer-store all-gather differs from the single-GPU packed forward"
         open(os.path.join(tmp, f"ok{rank}"), "w").write("ok")
     finally:
         dist.destroy_process_group()

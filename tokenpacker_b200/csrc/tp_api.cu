@@ -145,6 +145,8 @@ struct GemmItem {
   long long ldb;
   long long M, N, K;
   GemmEpilogue ep;
+  void* const* peer_c = nullptr;   // fused all-gather: the same output slot in every peer's gathered buffer
+  int n_peers = 0;
 };
 
 int check_item(const GemmItem& it) {
@@ -202,10 +204,18 @@ int launch_gemm_pair_group(const GemmItem* items, int count, int sms, cudaStream
   }
   if (total > 0x7fffffffll) return TP_ERR_INVALID_ARGUMENT;
   g.total_tiles = static_cast<int>(total);
+  PeerStores peers;
+  memset(&peers, 0, sizeof(peers));
+  if (items[0].n_peers > 0) {
+    if (count != 1 || items[0].n_peers > kMaxPeers || items[0].ep.seg_row_offset != nullptr) return TP_ERR_INVALID_ARGUMENT;
+    for (int p = 0; p < items[0].n_peers; ++p)
+      TP_TRY(make_map_2d(&peers.m[p], items[0].peer_c[p], items[0].M, items[0].N, items[0].ep.ldc, kBlockM));
+    peers.count = items[0].n_peers;
+  }
   TP_CUDA(cudaFuncSetAttribute(tp_gemm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
   const long long max_pairs = sms / 2;
   const int grid = 2 * static_cast<int>(total < max_pairs ? total : max_pairs);
-  TP_CUDA(launch_pdl(tp_gemm2_kernel, dim3(grid), dim3(kGemmThreads), Cfg::kSmemBytes, stream, g));
+  TP_CUDA(launch_pdl(tp_gemm2_kernel, dim3(grid), dim3(kGemmThreads), Cfg::kSmemBytes, stream, g, peers));
   return TP_OK;
 }
 
@@ -222,7 +232,8 @@ int launch_gemms(const GemmItem* items, int count, int sms, cudaStream_t stream)
     TP_TRY(check_item(items[i]));
     const GemmItem& it = items[i];
     const bool pair_ok = (it.N % 256 == 0) && sms >= 2;
-    const bool want_pair = mode == 2 || mode == 3 || (mode == 0 && it.M >= 256);
+    if (it.n_peers > 0 && (!pair_ok || count != 1)) return TP_ERR_INVALID_ARGUMENT;   // peer stores live in the pair kernel only
+    const bool want_pair = mode == 2 || mode == 3 || (mode == 0 && it.M >= 256) || it.n_peers > 0;
     if (pair_ok && want_pair) {
       if (mode == 3) TP_TRY(launch_gemm_pair_group(&it, 1, sms, stream));
       else grouped[n_grouped++] = it;
@@ -425,9 +436,12 @@ size_t tp_workspace_bytes(int64_t n_crops, int scale_factor, int hidden) {
   return work_layout(n_crops, scale_factor, hidden).total;
 }
 
-int tp_forward(const void* packed, const void* x0, const void* xm, int64_t n_crops, int64_t x0_crop_stride, int64_t xm_crop_stride,
-               int scale_factor, int hidden, void* out, const int64_t* seg_row_offset, void* workspace, size_t workspace_bytes,
-               void* stream_) {
+}  // extern "C"
+
+namespace {
+int forward_impl(const void* packed, const void* x0, const void* xm, int64_t n_crops, int64_t x0_crop_stride, int64_t xm_crop_stride,
+                 int scale_factor, int hidden, void* out, const int64_t* seg_row_offset, void* const* peer_out, int n_peers,
+                 void* workspace, size_t workspace_bytes, void* stream_) {
   if (scale_factor <= 0 || kGrid % scale_factor != 0) return TP_ERR_BAD_SCALE_FACTOR;          // builder.py:51-52
   if (scale_factor < 2 || scale_factor > 4) return TP_ERR_INVALID_ARGUMENT;   // released configurations: 144/64/36 tokens
   if (packed == nullptr || x0 == nullptr || xm == nullptr || out == nullptr || workspace == nullptr || n_crops <= 0 ||
@@ -517,9 +531,38 @@ int tp_forward(const void* packed, const void* x0, const void* xm, int64_t n_cro
       ep.seg_row_offset = reinterpret_cast<const long long*>(seg_row_offset);
       ep.seg_len = Mq;
     }
-    TP_TRY(launch_gemm(AOperand{bf(W.h_m), H, 0, 0}, P + L.w_m2, H, Q, H, H, ep, dev.sms, stream));
+    GemmItem it{AOperand{bf(W.h_m), H, 0, 0}, P + L.w_m2, H, Q, H, H, ep};
+    it.peer_c = peer_out;
+    it.n_peers = n_peers;
+    TP_TRY(launch_gemms(&it, 1, dev.sms, stream));
   }
   return TP_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int tp_forward(const void* packed, const void* x0, const void* xm, int64_t n_crops, int64_t x0_crop_stride, int64_t xm_crop_stride,
+               int scale_factor, int hidden, void* out, const int64_t* seg_row_offset, void* workspace, size_t workspace_bytes,
+               void* stream) {
+  return forward_impl(packed, x0, xm, n_crops, x0_crop_stride, xm_crop_stride, scale_factor, hidden, out, seg_row_offset, nullptr, 0,
+                      workspace, workspace_bytes, stream);
+}
+
+int tp_forward_allgather(const void* packed, const void* x0, const void* xm, int64_t n_crops, int64_t x0_crop_stride,
+                         int64_t xm_crop_stride, int scale_factor, int hidden, void* const* peer_out, int n_peers, int64_t crop_offset,
+                         void* workspace, size_t workspace_bytes, void* stream) {
+  if (peer_out == nullptr || n_peers <= 0 || n_peers > kMaxPeers || crop_offset < 0 || hidden % 256 != 0) return TP_ERR_INVALID_ARGUMENT;
+  if (scale_factor <= 0 || kGrid % scale_factor != 0) return TP_ERR_BAD_SCALE_FACTOR;
+  const int g = kGrid / scale_factor;
+  const size_t slot = static_cast<size_t>(crop_offset) * g * g * hidden * 2;      // this rank's first row in every gathered buffer
+  void* dst[kMaxPeers];
+  for (int p = 0; p < n_peers; ++p) {
+    if (peer_out[p] == nullptr) return TP_ERR_INVALID_ARGUMENT;
+    dst[p] = static_cast<uint8_t*>(peer_out[p]) + slot;
+  }
+  return forward_impl(packed, x0, xm, n_crops, x0_crop_stride, xm_crop_stride, scale_factor, hidden, dst[0], nullptr, dst, n_peers,
+                      workspace, workspace_bytes, stream);
 }
 
 int tp_forward_host(const void* packed, const void* x0_host, const void* xm_host, int64_t n_crops, int scale_factor, int hidden,

@@ -97,9 +97,18 @@ constexpr int kEpiBarrierId = 1;
 // Output staging for TMA stores: each column half of the tile (4 warps) owns two 16 KiB buffers holding a 128-row x 64-col
 // slab in the 128B-swizzled layout; a slab is written with conflict-free 16-byte st.shared, then ONE thread hands it
 // to the TMA unit (full 128-byte row segments instead of 16-byte scattered stores: less L1/L2 work and less power).
+constexpr int kMaxPeers = 8;
+// Fused all-gather: tensor maps of the SAME output slot in every peer GPU's gathered buffer (peer-mapped over NVLink);
+// each finished slab is TMA-stored to all of them instead of to one local matrix.
+struct PeerStores {
+  CUtensorMap m[kMaxPeers];
+  int count;                 // 0: ordinary local output through GemmProblem::tmap_c
+};
+
 struct OutStage {
   uint8_t* buf;              // this half's 2 x 16 KiB staging buffers (nullptr: direct 16-byte global stores)
-  const CUtensorMap* tmap;   // C tensor map, box = 64 cols x 128 rows, SWIZZLE_128B
+  const CUtensorMap* tmap;   // C tensor map(s), box = 64 cols x 128 rows, SWIZZLE_128B
+  int n_maps;                // 1, or the number of peer maps (consecutive CUtensorMaps starting at tmap)
   int row_tile0;             // first global row of this CTA's 128-row tile
   uint32_t barrier_id;       // named barrier shared by the 4 warps (128 threads) of this half
   bool issuer;               // this thread issues (and tracks) the half's TMA stores
@@ -199,7 +208,8 @@ __device__ __forceinline__ void epilogue_tile(const GemmEpilogue& ep, int M, int
       named_bar_sync(out.barrier_id, 128);
       if (out.issuer) {
         const int slab = chunk >> 1;
-        tma_store_2d(out.tmap, out.buf + (slab & 1) * kOutSlabBytes, col_tile0 + half * kColsPerWarp + slab * 64, out.row_tile0);
+        for (int p = 0; p < out.n_maps; ++p)
+          tma_store_2d(out.tmap + p, out.buf + (slab & 1) * kOutSlabBytes, col_tile0 + half * kColsPerWarp + slab * 64, out.row_tile0);
         bulk_commit_group();
       }
     }
@@ -364,7 +374,7 @@ tp_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tcgen05_fence_after();
       uint64_t* release_bar = &tmem_empty_bar[acc];
-      const OutStage no_stage{nullptr, nullptr, 0, 0, false};
+      const OutStage no_stage{nullptr, nullptr, 0, 0, 0, false};
       epilogue_tile<kBlockN>(ep, M, N, tmem_base + static_cast<uint32_t>(acc * kBlockN),
                              m_blk * kBlockM + quarter * 32 + static_cast<int>(lane), n_blk * kBlockN, quarter, half, s_col, no_stage, [&]() {
                                tcgen05_fence_before();
@@ -441,7 +451,7 @@ __device__ __forceinline__ TileRef decode_tile(const GemmGroup& g, int tile) {
 }
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
-tp_gemm2_kernel(const __grid_constant__ GemmGroup grp) {
+tp_gemm2_kernel(const __grid_constant__ GemmGroup grp, const __grid_constant__ PeerStores peers) {
   using Cfg = Gemm2Config;
   constexpr int kStages = Cfg::kStages;
   constexpr int kTileN = Cfg::kTileN;
@@ -618,8 +628,8 @@ tp_gemm2_kernel(const __grid_constant__ GemmGroup grp) {
       uint64_t* release_bar = &tmem_empty_bar[acc];
       const int row_tile0 = t.m_blk * Cfg::kTileM + static_cast<int>(cta_rank) * kBlockM;
       const int row = row_tile0 + quarter * 32 + static_cast<int>(lane);
-      const OutStage out{pr.use_tma_store ? s_out + half * 2 * kOutSlabBytes : nullptr, &pr.tmap_c, row_tile0, static_cast<uint32_t>(2 + half),
-                         quarter == 0 && lane == 0};
+      const OutStage out{pr.use_tma_store ? s_out + half * 2 * kOutSlabBytes : nullptr, peers.count > 0 ? &peers.m[0] : &pr.tmap_c,
+                         peers.count > 0 ? peers.count : 1, row_tile0, static_cast<uint32_t>(2 + half), quarter == 0 && lane == 0};
       stored = stored || pr.use_tma_store;
       epilogue_tile<kTileN>(pr.ep, pr.M, pr.N, tmem_base + static_cast<uint32_t>(acc * kTileN), row, t.n_blk * kTileN, quarter, half, s_col,
                             out, [&]() {
@@ -633,7 +643,10 @@ tp_gemm2_kernel(const __grid_constant__ GemmGroup grp) {
       TP_PROF_ADD(t_work);
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
-    if (stored && quarter == 0 && lane == 0) bulk_wait_group<0>();   // my half's last TMA stores have been performed
+    if (stored && quarter == 0 && lane == 0) {
+      bulk_wait_group<0>();                      // my half's last TMA stores have been performed
+      if (peers.count > 0) __threadfence_system();   // ... and are ordered before the cross-GPU barrier that follows the kernel
+    }
 #ifdef TP_GEMM_PROFILE
     if (grp.p[0].ep.prof != nullptr && e == 0 && lane == 0) {
       grp.p[0].ep.prof[blockIdx.x * 8 + 5] = w_acc;

@@ -69,3 +69,40 @@ class ShardedTokenPacker:
         from .hd import hd_assemble
         feats = self.forward_gathered(x_local, counts)
         return hd_assemble(feats, h_block, w_block, sep_row, ret_row)
+
+
+class FusedGatherTokenPacker:
+    """Projector whose last GEMM stores straight into every rank's gathered buffer over NVLink (TMA stores to peer-mapped
+    memory from ``torch.distributed._symmetric_memory``): compute and the all-gather are ONE kernel, transfers overlap the
+    remaining tiles' math.  CUDA + NCCL-capable ranks of one NVLink domain only."""
+
+    def __init__(self, projector, group=None):
+        self.projector = projector
+        self.group = group if group is not None else dist.group.WORLD
+        self._buf = None
+        self._hdl = None
+        self._shape = None
+
+    def _gathered_buffer(self, total_crops: int, device):
+        import torch.distributed._symmetric_memory as symm_mem
+        shape = (total_crops, self.projector.num_queries, self.projector.hidden_size)
+        if self._buf is None or self._shape != shape:
+            self._buf = symm_mem.empty(shape, dtype=torch.bfloat16, device=device)
+            self._hdl = symm_mem.rendezvous(self._buf, self.group)
+            self._shape = shape
+        return self._buf, self._hdl
+
+    def forward_gathered(self, x_local, counts: Sequence[int]):
+        """Returns the gathered [sum(counts), M, H] crop blocks (a view of the symmetric buffer: consume before the next call)."""
+        rank = dist.get_rank(self.group)
+        device = x_local[0].device
+        buf, hdl = self._gathered_buffer(int(sum(counts)), device)
+        crop_offset = int(sum(counts[:rank]))
+        hdl.barrier(channel=0)          # every rank has finished reading the previous call's gathered buffer
+        self.projector.forward_into_peers(x_local, list(hdl.buffer_ptrs), crop_offset)
+        hdl.barrier(channel=1)          # every rank's stores have landed everywhere
+        return buf
+
+    def forward_hd(self, x_local, counts: Sequence[int], h_block, w_block, sep_row, ret_row):
+        from .hd import hd_assemble
+        return hd_assemble(self.forward_gathered(x_local, counts), h_block, w_block, sep_row, ret_row)

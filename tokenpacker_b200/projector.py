@@ -160,6 +160,25 @@ class TokenPackerB200(nn.Module):
         check(lib.tp_forward(packed.data_ptr(), x0b.data_ptr(), xmb.data_ptr(), n, s0, sm, self.scale_factor,
                              self.hidden_size, out.data_ptr(), seg_ptr, ws.data_ptr(), ws_bytes, stream), "tp_forward")
 
+    def forward_into_peers(self, x, peer_ptrs, crop_offset: int):
+        """Fused projector + all-gather: this rank's crops are written by the last GEMM's TMA stores into the gathered buffer of
+        every peer GPU (``peer_ptrs``: device pointers of the [total_crops, M, H] bf16 buffers, one per rank, mapped into this
+        process — e.g. ``torch.distributed._symmetric_memory`` ``buffer_ptrs``).  Asynchronous; a cross-rank barrier must follow."""
+        x0, xm = self._check_inputs(x, None)
+        device = x0.device
+        with torch.cuda.device(device):
+            x0b, s0 = self._as_crop_strided(x0.to(torch.bfloat16), 1024)
+            xmb, sm = self._as_crop_strided(xm.to(torch.bfloat16), 4096)
+            n = x0b.shape[0]
+            packed = self._packed_weights(device)
+            ws_bytes = lib.tp_workspace_bytes(n, self.scale_factor, self.hidden_size)
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=device)
+            stream = torch.cuda.current_stream(device).cuda_stream
+            arr = (C.c_void_p * len(peer_ptrs))(*[int(p) for p in peer_ptrs])
+            check(lib.tp_forward_allgather(packed.data_ptr(), x0b.data_ptr(), xmb.data_ptr(), n, s0, sm, self.scale_factor,
+                                           self.hidden_size, arr, len(peer_ptrs), int(crop_offset), ws.data_ptr(), ws_bytes, stream),
+                  "tp_forward_allgather")
+
     def forward_host(self, x, out: torch.Tensor | None = None, chunk_crops: int = 8, device=None):
         """End-to-end call with HOST tensors (pinned recommended): (feat, feat_multi) bf16 CPU tensors in, [N,M,H] bf16 CPU
         tensor out.  Host->device copies, the kernels and the device->host copy are pipelined over chunks of crops inside
