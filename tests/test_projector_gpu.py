@@ -151,3 +151,46 @@ def test_kernel_variants_agree_bitwise(monkeypatch):
         assert torch.equal(outs["0"], outs[mode]), mode
         assert torch.equal(outs["0"][5:], outs["half" + mode]), mode
     assert torch.equal(outs["0"][5:], outs["half0"])       # Q=180 (one-CTA kernels) vs Q=360 (pair kernels) under auto selection
+
+
+@pytest.mark.parametrize("n,s,hidden", [(1, 2, 5120), (3, 3, 5120), (7, 4, 4096)])
+def test_other_shapes_against_oracle(n, s, hidden):
+    """13B hidden size (5120 = 20 x 256), odd crop counts, single crop: M/N tails of every kernel."""
+    m, params = make_module(hidden, s, seed=11)
+    x0, xm = tpo.make_inputs(n, seed=12)
+    x0, xm = tpo.round_bf16(x0), tpo.round_bf16(xm)
+    ref = tpo.tokenpacker_forward(params, x0, xm, s, dtype=np.float32)
+    with torch.no_grad():
+        out = m((torch.from_numpy(x0).cuda().bfloat16(), torch.from_numpy(xm).cuda().bfloat16()))
+    assert out.shape == (n, (24 // s) ** 2, hidden)
+    rel, mx = errors(out.float().cpu().numpy(), ref)
+    assert rel <= REL_RMS_TOL and mx <= MAX_ABS_TOL, (rel, mx)
+
+
+def test_empty_batch_and_bad_inputs():
+    m, _ = make_module(128, 2, seed=1)
+    with torch.no_grad():
+        out = m((torch.zeros(0, 576, 1024, device="cuda", dtype=torch.bfloat16), torch.zeros(0, 576, 4096, device="cuda", dtype=torch.bfloat16)))
+    assert out.shape == (0, 144, 128)
+    with pytest.raises(TypeError):
+        m(torch.zeros(1, 576, 1024, device="cuda"))
+    with pytest.raises(ValueError):
+        with torch.no_grad():
+            m((torch.zeros(2, 576, 1024, device="cuda"), torch.zeros(3, 576, 4096, device="cuda")))
+
+
+def test_full_size_sweep_properties():
+    """BASELINE configs[2] sizes (batch 128, s in {2,3,4}, H=4096): finite, deterministic, and every crop equals its own
+    single-crop forward (checked on 3 crops) — size-independent properties where the oracle would take minutes."""
+    for s in (2, 3, 4):
+        m, _ = make_module(4096, s, seed=0)
+        g = torch.Generator(device="cuda").manual_seed(100 + s)
+        x0 = torch.randn(128, 576, 1024, device="cuda", generator=g).bfloat16()
+        xm = torch.randn(128, 576, 4096, device="cuda", generator=g).bfloat16()
+        with torch.no_grad():
+            a = m((x0, xm))
+            b = m((x0, xm))
+            assert torch.isfinite(a).all() and torch.equal(a, b)
+            for c in (0, 77, 127):
+                assert torch.equal(a[c:c + 1], m((x0[c:c + 1], xm[c:c + 1])))
+        del m
