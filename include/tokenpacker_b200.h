@@ -104,6 +104,22 @@ TP_API int tp_forward_host(const void* packed, const void* x0_host, const void* 
                     int hidden, void* out_host, void* d_x0, void* d_xm, void* d_out, void* workspace,
                     size_t workspace_bytes, int64_t chunk_crops, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * Training path.  The reference trains this module through PyTorch autograd over builder.py:107-137 (it is the only
+ * trainable module of stage 1, train.py:950-953).  tp_forward_train computes the same output as tp_forward while keeping
+ * the intermediates the backward needs in ``saved`` (caller-owned, tp_train_saved_bytes); tp_backward turns dL/d(out)
+ * into dL/d(parameter) for every entry of tp_weights (``grads``: same struct, device bf16 buffers of the parameter shapes,
+ * overwritten).  No gradient is produced for x0 / xm (frozen CLIP tower).  xm must be contiguous for tp_backward.
+ * ------------------------------------------------------------------------------------------------------------- */
+TP_API size_t tp_train_saved_bytes(int64_t n_crops, int scale_factor, int hidden);
+TP_API size_t tp_backward_workspace_bytes(int64_t n_crops, int scale_factor, int hidden);
+TP_API int tp_forward_train(const void* packed, const void* x0, const void* xm, int64_t n_crops, int64_t x0_crop_stride,
+                            int64_t xm_crop_stride, int scale_factor, int hidden, void* out, void* saved, size_t saved_bytes,
+                            void* stream);
+TP_API int tp_backward(const tp_weights* w, const void* xm, int64_t xm_crop_stride, int64_t n_crops, int scale_factor, int hidden,
+                       const void* grad_out, const void* saved, const tp_weights* grads, void* workspace, size_t workspace_bytes,
+                       void* stream);
+
 /* A single fused-epilogue GEMM of the path, exposed for unit tests and microbenchmarks:
  *   C[M,N] = alpha * act( A[M,K] . B[N,K]^T + bias ),  bf16 in/out, fp32 accumulate; bias fp32 [N] or NULL. */
 TP_API int tp_gemm_bf16(const void* a, int64_t lda, const void* b, int64_t ldb, void* c, int64_t ldc, int64_t m, int64_t n,

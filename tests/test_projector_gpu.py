@@ -129,7 +129,7 @@ def test_dtype_roundtrip_and_errors():
     with pytest.raises(ValueError):
         m((x0[:, :100].bfloat16(), xm.bfloat16()))
     with pytest.raises(NotImplementedError):
-        m((x0.bfloat16(), xm.bfloat16()))              # grad enabled + trainable params: backward not implemented
+        m((x0.bfloat16().requires_grad_(True), xm.bfloat16()))     # gradients w.r.t. the CLIP features are not provided
 
 
 def test_kernel_variants_agree_bitwise(monkeypatch):

@@ -54,6 +54,12 @@ SIGNATURES = {
                                        C.POINTER(C.c_void_p), C.c_int, C.c_int64, C.c_void_p, C.c_size_t, C.c_void_p]),
     "tp_forward_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int64, C.c_void_p]),
+    "tp_train_saved_bytes": (C.c_size_t, [C.c_int64, C.c_int, C.c_int]),
+    "tp_backward_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int, C.c_int]),
+    "tp_forward_train": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_void_p,
+                                   C.c_void_p, C.c_size_t, C.c_void_p]),
+    "tp_backward": (C.c_int, [C.POINTER(TpWeights), C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                              C.POINTER(TpWeights), C.c_void_p, C.c_size_t, C.c_void_p]),
     "tp_gemm_bf16": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int64,
                                C.c_int64, C.c_void_p, C.c_int, C.c_float, C.c_void_p]),
     "tp_hd_grid": (C.c_int, [C.c_int64, C.c_int64, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),

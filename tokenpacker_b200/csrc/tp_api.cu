@@ -9,6 +9,7 @@
 #include "../../include/tokenpacker_b200.h"
 #include "tp_gemm.cuh"
 #include "tp_kernels.cuh"
+#include "tp_backward.cuh"
 
 namespace {
 
@@ -150,7 +151,7 @@ struct GemmItem {
 };
 
 int check_item(const GemmItem& it) {
-  if (it.M <= 0 || it.N <= 0 || it.K <= 0 || it.N % 32 != 0 || it.K % 8 != 0 || it.M > 0x7fffff00ll) return TP_ERR_INVALID_ARGUMENT;
+  if (it.M <= 0 || it.N <= 0 || it.K <= 0 || it.N % 32 != 0 || it.M > 0x7fffff00ll) return TP_ERR_INVALID_ARGUMENT;   // K: any (TMA zero-fills)
   if ((reinterpret_cast<uintptr_t>(it.ep.c) & 15) != 0 || (it.ep.ldc * 2) % 16 != 0) return TP_ERR_INVALID_ARGUMENT;
   if (it.ep.stats_out != nullptr && (it.N % 256 != 0 || it.ep.stats_out_slots != it.N / 128)) return TP_ERR_INVALID_ARGUMENT;
   if (it.ep.col_a != nullptr && (it.ep.stats_in == nullptr || it.ep.stats_in_slots <= 0)) return TP_ERR_INVALID_ARGUMENT;
@@ -279,6 +280,7 @@ struct PackedLayout {
   size_t w_ot;                         // W_o^T scratch (pack time only)
   size_t w_om, b_om;                   // out_proj folded into mlp.0: W_m0 W_o [H,1024] bf16, W_m0 b_o + b_m0 [H] f32
   size_t w_m2, b_m2;
+  size_t w_o, b_o, w_m0, b_m0;         // unfolded copies for the training forward (gradients go to the original parameters)
   size_t total;
 };
 
@@ -296,6 +298,8 @@ PackedLayout packed_layout(int H) {
   L.w_ot = take(mat);
   L.w_om = take(static_cast<size_t>(H) * kC * 2); L.b_om = take(static_cast<size_t>(H) * 4);
   L.w_m2 = take(static_cast<size_t>(H) * H * 2); L.b_m2 = take(static_cast<size_t>(H) * 4);
+  L.w_o = take(mat); L.b_o = take(vec);
+  L.w_m0 = take(static_cast<size_t>(H) * kC * 2); L.b_m0 = take(static_cast<size_t>(H) * 4);
   L.total = off;
   return L;
 }
@@ -426,6 +430,10 @@ int tp_pack_weights(const tp_weights* w, int hidden, void* packed, size_t packed
                                                                       reinterpret_cast<float*>(P + L.b_om), hidden, kC);
     TP_CUDA(cudaGetLastError());
   }
+  TP_CUDA(copy(L.w_o, w->out_proj_w, mat));
+  TP_CUDA(bias(L.b_o, w->out_proj_b, kC));
+  TP_CUDA(copy(L.w_m0, w->mlp_0_w, static_cast<size_t>(hidden) * kC * 2));
+  TP_CUDA(bias(L.b_m0, w->mlp_0_b, hidden));
   TP_CUDA(copy(L.w_m2, w->mlp_2_w, static_cast<size_t>(hidden) * hidden * 2));
   TP_CUDA(bias(L.b_m2, w->mlp_2_b, hidden));
   return TP_OK;
@@ -646,6 +654,8 @@ int tp_gemm_bf16(const void* a, int64_t lda, const void* b, int64_t ldb, void* c
   ep.alpha = alpha;
   return launch_gemm(AOperand{a, lda, 0, 0}, b, ldb, m, n, k, ep, dev.sms, static_cast<cudaStream_t>(stream));
 }
+
+#include "tp_train.inl"
 
 // ------------------------------------------------------------------------------------------------
 // HD front end

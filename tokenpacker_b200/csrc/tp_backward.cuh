@@ -1,0 +1,324 @@
+// Kernels of the projector's backward pass that are not GEMMs: transposes (wgrad operands), GELU forward/backward as
+// elementwise passes, LayerNorm backward, window-attention backward, row sums (bias gradients).  All HBM-bound.
+// The GEMMs of the backward (dgrad = dY . W, wgrad = dY^T . X) run on the same tcgen05 kernels as the forward: dgrad takes a
+// transposed copy of the weight as its K-major B operand, wgrad takes transposed activations (contraction over rows).
+#pragma once
+
+#include "tp_kernels.cuh"
+
+namespace tp {
+
+constexpr int kStatSlotsBwd = kC / 128;
+
+__device__ __forceinline__ void row_mean_rstd(const float* stats, long long row, float& mu, float& rstd) {
+  const float2* st = reinterpret_cast<const float2*>(stats) + row * kStatSlotsBwd;
+  float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < kStatSlotsBwd; ++i) {
+    const float2 v = st[i];
+    t1 = __fadd_rn(t1, v.x);
+    t2 = __fadd_rn(t2, v.y);
+  }
+  mu = __fmul_rn(t1, 1.0f / kC);
+  const float var = fmaxf(fmaf(-mu, mu, __fmul_rn(t2, 1.0f / kC)), 0.f);
+  rstd = rsqrtf(__fadd_rn(var, 1e-6f));
+}
+
+// d/dz [ z * Phi(z) ] = Phi(z) + z * phi(z)
+__device__ __forceinline__ float gelu_grad(float z) {
+  const float t = fabsf(z) * 0.70710678118654752440f;
+  float p = 0.0000430638f;
+  p = fmaf(p, t, 0.0002765672f);
+  p = fmaf(p, t, 0.0001520143f);
+  p = fmaf(p, t, 0.0092705272f);
+  p = fmaf(p, t, 0.0422820123f);
+  p = fmaf(p, t, 0.0705230784f);
+  p = fmaf(p, t, 1.0f);
+  p *= p; p *= p; p *= p; p *= p;
+  const float e = 1.0f - __fdividef(1.0f, p);                 // erf(|z|/sqrt2)
+  const float cdf = 0.5f * (1.0f + copysignf(e, z));
+  const float pdf = 0.3989422804014327f * __expf(-0.5f * z * z);
+  return fmaf(z, pdf, cdf);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Transpose  out[c, r] = f(in[r, c])   (bf16; in: [rows, cols] row stride ld_in; out: [cols, rows] row stride ld_out)
+//   kMode 0: identity   1: GELU(in)   2: LayerNorm-apply ((in - mu_r) rstd_r gamma_c + beta_c), stats = per-row partial sums
+// ------------------------------------------------------------------------------------------------
+template <int kMode>
+__global__ void transpose_kernel(const __nv_bfloat16* __restrict__ in, long long ld_in, __nv_bfloat16* __restrict__ out, long long ld_out,
+                                 long long rows, int cols, const float* __restrict__ stats, const __nv_bfloat16* __restrict__ gamma,
+                                 const __nv_bfloat16* __restrict__ beta) {
+  __shared__ float tile[32][33];
+  __shared__ float s_mu[32], s_rstd[32];
+  const long long r0 = static_cast<long long>(blockIdx.y) * 32;
+  const int c0 = blockIdx.x * 32;
+  if (kMode == 2) {
+    if (threadIdx.y == 0) {
+      const long long r = r0 + threadIdx.x;
+      float mu = 0.f, rstd = 0.f;
+      if (r < rows) row_mean_rstd(stats, r, mu, rstd);
+      s_mu[threadIdx.x] = mu;
+      s_rstd[threadIdx.x] = rstd;
+    }
+    __syncthreads();
+  }
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const long long r = r0 + i;
+    const int c = c0 + threadIdx.x;
+    float v = 0.f;
+    if (r < rows && c < cols) {
+      v = __bfloat162float(in[r * ld_in + c]);
+      if (kMode == 1) v = gelu_erf(v);
+      if (kMode == 2) v = fmaf((v - s_mu[i]) * s_rstd[i], __bfloat162float(gamma[c]), __bfloat162float(beta[c]));
+    }
+    tile[i][threadIdx.x] = v;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i;
+    const long long r = r0 + threadIdx.x;
+    if (c < cols && r < rows) out[static_cast<long long>(c) * ld_out + r] = __float2bfloat16_rn(tile[threadIdx.x][i]);
+  }
+}
+
+// h = GELU(z), 8 elements per thread (n8 = number of 8-element vectors)
+__global__ void gelu_fwd_kernel(const __nv_bfloat16* __restrict__ z, __nv_bfloat16* __restrict__ h, long long n8) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n8) return;
+  float f[8];
+  unpack8(__ldg(reinterpret_cast<const uint4*>(z) + i), f);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) f[j] = gelu_erf(f[j]);
+  reinterpret_cast<uint4*>(h)[i] = pack8(f);
+}
+
+// dz = dh * GELU'(z), in place over dh
+__global__ void gelu_bwd_kernel(__nv_bfloat16* __restrict__ dh, const __nv_bfloat16* __restrict__ z, long long n8) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n8) return;
+  float g[8], zz[8];
+  unpack8(reinterpret_cast<const uint4*>(dh)[i], g);
+  unpack8(__ldg(reinterpret_cast<const uint4*>(z) + i), zz);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) g[j] *= gelu_grad(zz[j]);
+  reinterpret_cast<uint4*>(dh)[i] = pack8(g);
+}
+
+// out[i] (fp32 -> bf16) = scale * sum_j in[i, j], j < n; one warp per row (bias gradients from transposed dY)
+__global__ void rowsum_kernel(const __nv_bfloat16* __restrict__ in, long long ld, long long n, int rows, float scale,
+                              __nv_bfloat16* __restrict__ out) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const __nv_bfloat16* p = in + static_cast<long long>(row) * ld;
+  float acc = 0.f;
+  const long long n8 = n / 8;
+  for (long long i = lane; i < n8; i += 32) {
+    float f[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(p) + i), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc += f[j];
+  }
+  for (long long i = n8 * 8 + lane; i < n; i += 32) acc += __bfloat162float(p[i]);
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+  if (lane == 0) out[row] = __float2bfloat16_rn(acc * scale);
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm backward (eps 1e-6, 1024 wide).  g = dL/d(LN output) [rows,1024], y = LN input, stats = its partial sums.
+//   yhat = (y - mu) rstd;  gg = gamma * g;  dy = rstd (gg - mean(gg) - yhat mean(gg yhat))
+// One warp per row (lane owns 4 x 8 channels), rows strided over the grid; per-CTA column partials of
+// dgamma = sum_r g yhat and dbeta = sum_r g are written to partial[blockIdx][2][1024] (fp32) for ln_param_reduce_kernel.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) ln_bwd_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* __restrict__ y,
+                                                     const float* __restrict__ stats, const __nv_bfloat16* __restrict__ gamma,
+                                                     __nv_bfloat16* __restrict__ dy, float* __restrict__ partial, long long rows) {
+  __shared__ float s_part[8][2][kC / 4];   // staged in 4 passes of 256 columns to keep smem small
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float gam[4][8];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) unpack8(__ldg(reinterpret_cast<const uint4*>(gamma + i * 256 + lane * 8)), gam[i]);
+  float dg[4][8], db[4][8];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dg[i][j] = db[i][j] = 0.f;
+  for (long long row = static_cast<long long>(blockIdx.x) * 8 + warp; row < rows; row += static_cast<long long>(gridDim.x) * 8) {
+    float mu, rstd;
+    row_mean_rstd(stats, row, mu, rstd);
+    float gv[4][8], yh[4][8];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float yv[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(g + row * kC + i * 256 + lane * 8)), gv[i]);
+      unpack8(__ldg(reinterpret_cast<const uint4*>(y + row * kC + i * 256 + lane * 8)), yv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        yh[i][j] = (yv[j] - mu) * rstd;
+        const float gg = gam[i][j] * gv[i][j];
+        s1 += gg;
+        s2 = fmaf(gg, yh[i][j], s2);
+        dg[i][j] = fmaf(gv[i][j], yh[i][j], dg[i][j]);
+        db[i][j] += gv[i][j];
+      }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      s1 += __shfl_xor_sync(0xffffffffu, s1, off);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, off);
+    }
+    const float c1 = s1 * (1.0f / kC), c2 = s2 * (1.0f / kC);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = rstd * (gam[i][j] * gv[i][j] - c1 - yh[i][j] * c2);
+      *reinterpret_cast<uint4*>(dy + row * kC + i * 256 + lane * 8) = pack8(o);
+    }
+  }
+  // cross-warp reduction of the column partials, 256 columns (one channel block i) at a time
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      s_part[warp][0][lane * 8 + j] = dg[i][j];
+      s_part[warp][1][lane * 8 + j] = db[i][j];
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < 2 * 256; idx += blockDim.x) {
+      const int which = idx >> 8, c = idx & 255;
+      float acc = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) acc += s_part[w][which][c];
+      partial[(static_cast<long long>(blockIdx.x) * 2 + which) * kC + i * 256 + c] = acc;
+    }
+    __syncthreads();
+  }
+}
+
+// dgamma / dbeta = sum over CTAs of the partials (fixed order -> deterministic); one thread per column
+__global__ void ln_param_reduce_kernel(const float* __restrict__ partial, int n_blocks, __nv_bfloat16* __restrict__ dgamma,
+                                       __nv_bfloat16* __restrict__ dbeta) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= kC) return;
+  float a = 0.f, b = 0.f;
+  for (int i = 0; i < n_blocks; ++i) {
+    a += partial[(static_cast<long long>(i) * 2 + 0) * kC + c];
+    b += partial[(static_cast<long long>(i) * 2 + 1) * kC + c];
+  }
+  dgamma[c] = __float2bfloat16_rn(a);
+  dbeta[c] = __float2bfloat16_rn(b);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Window attention backward.  Forward (window_attn_kernel): p = softmax_j(q'_h . k'_{j,h}), ctx_h = sum_j p_j v'_{j,h}.
+//   dv'_j = p_j dctx_h;  dp_j = dctx_h . v'_j;  ds_j = p_j (dp_j - sum_i p_i dp_i);  dq'_h = sum_j ds_j k'_j;  dk'_j = ds_j q'_h
+// Every fine token belongs to exactly one query window, so dk'/dv' rows are written once: no atomics.  One warp per query,
+// same channel ownership as the forward kernel.
+// ------------------------------------------------------------------------------------------------
+template <int S>
+__global__ void __launch_bounds__(256) window_attn_bwd_kernel(const __nv_bfloat16* __restrict__ qp, const __nv_bfloat16* __restrict__ kp,
+                                                              const __nv_bfloat16* __restrict__ vp, const __nv_bfloat16* __restrict__ dctx,
+                                                              __nv_bfloat16* __restrict__ dqp, __nv_bfloat16* __restrict__ dkp,
+                                                              __nv_bfloat16* __restrict__ dvp, long long n_queries) {
+  constexpr int G = kGrid / S;
+  constexpr int M = G * G;
+  constexpr int W = S * S;
+  const long long query = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (query >= n_queries) return;
+  const long long n = query / M;
+  const int m = static_cast<int>(query - n * M);
+  const int hb = m / G, wb = m - hb * G;
+  const long long tok0 = n * kTokens + static_cast<long long>(hb * S) * kGrid + wb * S;
+
+  float qf[4][8], dc[4][8];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    unpack8(__ldg(reinterpret_cast<const uint4*>(qp + query * kC + i * 256 + lane * 8)), qf[i]);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(dctx + query * kC + i * 256 + lane * 8)), dc[i]);
+  }
+  float sc[4][W], dp[4][W];
+#pragma unroll
+  for (int j = 0; j < W; ++j) {
+    const long long tok = tok0 + (j / S) * kGrid + (j % S);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float kf[8], vf[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(kp + tok * kC + i * 256 + lane * 8)), kf);
+      unpack8(__ldg(reinterpret_cast<const uint4*>(vp + tok * kC + i * 256 + lane * 8)), vf);
+      float d = 0.f, e = 0.f;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        d = fmaf(qf[i][c], kf[c], d);
+        e = fmaf(dc[i][c], vf[c], e);
+      }
+      sc[i][j] = d;
+      dp[i][j] = e;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < W; ++j) {
+      float d = sc[i][j], e = dp[i][j];
+#pragma unroll
+      for (int off = 8; off > 0; off >>= 1) {
+        d += __shfl_xor_sync(0xffffffffu, d, off);
+        e += __shfl_xor_sync(0xffffffffu, e, off);
+      }
+      sc[i][j] = d;
+      dp[i][j] = e;
+    }
+  // p (into sc) and ds (into dp)
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float mx = sc[i][0];
+#pragma unroll
+    for (int j = 1; j < W; ++j) mx = fmaxf(mx, sc[i][j]);
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < W; ++j) {
+      sc[i][j] = __expf(sc[i][j] - mx);
+      sum += sc[i][j];
+    }
+    const float inv = 1.0f / sum;
+    float dot = 0.f;
+#pragma unroll
+    for (int j = 0; j < W; ++j) {
+      sc[i][j] *= inv;
+      dot = fmaf(sc[i][j], dp[i][j], dot);
+    }
+#pragma unroll
+    for (int j = 0; j < W; ++j) dp[i][j] = sc[i][j] * (dp[i][j] - dot);
+  }
+  float dq[4][8];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) dq[i][c] = 0.f;
+#pragma unroll
+  for (int j = 0; j < W; ++j) {
+    const long long tok = tok0 + (j / S) * kGrid + (j % S);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float kf[8], dk[8], dv[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(kp + tok * kC + i * 256 + lane * 8)), kf);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        dq[i][c] = fmaf(dp[i][j], kf[c], dq[i][c]);
+        dk[c] = dp[i][j] * qf[i][c];
+        dv[c] = sc[i][j] * dc[i][c];
+      }
+      *reinterpret_cast<uint4*>(dkp + tok * kC + i * 256 + lane * 8) = pack8(dk);
+      *reinterpret_cast<uint4*>(dvp + tok * kC + i * 256 + lane * 8) = pack8(dv);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(dqp + query * kC + i * 256 + lane * 8) = pack8(dq[i]);
+}
+
+}  // namespace tp

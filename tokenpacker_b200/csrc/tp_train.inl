@@ -1,0 +1,367 @@
+// Training path of the projector: forward that keeps what the backward needs, and the backward itself.
+// Included by tp_api.cu inside its extern "C" block (shares the launch helpers of that translation unit).
+//
+// The reference trains this module (it is the only trainable module of stage 1 and is trained in stage 2:
+// llava/train/train.py:950-958, scripts/v1_5/pretrain*.sh), through PyTorch autograd over builder.py:107-137.  Here:
+//   forward_train = the inference launch plan without the out_proj fold and with GELU as a separate pass, so that the
+//                   pre-activations z exist in memory (GELU'(z) needs z; GELU(z) is not invertible);
+//   backward      = dgrad GEMMs (dY . W, B operand = transposed weight), wgrad GEMMs (dY^T . X, operands = transposed
+//                   activations: contraction over rows), LayerNorm / GELU / window-attention backward kernels, bias
+//                   gradients as row sums of the transposed dY that the wgrad needs anyway.
+// Gradients w.r.t. the CLIP features are not produced (the tower is frozen in every released recipe; the Python layer raises
+// if the inputs require grad).
+
+}  // extern "C"  (reopened below)
+
+namespace {
+
+struct SavedLayout {
+  size_t z_kv, h_kv;        // [R,2048]
+  size_t y_k, y_v;          // [R,1024]
+  size_t stats;             // f32 [(2R+Q), 8, 2]
+  size_t k_p, v_p;          // [R,1024]
+  size_t q, y_q, q_p, ctx, o;   // [Q,1024]
+  size_t z_m, h_m;          // [Q,H]
+  size_t total;
+};
+
+SavedLayout saved_layout(long long n_crops, int s, int H) {
+  const size_t R = static_cast<size_t>(n_crops) * kTokens;
+  const int g = kGrid / s;
+  const size_t Q = static_cast<size_t>(n_crops) * g * g;
+  SavedLayout L;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 1024); return o; };
+  L.z_kv = take(R * 2 * kC * 2); L.h_kv = take(R * 2 * kC * 2);
+  L.y_k = take(R * kC * 2); L.y_v = take(R * kC * 2);
+  L.stats = take((2 * R + Q) * kStatSlots * 2 * 4);
+  L.k_p = take(R * kC * 2); L.v_p = take(R * kC * 2);
+  L.q = take(Q * kC * 2); L.y_q = take(Q * kC * 2); L.q_p = take(Q * kC * 2); L.ctx = take(Q * kC * 2); L.o = take(Q * kC * 2);
+  L.z_m = take(Q * static_cast<size_t>(H) * 2); L.h_m = take(Q * static_cast<size_t>(H) * 2);
+  L.total = off;
+  return L;
+}
+
+struct BwdLayout {
+  size_t w_m2t, w_m0t, w_ot, w_iqt, w_ikt, w_ivt, w_k2t, w_v2t;   // transposed weights (dgrad B operands)
+  size_t g_t, hm_t, dzm, dzm_t, o_t, d_o, do_t, ctx_t, dctx;
+  size_t dqp, dkp, dvp, dqp_t, dkp_t, dvp_t, lnq_t, lnk_t, lnv_t;
+  size_t dqh, dkh, dvh, dyq, dyk, dyv, dyq_t, dyk_t, dyv_t, q_t, hkv_t;
+  size_t dzkv, dzkv_t, xm_t;
+  size_t ln_part;        // f32 [3][kLnBlocks][2][1024]
+  size_t total;
+  long long Rp, Qp;
+};
+
+constexpr int kLnBlocks = 296;
+
+BwdLayout bwd_layout(long long n_crops, int s, int H) {
+  const size_t R = static_cast<size_t>(n_crops) * kTokens;
+  const int g = kGrid / s;
+  const size_t Q = static_cast<size_t>(n_crops) * g * g;
+  BwdLayout L;
+  L.Rp = static_cast<long long>(align_up(R, 8));
+  L.Qp = static_cast<long long>(align_up(Q, 8));
+  const size_t Rp = L.Rp, Qp = L.Qp, Hs = H;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 1024); return o; };
+  const size_t mat = static_cast<size_t>(kC) * kC * 2;
+  L.w_m2t = take(Hs * Hs * 2); L.w_m0t = take(kC * Hs * 2); L.w_ot = take(mat);
+  L.w_iqt = take(mat); L.w_ikt = take(mat); L.w_ivt = take(mat); L.w_k2t = take(mat); L.w_v2t = take(mat);
+  L.g_t = take(Hs * Qp * 2); L.hm_t = take(Hs * Qp * 2); L.dzm = take(Q * Hs * 2); L.dzm_t = take(Hs * Qp * 2);
+  L.o_t = take(kC * Qp * 2); L.d_o = take(Q * kC * 2); L.do_t = take(kC * Qp * 2); L.ctx_t = take(kC * Qp * 2); L.dctx = take(Q * kC * 2);
+  L.dqp = take(Q * kC * 2); L.dkp = take(R * kC * 2); L.dvp = take(R * kC * 2);
+  L.dqp_t = take(kC * Qp * 2); L.dkp_t = take(kC * Rp * 2); L.dvp_t = take(kC * Rp * 2);
+  L.lnq_t = take(kC * Qp * 2); L.lnk_t = take(kC * Rp * 2); L.lnv_t = take(kC * Rp * 2);
+  L.dqh = take(Q * kC * 2); L.dkh = take(R * kC * 2); L.dvh = take(R * kC * 2);
+  L.dyq = take(Q * kC * 2); L.dyk = take(R * kC * 2); L.dyv = take(R * kC * 2);
+  L.dyq_t = take(kC * Qp * 2); L.dyk_t = take(kC * Rp * 2); L.dyv_t = take(kC * Rp * 2);
+  L.q_t = take(kC * Qp * 2); L.hkv_t = take(2 * kC * Rp * 2);
+  L.dzkv = take(R * 2 * kC * 2); L.dzkv_t = take(2 * kC * Rp * 2); L.xm_t = take(static_cast<size_t>(kCm) * Rp * 2);
+  L.ln_part = take(3ull * kLnBlocks * 2 * kC * 4);
+  L.total = off;
+  return L;
+}
+
+template <int kMode>
+int launch_transpose(const void* in, long long ld_in, void* out, long long ld_out, long long rows, int cols, const float* stats,
+                     const void* gamma, const void* beta, cudaStream_t stream) {
+  const dim3 grid(static_cast<unsigned>((cols + 31) / 32), static_cast<unsigned>((rows + 31) / 32));
+  transpose_kernel<kMode><<<grid, dim3(32, 8), 0, stream>>>(static_cast<const __nv_bfloat16*>(in), ld_in, static_cast<__nv_bfloat16*>(out), ld_out,
+                                                             rows, cols, stats, static_cast<const __nv_bfloat16*>(gamma),
+                                                             static_cast<const __nv_bfloat16*>(beta));
+  TP_CUDA(cudaGetLastError());
+  return TP_OK;
+}
+
+int launch_rowsum(const void* in, long long ld, long long n, int rows, float scale, void* out, cudaStream_t stream) {
+  rowsum_kernel<<<(rows * 32 + 255) / 256, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(in), ld, n, rows, scale,
+                                                             static_cast<__nv_bfloat16*>(out));
+  TP_CUDA(cudaGetLastError());
+  return TP_OK;
+}
+
+int launch_gelu_fwd(const void* z, void* h, size_t elems, cudaStream_t stream) {
+  const long long n8 = static_cast<long long>(elems / 8);
+  gelu_fwd_kernel<<<static_cast<unsigned>((n8 + 255) / 256), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(z),
+                                                                                static_cast<__nv_bfloat16*>(h), n8);
+  TP_CUDA(cudaGetLastError());
+  return TP_OK;
+}
+
+int launch_gelu_bwd(void* dh, const void* z, size_t elems, cudaStream_t stream) {
+  const long long n8 = static_cast<long long>(elems / 8);
+  gelu_bwd_kernel<<<static_cast<unsigned>((n8 + 255) / 256), 256, 0, stream>>>(static_cast<__nv_bfloat16*>(dh),
+                                                                                static_cast<const __nv_bfloat16*>(z), n8);
+  TP_CUDA(cudaGetLastError());
+  return TP_OK;
+}
+
+int launch_ln_bwd(const void* g, const void* y, const float* stats, const void* gamma, void* dy, float* partial, long long rows,
+                  void* dgamma, void* dbeta, cudaStream_t stream) {
+  ln_bwd_kernel<<<kLnBlocks, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(g), static_cast<const __nv_bfloat16*>(y), stats,
+                                               static_cast<const __nv_bfloat16*>(gamma), static_cast<__nv_bfloat16*>(dy), partial, rows);
+  TP_CUDA(cudaGetLastError());
+  ln_param_reduce_kernel<<<kC / 256, 256, 0, stream>>>(partial, kLnBlocks, static_cast<__nv_bfloat16*>(dgamma),
+                                                       static_cast<__nv_bfloat16*>(dbeta));
+  TP_CUDA(cudaGetLastError());
+  return TP_OK;
+}
+
+GemmItem plain_item(const void* a, long long lda, const void* b, long long ldb, void* c, long long ldc, long long M, long long N, long long K,
+                    const float* bias = nullptr, float alpha = 1.0f) {
+  GemmItem it{AOperand{a, lda, 0, 0}, b, ldb, M, N, K, plain_epilogue(c, ldc, bias, 0)};
+  it.ep.alpha = alpha;
+  return it;
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t tp_train_saved_bytes(int64_t n_crops, int scale_factor, int hidden) {
+  if (n_crops <= 0 || scale_factor < 2 || scale_factor > 4 || !valid_hidden(hidden)) return 0;
+  return saved_layout(n_crops, scale_factor, hidden).total;
+}
+
+size_t tp_backward_workspace_bytes(int64_t n_crops, int scale_factor, int hidden) {
+  if (n_crops <= 0 || scale_factor < 2 || scale_factor > 4 || !valid_hidden(hidden)) return 0;
+  return bwd_layout(n_crops, scale_factor, hidden).total;
+}
+
+int tp_forward_train(const void* packed, const void* x0, const void* xm, int64_t n_crops, int64_t x0_crop_stride, int64_t xm_crop_stride,
+                     int scale_factor, int hidden, void* out, void* saved, size_t saved_bytes, void* stream_) {
+  if (scale_factor <= 0 || kGrid % scale_factor != 0) return TP_ERR_BAD_SCALE_FACTOR;
+  if (scale_factor < 2 || scale_factor > 4) return TP_ERR_INVALID_ARGUMENT;
+  if (packed == nullptr || x0 == nullptr || xm == nullptr || out == nullptr || saved == nullptr || n_crops <= 0 || !valid_hidden(hidden))
+    return TP_ERR_INVALID_ARGUMENT;
+  if (x0_crop_stride < static_cast<int64_t>(kTokens) * kC || xm_crop_stride < static_cast<int64_t>(kTokens) * kCm || x0_crop_stride % 8 != 0 ||
+      xm_crop_stride % 8 != 0 || n_crops * kTokens > 0x7fff0000ll)
+    return TP_ERR_INVALID_ARGUMENT;
+  DeviceInfo dev;
+  TP_TRY(device_info(&dev));
+  const int s = scale_factor, H = hidden;
+  const int g = kGrid / s, Mq = g * g;
+  const long long R = n_crops * kTokens, Q = n_crops * Mq;
+  const SavedLayout S = saved_layout(n_crops, s, H);
+  if (saved_bytes < S.total) return TP_ERR_WORKSPACE_TOO_SMALL;
+  const PackedLayout L = packed_layout(H);
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const uint8_t* P = static_cast<const uint8_t*>(packed);
+  uint8_t* sv = static_cast<uint8_t*>(saved);
+  auto wf = [&](size_t off) { return reinterpret_cast<const float*>(P + off); };
+  auto bf = [&](size_t off) { return reinterpret_cast<__nv_bfloat16*>(sv + off); };
+  float* stats_k = reinterpret_cast<float*>(sv + S.stats);
+  float* stats_v = stats_k + 2 * kStatSlots * R;
+  float* stats_q = stats_v + 2 * kStatSlots * R;
+
+  {
+    const __nv_bfloat16* x0p = static_cast<const __nv_bfloat16*>(x0);
+    if (s == 2) TP_TRY(launch_front<2>(x0p, x0_crop_stride, bf(S.q), Q, stream));
+    else if (s == 3) TP_TRY(launch_front<3>(x0p, x0_crop_stride, bf(S.q), Q, stream));
+    else TP_TRY(launch_front<4>(x0p, x0_crop_stride, bf(S.q), Q, stream));
+  }
+  {
+    AOperand a{xm, kCm, 0, 0};
+    if (xm_crop_stride != static_cast<int64_t>(kTokens) * kCm) a = AOperand{xm, kCm, kTokens, xm_crop_stride};
+    TP_TRY(launch_gemm(a, P + L.w_kv0, kCm, R, 2 * kC, kCm, plain_epilogue(bf(S.z_kv), 2 * kC, wf(L.b_kv0), 0), dev.sms, stream));
+    TP_TRY(launch_gelu_fwd(bf(S.z_kv), bf(S.h_kv), static_cast<size_t>(R) * 2 * kC, stream));
+  }
+  {
+    GemmItem gi[3];
+    gi[0] = GemmItem{AOperand{bf(S.h_kv), 2 * kC, 0, 0}, P + L.w_k2, kC, R, kC, kC, plain_epilogue(bf(S.y_k), kC, wf(L.b_k2), 0)};
+    gi[0].ep.stats_out = stats_k; gi[0].ep.stats_out_slots = kStatSlots;
+    gi[1] = GemmItem{AOperand{bf(S.h_kv) + kC, 2 * kC, 0, 0}, P + L.w_v2, kC, R, kC, kC, plain_epilogue(bf(S.y_v), kC, wf(L.b_v2), 0)};
+    gi[1].ep.stats_out = stats_v; gi[1].ep.stats_out_slots = kStatSlots;
+    gi[2] = GemmItem{AOperand{bf(S.q), kC, 0, 0}, P + L.w_q, kC, Q, kC, kC, plain_epilogue(bf(S.y_q), kC, nullptr, 0)};
+    gi[2].ep.stats_out = stats_q; gi[2].ep.stats_out_slots = kStatSlots;
+    TP_TRY(launch_gemms(gi, 3, dev.sms, stream));
+  }
+  {
+    GemmItem gi[3];
+    gi[0] = GemmItem{AOperand{bf(S.y_k), kC, 0, 0}, P + L.w_ik, kC, R, kC, kC, plain_epilogue(bf(S.k_p), kC, wf(L.c_k), 0)};
+    gi[0].ep.col_a = wf(L.wsum_k); gi[0].ep.stats_in = stats_k; gi[0].ep.stats_in_slots = kStatSlots;
+    gi[1] = GemmItem{AOperand{bf(S.y_v), kC, 0, 0}, P + L.w_iv, kC, R, kC, kC, plain_epilogue(bf(S.v_p), kC, wf(L.c_v), 0)};
+    gi[1].ep.col_a = wf(L.wsum_v); gi[1].ep.stats_in = stats_v; gi[1].ep.stats_in_slots = kStatSlots;
+    gi[2] = GemmItem{AOperand{bf(S.y_q), kC, 0, 0}, P + L.w_iq, kC, Q, kC, kC, plain_epilogue(bf(S.q_p), kC, wf(L.c_q), 0)};
+    gi[2].ep.col_a = wf(L.wsum_q); gi[2].ep.stats_in = stats_q; gi[2].ep.stats_in_slots = kStatSlots;
+    gi[2].ep.alpha = 0.08838834764831845f;
+    TP_TRY(launch_gemms(gi, 3, dev.sms, stream));
+  }
+  if (s == 2) TP_TRY(launch_attn<2>(bf(S.q_p), bf(S.k_p), bf(S.v_p), bf(S.ctx), Q, stream));
+  else if (s == 3) TP_TRY(launch_attn<3>(bf(S.q_p), bf(S.k_p), bf(S.v_p), bf(S.ctx), Q, stream));
+  else TP_TRY(launch_attn<4>(bf(S.q_p), bf(S.k_p), bf(S.v_p), bf(S.ctx), Q, stream));
+  TP_TRY(launch_gemm(AOperand{bf(S.ctx), kC, 0, 0}, P + L.w_o, kC, Q, kC, kC, plain_epilogue(bf(S.o), kC, wf(L.b_o), 0), dev.sms, stream));
+  TP_TRY(launch_gemm(AOperand{bf(S.o), kC, 0, 0}, P + L.w_m0, kC, Q, H, kC, plain_epilogue(bf(S.z_m), H, wf(L.b_m0), 0), dev.sms, stream));
+  TP_TRY(launch_gelu_fwd(bf(S.z_m), bf(S.h_m), static_cast<size_t>(Q) * H, stream));
+  TP_TRY(launch_gemm(AOperand{bf(S.h_m), H, 0, 0}, P + L.w_m2, H, Q, H, H, plain_epilogue(out, H, wf(L.b_m2), 0), dev.sms, stream));
+  return TP_OK;
+}
+
+int tp_backward(const tp_weights* w, const void* xm, int64_t xm_crop_stride, int64_t n_crops, int scale_factor, int hidden,
+                const void* grad_out, const void* saved, const tp_weights* grads, void* workspace, size_t workspace_bytes, void* stream_) {
+  if (w == nullptr || grads == nullptr || xm == nullptr || grad_out == nullptr || saved == nullptr || workspace == nullptr || n_crops <= 0 ||
+      !valid_hidden(hidden))
+    return TP_ERR_INVALID_ARGUMENT;
+  if (scale_factor <= 0 || kGrid % scale_factor != 0) return TP_ERR_BAD_SCALE_FACTOR;
+  if (scale_factor < 2 || scale_factor > 4) return TP_ERR_INVALID_ARGUMENT;
+  if (xm_crop_stride != static_cast<int64_t>(kTokens) * kCm) return TP_ERR_INVALID_ARGUMENT;   // backward takes contiguous xm
+  {
+    const void* const* f = reinterpret_cast<const void* const*>(w);
+    const void* const* gptr = reinterpret_cast<const void* const*>(grads);
+    for (size_t i = 0; i < sizeof(tp_weights) / sizeof(void*); ++i)
+      if (f[i] == nullptr || gptr[i] == nullptr) return TP_ERR_INVALID_ARGUMENT;
+  }
+  DeviceInfo dev;
+  TP_TRY(device_info(&dev));
+  const int s = scale_factor, H = hidden;
+  const int g = kGrid / s, Mq = g * g;
+  const long long R = n_crops * kTokens, Q = n_crops * Mq;
+  const SavedLayout S = saved_layout(n_crops, s, H);
+  const BwdLayout B = bwd_layout(n_crops, s, H);
+  if (workspace_bytes < B.total) return TP_ERR_WORKSPACE_TOO_SMALL;
+  const long long Rp = B.Rp, Qp = B.Qp;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const uint8_t* sv = static_cast<const uint8_t*>(saved);
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  auto sb = [&](size_t off) { return reinterpret_cast<const __nv_bfloat16*>(sv + off); };
+  auto wb = [&](size_t off) { return reinterpret_cast<__nv_bfloat16*>(ws + off); };
+  const float* stats_k = reinterpret_cast<const float*>(sv + S.stats);
+  const float* stats_v = stats_k + 2 * kStatSlots * R;
+  const float* stats_q = stats_v + 2 * kStatSlots * R;
+  float* ln_part = reinterpret_cast<float*>(ws + B.ln_part);
+  const __nv_bfloat16* in_w = static_cast<const __nv_bfloat16*>(w->in_proj_w);
+  __nv_bfloat16* d_in_w = static_cast<__nv_bfloat16*>(const_cast<void*>(grads->in_proj_w));
+  __nv_bfloat16* d_in_b = static_cast<__nv_bfloat16*>(const_cast<void*>(grads->in_proj_b));
+  auto G = [&](const void* p) { return const_cast<void*>(p); };
+  const float alpha_q = 0.08838834764831845f;
+
+  // transposed weights: B operands of the dgrad GEMMs (dX = dY . W  ==  dY . (W^T)^T in the kernel's A.B^T form)
+  TP_TRY(launch_transpose<0>(w->mlp_2_w, H, wb(B.w_m2t), H, H, H, nullptr, nullptr, nullptr, stream));
+  TP_TRY(launch_transpose<0>(w->mlp_0_w, kC, wb(B.w_m0t), H, H, kC, nullptr, nullptr, nullptr, stream));
+  TP_TRY(launch_transpose<0>(w->out_proj_w, kC, wb(B.w_ot), kC, kC, kC, nullptr, nullptr, nullptr, stream));
+  TP_TRY(launch_transpose<0>(in_w, kC, wb(B.w_iqt), kC, kC, kC, nullptr, nullptr, nullptr, stream));
+  TP_TRY(launch_transpose<0>(in_w + static_cast<size_t>(kC) * kC, kC, wb(B.w_ikt), kC, kC, kC, nullptr, nullptr, nullptr, stream));
+  TP_TRY(launch_transpose<0>(in_w + 2 * static_cast<size_t>(kC) * kC, kC, wb(B.w_ivt), kC, kC, kC, nullptr, nullptr, nullptr, stream));
+  TP_TRY(launch_transpose<0>(w->k_proj_2_w, kC, wb(B.w_k2t), kC, kC, kC, nullptr, nullptr, nullptr, stream));
+  TP_TRY(launch_transpose<0>(w->v_proj_2_w, kC, wb(B.w_v2t), kC, kC, kC, nullptr, nullptr, nullptr, stream));
+
+  // ---- mlp.2:  out = h_m W_m2^T + b
+  TP_TRY(launch_transpose<0>(grad_out, H, wb(B.g_t), Qp, Q, H, nullptr, nullptr, nullptr, stream));
+  TP_TRY(launch_transpose<0>(sb(S.h_m), H, wb(B.hm_t), Qp, Q, H, nullptr, nullptr, nullptr, stream));
+  TP_TRY(launch_rowsum(wb(B.g_t), Qp, Q, H, 1.0f, G(grads->mlp_2_b), stream));
+  {
+    GemmItem gi[2];
+    gi[0] = plain_item(wb(B.g_t), Qp, wb(B.hm_t), Qp, G(grads->mlp_2_w), H, H, H, Q);          // dW_m2 = G^T h_m
+    gi[1] = plain_item(grad_out, H, wb(B.w_m2t), H, wb(B.dzm), H, Q, H, H);                      // dh_m = G W_m2
+    TP_TRY(launch_gemms(gi, 2, dev.sms, stream));
+  }
+  TP_TRY(launch_gelu_bwd(wb(B.dzm), sb(S.z_m), static_cast<size_t>(Q) * H, stream));            // dz_m
+  // ---- mlp.0:  z_m = o W_m0^T + b
+  TP_TRY(launch_transpose<0>(wb(B.dzm), H, wb(B.dzm_t), Qp, Q, H, nullptr, nullptr, nullptr, stream));
+  TP_TRY(launch_transpose<0>(sb(S.o), kC, wb(B.o_t), Qp, Q, kC, nullptr, nullptr, nullptr, stream));
+  TP_TRY(launch_rowsum(wb(B.dzm_t), Qp, Q, H, 1.0f, G(grads->mlp_0_b), stream));
+  {
+    GemmItem gi[2];
+    gi[0] = plain_item(wb(B.dzm_t), Qp, wb(B.o_t), Qp, G(grads->mlp_0_w), kC, H, kC, Q);         // dW_m0 = dz_m^T o
+    gi[1] = plain_item(wb(B.dzm), H, wb(B.w_m0t), H, wb(B.d_o), kC, Q, kC, H);                   // do = dz_m W_m0
+    TP_TRY(launch_gemms(gi, 2, dev.sms, stream));
+  }
+  // ---- out_proj:  o = ctx W_o^T + b
+  TP_TRY(launch_transpose<0>(wb(B.d_o), kC, wb(B.do_t), Qp, Q, kC, nullptr, nullptr, nullptr, stream));
+  TP_TRY(launch_transpose<0>(sb(S.ctx), kC, wb(B.ctx_t), Qp, Q, kC, nullptr, nullptr, nullptr, stream));
+  TP_TRY(launch_rowsum(wb(B.do_t), Qp, Q, kC, 1.0f, G(grads->out_proj_b), stream));
+  {
+    GemmItem gi[2];
+    gi[0] = plain_item(wb(B.do_t), Qp, wb(B.ctx_t), Qp, G(grads->out_proj_w), kC, kC, kC, Q);    // dW_o = do^T ctx
+    gi[1] = plain_item(wb(B.d_o), kC, wb(B.w_ot), kC, wb(B.dctx), kC, Q, kC, kC);                // dctx = do W_o
+    TP_TRY(launch_gemms(gi, 2, dev.sms, stream));
+  }
+  // ---- window attention
+  {
+    const long long threads = Q * 32;
+    const unsigned blocks = static_cast<unsigned>((threads + 255) / 256);
+    if (s == 2) window_attn_bwd_kernel<2><<<blocks, 256, 0, stream>>>(sb(S.q_p), sb(S.k_p), sb(S.v_p), wb(B.dctx), wb(B.dqp), wb(B.dkp), wb(B.dvp), Q);
+    else if (s == 3) window_attn_bwd_kernel<3><<<blocks, 256, 0, stream>>>(sb(S.q_p), sb(S.k_p), sb(S.v_p), wb(B.dctx), wb(B.dqp), wb(B.dkp), wb(B.dvp), Q);
+    else window_attn_bwd_kernel<4><<<blocks, 256, 0, stream>>>(sb(S.q_p), sb(S.k_p), sb(S.v_p), wb(B.dctx), wb(B.dqp), wb(B.dkp), wb(B.dvp), Q);
+    TP_CUDA(cudaGetLastError());
+  }
+  // ---- MHA in-projections:  q' = alpha (LN(y_q) W_iq^T + b),  k' = LN(y_k) W_ik^T + b,  v' likewise
+  TP_TRY(launch_transpose<0>(wb(B.dqp), kC, wb(B.dqp_t), Qp, Q, kC, nullptr, nullptr, nullptr, stream));
+  TP_TRY(launch_transpose<0>(wb(B.dkp), kC, wb(B.dkp_t), Rp, R, kC, nullptr, nullptr, nullptr, stream));
+  TP_TRY(launch_transpose<0>(wb(B.dvp), kC, wb(B.dvp_t), Rp, R, kC, nullptr, nullptr, nullptr, stream));
+  TP_TRY(launch_transpose<2>(sb(S.y_q), kC, wb(B.lnq_t), Qp, Q, kC, stats_q, w->ln_q_w, w->ln_q_b, stream));
+  TP_TRY(launch_transpose<2>(sb(S.y_k), kC, wb(B.lnk_t), Rp, R, kC, stats_k, w->ln_k_w, w->ln_k_b, stream));
+  TP_TRY(launch_transpose<2>(sb(S.y_v), kC, wb(B.lnv_t), Rp, R, kC, stats_v, w->ln_v_w, w->ln_v_b, stream));
+  TP_TRY(launch_rowsum(wb(B.dqp_t), Qp, Q, kC, alpha_q, d_in_b, stream));
+  TP_TRY(launch_rowsum(wb(B.dkp_t), Rp, R, kC, 1.0f, d_in_b + kC, stream));
+  TP_TRY(launch_rowsum(wb(B.dvp_t), Rp, R, kC, 1.0f, d_in_b + 2 * kC, stream));
+  {
+    GemmItem gi[3];
+    gi[0] = plain_item(wb(B.dqp_t), Qp, wb(B.lnq_t), Qp, d_in_w, kC, kC, kC, Q, nullptr, alpha_q);
+    gi[1] = plain_item(wb(B.dkp_t), Rp, wb(B.lnk_t), Rp, d_in_w + static_cast<size_t>(kC) * kC, kC, kC, kC, R);
+    gi[2] = plain_item(wb(B.dvp_t), Rp, wb(B.lnv_t), Rp, d_in_w + 2 * static_cast<size_t>(kC) * kC, kC, kC, kC, R);
+    TP_TRY(launch_gemms(gi, 3, dev.sms, stream));
+    gi[0] = plain_item(wb(B.dqp), kC, wb(B.w_iqt), kC, wb(B.dqh), kC, Q, kC, kC, nullptr, alpha_q);   // d LN(y_q)
+    gi[1] = plain_item(wb(B.dkp), kC, wb(B.w_ikt), kC, wb(B.dkh), kC, R, kC, kC);
+    gi[2] = plain_item(wb(B.dvp), kC, wb(B.w_ivt), kC, wb(B.dvh), kC, R, kC, kC);
+    TP_TRY(launch_gemms(gi, 3, dev.sms, stream));
+  }
+  // ---- LayerNorms
+  TP_TRY(launch_ln_bwd(wb(B.dqh), sb(S.y_q), stats_q, w->ln_q_w, wb(B.dyq), ln_part, Q, G(grads->ln_q_w), G(grads->ln_q_b), stream));
+  TP_TRY(launch_ln_bwd(wb(B.dkh), sb(S.y_k), stats_k, w->ln_k_w, wb(B.dyk), ln_part + 2ll * kLnBlocks * kC, R, G(grads->ln_k_w),
+                       G(grads->ln_k_b), stream));
+  TP_TRY(launch_ln_bwd(wb(B.dvh), sb(S.y_v), stats_v, w->ln_v_w, wb(B.dyv), ln_part + 4ll * kLnBlocks * kC, R, G(grads->ln_v_w),
+                       G(grads->ln_v_b), stream));
+  // ---- q_proj_1 (no bias), k_proj_1.2, v_proj_1.2
+  TP_TRY(launch_transpose<0>(wb(B.dyq), kC, wb(B.dyq_t), Qp, Q, kC, nullptr, nullptr, nullptr, stream));
+  TP_TRY(launch_transpose<0>(wb(B.dyk), kC, wb(B.dyk_t), Rp, R, kC, nullptr, nullptr, nullptr, stream));
+  TP_TRY(launch_transpose<0>(wb(B.dyv), kC, wb(B.dyv_t), Rp, R, kC, nullptr, nullptr, nullptr, stream));
+  TP_TRY(launch_transpose<0>(sb(S.q), kC, wb(B.q_t), Qp, Q, kC, nullptr, nullptr, nullptr, stream));
+  TP_TRY(launch_transpose<0>(sb(S.h_kv), 2 * kC, wb(B.hkv_t), Rp, R, 2 * kC, nullptr, nullptr, nullptr, stream));
+  TP_TRY(launch_rowsum(wb(B.dyk_t), Rp, R, kC, 1.0f, G(grads->k_proj_2_b), stream));
+  TP_TRY(launch_rowsum(wb(B.dyv_t), Rp, R, kC, 1.0f, G(grads->v_proj_2_b), stream));
+  {
+    GemmItem gi[3];
+    gi[0] = plain_item(wb(B.dyq_t), Qp, wb(B.q_t), Qp, G(grads->q_proj_w), kC, kC, kC, Q);
+    gi[1] = plain_item(wb(B.dyk_t), Rp, wb(B.hkv_t), Rp, G(grads->k_proj_2_w), kC, kC, kC, R);
+    gi[2] = plain_item(wb(B.dyv_t), Rp, wb(B.hkv_t) + static_cast<size_t>(kC) * Rp, Rp, G(grads->v_proj_2_w), kC, kC, kC, R);
+    TP_TRY(launch_gemms(gi, 3, dev.sms, stream));
+    gi[0] = plain_item(wb(B.dyk), kC, wb(B.w_k2t), kC, wb(B.dzkv), 2 * kC, R, kC, kC);               // dh_k  -> dzkv[:, :1024]
+    gi[1] = plain_item(wb(B.dyv), kC, wb(B.w_v2t), kC, wb(B.dzkv) + kC, 2 * kC, R, kC, kC);          // dh_v  -> dzkv[:, 1024:]
+    TP_TRY(launch_gemms(gi, 2, dev.sms, stream));
+  }
+  TP_TRY(launch_gelu_bwd(wb(B.dzkv), sb(S.z_kv), static_cast<size_t>(R) * 2 * kC, stream));        // dz_kv
+  // ---- k_proj_1.0 / v_proj_1.0:  z = xm W0^T + b   (no gradient to xm: the CLIP tower is frozen)
+  TP_TRY(launch_transpose<0>(wb(B.dzkv), 2 * kC, wb(B.dzkv_t), Rp, R, 2 * kC, nullptr, nullptr, nullptr, stream));
+  TP_TRY(launch_transpose<0>(xm, kCm, wb(B.xm_t), Rp, R, kCm, nullptr, nullptr, nullptr, stream));
+  TP_TRY(launch_rowsum(wb(B.dzkv_t), Rp, R, kC, 1.0f, G(grads->k_proj_0_b), stream));
+  TP_TRY(launch_rowsum(wb(B.dzkv_t) + static_cast<size_t>(kC) * Rp, Rp, R, kC, 1.0f, G(grads->v_proj_0_b), stream));
+  {
+    GemmItem gi[2];
+    gi[0] = plain_item(wb(B.dzkv_t), Rp, wb(B.xm_t), Rp, G(grads->k_proj_0_w), kCm, kC, kCm, R);
+    gi[1] = plain_item(wb(B.dzkv_t) + static_cast<size_t>(kC) * Rp, Rp, wb(B.xm_t), Rp, G(grads->v_proj_0_w), kCm, kC, kCm, R);
+    TP_TRY(launch_gemms(gi, 2, dev.sms, stream));
+  }
+  return TP_OK;
+}

@@ -38,6 +38,47 @@ def _two_layer(in_dim: int, mid: int, out: int) -> nn.Sequential:
     return nn.Sequential(nn.Linear(in_dim, mid), nn.GELU(), nn.Linear(mid, out))
 
 
+class _ProjectorFunction(torch.autograd.Function):
+    """autograd bridge: forward = tp_forward_train (keeps intermediates), backward = tp_backward (parameter gradients)."""
+
+    @staticmethod
+    def forward(ctx, module, x0b, s0, xmb, sm, *params):
+        device = x0b.device
+        n = x0b.shape[0]
+        packed = module._packed_weights(device)
+        out = torch.empty((n, module.num_queries, module.hidden_size), dtype=torch.bfloat16, device=device)
+        nbytes = lib.tp_train_saved_bytes(n, module.scale_factor, module.hidden_size)
+        saved = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        stream = torch.cuda.current_stream(device).cuda_stream
+        check(lib.tp_forward_train(packed.data_ptr(), x0b.data_ptr(), xmb.data_ptr(), n, s0, sm, module.scale_factor,
+                                   module.hidden_size, out.data_ptr(), saved.data_ptr(), nbytes, stream), "tp_forward_train")
+        ctx.module = module
+        ctx.saved = saved
+        ctx.xm = xmb if xmb.is_contiguous() else xmb.contiguous()
+        ctx.weights_bf16 = list(module._keepalive)           # bf16 parameter snapshots this forward used
+        ctx.param_meta = [(p.dtype, p.requires_grad) for p in params]
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_out):
+        module = ctx.module
+        device = grad_out.device
+        n = ctx.xm.shape[0]
+        g = grad_out.to(torch.bfloat16).contiguous()
+        grads = [torch.empty_like(w) for w in ctx.weights_bf16]
+        w_struct = _lib.TpWeights(*[t.data_ptr() for t in ctx.weights_bf16])
+        g_struct = _lib.TpWeights(*[t.data_ptr() for t in grads])
+        with torch.cuda.device(device):
+            ws_bytes = lib.tp_backward_workspace_bytes(n, module.scale_factor, module.hidden_size)
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=device)
+            stream = torch.cuda.current_stream(device).cuda_stream
+            check(lib.tp_backward(C.byref(w_struct), ctx.xm.data_ptr(), ctx.xm.stride(0), n, module.scale_factor, module.hidden_size,
+                                  g.data_ptr(), ctx.saved.data_ptr(), C.byref(g_struct), ws.data_ptr(), ws_bytes, stream), "tp_backward")
+        out = [gr.to(dt) if need else None for gr, (dt, need) in zip(grads, ctx.param_meta)]
+        return (None, None, None, None, None) + tuple(out)
+
+
 class TokenPackerB200(nn.Module):
     def __init__(self, raw_grid=24, embed_dim=1024, num_heads=1024 // 128, kv_dim=1024, hidden_size=4096, scale_factor=2,
                  norm_layer=partial(nn.LayerNorm, eps=1e-6)):
@@ -131,8 +172,9 @@ class TokenPackerB200(nn.Module):
             raise ValueError(f"expected feat [N,576,1024] and feat_multi [N,576,4096], got {tuple(x0.shape)} {tuple(xm.shape)}")
         if not (x0.is_cuda and xm.is_cuda):
             raise RuntimeError("tokenpacker_b200 has no CPU path: inputs must be CUDA tensors on a B200")
-        if torch.is_grad_enabled() and (x0.requires_grad or xm.requires_grad or any(p.requires_grad for p in self.parameters())):
-            raise NotImplementedError("backward is not implemented yet: call under torch.no_grad() / inference_mode()")
+        if torch.is_grad_enabled() and (x0.requires_grad or xm.requires_grad):
+            raise NotImplementedError("gradients w.r.t. the CLIP features are not implemented (the vision tower is frozen in every "
+                                      "released TokenPacker recipe): detach the features or run under torch.no_grad()")
         return x0, xm
 
     def forward(self, x, attn_mask=None):
@@ -145,8 +187,12 @@ class TokenPackerB200(nn.Module):
         with torch.cuda.device(device):
             x0b, s0 = self._as_crop_strided(x0.to(torch.bfloat16), 1024)
             xmb, sm = self._as_crop_strided(xm.to(torch.bfloat16), 4096)
-            out = torch.empty((n, self.num_queries, self.hidden_size), dtype=torch.bfloat16, device=device)
-            self._launch(x0b, s0, xmb, sm, out, None)
+            if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+                # training: same output, intermediates kept, gradients for every parameter (tp_forward_train / tp_backward)
+                out = _ProjectorFunction.apply(self, x0b, s0, xmb, sm, *self._raw_params())
+            else:
+                out = torch.empty((n, self.num_queries, self.hidden_size), dtype=torch.bfloat16, device=device)
+                self._launch(x0b, s0, xmb, sm, out, None)
         return out if out_dtype == torch.bfloat16 else out.to(out_dtype)
 
     def _launch(self, x0b, s0, xmb, sm, out, seg_row_offset):

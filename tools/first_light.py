@@ -182,6 +182,36 @@ def projector_timing():
     print(f"N=64 s=2 H=4096: {ms:.3f} ms/call -> {n * 144 / ms * 1e3:.3e} tok/s, {tpo.flops_per_crop(2) * n / ms / 1e9:.1f} TFLOP/s", flush=True)
 
 
+@stage
+def train_step_timing():
+    import torch
+    from tokenpacker_b200 import TokenPackerB200
+    from tokenpacker_b200 import synthetic as syn
+    m = TokenPackerB200(hidden_size=4096, scale_factor=2).to("cuda", torch.bfloat16).train()
+    n = 64
+    x0 = torch.randn(n, 576, 1024, device="cuda").bfloat16()
+    xm = torch.randn(n, 576, 4096, device="cuda").bfloat16()
+    gw = torch.randn(n, 144, 4096, device="cuda").bfloat16()
+    def step():
+        for p in m.parameters():
+            p.grad = None
+        out = m((x0, xm))
+        out.backward(gw)
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 10
+    fl = syn.flops_per_crop(2) * n
+    print(f"train step (fwd+bwd, N=64 s=2 H=4096): {ms:.3f} ms; fwd F_alg x3 = {3 * fl / 1e12:.2f} TF -> {3 * fl / ms / 1e9:.0f} TF/s equivalent; "
+          f"peak mem {torch.cuda.max_memory_allocated() / 2**30:.2f} GiB", flush=True)
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1:
         STAGES[sys.argv[1]]()
