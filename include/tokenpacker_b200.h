@@ -125,6 +125,12 @@ TP_API int tp_backward(const tp_weights* w, const void* xm, int64_t xm_crop_stri
 TP_API int tp_gemm_bf16(const void* a, int64_t lda, const void* b, int64_t ldb, void* c, int64_t ldc, int64_t m, int64_t n,
                  int64_t k, const float* bias, int gelu, float alpha, void* stream);
 
+/* The wgrad form of the same kernel:  C[M,N] = alpha * A^T . B  with A given as a row-major [K, M] matrix and B as [K, N]
+ * (contraction over ROWS; both operands reach the tensor cores as MN-major shared-memory tiles — no transposes).
+ * Needs N % 256 == 0. */
+TP_API int tp_gemm_tn_bf16(const void* a, int64_t lda, const void* b, int64_t ldb, void* c, int64_t ldc, int64_t m, int64_t n,
+                           int64_t k, float alpha, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------------------
  * TokenPacker-HD front end.
  * ------------------------------------------------------------------------------------------------------------- */

@@ -59,3 +59,24 @@ def test_gemm_linearity():
     # small integers: every product and partial sum is exact in fp32, so the only rounding is the final fp32 -> bf16
     out = gemm_bf16(a, b)
     assert torch.equal(out, (a.float() @ b.float().t()).to(torch.bfloat16))
+
+
+@pytest.mark.parametrize("m,n,k", [(256, 256, 64), (256, 256, 512), (1024, 1024, 9216), (128, 256, 300), (1024, 4096, 1000), (4096, 1024, 36864)])
+def test_gemm_tn_wgrad_form(m, n, k):
+    """C = A^T B with row-major [K,M] / [K,N] operands: MN-major UMMA descriptors, contraction over rows (wgrad)."""
+    from tokenpacker_b200.kernels import gemm_tn_bf16
+    g = torch.Generator(device="cuda").manual_seed(m + n + k)
+    a = torch.randn(k, m, device="cuda", generator=g).to(torch.bfloat16)
+    b = (torch.randn(k, n, device="cuda", generator=g) * 0.05).to(torch.bfloat16)
+    out = gemm_tn_bf16(a, b)
+    ref = a.float().t() @ b.float()
+    err = (out.float() - ref).abs().max().item()
+    assert err <= 1e-2 * ref.abs().max().item() + 1e-3, (err, ref.abs().max().item())
+
+
+def test_gemm_tn_exact_small_integers():
+    from tokenpacker_b200.kernels import gemm_tn_bf16
+    g = torch.Generator(device="cuda").manual_seed(3)
+    a = torch.randint(-3, 4, (640, 512), device="cuda", generator=g).to(torch.bfloat16)
+    b = torch.randint(-3, 4, (640, 256), device="cuda", generator=g).to(torch.bfloat16)
+    assert torch.equal(gemm_tn_bf16(a, b), (a.float().t() @ b.float()).to(torch.bfloat16))

@@ -148,6 +148,7 @@ struct GemmItem {
   GemmEpilogue ep;
   void* const* peer_c = nullptr;   // fused all-gather: the same output slot in every peer's gathered buffer
   int n_peers = 0;
+  int tn = 0;                      // 1: C[M,N] = A^T . B with A given as [K, M] (ld = a.ld) and B as [K, N] (ld = ldb), both row-major
 };
 
 int check_item(const GemmItem& it) {
@@ -188,8 +189,15 @@ int launch_gemm_pair_group(const GemmItem* items, int count, int sms, cudaStream
   for (int i = 0; i < count; ++i) {
     const GemmItem& it = items[i];
     GemmProblem& p = g.p[i];
-    TP_TRY(make_a_map(&p.tmap_a, it.a, it.M, it.K));
-    TP_TRY(make_map_2d(&p.tmap_b, it.b, it.N, it.K, it.ldb, Cfg::kTileN / 2));
+    if (it.tn) {
+      // row-major [K, M] / [K, N] operands: box = 64 MN-elements x 64 K-rows
+      TP_TRY(make_map_2d(&p.tmap_a, it.a.ptr, it.K, it.M, it.a.ld, 64));
+      TP_TRY(make_map_2d(&p.tmap_b, it.b, it.K, it.N, it.ldb, 64));
+      p.ab_mn_major = 1;
+    } else {
+      TP_TRY(make_a_map(&p.tmap_a, it.a, it.M, it.K));
+      TP_TRY(make_map_2d(&p.tmap_b, it.b, it.N, it.K, it.ldb, Cfg::kTileN / 2));
+    }
     // C goes out through TMA stores (64-col x 128-row swizzled slabs) unless rows are scattered to segment offsets
     TP_TRY(make_map_2d(&p.tmap_c, it.ep.c, it.M, it.N, it.ep.ldc, kBlockM));
     p.use_tma_store = it.ep.seg_row_offset == nullptr ? 1 : 0;
@@ -234,7 +242,8 @@ int launch_gemms(const GemmItem* items, int count, int sms, cudaStream_t stream)
     const GemmItem& it = items[i];
     const bool pair_ok = (it.N % 256 == 0) && sms >= 2;
     if (it.n_peers > 0 && (!pair_ok || count != 1)) return TP_ERR_INVALID_ARGUMENT;   // peer stores live in the pair kernel only
-    const bool want_pair = mode == 2 || mode == 3 || (mode == 0 && it.M >= 256) || it.n_peers > 0;
+    if (it.tn && !pair_ok) return TP_ERR_INVALID_ARGUMENT;                              // MN-major operands: pair kernel only
+    const bool want_pair = mode == 2 || mode == 3 || (mode == 0 && it.M >= 256) || it.n_peers > 0 || it.tn;
     if (pair_ok && want_pair) {
       if (mode == 3) TP_TRY(launch_gemm_pair_group(&it, 1, sms, stream));
       else grouped[n_grouped++] = it;
@@ -644,6 +653,17 @@ TP_API int tp_gemm_bf16_prof(const void* a, int64_t lda, const void* b, int64_t 
   return launch_gemm(AOperand{a, lda, 0, 0}, b, ldb, m, n, k, ep, dev.sms, static_cast<cudaStream_t>(stream));
 }
 #endif
+
+int tp_gemm_tn_bf16(const void* a, int64_t lda, const void* b, int64_t ldb, void* c, int64_t ldc, int64_t m, int64_t n, int64_t k,
+                    float alpha, void* stream) {
+  if (a == nullptr || b == nullptr || c == nullptr) return TP_ERR_INVALID_ARGUMENT;
+  DeviceInfo dev;
+  TP_TRY(device_info(&dev));
+  GemmItem it{AOperand{a, lda, 0, 0}, b, ldb, m, n, k, plain_epilogue(c, ldc, nullptr, 0)};
+  it.ep.alpha = alpha;
+  it.tn = 1;
+  return launch_gemms(&it, 1, dev.sms, static_cast<cudaStream_t>(stream));
+}
 
 int tp_gemm_bf16(const void* a, int64_t lda, const void* b, int64_t ldb, void* c, int64_t ldc, int64_t m, int64_t n, int64_t k,
                  const float* bias, int gelu, float alpha, void* stream) {

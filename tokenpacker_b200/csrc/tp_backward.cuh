@@ -105,6 +105,54 @@ __global__ void gelu_bwd_kernel(__nv_bfloat16* __restrict__ dh, const __nv_bfloa
   reinterpret_cast<uint4*>(dh)[i] = pack8(g);
 }
 
+// LayerNorm output  out[r,:] = (y[r,:] - mu_r) rstd_r gamma + beta  (bf16; one warp per row): B operand of the in-projection wgrad
+__global__ void __launch_bounds__(256) ln_apply_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ stats,
+                                                       const __nv_bfloat16* __restrict__ gamma, const __nv_bfloat16* __restrict__ beta,
+                                                       __nv_bfloat16* __restrict__ out, long long rows) {
+  const long long row = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  float mu, rstd;
+  row_mean_rstd(stats, row, mu, rstd);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float v[8], g[8], b[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(y + row * kC + i * 256 + lane * 8)), v);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(gamma + i * 256 + lane * 8)), g);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(beta + i * 256 + lane * 8)), b);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = fmaf((v[j] - mu) * rstd, g[j], b[j]);
+    *reinterpret_cast<uint4*>(out + row * kC + i * 256 + lane * 8) = pack8(v);
+  }
+}
+
+// Column sums (bias gradients), deterministic two-stage:  partial[chunk][c] = sum over the chunk's rows of in[r, c]
+// grid = (ceil(cols / 1024), n_chunks), 128 threads x 8 columns
+__global__ void colsum_partial_kernel(const __nv_bfloat16* __restrict__ in, long long ld, long long rows, int cols, int n_chunks,
+                                      float* __restrict__ partial) {
+  const int c0 = (blockIdx.x * 128 + threadIdx.x) * 8;
+  if (c0 >= cols) return;
+  const long long per = (rows + n_chunks - 1) / n_chunks;
+  const long long r0 = per * blockIdx.y, r1 = min(rows, r0 + per);
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (long long r = r0; r < r1; ++r) {
+    float f[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(in + r * ld + c0)), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] += f[j];
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) partial[static_cast<long long>(blockIdx.y) * cols + c0 + j] = acc[j];
+}
+
+__global__ void colsum_reduce_kernel(const float* __restrict__ partial, int n_chunks, int cols, float scale, __nv_bfloat16* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  float a = 0.f;
+  for (int i = 0; i < n_chunks; ++i) a += partial[static_cast<long long>(i) * cols + c];
+  out[c] = __float2bfloat16_rn(a * scale);
+}
+
 // out[i] (fp32 -> bf16) = scale * sum_j in[i, j], j < n; one warp per row (bias gradients from transposed dY)
 __global__ void rowsum_kernel(const __nv_bfloat16* __restrict__ in, long long ld, long long n, int rows, float scale,
                               __nv_bfloat16* __restrict__ out) {

@@ -419,6 +419,7 @@ struct GemmProblem {
   CUtensorMap tmap_a, tmap_b, tmap_c;
   int M, N, K;
   int a_seg_rows;        // 0: plain 2-D A; else rows per segment of the 3-D (crop-strided) A map
+  int ab_mn_major;       // 1: BOTH operands are given as row-major [K, M] / [K, N] matrices (wgrad: C = A^T . B, contraction over rows)
   int use_tma_store;     // C through TMA stores (0 when rows are scattered to segment offsets)
   int num_n_blocks;
   int num_tiles;
@@ -534,13 +535,19 @@ tp_gemm2_kernel(const __grid_constant__ GemmGroup grp, const __grid_constant__ P
           uint8_t* sb = sa + Cfg::kABytes;
           if (is_leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
           else mbar_arrive_cluster(&full_bar[stage], 0);
-          if (pr.a_seg_rows == 0) {
+          if (pr.ab_mn_major) {
+            // boxes of [64 K-rows x 64 MN-elements]: coordinates (mn, k); two MN atoms per operand per CTA
+            tma_load_2d_pair(sa, &pr.tmap_a, &full_bar[stage], row0, kb * kBlockK);
+            tma_load_2d_pair(sa + Cfg::kABytes / 2, &pr.tmap_a, &full_bar[stage], row0 + 64, kb * kBlockK);
+            tma_load_2d_pair(sb, &pr.tmap_b, &full_bar[stage], brow0, kb * kBlockK);
+            tma_load_2d_pair(sb + Cfg::kBBytes / 2, &pr.tmap_b, &full_bar[stage], brow0 + 64, kb * kBlockK);
+          } else if (pr.a_seg_rows == 0) {
             tma_load_2d_pair(sa, &pr.tmap_a, &full_bar[stage], kb * kBlockK, row0);
           } else {
             tma_load_3d_pair(sa, &pr.tmap_a, &full_bar[stage], kb * kBlockK, srow0, seg0);
             tma_load_3d_pair(sa + Cfg::kABytes / 2, &pr.tmap_a, &full_bar[stage], kb * kBlockK, srow1, seg1);
           }
-          tma_load_2d_pair(sb, &pr.tmap_b, &full_bar[stage], kb * kBlockK, brow0);
+          if (!pr.ab_mn_major) tma_load_2d_pair(sb, &pr.tmap_b, &full_bar[stage], kb * kBlockK, brow0);
         }
         __syncwarp();
         if (++stage == kStages) { stage = 0; phase ^= 1u; }
@@ -555,7 +562,6 @@ tp_gemm2_kernel(const __grid_constant__ GemmGroup grp, const __grid_constant__ P
   } else if (warp_idx == kMmaWarp) {
     // ======================================= MMA issuer (leader CTA only) ========================
     if (is_leader) {
-      constexpr uint32_t idesc = make_idesc_bf16_f32(Cfg::kTileM, kTileN);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -563,7 +569,10 @@ tp_gemm2_kernel(const __grid_constant__ GemmGroup grp, const __grid_constant__ P
       [[maybe_unused]] long long w_full = 0, w_tmem = 0;
       [[maybe_unused]] const long long t_begin = clock64();
       for (int tile = pair_idx; tile < num_tiles; tile += num_pairs) {
-        const int num_k_blocks = decode_tile(grp, tile).pr->num_k_blocks;
+        const GemmProblem& mpr = *decode_tile(grp, tile).pr;
+        const int num_k_blocks = mpr.num_k_blocks;
+        const bool mn_major = mpr.ab_mn_major != 0;
+        const uint32_t idesc = mn_major ? make_idesc_bf16_f32(Cfg::kTileM, kTileN, 1, 1) : make_idesc_bf16_f32(Cfg::kTileM, kTileN);
         {
           TP_PROF_T0();
           mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1u);   // both epilogues have drained this accumulator buffer
@@ -580,12 +589,23 @@ tp_gemm2_kernel(const __grid_constant__ GemmGroup grp, const __grid_constant__ P
           tcgen05_fence_after();
           if (elect_one()) {
             const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
-            const uint64_t desc_a = make_smem_desc_kmajor_sw128(sa);
-            const uint64_t desc_b = make_smem_desc_kmajor_sw128(sa + Cfg::kABytes);
+            if (!mn_major) {
+              const uint64_t desc_a = make_smem_desc_kmajor_sw128(sa);
+              const uint64_t desc_b = make_smem_desc_kmajor_sw128(sa + Cfg::kABytes);
 #pragma unroll
-            for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-              umma_bf16_pair(tmem_d, desc_a + static_cast<uint64_t>(k * 2), desc_b + static_cast<uint64_t>(k * 2), idesc,
-                             static_cast<uint32_t>((kb | k) != 0));
+              for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+                umma_bf16_pair(tmem_d, desc_a + static_cast<uint64_t>(k * 2), desc_b + static_cast<uint64_t>(k * 2), idesc,
+                               static_cast<uint32_t>((kb | k) != 0));
+              }
+            } else {
+              // MN-major tiles: two 64-wide MN atoms 8 KiB apart per operand; one UMMA (K = 16) consumes two 8-row K groups = 2 KiB
+              const uint64_t desc_a = make_smem_desc_mnmajor_sw128(sa, Cfg::kABytes / 2);
+              const uint64_t desc_b = make_smem_desc_mnmajor_sw128(sa + Cfg::kABytes, Cfg::kBBytes / 2);
+#pragma unroll
+              for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+                umma_bf16_pair(tmem_d, desc_a + static_cast<uint64_t>(k * (2048 >> 4)), desc_b + static_cast<uint64_t>(k * (2048 >> 4)), idesc,
+                               static_cast<uint32_t>((kb | k) != 0));
+              }
             }
             umma_commit_pair(&empty_bar[stage], 0x3);        // frees the slot in BOTH CTAs
             if (kb == num_k_blocks - 1) umma_commit_pair(&tmem_full_bar[acc], 0x3);   // accumulator complete -> both epilogues

@@ -194,13 +194,27 @@ __device__ __forceinline__ uint64_t make_smem_desc_kmajor_sw128(uint32_t smem_ad
   return d;
 }
 
+// Same for an MN-major operand tile (the contraction index K is the SLOW dimension in shared memory: what a TMA box of
+// [64 K-rows x 64 MN-elements] of a row-major [K, MN] matrix produces).  Canonical layout (uint128 units):
+// Swizzle<3,4,3> o ((8,n),(8,k)) : ((1,LBO),(8,SBO)) — 64 MN-elements contiguous per 128-byte row, 8 K-rows per swizzle
+// atom; SBO = distance between consecutive 8-row K groups (1024 B), LBO = distance between 64-wide MN atoms.
+__device__ __forceinline__ uint64_t make_smem_desc_mnmajor_sw128(uint32_t smem_addr, uint32_t mn_atom_stride_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(mn_atom_stride_bytes >> 4) << 16;   // leading byte offset: next 64-element MN atom
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;                   // stride byte offset: next group of 8 K-rows
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+
 // Instruction descriptor for kind::f16: A,B = bf16 (format 1), D = fp32 (format 1), both operands K-major.
-__host__ __device__ constexpr uint32_t make_idesc_bf16_f32(uint32_t m, uint32_t n) {
+__host__ __device__ constexpr uint32_t make_idesc_bf16_f32(uint32_t m, uint32_t n, uint32_t a_mn_major = 0, uint32_t b_mn_major = 0) {
   return (1u << 4)            // [4,6)   D format  : 1 = F32
          | (1u << 7)          // [7,10)  A format  : 1 = BF16
          | (1u << 10)         // [10,13) B format  : 1 = BF16
-         | (0u << 15)         // [15]    A major   : 0 = K
-         | (0u << 16)         // [16]    B major   : 0 = K
+         | (a_mn_major << 15) // [15]    A major   : 0 = K, 1 = MN
+         | (b_mn_major << 16) // [16]    B major   : 0 = K, 1 = MN
          | ((n >> 3) << 17)   // [17,23) N >> 3
          | ((m >> 4) << 24);  // [24,29) M >> 4
 }

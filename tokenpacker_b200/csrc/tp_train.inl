@@ -5,9 +5,9 @@
 // llava/train/train.py:950-958, scripts/v1_5/pretrain*.sh), through PyTorch autograd over builder.py:107-137.  Here:
 //   forward_train = the inference launch plan without the out_proj fold and with GELU as a separate pass, so that the
 //                   pre-activations z exist in memory (GELU'(z) needs z; GELU(z) is not invertible);
-//   backward      = dgrad GEMMs (dY . W, B operand = transposed weight), wgrad GEMMs (dY^T . X, operands = transposed
-//                   activations: contraction over rows), LayerNorm / GELU / window-attention backward kernels, bias
-//                   gradients as row sums of the transposed dY that the wgrad needs anyway.
+//   backward      = dgrad GEMMs (dY . W, B operand = transposed weight), wgrad GEMMs in the TN form of the pair kernel
+//                   (dW = dY^T . X straight from the row-major activations: MN-major UMMA tiles, contraction over rows),
+//                   LayerNorm / GELU / window-attention backward kernels, bias gradients as deterministic column sums.
 // Gradients w.r.t. the CLIP features are not produced (the tower is frozen in every released recipe; the Python layer raises
 // if the inputs require grad).
 
@@ -62,22 +62,23 @@ BwdLayout bwd_layout(long long n_crops, int s, int H) {
   BwdLayout L;
   L.Rp = static_cast<long long>(align_up(R, 8));
   L.Qp = static_cast<long long>(align_up(Q, 8));
-  const size_t Rp = L.Rp, Qp = L.Qp, Hs = H;
+  const size_t Qp = L.Qp, Hs = H;
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 1024); return o; };
   const size_t mat = static_cast<size_t>(kC) * kC * 2;
   L.w_m2t = take(Hs * Hs * 2); L.w_m0t = take(kC * Hs * 2); L.w_ot = take(mat);
   L.w_iqt = take(mat); L.w_ikt = take(mat); L.w_ivt = take(mat); L.w_k2t = take(mat); L.w_v2t = take(mat);
-  L.g_t = take(Hs * Qp * 2); L.hm_t = take(Hs * Qp * 2); L.dzm = take(Q * Hs * 2); L.dzm_t = take(Hs * Qp * 2);
-  L.o_t = take(kC * Qp * 2); L.d_o = take(Q * kC * 2); L.do_t = take(kC * Qp * 2); L.ctx_t = take(kC * Qp * 2); L.dctx = take(Q * kC * 2);
+  // scratch for the transposing wgrad fallback: only mlp.2's weight gradient with hidden % 256 != 0 ever takes it
+  const size_t fb = (H % 256 != 0) ? Hs * Qp * 2 : 0;
+  L.g_t = take(fb); L.hm_t = take(fb);
+  L.dzm = take(Q * Hs * 2);
+  L.d_o = take(Q * kC * 2); L.dctx = take(Q * kC * 2);
   L.dqp = take(Q * kC * 2); L.dkp = take(R * kC * 2); L.dvp = take(R * kC * 2);
-  L.dqp_t = take(kC * Qp * 2); L.dkp_t = take(kC * Rp * 2); L.dvp_t = take(kC * Rp * 2);
-  L.lnq_t = take(kC * Qp * 2); L.lnk_t = take(kC * Rp * 2); L.lnv_t = take(kC * Rp * 2);
+  L.lnq_t = take(Q * kC * 2); L.lnk_t = take(R * kC * 2); L.lnv_t = take(R * kC * 2);      // LayerNorm outputs (not transposed)
   L.dqh = take(Q * kC * 2); L.dkh = take(R * kC * 2); L.dvh = take(R * kC * 2);
   L.dyq = take(Q * kC * 2); L.dyk = take(R * kC * 2); L.dyv = take(R * kC * 2);
-  L.dyq_t = take(kC * Qp * 2); L.dyk_t = take(kC * Rp * 2); L.dyv_t = take(kC * Rp * 2);
-  L.q_t = take(kC * Qp * 2); L.hkv_t = take(2 * kC * Rp * 2);
-  L.dzkv = take(R * 2 * kC * 2); L.dzkv_t = take(2 * kC * Rp * 2); L.xm_t = take(static_cast<size_t>(kCm) * Rp * 2);
+  L.dzkv = take(R * 2 * kC * 2);
+  L.dzm_t = L.o_t = L.do_t = L.ctx_t = L.dqp_t = L.dkp_t = L.dvp_t = L.dyq_t = L.dyk_t = L.dyv_t = L.q_t = L.hkv_t = L.dzkv_t = L.xm_t = 0;   // unused (TN wgrad)
   L.ln_part = take(3ull * kLnBlocks * 2 * kC * 4);
   L.total = off;
   return L;
@@ -240,7 +241,7 @@ int tp_backward(const tp_weights* w, const void* xm, int64_t xm_crop_stride, int
   const SavedLayout S = saved_layout(n_crops, s, H);
   const BwdLayout B = bwd_layout(n_crops, s, H);
   if (workspace_bytes < B.total) return TP_ERR_WORKSPACE_TOO_SMALL;
-  const long long Rp = B.Rp, Qp = B.Qp;
+  const long long Rp = B.Rp;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const uint8_t* sv = static_cast<const uint8_t*>(saved);
   uint8_t* ws = static_cast<uint8_t*>(workspace);
@@ -266,35 +267,65 @@ int tp_backward(const tp_weights* w, const void* xm, int64_t xm_crop_stride, int
   TP_TRY(launch_transpose<0>(w->k_proj_2_w, kC, wb(B.w_k2t), kC, kC, kC, nullptr, nullptr, nullptr, stream));
   TP_TRY(launch_transpose<0>(w->v_proj_2_w, kC, wb(B.w_v2t), kC, kC, kC, nullptr, nullptr, nullptr, stream));
 
+  // wgrad  dW[n_out, n_in] = alpha * dY^T X  (dY: [rows, n_out], X: [rows, n_in], both as stored).  Normal case: the TN form of
+  // the pair kernel reads both operands in place (MN-major UMMA tiles).  Fallback for n_in not a multiple of 256 (tiny hidden
+  // sizes): explicit transposes into scratch + the NT kernel.
+  auto wgrad = [&](const void* dy, long long ld_dy, const void* x, long long ld_x, long long rows, int n_out, int n_in, void* dw,
+                   long long ld_dw, float alpha, size_t dy_t_off, size_t x_t_off, GemmItem* item) -> int {
+    if (n_in % 256 == 0) {
+      *item = GemmItem{AOperand{dy, ld_dy, 0, 0}, x, ld_x, n_out, n_in, rows, plain_epilogue(dw, ld_dw, nullptr, 0)};
+      item->ep.alpha = alpha;
+      item->tn = 1;
+      return TP_OK;
+    }
+    const long long ldt = static_cast<long long>(align_up(static_cast<size_t>(rows), 8));
+    TP_TRY(launch_transpose<0>(dy, ld_dy, wb(dy_t_off), ldt, rows, n_out, nullptr, nullptr, nullptr, stream));
+    TP_TRY(launch_transpose<0>(x, ld_x, wb(x_t_off), ldt, rows, n_in, nullptr, nullptr, nullptr, stream));
+    *item = plain_item(wb(dy_t_off), ldt, wb(x_t_off), ldt, dw, ld_dw, n_out, n_in, rows, nullptr, alpha);
+    return TP_OK;
+  };
+  // bias gradient = column sums of dY (deterministic two-stage reduction); ln_part doubles as the partial buffer
+  constexpr int kChunks = 64;
+  auto bias_grad = [&](const void* dy, long long ld_dy, long long rows, int cols, float scale, void* out) -> int {
+    float* partial = ln_part;     // [kChunks, cols] fp32, cols <= 4096... guarded below
+    if (static_cast<size_t>(kChunks) * cols * 4 > 3ull * kLnBlocks * 2 * kC * 4) return TP_ERR_INVALID_ARGUMENT;
+    colsum_partial_kernel<<<dim3((cols + 1023) / 1024, kChunks), 128, 0, stream>>>(static_cast<const __nv_bfloat16*>(dy), ld_dy, rows, cols,
+                                                                                   kChunks, partial);
+    TP_CUDA(cudaGetLastError());
+    colsum_reduce_kernel<<<(cols + 255) / 256, 256, 0, stream>>>(partial, kChunks, cols, scale, static_cast<__nv_bfloat16*>(out));
+    TP_CUDA(cudaGetLastError());
+    return TP_OK;
+  };
+  auto ln_apply = [&](const __nv_bfloat16* y, const float* stats, const void* gamma, const void* beta, __nv_bfloat16* out, long long rows) -> int {
+    ln_apply_kernel<<<static_cast<unsigned>((rows * 32 + 255) / 256), 256, 0, stream>>>(y, stats, static_cast<const __nv_bfloat16*>(gamma),
+                                                                                        static_cast<const __nv_bfloat16*>(beta), out, rows);
+    TP_CUDA(cudaGetLastError());
+    return TP_OK;
+  };
+
   // ---- mlp.2:  out = h_m W_m2^T + b
-  TP_TRY(launch_transpose<0>(grad_out, H, wb(B.g_t), Qp, Q, H, nullptr, nullptr, nullptr, stream));
-  TP_TRY(launch_transpose<0>(sb(S.h_m), H, wb(B.hm_t), Qp, Q, H, nullptr, nullptr, nullptr, stream));
-  TP_TRY(launch_rowsum(wb(B.g_t), Qp, Q, H, 1.0f, G(grads->mlp_2_b), stream));
+  TP_TRY(bias_grad(grad_out, H, Q, H, 1.0f, G(grads->mlp_2_b)));
   {
     GemmItem gi[2];
-    gi[0] = plain_item(wb(B.g_t), Qp, wb(B.hm_t), Qp, G(grads->mlp_2_w), H, H, H, Q);          // dW_m2 = G^T h_m
-    gi[1] = plain_item(grad_out, H, wb(B.w_m2t), H, wb(B.dzm), H, Q, H, H);                      // dh_m = G W_m2
+    TP_TRY(wgrad(grad_out, H, sb(S.h_m), H, Q, H, H, G(grads->mlp_2_w), H, 1.0f, B.g_t, B.hm_t, &gi[0]));      // dW_m2 = G^T h_m
+    gi[1] = plain_item(grad_out, H, wb(B.w_m2t), H, wb(B.dzm), H, Q, H, H);                                    // dh_m = G W_m2
     TP_TRY(launch_gemms(gi, 2, dev.sms, stream));
   }
-  TP_TRY(launch_gelu_bwd(wb(B.dzm), sb(S.z_m), static_cast<size_t>(Q) * H, stream));            // dz_m
+  TP_TRY(launch_gelu_bwd(wb(B.dzm), sb(S.z_m), static_cast<size_t>(Q) * H, stream));                          // dz_m
   // ---- mlp.0:  z_m = o W_m0^T + b
-  TP_TRY(launch_transpose<0>(wb(B.dzm), H, wb(B.dzm_t), Qp, Q, H, nullptr, nullptr, nullptr, stream));
-  TP_TRY(launch_transpose<0>(sb(S.o), kC, wb(B.o_t), Qp, Q, kC, nullptr, nullptr, nullptr, stream));
-  TP_TRY(launch_rowsum(wb(B.dzm_t), Qp, Q, H, 1.0f, G(grads->mlp_0_b), stream));
+  TP_TRY(bias_grad(wb(B.dzm), H, Q, H, 1.0f, G(grads->mlp_0_b)));
   {
     GemmItem gi[2];
-    gi[0] = plain_item(wb(B.dzm_t), Qp, wb(B.o_t), Qp, G(grads->mlp_0_w), kC, H, kC, Q);         // dW_m0 = dz_m^T o
-    gi[1] = plain_item(wb(B.dzm), H, wb(B.w_m0t), H, wb(B.d_o), kC, Q, kC, H);                   // do = dz_m W_m0
+    TP_TRY(wgrad(wb(B.dzm), H, sb(S.o), kC, Q, H, kC, G(grads->mlp_0_w), kC, 1.0f, B.dzm_t, B.o_t, &gi[0]));   // dW_m0 = dz_m^T o
+    gi[1] = plain_item(wb(B.dzm), H, wb(B.w_m0t), H, wb(B.d_o), kC, Q, kC, H);                                 // do = dz_m W_m0
     TP_TRY(launch_gemms(gi, 2, dev.sms, stream));
   }
   // ---- out_proj:  o = ctx W_o^T + b
-  TP_TRY(launch_transpose<0>(wb(B.d_o), kC, wb(B.do_t), Qp, Q, kC, nullptr, nullptr, nullptr, stream));
-  TP_TRY(launch_transpose<0>(sb(S.ctx), kC, wb(B.ctx_t), Qp, Q, kC, nullptr, nullptr, nullptr, stream));
-  TP_TRY(launch_rowsum(wb(B.do_t), Qp, Q, kC, 1.0f, G(grads->out_proj_b), stream));
+  TP_TRY(bias_grad(wb(B.d_o), kC, Q, kC, 1.0f, G(grads->out_proj_b)));
   {
     GemmItem gi[2];
-    gi[0] = plain_item(wb(B.do_t), Qp, wb(B.ctx_t), Qp, G(grads->out_proj_w), kC, kC, kC, Q);    // dW_o = do^T ctx
-    gi[1] = plain_item(wb(B.d_o), kC, wb(B.w_ot), kC, wb(B.dctx), kC, Q, kC, kC);                // dctx = do W_o
+    TP_TRY(wgrad(wb(B.d_o), kC, sb(S.ctx), kC, Q, kC, kC, G(grads->out_proj_w), kC, 1.0f, B.do_t, B.ctx_t, &gi[0]));   // dW_o = do^T ctx
+    gi[1] = plain_item(wb(B.d_o), kC, wb(B.w_ot), kC, wb(B.dctx), kC, Q, kC, kC);                               // dctx = do W_o
     TP_TRY(launch_gemms(gi, 2, dev.sms, stream));
   }
   // ---- window attention
@@ -307,20 +338,17 @@ int tp_backward(const tp_weights* w, const void* xm, int64_t xm_crop_stride, int
     TP_CUDA(cudaGetLastError());
   }
   // ---- MHA in-projections:  q' = alpha (LN(y_q) W_iq^T + b),  k' = LN(y_k) W_ik^T + b,  v' likewise
-  TP_TRY(launch_transpose<0>(wb(B.dqp), kC, wb(B.dqp_t), Qp, Q, kC, nullptr, nullptr, nullptr, stream));
-  TP_TRY(launch_transpose<0>(wb(B.dkp), kC, wb(B.dkp_t), Rp, R, kC, nullptr, nullptr, nullptr, stream));
-  TP_TRY(launch_transpose<0>(wb(B.dvp), kC, wb(B.dvp_t), Rp, R, kC, nullptr, nullptr, nullptr, stream));
-  TP_TRY(launch_transpose<2>(sb(S.y_q), kC, wb(B.lnq_t), Qp, Q, kC, stats_q, w->ln_q_w, w->ln_q_b, stream));
-  TP_TRY(launch_transpose<2>(sb(S.y_k), kC, wb(B.lnk_t), Rp, R, kC, stats_k, w->ln_k_w, w->ln_k_b, stream));
-  TP_TRY(launch_transpose<2>(sb(S.y_v), kC, wb(B.lnv_t), Rp, R, kC, stats_v, w->ln_v_w, w->ln_v_b, stream));
-  TP_TRY(launch_rowsum(wb(B.dqp_t), Qp, Q, kC, alpha_q, d_in_b, stream));
-  TP_TRY(launch_rowsum(wb(B.dkp_t), Rp, R, kC, 1.0f, d_in_b + kC, stream));
-  TP_TRY(launch_rowsum(wb(B.dvp_t), Rp, R, kC, 1.0f, d_in_b + 2 * kC, stream));
+  TP_TRY(ln_apply(sb(S.y_q), stats_q, w->ln_q_w, w->ln_q_b, wb(B.lnq_t), Q));      // LN outputs, [rows,1024] as stored (not transposed)
+  TP_TRY(ln_apply(sb(S.y_k), stats_k, w->ln_k_w, w->ln_k_b, wb(B.lnk_t), R));
+  TP_TRY(ln_apply(sb(S.y_v), stats_v, w->ln_v_w, w->ln_v_b, wb(B.lnv_t), R));
+  TP_TRY(bias_grad(wb(B.dqp), kC, Q, kC, alpha_q, d_in_b));
+  TP_TRY(bias_grad(wb(B.dkp), kC, R, kC, 1.0f, d_in_b + kC));
+  TP_TRY(bias_grad(wb(B.dvp), kC, R, kC, 1.0f, d_in_b + 2 * kC));
   {
     GemmItem gi[3];
-    gi[0] = plain_item(wb(B.dqp_t), Qp, wb(B.lnq_t), Qp, d_in_w, kC, kC, kC, Q, nullptr, alpha_q);
-    gi[1] = plain_item(wb(B.dkp_t), Rp, wb(B.lnk_t), Rp, d_in_w + static_cast<size_t>(kC) * kC, kC, kC, kC, R);
-    gi[2] = plain_item(wb(B.dvp_t), Rp, wb(B.lnv_t), Rp, d_in_w + 2 * static_cast<size_t>(kC) * kC, kC, kC, kC, R);
+    TP_TRY(wgrad(wb(B.dqp), kC, wb(B.lnq_t), kC, Q, kC, kC, d_in_w, kC, alpha_q, B.dqp_t, B.q_t, &gi[0]));
+    TP_TRY(wgrad(wb(B.dkp), kC, wb(B.lnk_t), kC, R, kC, kC, d_in_w + static_cast<size_t>(kC) * kC, kC, 1.0f, B.dkp_t, B.dyk_t, &gi[1]));
+    TP_TRY(wgrad(wb(B.dvp), kC, wb(B.lnv_t), kC, R, kC, kC, d_in_w + 2 * static_cast<size_t>(kC) * kC, kC, 1.0f, B.dvp_t, B.dyv_t, &gi[2]));
     TP_TRY(launch_gemms(gi, 3, dev.sms, stream));
     gi[0] = plain_item(wb(B.dqp), kC, wb(B.w_iqt), kC, wb(B.dqh), kC, Q, kC, kC, nullptr, alpha_q);   // d LN(y_q)
     gi[1] = plain_item(wb(B.dkp), kC, wb(B.w_ikt), kC, wb(B.dkh), kC, R, kC, kC);
@@ -334,18 +362,13 @@ int tp_backward(const tp_weights* w, const void* xm, int64_t xm_crop_stride, int
   TP_TRY(launch_ln_bwd(wb(B.dvh), sb(S.y_v), stats_v, w->ln_v_w, wb(B.dyv), ln_part + 4ll * kLnBlocks * kC, R, G(grads->ln_v_w),
                        G(grads->ln_v_b), stream));
   // ---- q_proj_1 (no bias), k_proj_1.2, v_proj_1.2
-  TP_TRY(launch_transpose<0>(wb(B.dyq), kC, wb(B.dyq_t), Qp, Q, kC, nullptr, nullptr, nullptr, stream));
-  TP_TRY(launch_transpose<0>(wb(B.dyk), kC, wb(B.dyk_t), Rp, R, kC, nullptr, nullptr, nullptr, stream));
-  TP_TRY(launch_transpose<0>(wb(B.dyv), kC, wb(B.dyv_t), Rp, R, kC, nullptr, nullptr, nullptr, stream));
-  TP_TRY(launch_transpose<0>(sb(S.q), kC, wb(B.q_t), Qp, Q, kC, nullptr, nullptr, nullptr, stream));
-  TP_TRY(launch_transpose<0>(sb(S.h_kv), 2 * kC, wb(B.hkv_t), Rp, R, 2 * kC, nullptr, nullptr, nullptr, stream));
-  TP_TRY(launch_rowsum(wb(B.dyk_t), Rp, R, kC, 1.0f, G(grads->k_proj_2_b), stream));
-  TP_TRY(launch_rowsum(wb(B.dyv_t), Rp, R, kC, 1.0f, G(grads->v_proj_2_b), stream));
+  TP_TRY(bias_grad(wb(B.dyk), kC, R, kC, 1.0f, G(grads->k_proj_2_b)));
+  TP_TRY(bias_grad(wb(B.dyv), kC, R, kC, 1.0f, G(grads->v_proj_2_b)));
   {
     GemmItem gi[3];
-    gi[0] = plain_item(wb(B.dyq_t), Qp, wb(B.q_t), Qp, G(grads->q_proj_w), kC, kC, kC, Q);
-    gi[1] = plain_item(wb(B.dyk_t), Rp, wb(B.hkv_t), Rp, G(grads->k_proj_2_w), kC, kC, kC, R);
-    gi[2] = plain_item(wb(B.dyv_t), Rp, wb(B.hkv_t) + static_cast<size_t>(kC) * Rp, Rp, G(grads->v_proj_2_w), kC, kC, kC, R);
+    TP_TRY(wgrad(wb(B.dyq), kC, sb(S.q), kC, Q, kC, kC, G(grads->q_proj_w), kC, 1.0f, B.dyq_t, B.q_t, &gi[0]));
+    TP_TRY(wgrad(wb(B.dyk), kC, sb(S.h_kv), 2 * kC, R, kC, kC, G(grads->k_proj_2_w), kC, 1.0f, B.dyk_t, B.hkv_t, &gi[1]));
+    TP_TRY(wgrad(wb(B.dyv), kC, sb(S.h_kv) + kC, 2 * kC, R, kC, kC, G(grads->v_proj_2_w), kC, 1.0f, B.dyv_t, B.hkv_t + static_cast<size_t>(kC) * Rp * 2, &gi[2]));
     TP_TRY(launch_gemms(gi, 3, dev.sms, stream));
     gi[0] = plain_item(wb(B.dyk), kC, wb(B.w_k2t), kC, wb(B.dzkv), 2 * kC, R, kC, kC);               // dh_k  -> dzkv[:, :1024]
     gi[1] = plain_item(wb(B.dyv), kC, wb(B.w_v2t), kC, wb(B.dzkv) + kC, 2 * kC, R, kC, kC);          // dh_v  -> dzkv[:, 1024:]
@@ -353,14 +376,12 @@ int tp_backward(const tp_weights* w, const void* xm, int64_t xm_crop_stride, int
   }
   TP_TRY(launch_gelu_bwd(wb(B.dzkv), sb(S.z_kv), static_cast<size_t>(R) * 2 * kC, stream));        // dz_kv
   // ---- k_proj_1.0 / v_proj_1.0:  z = xm W0^T + b   (no gradient to xm: the CLIP tower is frozen)
-  TP_TRY(launch_transpose<0>(wb(B.dzkv), 2 * kC, wb(B.dzkv_t), Rp, R, 2 * kC, nullptr, nullptr, nullptr, stream));
-  TP_TRY(launch_transpose<0>(xm, kCm, wb(B.xm_t), Rp, R, kCm, nullptr, nullptr, nullptr, stream));
-  TP_TRY(launch_rowsum(wb(B.dzkv_t), Rp, R, kC, 1.0f, G(grads->k_proj_0_b), stream));
-  TP_TRY(launch_rowsum(wb(B.dzkv_t) + static_cast<size_t>(kC) * Rp, Rp, R, kC, 1.0f, G(grads->v_proj_0_b), stream));
+  TP_TRY(bias_grad(wb(B.dzkv), 2 * kC, R, kC, 1.0f, G(grads->k_proj_0_b)));
+  TP_TRY(bias_grad(wb(B.dzkv) + kC, 2 * kC, R, kC, 1.0f, G(grads->v_proj_0_b)));
   {
     GemmItem gi[2];
-    gi[0] = plain_item(wb(B.dzkv_t), Rp, wb(B.xm_t), Rp, G(grads->k_proj_0_w), kCm, kC, kCm, R);
-    gi[1] = plain_item(wb(B.dzkv_t) + static_cast<size_t>(kC) * Rp, Rp, wb(B.xm_t), Rp, G(grads->v_proj_0_w), kCm, kC, kCm, R);
+    TP_TRY(wgrad(wb(B.dzkv), 2 * kC, xm, kCm, R, kC, kCm, G(grads->k_proj_0_w), kCm, 1.0f, B.dzkv_t, B.xm_t, &gi[0]));
+    TP_TRY(wgrad(wb(B.dzkv) + kC, 2 * kC, xm, kCm, R, kC, kCm, G(grads->v_proj_0_w), kCm, 1.0f, B.dzkv_t + static_cast<size_t>(kC) * Rp * 2, B.xm_t, &gi[1]));
     TP_TRY(launch_gemms(gi, 2, dev.sms, stream));
   }
   return TP_OK;
