@@ -104,6 +104,23 @@ def hd_plan(h_block, w_block, tokens_per_crop: int) -> HdPlan:
     return HdPlan(nc.value, seg, sep, ret, cu)
 
 
+_PLAN_CACHE: dict = {}
+
+
+def hd_plan_device(h_block, w_block, tokens_per_crop: int, device):
+    """hd_plan with its index tensors resident on ``device`` (cached per grid signature: serving loops reuse the same few
+    grids, and the three small synchronous H2D copies would otherwise sit on the critical path of every call)."""
+    key = (tuple(int(v) for v in h_block), tuple(int(v) for v in w_block), int(tokens_per_crop), str(device))
+    hit = _PLAN_CACHE.get(key)
+    if hit is None:
+        plan = hd_plan(h_block, w_block, tokens_per_crop)
+        hit = (plan, plan.seg_row_offset.to(device), plan.sep_rows.to(device), plan.ret_rows.to(device))
+        if len(_PLAN_CACHE) > 256:
+            _PLAN_CACHE.clear()
+        _PLAN_CACHE[key] = hit
+    return hit
+
+
 def hd_assemble(feats: torch.Tensor, h_block, w_block, sep_row: torch.Tensor, ret_row: torch.Tensor):
     """llava_arch.py:139-155 for already-projected crop features [sum(crops), M, H] (bf16, CUDA).
 
@@ -112,17 +129,15 @@ def hd_assemble(feats: torch.Tensor, h_block, w_block, sep_row: torch.Tensor, re
     if not feats.is_cuda:
         raise RuntimeError("tokenpacker_b200 has no CPU path: feats must be a CUDA tensor")
     m, hdim = int(feats.shape[1]), int(feats.shape[2])
-    plan = hd_plan(h_block, w_block, m)
+    device = feats.device
+    plan, seg, sep_rows, ret_rows = hd_plan_device(h_block, w_block, m, device)
     if plan.n_crops != feats.shape[0]:
         raise ValueError(f"grids describe {plan.n_crops} crops but {feats.shape[0]} were given")
-    device = feats.device
     fb = feats.to(torch.bfloat16).contiguous()
     with torch.cuda.device(device):
         out = torch.empty((int(plan.cu_seqlens[-1]), hdim), dtype=torch.bfloat16, device=device)
-        seg = plan.seg_row_offset.to(device)
         stream = torch.cuda.current_stream(device).cuda_stream
         check(lib.tp_hd_scatter_crops(fb.data_ptr(), plan.n_crops, m, hdim, seg.data_ptr(), out.data_ptr(), stream), "tp_hd_scatter_crops")
-        sep_rows, ret_rows = plan.sep_rows.to(device), plan.ret_rows.to(device)
         sep_b = sep_row.to(device=device, dtype=torch.bfloat16).contiguous()
         ret_b = ret_row.to(device=device, dtype=torch.bfloat16).contiguous()
         check(lib.tp_hd_fill_separators(out.data_ptr(), hdim, sep_rows.data_ptr(), sep_rows.numel(), sep_b.data_ptr(),

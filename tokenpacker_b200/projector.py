@@ -262,10 +262,10 @@ class TokenPackerB200(nn.Module):
         per-image grids; sep_row / ret_row: the ',' and '\\n' embedding rows [hidden].  The last GEMM's epilogue writes
         every crop's tokens straight to its place in the packed sequence; separator rows are filled by a tiny kernel.
         Returns (packed [sum(L_i), hidden], cu_seqlens int64 [B+1] on the host)."""
-        from .hd import hd_plan
+        from .hd import hd_plan_device
         x0, xm = self._check_inputs(x, None)
         device = x0.device
-        plan = hd_plan(h_block, w_block, self.num_queries)
+        plan, seg, sep_rows, ret_rows = hd_plan_device(h_block, w_block, self.num_queries, device)
         if plan.n_crops != x0.shape[0]:
             raise ValueError(f"grids describe {plan.n_crops} crops but {x0.shape[0]} were given")
         with torch.cuda.device(device):
@@ -273,10 +273,7 @@ class TokenPackerB200(nn.Module):
             xmb, sm = self._as_crop_strided(xm.to(torch.bfloat16), 4096)
             total = int(plan.cu_seqlens[-1])
             out = torch.empty((total, self.hidden_size), dtype=torch.bfloat16, device=device)
-            seg = plan.seg_row_offset.to(device, non_blocking=True)
             self._launch(x0b, s0, xmb, sm, out, seg)
-            sep_rows = plan.sep_rows.to(device, non_blocking=True)
-            ret_rows = plan.ret_rows.to(device, non_blocking=True)
             sep_b = sep_row.to(device=device, dtype=torch.bfloat16).contiguous()
             ret_b = ret_row.to(device=device, dtype=torch.bfloat16).contiguous()
             stream = torch.cuda.current_stream(device).cuda_stream
