@@ -91,3 +91,29 @@ def test_synthetic_generators_agree_with_oracle_copy():
     for s in (2, 3, 4):
         assert syn.flops_per_crop(s) == tpo.flops_per_crop(s) and syn.bytes_per_crop(s) == tpo.bytes_per_crop(s)
     assert syn.weight_bytes(4096) == 2 * 36_722_688
+
+
+def test_argument_errors_are_status_codes_not_crashes():
+    """Invalid calls come back as integer statuses before any CUDA work (safe to exercise without a GPU)."""
+    import ctypes as C
+    from tokenpacker_b200 import _lib
+    lib = _lib.lib
+    # 24 % 5 != 0 -> the reference's ValueError condition (builder.py:51-52)
+    assert lib.tp_forward(None, None, None, 1, 576 * 1024, 576 * 4096, 5, 4096, None, None, None, 0, None) == _lib.TP_ERR_BAD_SCALE_FACTOR
+    # supported window sizes only
+    assert lib.tp_forward(None, None, None, 1, 576 * 1024, 576 * 4096, 6, 4096, None, None, None, 0, None) == _lib.TP_ERR_INVALID_ARGUMENT
+    # null pointers
+    assert lib.tp_forward(None, None, None, 1, 576 * 1024, 576 * 4096, 2, 4096, None, None, None, 0, None) == _lib.TP_ERR_INVALID_ARGUMENT
+    assert lib.tp_pack_weights(None, 4096, None, 0, None) == _lib.TP_ERR_INVALID_ARGUMENT
+    hb, wb = C.c_int(0), C.c_int(0)
+    assert lib.tp_hd_grid(100, 100, 7, 336, C.byref(hb), C.byref(wb)) == _lib.TP_ERR_BAD_PATCH_NUM
+    assert lib.tp_hd_grid(0, 100, 9, 336, C.byref(hb), C.byref(wb)) == _lib.TP_ERR_INVALID_ARGUMENT
+    assert lib.tp_hd_grid(1088, 1088, 9, 336, C.byref(hb), C.byref(wb)) == 0 and (hb.value, wb.value) == (3, 3)
+    assert lib.tp_train_saved_bytes(64, 2, 4096) > 0 and lib.tp_backward_workspace_bytes(64, 2, 4096) > 0
+    assert lib.tp_train_saved_bytes(64, 5, 4096) == 0
+    with pytest.raises(ValueError, match="scale_factor must be divisible by grid size"):
+        _lib.check(_lib.TP_ERR_BAD_SCALE_FACTOR, "x")
+    with pytest.raises(NotImplementedError):
+        _lib.check(_lib.TP_ERR_BAD_PATCH_NUM, "x")
+    with pytest.raises(_lib.TokenPackerError, match="workspace too small"):
+        _lib.check(_lib.TP_ERR_WORKSPACE_TOO_SMALL, "x")

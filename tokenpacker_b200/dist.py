@@ -74,33 +74,39 @@ class ShardedTokenPacker:
 class FusedGatherTokenPacker:
     """Projector whose last GEMM stores straight into every rank's gathered buffer over NVLink (TMA stores to peer-mapped
     memory from ``torch.distributed._symmetric_memory``): compute and the all-gather are ONE kernel, transfers overlap the
-    remaining tiles' math.  CUDA + NCCL-capable ranks of one NVLink domain only."""
+    remaining tiles' math.  CUDA + NCCL-capable ranks of one NVLink domain only.
+
+    Two gathered buffers alternate between calls, so ONE cross-rank barrier per call is enough: the barrier of call i+1 (which
+    every rank reaches only after its stream has consumed call i's buffer) is what licenses call i+2 to overwrite that buffer."""
 
     def __init__(self, projector, group=None):
         self.projector = projector
         self.group = group if group is not None else dist.group.WORLD
-        self._buf = None
-        self._hdl = None
+        self._bufs = None
         self._shape = None
+        self._calls = 0
 
-    def _gathered_buffer(self, total_crops: int, device):
+    def _gathered_buffers(self, total_crops: int, device):
         import torch.distributed._symmetric_memory as symm_mem
         shape = (total_crops, self.projector.num_queries, self.projector.hidden_size)
-        if self._buf is None or self._shape != shape:
-            self._buf = symm_mem.empty(shape, dtype=torch.bfloat16, device=device)
-            self._hdl = symm_mem.rendezvous(self._buf, self.group)
-            self._shape = shape
-        return self._buf, self._hdl
+        if self._bufs is None or self._shape != shape:
+            bufs = []
+            for _ in range(2):
+                t = symm_mem.empty(shape, dtype=torch.bfloat16, device=device)
+                bufs.append((t, symm_mem.rendezvous(t, self.group)))
+            bufs[0][1].barrier(channel=0)        # nobody starts writing before everybody has mapped the buffers
+            self._bufs, self._shape, self._calls = bufs, shape, 0
+        return self._bufs
 
     def forward_gathered(self, x_local, counts: Sequence[int]):
-        """Returns the gathered [sum(counts), M, H] crop blocks (a view of the symmetric buffer: consume before the next call)."""
+        """Returns the gathered [sum(counts), M, H] crop blocks — a view of a symmetric buffer that stays valid until the call
+        after next."""
         rank = dist.get_rank(self.group)
         device = x_local[0].device
-        buf, hdl = self._gathered_buffer(int(sum(counts)), device)
-        crop_offset = int(sum(counts[:rank]))
-        hdl.barrier(channel=0)          # every rank has finished reading the previous call's gathered buffer
-        self.projector.forward_into_peers(x_local, list(hdl.buffer_ptrs), crop_offset)
-        hdl.barrier(channel=1)          # every rank's stores have landed everywhere
+        buf, hdl = self._gathered_buffers(int(sum(counts)), device)[self._calls % 2]
+        self._calls += 1
+        self.projector.forward_into_peers(x_local, list(hdl.buffer_ptrs), int(sum(counts[:rank])))
+        hdl.barrier(channel=0)          # every rank's stores have landed everywhere
         return buf
 
     def forward_hd(self, x_local, counts: Sequence[int], h_block, w_block, sep_row, ret_row):

@@ -48,6 +48,24 @@ for name, n, s in [("configs[1] N=64 s=2", 64, 2), ("configs[2] N=128 s=2", 128,
     print(rows[-1], flush=True)
     del m, x0, xm
 
+# serving latency with the forward captured in a CUDA graph (removes Python / launch overhead)
+for n in (1, 10):
+    m = module(2)
+    sx0 = torch.randn(n, 576, 1024, device="cuda").bfloat16()
+    sxm = torch.randn(n, 576, 4096, device="cuda").bfloat16()
+    with torch.no_grad():
+        m((sx0, sxm))
+        torch.cuda.synchronize()
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr):
+            so = m((sx0, sxm))
+    ms = timed(lambda: gr.replay(), warm=10, iters=100)
+    ms_eager = timed(lambda: m((sx0, sxm)), warm=10, iters=100)
+    rows.append({"config": f"latency N={n} s=2, CUDA graph replay", "ms": round(ms, 4), "ms_eager_python": round(ms_eager, 4),
+                 "tokens_per_s": round(n * 144 / ms * 1e3)})
+    print(rows[-1], flush=True)
+    del m, gr
+
 # configs[3]: HD patch_num=9, s=2, 32 images with seeded sizes -> grids via the grid selector, packed output
 g = torch.Generator().manual_seed(0)
 hs = torch.randint(224, 1345, (32,), generator=g).tolist()

@@ -1,0 +1,27 @@
+"""Small end-to-end exercise of every kernel for compute-sanitizer (memcheck / racecheck / synccheck):
+    compute-sanitizer --tool memcheck python tools/sanitize_small.py"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+from tokenpacker_b200 import TokenPackerB200, hd_tile  # noqa: E402
+from tokenpacker_b200.kernels import gemm_bf16, gemm_tn_bf16  # noqa: E402
+
+torch.manual_seed(0)
+a = torch.randn(300, 200, device="cuda").bfloat16()
+b = torch.randn(512, 200, device="cuda").bfloat16()
+gemm_bf16(a, b, bias=torch.randn(512, device="cuda"), gelu=True)
+gemm_tn_bf16(torch.randn(200, 304, device="cuda").bfloat16(), torch.randn(200, 256, device="cuda").bfloat16())
+for s, hidden in ((2, 256), (3, 128)):
+    m = TokenPackerB200(hidden_size=hidden, scale_factor=s).to("cuda", torch.bfloat16)
+    x0 = torch.randn(2, 577, 1024, device="cuda").bfloat16()[:, 1:]
+    xm = torch.randn(2, 577, 4096, device="cuda").bfloat16()[:, 1:]
+    with torch.no_grad():
+        out = m((x0, xm))
+        packed, cu = m.forward_packed((x0, xm), [1, 1], [1, 1], torch.randn(hidden, device="cuda"), torch.randn(hidden, device="cuda"))
+    tr = m((x0, xm))
+    tr.float().pow(2).mean().backward()
+crops, hb, wb = hd_tile(torch.randn(1, 3, 500, 700, device="cuda"), 9)
+torch.cuda.synchronize()
+print("sanitize run complete", out.shape, packed.shape, crops.shape)
