@@ -41,8 +41,9 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clock / throttle sampling during the timed region (B200_PROFILING.md recipe)."""
-    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+    """nvidia-smi clock / throttle sampling during the timed region (B200_PROFILING.md recipe).  Samples carry nvidia-smi's own
+    timestamps (its stdout is block-buffered when piped, so arrival time means nothing) and are filtered to the timed window."""
+    Q = "timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, gpu_index: int):
@@ -61,33 +62,49 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append((time.perf_counter(), line.strip()))
+            self.rows.append(line.strip())
+
+    @staticmethod
+    def _epoch(ts: str):
+        import datetime
+        try:
+            return datetime.datetime.strptime(ts.strip(), "%Y/%m/%d %H:%M:%S.%f").timestamp()
+        except ValueError:
+            return None
 
     def stop(self, t0=None, t1=None):
+        """t0 / t1: time.time() bounds of the timed region."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        rows = [r for t, r in self.rows if (t0 is None or t >= t0) and (t1 is None or t <= t1)] or [r for _, r in self.rows]
-        sm, mx, pw, reasons = [], [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in rows:
+        if self.thread is not None:
+            self.thread.join(timeout=2)
+        parsed = []
+        for r in self.rows:
             f = [v.strip() for v in r.split(",")]
-            if len(f) < 7:
+            if len(f) < 8:
                 continue
             try:
-                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+                parsed.append((self._epoch(f[0]), float(f[1]), float(f[2]), float(f[3]), f[4:8]))
             except ValueError:
                 continue
-            for name, v in zip(names, f[3:7]):
+        inside = [p for p in parsed if p[0] is not None and t0 is not None and t1 is not None and t0 <= p[0] <= t1]
+        use = inside if len(inside) >= 3 else parsed
+        if not use:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = set()
+        for p in use:
+            for name, v in zip(names, p[4]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)), "samples": len(sm),
+        return {"sm_mhz": float(np.median([p[1] for p in use])), "sm_max_mhz": float(max(p[2] for p in use)),
+                "power_w_max": float(max(p[3] for p in use)), "samples": len(use), "in_timed_region": len(inside) >= 3,
                 "reasons": sorted(reasons)}
 
 
@@ -273,13 +290,13 @@ def main():
             time.sleep(0.3)
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        t_wall0 = time.perf_counter()
+        t_wall0 = time.time()
         e0.record()
         for _ in range(args.steps):
             out = model((x0, xm))
         e1.record()
         barrier()
-        t_wall1 = time.perf_counter()
+        t_wall1 = time.time()
         elapsed_ms = e0.elapsed_time(e1)
     if dist is not None:
         t = torch.tensor([elapsed_ms], device=dev)
