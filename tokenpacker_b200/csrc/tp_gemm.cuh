@@ -110,6 +110,7 @@ struct OutStage {
   const CUtensorMap* tmap;   // C tensor map(s), box = 64 cols x 128 rows, SWIZZLE_128B
   int n_maps;                // 1, or the number of peer maps (consecutive CUtensorMaps starting at tmap)
   int row_tile0;             // first global row of this CTA's 128-row tile
+  int n_bufs;                // 2: slabs alternate buffers (one barrier per slab); 1: single buffer (two barriers per slab)
   uint32_t barrier_id;       // named barrier shared by the 4 warps (128 threads) of this half
   bool issuer;               // this thread issues (and tracks) the half's TMA stores
 };
@@ -156,6 +157,11 @@ __device__ __forceinline__ void epilogue_tile(const GemmEpilogue& ep, int M, int
     if (chunk + 1 < kChunks) tmem_ld_32x32b_x32(taddr + static_cast<uint32_t>((chunk + 1) * 32), r[(chunk + 1) & 1]);
     else release();                                   // every TMEM read of this warp has landed in registers
     const int col0 = col_tile0 + half * kColsPerWarp + chunk * 32;
+    if (out.buf != nullptr && out.n_bufs == 1 && (chunk & 1) == 0) {
+      // single staging buffer: the previous slab's TMA store must have finished READING it before anyone overwrites it
+      if (out.issuer) bulk_wait_group_read<0>();
+      named_bar_sync(out.barrier_id, 128);
+    }
     if (col0 < N) {        // N is a multiple of 32 (checked on the host) -> whole chunk in or out
 #pragma unroll
       for (int g8 = 0; g8 < 4; ++g8) {     // 8 columns = one 16-byte store
@@ -193,7 +199,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmEpilogue& ep, int M, int
           // slab = 2 chunks; 16-byte chunk index inside the 128-byte row, XOR-swizzled with (row & 7) like TMA's SWIZZLE_128B
           const int rloc = quarter * 32 + static_cast<int>(lane_id());
           const int ci = (chunk & 1) * 4 + g8;
-          uint8_t* dst = out.buf + ((chunk >> 1) & 1) * kOutSlabBytes + rloc * 128 + ((ci ^ (rloc & 7)) << 4);
+          uint8_t* dst = out.buf + ((chunk >> 1) & (out.n_bufs - 1)) * kOutSlabBytes + rloc * 128 + ((ci ^ (rloc & 7)) << 4);
           *reinterpret_cast<uint4*>(dst) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
         } else if (row_ok) {
           *reinterpret_cast<uint4*>(c_row + col0 + g8 * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
@@ -204,12 +210,13 @@ __device__ __forceinline__ void epilogue_tile(const GemmEpilogue& ep, int M, int
       // slab complete: publish to the async proxy, make sure the previous store of this half has drained its buffer
       // (so the NEXT slab may overwrite it), then one thread issues the TMA store
       fence_proxy_async_smem();
-      if (out.issuer) bulk_wait_group_read<0>();
+      if (out.issuer && out.n_bufs == 2) bulk_wait_group_read<0>();
       named_bar_sync(out.barrier_id, 128);
       if (out.issuer) {
         const int slab = chunk >> 1;
         for (int p = 0; p < out.n_maps; ++p)
-          tma_store_2d(out.tmap + p, out.buf + (slab & 1) * kOutSlabBytes, col_tile0 + half * kColsPerWarp + slab * 64, out.row_tile0);
+          tma_store_2d(out.tmap + p, out.buf + (slab & (out.n_bufs - 1)) * kOutSlabBytes, col_tile0 + half * kColsPerWarp + slab * 64,
+                       out.row_tile0);
         bulk_commit_group();
       }
     }
@@ -374,7 +381,7 @@ tp_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tcgen05_fence_after();
       uint64_t* release_bar = &tmem_empty_bar[acc];
-      const OutStage no_stage{nullptr, nullptr, 0, 0, 0, false};
+      const OutStage no_stage{nullptr, nullptr, 0, 0, 0, 0, false};
       epilogue_tile<kBlockN>(ep, M, N, tmem_base + static_cast<uint32_t>(acc * kBlockN),
                              m_blk * kBlockM + quarter * 32 + static_cast<int>(lane), n_blk * kBlockN, quarter, half, s_col, no_stage, [&]() {
                                tcgen05_fence_before();
@@ -402,12 +409,16 @@ tp_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 struct Gemm2Config {
   static constexpr int kTileM = 256;
   static constexpr int kTileN = 256;
-  static constexpr int kStages = 4;
+#ifndef TP_PAIR_STAGES
+#define TP_PAIR_STAGES 4
+#endif
+  static constexpr int kStages = TP_PAIR_STAGES;                 // 4: double-buffered output slabs; 5: single-buffered (smem budget)
+  static constexpr int kOutBufs = (kStages <= 4) ? 2 : 1;
   static constexpr int kABytes = kBlockM * kBlockK * 2;          // this CTA's 128 rows of A
   static constexpr int kBBytes = (kTileN / 2) * kBlockK * 2;     // this CTA's half of the B tile
   static constexpr int kStageBytes = kABytes + kBBytes;          // 32 KiB
   static constexpr int kTmemCols = 2 * kTileN;
-  static constexpr int kOutBytes = 2 * 2 * kOutSlabBytes;        // [2 column halves][2 buffers] output slabs for TMA stores
+  static constexpr int kOutBytes = 2 * kOutBufs * kOutSlabBytes; // [2 column halves][kOutBufs] output slabs for TMA stores
   static constexpr int kColStageBytes = 2 * 2 * kTileN * 4;
   static constexpr int kBarrierBytes = (2 * kStages + 4) * 8 + 16;
   static constexpr int kSmemBytes = kStages * kStageBytes + kOutBytes + kColStageBytes + kBarrierBytes + 1024;
@@ -648,8 +659,9 @@ tp_gemm2_kernel(const __grid_constant__ GemmGroup grp, const __grid_constant__ P
       uint64_t* release_bar = &tmem_empty_bar[acc];
       const int row_tile0 = t.m_blk * Cfg::kTileM + static_cast<int>(cta_rank) * kBlockM;
       const int row = row_tile0 + quarter * 32 + static_cast<int>(lane);
-      const OutStage out{pr.use_tma_store ? s_out + half * 2 * kOutSlabBytes : nullptr, peers.count > 0 ? &peers.m[0] : &pr.tmap_c,
-                         peers.count > 0 ? peers.count : 1, row_tile0, static_cast<uint32_t>(2 + half), quarter == 0 && lane == 0};
+      const OutStage out{pr.use_tma_store ? s_out + half * Cfg::kOutBufs * kOutSlabBytes : nullptr, peers.count > 0 ? &peers.m[0] : &pr.tmap_c,
+                         peers.count > 0 ? peers.count : 1, row_tile0, Cfg::kOutBufs, static_cast<uint32_t>(2 + half),
+                         quarter == 0 && lane == 0};
       stored = stored || pr.use_tma_store;
       epilogue_tile<kTileN>(pr.ep, pr.M, pr.N, tmem_base + static_cast<uint32_t>(acc * kTileN), row, t.n_blk * kTileN, quarter, half, s_col,
                             out, [&]() {
