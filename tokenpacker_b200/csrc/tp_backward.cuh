@@ -1,7 +1,8 @@
-// Kernels of the projector's backward pass that are not GEMMs: transposes (wgrad operands), GELU forward/backward as
-// elementwise passes, LayerNorm backward, window-attention backward, row sums (bias gradients).  All HBM-bound.
-// The GEMMs of the backward (dgrad = dY . W, wgrad = dY^T . X) run on the same tcgen05 kernels as the forward: dgrad takes a
-// transposed copy of the weight as its K-major B operand, wgrad takes transposed activations (contraction over rows).
+// Kernels of the projector's backward pass that are not GEMMs: GELU forward/backward as elementwise passes, LayerNorm apply /
+// backward, window-attention backward, deterministic column sums (bias gradients), and a plain transpose (weights for the
+// dgrad GEMMs; activations only in the small-hidden wgrad fallback).  All HBM-bound, 16-byte vector accesses.
+// The GEMMs of the backward run on the forward's tcgen05 kernels: dgrad (dX = dY . W) takes a transposed copy of the weight as
+// its K-major B operand; wgrad (dW = dY^T . X) uses the TN form, reading both activations in place as MN-major tiles.
 #pragma once
 
 #include "tp_kernels.cuh"
@@ -42,43 +43,23 @@ __device__ __forceinline__ float gelu_grad(float z) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// Transpose  out[c, r] = f(in[r, c])   (bf16; in: [rows, cols] row stride ld_in; out: [cols, rows] row stride ld_out)
-//   kMode 0: identity   1: GELU(in)   2: LayerNorm-apply ((in - mu_r) rstd_r gamma_c + beta_c), stats = per-row partial sums
+// Transpose  out[c, r] = in[r, c]   (bf16; in: [rows, cols] row stride ld_in; out: [cols, rows] row stride ld_out)
 // ------------------------------------------------------------------------------------------------
-template <int kMode>
 __global__ void transpose_kernel(const __nv_bfloat16* __restrict__ in, long long ld_in, __nv_bfloat16* __restrict__ out, long long ld_out,
-                                 long long rows, int cols, const float* __restrict__ stats, const __nv_bfloat16* __restrict__ gamma,
-                                 const __nv_bfloat16* __restrict__ beta) {
-  __shared__ float tile[32][33];
-  __shared__ float s_mu[32], s_rstd[32];
+                                 long long rows, int cols) {
+  __shared__ __nv_bfloat16 tile[32][34];
   const long long r0 = static_cast<long long>(blockIdx.y) * 32;
   const int c0 = blockIdx.x * 32;
-  if (kMode == 2) {
-    if (threadIdx.y == 0) {
-      const long long r = r0 + threadIdx.x;
-      float mu = 0.f, rstd = 0.f;
-      if (r < rows) row_mean_rstd(stats, r, mu, rstd);
-      s_mu[threadIdx.x] = mu;
-      s_rstd[threadIdx.x] = rstd;
-    }
-    __syncthreads();
-  }
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
     const long long r = r0 + i;
     const int c = c0 + threadIdx.x;
-    float v = 0.f;
-    if (r < rows && c < cols) {
-      v = __bfloat162float(in[r * ld_in + c]);
-      if (kMode == 1) v = gelu_erf(v);
-      if (kMode == 2) v = fmaf((v - s_mu[i]) * s_rstd[i], __bfloat162float(gamma[c]), __bfloat162float(beta[c]));
-    }
-    tile[i][threadIdx.x] = v;
+    tile[i][threadIdx.x] = (r < rows && c < cols) ? in[r * ld_in + c] : __float2bfloat16_rn(0.f);
   }
   __syncthreads();
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
     const int c = c0 + i;
     const long long r = r0 + threadIdx.x;
-    if (c < cols && r < rows) out[static_cast<long long>(c) * ld_out + r] = __float2bfloat16_rn(tile[threadIdx.x][i]);
+    if (c < cols && r < rows) out[static_cast<long long>(c) * ld_out + r] = tile[threadIdx.x][i];
   }
 }
 
@@ -151,27 +132,6 @@ __global__ void colsum_reduce_kernel(const float* __restrict__ partial, int n_ch
   float a = 0.f;
   for (int i = 0; i < n_chunks; ++i) a += partial[static_cast<long long>(i) * cols + c];
   out[c] = __float2bfloat16_rn(a * scale);
-}
-
-// out[i] (fp32 -> bf16) = scale * sum_j in[i, j], j < n; one warp per row (bias gradients from transposed dY)
-__global__ void rowsum_kernel(const __nv_bfloat16* __restrict__ in, long long ld, long long n, int rows, float scale,
-                              __nv_bfloat16* __restrict__ out) {
-  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (row >= rows) return;
-  const __nv_bfloat16* p = in + static_cast<long long>(row) * ld;
-  float acc = 0.f;
-  const long long n8 = n / 8;
-  for (long long i = lane; i < n8; i += 32) {
-    float f[8];
-    unpack8(__ldg(reinterpret_cast<const uint4*>(p) + i), f);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc += f[j];
-  }
-  for (long long i = n8 * 8 + lane; i < n; i += 32) acc += __bfloat162float(p[i]);
-#pragma unroll
-  for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-  if (lane == 0) out[row] = __float2bfloat16_rn(acc * scale);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -49,11 +49,13 @@ struct BwdLayout {
   size_t dqh, dkh, dvh, dyq, dyk, dyv, dyq_t, dyk_t, dyv_t, q_t, hkv_t;
   size_t dzkv, dzkv_t, xm_t;
   size_t ln_part;        // f32 [3][kLnBlocks][2][1024]
+  size_t col_part;       // f32 [kColChunks][max(H, 2048)]  column-sum partials (bias gradients)
   size_t total;
   long long Rp, Qp;
 };
 
 constexpr int kLnBlocks = 296;
+constexpr int kColChunks = 592;     // 4 CTAs per SM: each sums ~rows/592 rows of 1024 columns
 
 BwdLayout bwd_layout(long long n_crops, int s, int H) {
   const size_t R = static_cast<size_t>(n_crops) * kTokens;
@@ -80,24 +82,15 @@ BwdLayout bwd_layout(long long n_crops, int s, int H) {
   L.dzkv = take(R * 2 * kC * 2);
   L.dzm_t = L.o_t = L.do_t = L.ctx_t = L.dqp_t = L.dkp_t = L.dvp_t = L.dyq_t = L.dyk_t = L.dyv_t = L.q_t = L.hkv_t = L.dzkv_t = L.xm_t = 0;   // unused (TN wgrad)
   L.ln_part = take(3ull * kLnBlocks * 2 * kC * 4);
+  L.col_part = take(static_cast<size_t>(kColChunks) * (Hs > 2048 ? Hs : 2048) * 4);
   L.total = off;
   return L;
 }
 
-template <int kMode>
-int launch_transpose(const void* in, long long ld_in, void* out, long long ld_out, long long rows, int cols, const float* stats,
-                     const void* gamma, const void* beta, cudaStream_t stream) {
+int launch_transpose(const void* in, long long ld_in, void* out, long long ld_out, long long rows, int cols, cudaStream_t stream) {
   const dim3 grid(static_cast<unsigned>((cols + 31) / 32), static_cast<unsigned>((rows + 31) / 32));
-  transpose_kernel<kMode><<<grid, dim3(32, 8), 0, stream>>>(static_cast<const __nv_bfloat16*>(in), ld_in, static_cast<__nv_bfloat16*>(out), ld_out,
-                                                             rows, cols, stats, static_cast<const __nv_bfloat16*>(gamma),
-                                                             static_cast<const __nv_bfloat16*>(beta));
-  TP_CUDA(cudaGetLastError());
-  return TP_OK;
-}
-
-int launch_rowsum(const void* in, long long ld, long long n, int rows, float scale, void* out, cudaStream_t stream) {
-  rowsum_kernel<<<(rows * 32 + 255) / 256, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(in), ld, n, rows, scale,
-                                                             static_cast<__nv_bfloat16*>(out));
+  transpose_kernel<<<grid, dim3(32, 8), 0, stream>>>(static_cast<const __nv_bfloat16*>(in), ld_in, static_cast<__nv_bfloat16*>(out), ld_out, rows,
+                                                      cols);
   TP_CUDA(cudaGetLastError());
   return TP_OK;
 }
@@ -258,14 +251,14 @@ int tp_backward(const tp_weights* w, const void* xm, int64_t xm_crop_stride, int
   const float alpha_q = 0.08838834764831845f;
 
   // transposed weights: B operands of the dgrad GEMMs (dX = dY . W  ==  dY . (W^T)^T in the kernel's A.B^T form)
-  TP_TRY(launch_transpose<0>(w->mlp_2_w, H, wb(B.w_m2t), H, H, H, nullptr, nullptr, nullptr, stream));
-  TP_TRY(launch_transpose<0>(w->mlp_0_w, kC, wb(B.w_m0t), H, H, kC, nullptr, nullptr, nullptr, stream));
-  TP_TRY(launch_transpose<0>(w->out_proj_w, kC, wb(B.w_ot), kC, kC, kC, nullptr, nullptr, nullptr, stream));
-  TP_TRY(launch_transpose<0>(in_w, kC, wb(B.w_iqt), kC, kC, kC, nullptr, nullptr, nullptr, stream));
-  TP_TRY(launch_transpose<0>(in_w + static_cast<size_t>(kC) * kC, kC, wb(B.w_ikt), kC, kC, kC, nullptr, nullptr, nullptr, stream));
-  TP_TRY(launch_transpose<0>(in_w + 2 * static_cast<size_t>(kC) * kC, kC, wb(B.w_ivt), kC, kC, kC, nullptr, nullptr, nullptr, stream));
-  TP_TRY(launch_transpose<0>(w->k_proj_2_w, kC, wb(B.w_k2t), kC, kC, kC, nullptr, nullptr, nullptr, stream));
-  TP_TRY(launch_transpose<0>(w->v_proj_2_w, kC, wb(B.w_v2t), kC, kC, kC, nullptr, nullptr, nullptr, stream));
+  TP_TRY(launch_transpose(w->mlp_2_w, H, wb(B.w_m2t), H, H, H, stream));
+  TP_TRY(launch_transpose(w->mlp_0_w, kC, wb(B.w_m0t), H, H, kC, stream));
+  TP_TRY(launch_transpose(w->out_proj_w, kC, wb(B.w_ot), kC, kC, kC, stream));
+  TP_TRY(launch_transpose(in_w, kC, wb(B.w_iqt), kC, kC, kC, stream));
+  TP_TRY(launch_transpose(in_w + static_cast<size_t>(kC) * kC, kC, wb(B.w_ikt), kC, kC, kC, stream));
+  TP_TRY(launch_transpose(in_w + 2 * static_cast<size_t>(kC) * kC, kC, wb(B.w_ivt), kC, kC, kC, stream));
+  TP_TRY(launch_transpose(w->k_proj_2_w, kC, wb(B.w_k2t), kC, kC, kC, stream));
+  TP_TRY(launch_transpose(w->v_proj_2_w, kC, wb(B.w_v2t), kC, kC, kC, stream));
 
   // wgrad  dW[n_out, n_in] = alpha * dY^T X  (dY: [rows, n_out], X: [rows, n_in], both as stored).  Normal case: the TN form of
   // the pair kernel reads both operands in place (MN-major UMMA tiles).  Fallback for n_in not a multiple of 256 (tiny hidden
@@ -279,20 +272,20 @@ int tp_backward(const tp_weights* w, const void* xm, int64_t xm_crop_stride, int
       return TP_OK;
     }
     const long long ldt = static_cast<long long>(align_up(static_cast<size_t>(rows), 8));
-    TP_TRY(launch_transpose<0>(dy, ld_dy, wb(dy_t_off), ldt, rows, n_out, nullptr, nullptr, nullptr, stream));
-    TP_TRY(launch_transpose<0>(x, ld_x, wb(x_t_off), ldt, rows, n_in, nullptr, nullptr, nullptr, stream));
+    TP_TRY(launch_transpose(dy, ld_dy, wb(dy_t_off), ldt, rows, n_out, stream));
+    TP_TRY(launch_transpose(x, ld_x, wb(x_t_off), ldt, rows, n_in, stream));
     *item = plain_item(wb(dy_t_off), ldt, wb(x_t_off), ldt, dw, ld_dw, n_out, n_in, rows, nullptr, alpha);
     return TP_OK;
   };
-  // bias gradient = column sums of dY (deterministic two-stage reduction); ln_part doubles as the partial buffer
-  constexpr int kChunks = 64;
+  // bias gradient = column sums of dY (deterministic two-stage reduction: kColChunks row chunks, then a fixed-order sum)
+  float* col_part = reinterpret_cast<float*>(ws + B.col_part);
   auto bias_grad = [&](const void* dy, long long ld_dy, long long rows, int cols, float scale, void* out) -> int {
-    float* partial = ln_part;     // [kChunks, cols] fp32, cols <= 4096... guarded below
-    if (static_cast<size_t>(kChunks) * cols * 4 > 3ull * kLnBlocks * 2 * kC * 4) return TP_ERR_INVALID_ARGUMENT;
-    colsum_partial_kernel<<<dim3((cols + 1023) / 1024, kChunks), 128, 0, stream>>>(static_cast<const __nv_bfloat16*>(dy), ld_dy, rows, cols,
-                                                                                   kChunks, partial);
+    if (cols > (H > 2048 ? H : 2048) || cols % 8 != 0) return TP_ERR_INVALID_ARGUMENT;
+    const int chunks = static_cast<int>(rows < kColChunks ? rows : kColChunks);
+    colsum_partial_kernel<<<dim3((cols + 1023) / 1024, chunks), 128, 0, stream>>>(static_cast<const __nv_bfloat16*>(dy), ld_dy, rows, cols,
+                                                                                  chunks, col_part);
     TP_CUDA(cudaGetLastError());
-    colsum_reduce_kernel<<<(cols + 255) / 256, 256, 0, stream>>>(partial, kChunks, cols, scale, static_cast<__nv_bfloat16*>(out));
+    colsum_reduce_kernel<<<(cols + 255) / 256, 256, 0, stream>>>(col_part, chunks, cols, scale, static_cast<__nv_bfloat16*>(out));
     TP_CUDA(cudaGetLastError());
     return TP_OK;
   };
