@@ -53,3 +53,35 @@ def test_forward_packed_matches_oracle_assembly():
     np.testing.assert_array_equal(cu2.numpy(), ref_cu)
     np.testing.assert_array_equal(packed.float().cpu().numpy(), ref)       # pure data movement: bit-exact
     np.testing.assert_array_equal(packed2.float().cpu().numpy(), ref)
+
+
+def test_hd_config3_full_size_packed_equals_assembled():
+    """BASELINE configs[3] at full size (patch_num=9, s=2, H=4096, 32 seeded image sizes -> 231 crops): the scatter-epilogue
+    packed output equals projecting the crops and assembling them separately, bit for bit; row counts match the reference's
+    sequence-length formula (README 'avg ~954 tokens' regime)."""
+    from tokenpacker_b200 import TokenPackerB200, hd_assemble, hd_grid, hd_seq_len
+    from tokenpacker_b200 import synthetic as syn
+    g = torch.Generator().manual_seed(0)
+    hs = torch.randint(224, 1345, (32,), generator=g).tolist()
+    ws = torch.randint(224, 1345, (32,), generator=g).tolist()
+    grids = [hd_grid(h, w, 9) for h, w in zip(hs, ws)]
+    for (h, w), gr in zip(zip(hs, ws), grids):
+        assert gr == hdo.hd_grid(h, w, 9)
+    n = sum(hdo.n_crops(a, b) for a, b in grids)
+    assert n == 231                                            # SURVEY.md §8d: these seeds give 231 crops
+    m = TokenPackerB200(hidden_size=4096, scale_factor=2)
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in syn.synthetic_state_dict(4096, seed=0).items()})
+    m = m.to("cuda", torch.bfloat16).eval()
+    gg = torch.Generator(device="cuda").manual_seed(1)
+    x0 = torch.randn(n, 576, 1024, device="cuda", generator=gg).bfloat16()
+    xm = torch.randn(n, 576, 4096, device="cuda", generator=gg).bfloat16()
+    sep = torch.randn(4096, device="cuda", generator=gg).bfloat16()
+    ret = torch.randn(4096, device="cuda", generator=gg).bfloat16()
+    hb, wb = [a for a, _ in grids], [b for _, b in grids]
+    with torch.no_grad():
+        packed, cu = m.forward_packed((x0, xm), hb, wb, sep, ret)
+        packed2, cu2 = hd_assemble(m((x0, xm)), hb, wb, sep, ret)
+    assert torch.equal(cu, cu2) and torch.equal(packed, packed2)
+    lens = (cu[1:] - cu[:-1]).tolist()
+    assert lens == [hd_seq_len(a, b, 144) for a, b in grids]
+    assert torch.isfinite(packed.float()).all()

@@ -219,3 +219,24 @@ def test_cuda_graph_capture_and_replay():
             graph.replay()
             torch.cuda.synchronize()
             assert torch.equal(sout, m((x0, xm)))
+
+
+def test_randomised_configurations_against_oracle():
+    """Seeded sweep over crop counts, scale factors, hidden sizes, input scales and memory layouts (contiguous / [:,1:] views)."""
+    rng = np.random.default_rng(2024)
+    for trial in range(10):
+        n = int(rng.integers(1, 10))
+        s = int(rng.choice([2, 3, 4]))
+        hidden = int(rng.choice([128, 256, 384, 512]))
+        scale = float(rng.choice([0.3, 1.0, 2.5]))
+        m, params = make_module(hidden, s, seed=1000 + trial)
+        x0 = tpo.round_bf16(rng.standard_normal((n, 577, 1024)).astype(np.float32) * scale)
+        xm = tpo.round_bf16(rng.standard_normal((n, 577, 4096)).astype(np.float32) * scale)
+        t0, tm = torch.from_numpy(x0).cuda().bfloat16(), torch.from_numpy(xm).cuda().bfloat16()
+        v0, vm = (t0[:, 1:], tm[:, 1:]) if trial % 2 == 0 else (t0[:, 1:].contiguous(), tm[:, 1:].contiguous())
+        ref = tpo.tokenpacker_forward(params, x0[:, 1:], xm[:, 1:], s, dtype=np.float32)
+        with torch.no_grad():
+            out = m((v0, vm)).float().cpu().numpy()
+        rel, mx = errors(out, ref)
+        rms = float(np.sqrt((ref.astype(np.float64) ** 2).mean()))
+        assert rel <= REL_RMS_TOL and mx <= MAX_ABS_TOL * max(1.0, rms / 0.1), (trial, n, s, hidden, scale, rel, mx)

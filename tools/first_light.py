@@ -210,6 +210,22 @@ def train_step_timing():
     fl = syn.flops_per_crop(2) * n
     print(f"train step (fwd+bwd, N=64 s=2 H=4096): {ms:.3f} ms; fwd F_alg x3 = {3 * fl / 1e12:.2f} TF -> {3 * fl / ms / 1e9:.0f} TF/s equivalent; "
           f"peak mem {torch.cuda.max_memory_allocated() / 2**30:.2f} GiB", flush=True)
+    # context: PyTorch eager autograd over the reference's op sequence (oracle/torch_port.py), bf16, same GPU
+    from oracle import torch_port
+    pd = {k: v.detach().clone().requires_grad_(True) for k, v in m.state_dict().items()}
+    def ref_step():
+        for p in pd.values():
+            p.grad = None
+        torch_port.forward(pd, x0, xm, 2).backward(gw)
+    for _ in range(2):
+        ref_step()
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(5):
+        ref_step()
+    e1.record()
+    torch.cuda.synchronize()
+    print(f"reference op sequence, eager autograd bf16 on the same GPU: {e0.elapsed_time(e1) / 5:.3f} ms per fwd+bwd step", flush=True)
 
 
 if __name__ == "__main__":
