@@ -240,3 +240,20 @@ def test_randomised_configurations_against_oracle():
         rel, mx = errors(out, ref)
         rms = float(np.sqrt((ref.astype(np.float64) ** 2).mean()))
         assert rel <= REL_RMS_TOL and mx <= MAX_ABS_TOL * max(1.0, rms / 0.1), (trial, n, s, hidden, scale, rel, mx)
+
+
+@pytest.mark.parametrize("chunk", [1, 3, 64])
+def test_host_buffer_path_matches_device_path(chunk):
+    """tp_forward_host (pinned host tensors in and out, chunked H2D | compute | D2H pipeline) == device-resident forward, bitwise."""
+    s, hidden, n = 3, 256, 7
+    m, _ = make_module(hidden, s, seed=4)
+    g = torch.Generator().manual_seed(8)
+    hx0 = torch.randn(n, 576, 1024, generator=g).bfloat16().pin_memory()
+    hxm = torch.randn(n, 576, 4096, generator=g).bfloat16().pin_memory()
+    with torch.no_grad():
+        ref = m((hx0.cuda(), hxm.cuda())).cpu()
+        out = m.forward_host((hx0, hxm), chunk_crops=chunk)
+    assert out.shape == ref.shape and not out.is_cuda
+    assert torch.equal(out, ref)
+    with pytest.raises(TypeError):
+        m.forward_host((hx0.float(), hxm))
