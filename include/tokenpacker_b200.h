@@ -86,6 +86,14 @@ TP_API int tp_forward(const void* packed, const void* x0, const void* xm, int64_
                int64_t xm_crop_stride, int scale_factor, int hidden, void* out, const int64_t* seg_row_offset,
                void* workspace, size_t workspace_bytes, void* stream);
 
+/* Same forward, taking the multi-level stack as its FOUR layers instead of their concatenation: layers[0..3] are the CLIP
+ * hidden states 12 / 16 / 22 / 23 that CLIPVisionTower.feature_select concatenates (clip_encoder.py:28-44), each
+ * [n_crops, 576, 1024] bf16 with row stride 1024 and crop stride ``crop_stride`` (577*1024 for the [:,1:] views of the raw
+ * hidden states); layers[3] is also x0 (select_layer = -2).  The first GEMM reads its K range from four tensor maps, so the
+ * 4.7 MB/crop concatenated copy upstream never has to exist. */
+TP_API int tp_forward_layers(const void* packed, const void* const* layers, int64_t n_crops, int64_t crop_stride, int scale_factor,
+                             int hidden, void* out, const int64_t* seg_row_offset, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Multi-GPU form with the all-gather FUSED into the last GEMM's epilogue.  peer_out[p] (p < n_peers <= 8) is the base of a
  * gathered buffer [total_crops, M, H] bf16 on GPU p, mapped into this process (CUDA IPC / symmetric memory; own buffer
  * included).  This rank's n_crops crops are written to rows [crop_offset*M, (crop_offset+n_crops)*M) of EVERY peer buffer by

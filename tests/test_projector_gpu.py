@@ -257,3 +257,18 @@ def test_host_buffer_path_matches_device_path(chunk):
     assert torch.equal(out, ref)
     with pytest.raises(TypeError):
         m.forward_host((hx0.float(), hxm))
+
+
+def test_forward_from_clip_layers_equals_forward_on_concatenation():
+    """tp_forward_layers reads the four hidden states through four tensor maps: same bits as feature_select's cat + forward."""
+    s, hidden, n = 2, 256, 3
+    m, _ = make_module(hidden, s, seed=6)
+    g = torch.Generator(device="cuda").manual_seed(9)
+    hs = [torch.randn(n, 577, 1024, device="cuda", generator=g).bfloat16() for _ in range(4)]     # layers 12, 16, 22, 23 with CLS
+    x0 = hs[3][:, 1:]
+    xm = torch.cat(hs, dim=-1)[:, 1:]                                                             # clip_encoder.py:39-43
+    with torch.no_grad():
+        ref = m((x0, xm))
+        out = m.forward_layers(hs)
+        out2 = m.forward_layers([h[:, 1:].contiguous() for h in hs])
+    assert torch.equal(out, ref) and torch.equal(out2, ref)

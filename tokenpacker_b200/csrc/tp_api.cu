@@ -119,6 +119,8 @@ struct AOperand {
   long long ld;          // row stride (elements)
   long long seg_rows;    // 0: plain 2-D [M,K]; else rows per segment of a 3-D [M/seg_rows, seg_rows, K] tensor
   long long seg_stride;  // elements between segments
+  const void* more[3] = {nullptr, nullptr, nullptr};   // further A tensors side by side along K (same ld / segmentation), pair kernel only
+  int parts = 1;
 };
 
 // Every kernel of the path is launched with the programmatic-stream-serialization attribute (PDL): its CTAs may be
@@ -194,10 +196,24 @@ int launch_gemm_pair_group(const GemmItem* items, int count, int sms, cudaStream
       TP_TRY(make_map_2d(&p.tmap_a, it.a.ptr, it.K, it.M, it.a.ld, 64));
       TP_TRY(make_map_2d(&p.tmap_b, it.b, it.K, it.N, it.ldb, 64));
       p.ab_mn_major = 1;
+    } else if (it.a.parts > 1) {
+      if (it.a.parts > kMaxAParts || it.K % (it.a.parts * kBlockK) != 0) return TP_ERR_INVALID_ARGUMENT;
+      const long long kp = it.K / it.a.parts;
+      AOperand part = it.a;
+      TP_TRY(make_a_map(&p.tmap_a, part, it.M, kp));
+      for (int q = 1; q < it.a.parts; ++q) {
+        part.ptr = it.a.more[q - 1];
+        if (part.ptr == nullptr) return TP_ERR_INVALID_ARGUMENT;
+        TP_TRY(make_a_map(&p.tmap_a_more[q - 1], part, it.M, kp));
+      }
+      TP_TRY(make_map_2d(&p.tmap_b, it.b, it.N, it.K, it.ldb, Cfg::kTileN / 2));
+      p.a_parts = it.a.parts;
+      p.a_kblocks_per_part = static_cast<int>(kp / kBlockK);
     } else {
       TP_TRY(make_a_map(&p.tmap_a, it.a, it.M, it.K));
       TP_TRY(make_map_2d(&p.tmap_b, it.b, it.N, it.K, it.ldb, Cfg::kTileN / 2));
     }
+    if (p.a_parts == 0) { p.a_parts = 1; p.a_kblocks_per_part = static_cast<int>((it.K + kBlockK - 1) / kBlockK); }
     // C goes out through TMA stores (64-col x 128-row swizzled slabs) unless rows are scattered to segment offsets
     TP_TRY(make_map_2d(&p.tmap_c, it.ep.c, it.M, it.N, it.ep.ldc, kBlockM));
     p.use_tma_store = it.ep.seg_row_offset == nullptr ? 1 : 0;
@@ -242,8 +258,8 @@ int launch_gemms(const GemmItem* items, int count, int sms, cudaStream_t stream)
     const GemmItem& it = items[i];
     const bool pair_ok = (it.N % 256 == 0) && sms >= 2;
     if (it.n_peers > 0 && (!pair_ok || count != 1)) return TP_ERR_INVALID_ARGUMENT;   // peer stores live in the pair kernel only
-    if (it.tn && !pair_ok) return TP_ERR_INVALID_ARGUMENT;                              // MN-major operands: pair kernel only
-    const bool want_pair = mode == 2 || mode == 3 || (mode == 0 && it.M >= 256) || it.n_peers > 0 || it.tn;
+    if ((it.tn || it.a.parts > 1) && !pair_ok) return TP_ERR_INVALID_ARGUMENT;          // MN-major / multi-part operands: pair kernel only
+    const bool want_pair = mode == 2 || mode == 3 || (mode == 0 && it.M >= 256) || it.n_peers > 0 || it.tn || it.a.parts > 1;
     if (pair_ok && want_pair) {
       if (mode == 3) TP_TRY(launch_gemm_pair_group(&it, 1, sms, stream));
       else grouped[n_grouped++] = it;
@@ -456,15 +472,23 @@ size_t tp_workspace_bytes(int64_t n_crops, int scale_factor, int hidden) {
 }  // extern "C"
 
 namespace {
-int forward_impl(const void* packed, const void* x0, const void* xm, int64_t n_crops, int64_t x0_crop_stride, int64_t xm_crop_stride,
-                 int scale_factor, int hidden, void* out, const int64_t* seg_row_offset, void* const* peer_out, int n_peers,
-                 void* workspace, size_t workspace_bytes, void* stream_) {
+// xm_layers != nullptr: the multi-level stack is given as its four [n_crops, 576, 1024] layers (row stride 1024, crop stride
+// xm_crop_stride) instead of one [n_crops, 576, 4096] tensor; ``xm`` is then ignored.
+int forward_impl(const void* packed, const void* x0, const void* xm, const void* const* xm_layers, int64_t n_crops, int64_t x0_crop_stride,
+                 int64_t xm_crop_stride, int scale_factor, int hidden, void* out, const int64_t* seg_row_offset, void* const* peer_out,
+                 int n_peers, void* workspace, size_t workspace_bytes, void* stream_) {
+  if (xm_layers != nullptr) {
+    for (int i = 0; i < 4; ++i)
+      if (xm_layers[i] == nullptr) return TP_ERR_INVALID_ARGUMENT;
+    xm = xm_layers[0];
+  }
   if (scale_factor <= 0 || kGrid % scale_factor != 0) return TP_ERR_BAD_SCALE_FACTOR;          // builder.py:51-52
   if (scale_factor < 2 || scale_factor > 4) return TP_ERR_INVALID_ARGUMENT;   // released configurations: 144/64/36 tokens
   if (packed == nullptr || x0 == nullptr || xm == nullptr || out == nullptr || workspace == nullptr || n_crops <= 0 ||
       !valid_hidden(hidden))
     return TP_ERR_INVALID_ARGUMENT;
-  if (x0_crop_stride < static_cast<int64_t>(kTokens) * kC || xm_crop_stride < static_cast<int64_t>(kTokens) * kCm ||
+  const int64_t xm_width = xm_layers != nullptr ? kC : kCm;
+  if (x0_crop_stride < static_cast<int64_t>(kTokens) * kC || xm_crop_stride < static_cast<int64_t>(kTokens) * xm_width ||
       x0_crop_stride % 8 != 0 || xm_crop_stride % 8 != 0)
     return TP_ERR_INVALID_ARGUMENT;
   if (n_crops * kTokens > 0x7fff0000ll) return TP_ERR_INVALID_ARGUMENT;
@@ -501,8 +525,12 @@ int forward_impl(const void* packed, const void* x0, const void* xm, int64_t n_c
     else TP_TRY(launch_front<4>(x0p, x0_crop_stride, bf(W.q), Q, stream));
   }
   {
-    AOperand a{xm, kCm, 0, 0};
-    if (xm_crop_stride != static_cast<int64_t>(kTokens) * kCm) a = AOperand{xm, kCm, kTokens, xm_crop_stride};
+    AOperand a{xm, xm_width, 0, 0};
+    if (xm_crop_stride != static_cast<int64_t>(kTokens) * xm_width) a = AOperand{xm, xm_width, kTokens, xm_crop_stride};
+    if (xm_layers != nullptr) {
+      a.parts = 4;
+      for (int i = 1; i < 4; ++i) a.more[i - 1] = xm_layers[i];
+    }
     TP_TRY(launch_gemm(a, P + L.w_kv0, kCm, R, 2 * kC, kCm, plain_epilogue(bf(W.h_kv), 2 * kC, wf(L.b_kv0), 1), dev.sms, stream));
   }
   {
@@ -562,8 +590,15 @@ extern "C" {
 int tp_forward(const void* packed, const void* x0, const void* xm, int64_t n_crops, int64_t x0_crop_stride, int64_t xm_crop_stride,
                int scale_factor, int hidden, void* out, const int64_t* seg_row_offset, void* workspace, size_t workspace_bytes,
                void* stream) {
-  return forward_impl(packed, x0, xm, n_crops, x0_crop_stride, xm_crop_stride, scale_factor, hidden, out, seg_row_offset, nullptr, 0,
+  return forward_impl(packed, x0, xm, nullptr, n_crops, x0_crop_stride, xm_crop_stride, scale_factor, hidden, out, seg_row_offset, nullptr, 0,
                       workspace, workspace_bytes, stream);
+}
+
+int tp_forward_layers(const void* packed, const void* const* layers, int64_t n_crops, int64_t crop_stride, int scale_factor, int hidden,
+                      void* out, const int64_t* seg_row_offset, void* workspace, size_t workspace_bytes, void* stream) {
+  if (layers == nullptr) return TP_ERR_INVALID_ARGUMENT;
+  return forward_impl(packed, layers[3], nullptr, layers, n_crops, crop_stride, crop_stride, scale_factor, hidden, out, seg_row_offset,
+                      nullptr, 0, workspace, workspace_bytes, stream);
 }
 
 int tp_forward_allgather(const void* packed, const void* x0, const void* xm, int64_t n_crops, int64_t x0_crop_stride,
@@ -578,7 +613,7 @@ int tp_forward_allgather(const void* packed, const void* x0, const void* xm, int
     if (peer_out[p] == nullptr) return TP_ERR_INVALID_ARGUMENT;
     dst[p] = static_cast<uint8_t*>(peer_out[p]) + slot;
   }
-  return forward_impl(packed, x0, xm, n_crops, x0_crop_stride, xm_crop_stride, scale_factor, hidden, dst[0], nullptr, dst, n_peers,
+  return forward_impl(packed, x0, xm, nullptr, n_crops, x0_crop_stride, xm_crop_stride, scale_factor, hidden, dst[0], nullptr, dst, n_peers,
                       workspace, workspace_bytes, stream);
 }
 

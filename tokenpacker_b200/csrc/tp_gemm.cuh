@@ -426,8 +426,15 @@ struct Gemm2Config {
 
 constexpr int kMaxGroup = 3;
 
+constexpr int kMaxAParts = 4;
+
 struct GemmProblem {
   CUtensorMap tmap_a, tmap_b, tmap_c;
+  CUtensorMap tmap_a_more[kMaxAParts - 1];   // A given as several tensors side by side along K (e.g. the four CLIP hidden states
+                                             // that the reference concatenates, clip_encoder.py:28-44): part p covers k-blocks
+                                             // [p * a_kblocks_per_part, (p+1) * a_kblocks_per_part)
+  int a_parts;           // 1: a single A tensor
+  int a_kblocks_per_part;
   int M, N, K;
   int a_seg_rows;        // 0: plain 2-D A; else rows per segment of the 3-D (crop-strided) A map
   int ab_mn_major;       // 1: BOTH operands are given as row-major [K, M] / [K, N] matrices (wgrad: C = A^T . B, contraction over rows)
@@ -490,6 +497,7 @@ tp_gemm2_kernel(const __grid_constant__ GemmGroup grp, const __grid_constant__ P
   if (warp_idx == kTmaWarp && lane == 0) {
     for (int i = 0; i < grp.count; ++i) {
       tma_prefetch_desc(&grp.p[i].tmap_a);
+      for (int q = 1; q < grp.p[i].a_parts; ++q) tma_prefetch_desc(&grp.p[i].tmap_a_more[q - 1]);
       tma_prefetch_desc(&grp.p[i].tmap_b);
       if (grp.p[i].use_tma_store) tma_prefetch_desc(&grp.p[i].tmap_c);
     }
@@ -552,11 +560,16 @@ tp_gemm2_kernel(const __grid_constant__ GemmGroup grp, const __grid_constant__ P
             tma_load_2d_pair(sa + Cfg::kABytes / 2, &pr.tmap_a, &full_bar[stage], row0 + 64, kb * kBlockK);
             tma_load_2d_pair(sb, &pr.tmap_b, &full_bar[stage], brow0, kb * kBlockK);
             tma_load_2d_pair(sb + Cfg::kBBytes / 2, &pr.tmap_b, &full_bar[stage], brow0 + 64, kb * kBlockK);
-          } else if (pr.a_seg_rows == 0) {
-            tma_load_2d_pair(sa, &pr.tmap_a, &full_bar[stage], kb * kBlockK, row0);
           } else {
-            tma_load_3d_pair(sa, &pr.tmap_a, &full_bar[stage], kb * kBlockK, srow0, seg0);
-            tma_load_3d_pair(sa + Cfg::kABytes / 2, &pr.tmap_a, &full_bar[stage], kb * kBlockK, srow1, seg1);
+            const int part = pr.a_parts > 1 ? kb / pr.a_kblocks_per_part : 0;
+            const CUtensorMap* ta = part == 0 ? &pr.tmap_a : &pr.tmap_a_more[part - 1];
+            const int ka = (kb - part * pr.a_kblocks_per_part) * kBlockK;      // K coordinate inside this part
+            if (pr.a_seg_rows == 0) {
+              tma_load_2d_pair(sa, ta, &full_bar[stage], ka, row0);
+            } else {
+              tma_load_3d_pair(sa, ta, &full_bar[stage], ka, srow0, seg0);
+              tma_load_3d_pair(sa + Cfg::kABytes / 2, ta, &full_bar[stage], ka, srow1, seg1);
+            }
           }
           if (!pr.ab_mn_major) tma_load_2d_pair(sb, &pr.tmap_b, &full_bar[stage], kb * kBlockK, brow0);
         }

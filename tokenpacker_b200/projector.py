@@ -206,6 +206,38 @@ class TokenPackerB200(nn.Module):
         check(lib.tp_forward(packed.data_ptr(), x0b.data_ptr(), xmb.data_ptr(), n, s0, sm, self.scale_factor,
                              self.hidden_size, out.data_ptr(), seg_ptr, ws.data_ptr(), ws_bytes, stream), "tp_forward")
 
+    def forward_layers(self, layers):
+        """Forward from the four CLIP hidden states (layers 12, 16, 22, 23; each [N,577,1024] with the CLS token, or [N,576,1024])
+        WITHOUT materialising their concatenation: replaces ``feature_select`` + ``torch.cat`` (clip_encoder.py:28-44) followed by
+        ``forward``; the last layer doubles as the single-level feature (select_layer = -2).  Inference only."""
+        if len(layers) != 4:
+            raise ValueError("expected the 4 hidden states (12, 16, 22, 23)")
+        views = []
+        for t in layers:
+            if t.dim() != 3 or t.shape[2] != 1024 or t.shape[1] not in (576, 577) or not t.is_cuda:
+                raise ValueError("each layer must be a CUDA tensor [N,577,1024] or [N,576,1024]")
+            t = t.to(torch.bfloat16)
+            views.append(t[:, 1:] if t.shape[1] == 577 else t)
+        n = views[0].shape[0]
+        stride = views[0].stride(0)
+        for i, v in enumerate(views):
+            if v.shape[0] != n or v.stride(2) != 1 or v.stride(1) != 1024 or v.stride(0) != stride or v.data_ptr() % 16 != 0:
+                views[i] = None
+        if any(v is None for v in views) or stride % 8 != 0:
+            views = [(t[:, 1:] if t.shape[1] == 577 else t).to(torch.bfloat16).contiguous() for t in layers]
+            stride = views[0].stride(0)
+        device = views[0].device
+        with torch.no_grad(), torch.cuda.device(device):
+            packed = self._packed_weights(device)
+            out = torch.empty((n, self.num_queries, self.hidden_size), dtype=torch.bfloat16, device=device)
+            ws_bytes = lib.tp_workspace_bytes(n, self.scale_factor, self.hidden_size)
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=device)
+            arr = (C.c_void_p * 4)(*[v.data_ptr() for v in views])
+            stream = torch.cuda.current_stream(device).cuda_stream
+            check(lib.tp_forward_layers(packed.data_ptr(), arr, n, stride, self.scale_factor, self.hidden_size, out.data_ptr(), None,
+                                        ws.data_ptr(), ws_bytes, stream), "tp_forward_layers")
+        return out
+
     def forward_into_peers(self, x, peer_ptrs, crop_offset: int):
         """Fused projector + all-gather: this rank's crops are written by the last GEMM's TMA stores into the gathered buffer of
         every peer GPU (``peer_ptrs``: device pointers of the [total_crops, M, H] bf16 buffers, one per rank, mapped into this
