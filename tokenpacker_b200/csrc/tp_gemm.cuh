@@ -185,7 +185,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmEpilogue& ep, int M, int
         }
         if (ep.gelu) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] = gelu_erf(v[j]);
+          for (int j = 0; j < 8; j += 2) gelu_erf_x2(v[j], v[j + 1]);      // packed fp32 pipe; same bits as gelu_erf
         }
         uint32_t pk[4];
 #pragma unroll

@@ -367,6 +367,44 @@ __device__ __forceinline__ float gelu_erf(float x) {
   return fmaf(fabsf(hx), e, hx);                        // 0.5 x (1 + sign(x) erf(|x|/sqrt 2)) = hx + |hx| e
 }
 
+// Two GELUs at once on Blackwell's packed-fp32 pipe (fma/mul .f32x2 = FFMA2/FMUL2: two independent IEEE operations per
+// instruction, so the results are bit-identical to two gelu_erf calls) — the polynomial is 11 of the 17 instructions.
+__device__ __forceinline__ uint64_t pk2(float a, float b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void upk2(uint64_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+
+__device__ __forceinline__ void gelu_erf_x2(float& x0, float& x1) {
+  constexpr uint64_t kAbs = 0x7fffffff7fffffffull;
+  const uint64_t x = pk2(x0, x1);
+  const uint64_t t = mul2(x & kAbs, pk2(0.70710678118654752440f, 0.70710678118654752440f));
+  uint64_t p = pk2(0.0000430638f, 0.0000430638f);
+  p = fma2(p, t, pk2(0.0002765672f, 0.0002765672f));
+  p = fma2(p, t, pk2(0.0001520143f, 0.0001520143f));
+  p = fma2(p, t, pk2(0.0092705272f, 0.0092705272f));
+  p = fma2(p, t, pk2(0.0422820123f, 0.0422820123f));
+  p = fma2(p, t, pk2(0.0705230784f, 0.0705230784f));
+  p = fma2(p, t, pk2(1.0f, 1.0f));
+  p = mul2(p, p); p = mul2(p, p); p = mul2(p, p); p = mul2(p, p);
+  float p0, p1;
+  upk2(p, p0, p1);
+  const uint64_t e = pk2(__fsub_rn(1.0f, __fdividef(1.0f, p0)), __fsub_rn(1.0f, __fdividef(1.0f, p1)));
+  const uint64_t hx = mul2(pk2(0.5f, 0.5f), x);
+  upk2(fma2(hx & kAbs, e, hx), x0, x1);
+}
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
