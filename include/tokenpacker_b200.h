@@ -166,6 +166,12 @@ TP_API int tp_hd_plan(const int* h_block, const int* w_block, int64_t n_images, 
 TP_API int tp_hd_scatter_crops(const void* feats, int64_t n_crops, int tokens_per_crop, int hidden, const int64_t* seg_row_offset,
                                void* out, void* stream);
 
+/* Text/vision splice as ONE gather (replaces the Python list / torch.cat loops of llava_arch.py:119-233): row i of ``out``
+ * [n_rows, hidden] bf16 is table[src_index[i]] (text token embedding) when src_index[i] >= 0, a zero row (right padding) when
+ * it is -1, and visual[-src_index[i] - 2] (a projected visual token) otherwise.  All device pointers. */
+TP_API int tp_gather_rows(const void* table, const void* visual, int hidden, const int64_t* src_index, int64_t n_rows, void* out,
+                          void* stream);
+
 /* Writes the separator rows of the packed output: out[sep_rows[i], :] = sep_row, out[ret_rows[i], :] = ret_row
  * (bf16 vectors of length hidden).  Device pointers. */
 TP_API int tp_hd_fill_separators(void* out, int hidden, const int64_t* sep_rows, int64_t n_sep, const void* sep_row,

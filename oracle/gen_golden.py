@@ -155,6 +155,80 @@ def gen_assemble():
     print("assemble", cu)
 
 
+def gen_splice():
+    """Call the reference's own prepare_inputs_labels_for_multimodal (llava_arch.py:100-233) on a stand-in model."""
+    import importlib
+    import types
+    for name, sub in (("llava", "llava"), ("llava.model", "llava/model")):      # bypass the two __init__.py (they import transformers-4.31 symbols)
+        mod = types.ModuleType(name)
+        mod.__path__ = [os.path.join(REF, sub)]
+        sys.modules[name] = mod
+    arch = importlib.import_module("llava.model.llava_arch")
+
+    class _Model:
+        def __init__(self, table):
+            self.table = table
+
+        def embed_tokens(self, ids):
+            return self.table[ids]
+
+    class _Tok:
+        def convert_tokens_to_ids(self, toks):
+            return [{",": 5, "\n": 6}[t] for t in toks]
+
+    class _Fake(arch.LlavaMetaForCausalLM):
+        def __init__(self, table, feats):
+            self._m, self._f, self.tokenizer = _Model(table), feats, _Tok()
+            self.config = types.SimpleNamespace(tune_mm_mlp_adapter=False, mm_use_im_start_end=False)
+            self.device = torch.device("cpu")
+
+        def get_model(self):
+            return self._m
+
+        def get_vision_tower(self):
+            return object()
+
+        def encode_images(self, images):
+            return self._f
+
+    rng = np.random.default_rng(77)
+    hdim, vocab, m = 16, 64, 4
+    table = rng.standard_normal((vocab, hdim)).astype(np.float32)
+    out = {"table": table}
+    cases = {
+        # name: (input_ids, n_images/crop grids, mode, with_labels)
+        "equal": ([[1, 2, -200, 3, 4, 7], [9, -200, 8, 10, 11, 12]], None, "pad", True),
+        "ragged": ([[1, -200, 3, 4, -200, 7], [9, 13, 8, -200, 11, 12], [20, 21, 22, 23, 24, 25]], None, "pad", True),
+        "infer": ([[1, 2, 3, -200, 4]], None, "pad", False),
+        "slice": ([[1, -200, 3, 4], [9, 8, -200, 11]], [(2, 2), (1, 1)], "slice", True),
+    }
+    for name, (ids, grids, mode, with_labels) in cases.items():
+        ids_t = torch.tensor(ids)
+        n_tok = int((ids_t == -200).sum()) + sum(1 for row in ids if -200 not in row)
+        if mode == "slice":
+            crops = sum(hdo.n_crops(a, b) for a, b in grids)
+            feats = rng.standard_normal((crops, m, hdim)).astype(np.float32)
+            hb, wb = [g[0] for g in grids], [g[1] for g in grids]
+        else:
+            feats = rng.standard_normal((n_tok, m, hdim)).astype(np.float32)
+            hb = wb = None
+        labels = ids_t.clone() if with_labels else None
+        mask = torch.ones_like(ids_t, dtype=torch.bool)
+        fake = _Fake(torch.from_numpy(table), torch.from_numpy(feats))
+        _, new_mask, _, embeds, new_labels = fake.prepare_inputs_labels_for_multimodal(ids_t, mask, None, labels, object(), mode, hb, wb)
+        out[f"{name}_ids"] = np.asarray(ids, dtype=np.int64)
+        out[f"{name}_feats"] = feats
+        out[f"{name}_embeds"] = embeds.numpy()
+        out[f"{name}_mask"] = new_mask.numpy()
+        if with_labels:
+            out[f"{name}_labels"] = new_labels.numpy()
+        if grids is not None:
+            out[f"{name}_grids"] = np.asarray(grids, dtype=np.int64)
+        print("splice", name, tuple(embeds.shape))
+    out["sep_id"], out["ret_id"] = np.asarray(5), np.asarray(6)
+    np.savez(os.path.join(OUT, "splice.npz"), **out)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     builder = load_by_path("ref_builder", "llava/model/multimodal_projector/builder.py")
@@ -163,3 +237,4 @@ if __name__ == "__main__":
     gen_grid(pd)
     gen_tile(pd)
     gen_assemble()
+    gen_splice()

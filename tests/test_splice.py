@@ -1,0 +1,81 @@
+"""Text/vision splice: oracle and product plan vs fixtures produced by the reference's own prepare_inputs_labels_for_multimodal
+(llava_arch.py:100-233, oracle/gen_golden.py:gen_splice); the gather kernel itself is checked on the GPU."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import hd_oracle as hdo
+from oracle import splice_oracle as spo
+
+CASES = ["equal", "ragged", "infer", "slice"]
+
+
+def _image_seqs(g, name):
+    feats = g[f"{name}_feats"]
+    if f"{name}_grids" in g.files:
+        grids = g[f"{name}_grids"].tolist()
+        sep, ret = g["table"][int(g["sep_id"])], g["table"][int(g["ret_id"])]
+        packed, cu = hdo.hd_assemble(feats, [a for a, _ in grids], [b for _, b in grids], sep, ret)
+        return [packed[cu[i]:cu[i + 1]] for i in range(len(grids))]
+    return [feats[i] for i in range(feats.shape[0])]
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_oracle_matches_reference(golden_dir, name):
+    g = np.load(os.path.join(golden_dir, "splice.npz"))
+    ids = g[f"{name}_ids"]
+    labels = ids.copy() if f"{name}_labels" in g.files else None
+    mask, embeds, new_labels = spo.splice(ids, np.ones_like(ids, dtype=bool), labels, _image_seqs(g, name), g["table"])
+    np.testing.assert_array_equal(embeds, g[f"{name}_embeds"])
+    np.testing.assert_array_equal(mask, g[f"{name}_mask"])
+    if labels is not None:
+        np.testing.assert_array_equal(new_labels, g[f"{name}_labels"])
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_product_plan_matches_reference(golden_dir, name):
+    """The product's host planner (pure index arithmetic, no CUDA) applied with numpy reproduces the reference outputs."""
+    from tokenpacker_b200 import splice_plan
+    g = np.load(os.path.join(golden_dir, "splice.npz"))
+    ids = g[f"{name}_ids"]
+    seqs = _image_seqs(g, name)
+    visual = np.concatenate(seqs, axis=0)
+    cu = np.concatenate([[0], np.cumsum([s.shape[0] for s in seqs])])
+    labels = ids.copy() if f"{name}_labels" in g.files else None
+    plan = splice_plan(ids, cu, labels, np.ones_like(ids, dtype=bool))
+    src = plan.src_index
+    rows = np.zeros((src.shape[0], g["table"].shape[1]), dtype=np.float32)
+    rows[src >= 0] = g["table"][src[src >= 0]]
+    rows[src <= -2] = visual[-src[src <= -2] - 2]
+    np.testing.assert_array_equal(rows.reshape(ids.shape[0], plan.lmax, -1), g[f"{name}_embeds"])
+    np.testing.assert_array_equal(plan.attention_mask, g[f"{name}_mask"])
+    if labels is not None:
+        np.testing.assert_array_equal(plan.labels, g[f"{name}_labels"])
+
+
+def test_ragged_without_labels_is_rejected_like_the_reference():
+    from tokenpacker_b200 import splice_plan
+    with pytest.raises(ValueError):
+        splice_plan(np.array([[1, -200, 3], [4, 5, 6]]), [0, 4, 8], None, np.ones((2, 3), dtype=bool))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", CASES)
+def test_gather_kernel_matches_reference(golden_dir, name):
+    import torch
+    from tokenpacker_b200 import splice_multimodal
+    g = np.load(os.path.join(golden_dir, "splice.npz"))
+    ids = torch.from_numpy(g[f"{name}_ids"])
+    seqs = _image_seqs(g, name)
+    visual = torch.from_numpy(np.concatenate(seqs, axis=0)).cuda().bfloat16()
+    cu = np.concatenate([[0], np.cumsum([s.shape[0] for s in seqs])])
+    table = torch.from_numpy(g["table"]).cuda().bfloat16()
+    labels = ids.clone() if f"{name}_labels" in g.files else None
+    mask, embeds, new_labels = splice_multimodal(ids.cuda(), table, visual, cu, None if labels is None else labels.cuda(),
+                                                 torch.ones_like(ids, dtype=torch.bool).cuda())
+    ref = torch.from_numpy(g[f"{name}_embeds"]).bfloat16()          # pure data movement: bit-exact on the bf16-rounded values
+    assert torch.equal(embeds.cpu(), ref)
+    np.testing.assert_array_equal(mask.cpu().numpy(), g[f"{name}_mask"])
+    if labels is not None:
+        np.testing.assert_array_equal(new_labels.cpu().numpy(), g[f"{name}_labels"])

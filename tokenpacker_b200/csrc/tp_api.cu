@@ -875,6 +875,18 @@ int tp_hd_scatter_crops(const void* feats, int64_t n_crops, int tokens_per_crop,
   return TP_OK;
 }
 
+int tp_gather_rows(const void* table, const void* visual, int hidden, const int64_t* src_index, int64_t n_rows, void* out, void* stream_) {
+  if (table == nullptr || out == nullptr || src_index == nullptr || hidden <= 0 || hidden % 8 != 0 || n_rows < 0) return TP_ERR_INVALID_ARGUMENT;
+  if (n_rows == 0) return TP_OK;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const long long threads = n_rows * (hidden / 8);
+  gather_rows_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, stream>>>(
+      static_cast<const __nv_bfloat16*>(table), static_cast<const __nv_bfloat16*>(visual), hidden, reinterpret_cast<const long long*>(src_index),
+      n_rows, static_cast<__nv_bfloat16*>(out));
+  TP_CUDA(cudaGetLastError());
+  return TP_OK;
+}
+
 int tp_hd_fill_separators(void* out, int hidden, const int64_t* sep_rows, int64_t n_sep, const void* sep_row, const int64_t* ret_rows,
                           int64_t n_ret, const void* ret_row, void* stream_) {
   if (out == nullptr || hidden <= 0 || hidden % 8 != 0 || n_sep < 0 || n_ret < 0) return TP_ERR_INVALID_ARGUMENT;

@@ -300,6 +300,22 @@ __global__ void scatter_crops_kernel(const __nv_bfloat16* __restrict__ feats, lo
   *reinterpret_cast<uint4*>(out + dst * hidden + v * 8) = __ldg(reinterpret_cast<const uint4*>(feats + r * hidden + v * 8));
 }
 
+// Text/vision splice (llava_arch.py:119-233 as one gather): out[i,:] = table[src[i]] if src[i] >= 0, zeros if src[i] == -1,
+// visual[-src[i]-2] otherwise.  bf16 rows, one thread per 8 channels.
+__global__ void gather_rows_kernel(const __nv_bfloat16* __restrict__ table, const __nv_bfloat16* __restrict__ visual, int hidden,
+                                   const long long* __restrict__ src, long long n_rows, __nv_bfloat16* __restrict__ out) {
+  const int vecs = hidden / 8;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= n_rows * vecs) return;
+  const long long r = idx / vecs;
+  const int v = static_cast<int>(idx - r * vecs);
+  const long long sidx = src[r];
+  uint4 val = make_uint4(0u, 0u, 0u, 0u);
+  if (sidx >= 0) val = __ldg(reinterpret_cast<const uint4*>(table + sidx * hidden + v * 8));
+  else if (sidx <= -2) val = __ldg(reinterpret_cast<const uint4*>(visual + (-sidx - 2) * hidden + v * 8));
+  *reinterpret_cast<uint4*>(out + r * hidden + v * 8) = val;
+}
+
 // out[rows[i], :] = row (bf16 [hidden]); one thread per 8 channels.
 __global__ void fill_rows_kernel(__nv_bfloat16* __restrict__ out, int hidden, const long long* __restrict__ rows, long long n_rows,
                                  const __nv_bfloat16* __restrict__ row) {
