@@ -1,6 +1,7 @@
 // C ABI of libtokenpacker_b200.so (see include/tokenpacker_b200.h).  Host-side orchestration only: tensor-map
 // encoding, workspace carving and kernel launches on the caller's stream.  No allocation, no synchronisation
 // (except tp_forward_host), no global mutable state.
+#include <limits.h>
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -257,13 +258,32 @@ int launch_gemms(const GemmItem* items, int count, int sms, cudaStream_t stream)
     TP_TRY(check_item(items[i]));
     const GemmItem& it = items[i];
     const bool pair_ok = (it.N % 256 == 0) && sms >= 2;
-    if (it.n_peers > 0 && (!pair_ok || count != 1)) return TP_ERR_INVALID_ARGUMENT;   // peer stores live in the pair kernel only
-    if ((it.tn || it.a.parts > 1) && !pair_ok) return TP_ERR_INVALID_ARGUMENT;          // MN-major / multi-part operands: pair kernel only
-    const bool want_pair = mode == 2 || mode == 3 || (mode == 0 && it.M >= 256) || it.n_peers > 0 || it.tn || it.a.parts > 1;
-    if (pair_ok && want_pair) {
+    const bool pair_only = it.n_peers > 0 || it.tn || it.a.parts > 1;        // features that live in the pair kernel only
+    if (pair_only && (!pair_ok || (it.n_peers > 0 && count != 1))) return TP_ERR_INVALID_ARGUMENT;
+    const bool needs_256 = it.ep.stats_out != nullptr;                        // statistics slots assume 256-column tiles
+    // Estimated tensor-pipe cycles of each candidate = waves x k-blocks x cycles per k-block.  Large problems always land
+    // on the pair kernel; small ones (single crops: the serving latency case) get the tile shape that fills more SMs.  All
+    // kernels produce identical bits, so the choice never changes results.
+    const long long kb = (it.K + kBlockK - 1) / kBlockK;
+    auto waves = [](long long tiles, long long units) { return (tiles + units - 1) / units; };
+    const long long t_pair = ((it.M + 255) / 256) * ((it.N + 255) / 256);
+    const long long t_256 = ((it.M + 127) / 128) * ((it.N + 255) / 256);
+    const long long t_128 = ((it.M + 127) / 128) * ((it.N + 127) / 128);
+    const long long c_pair = pair_ok ? waves(t_pair, sms / 2) * kb * 512 : LLONG_MAX;
+    // one-CTA kernels pay ~40 % over their nominal MMA time (more operand traffic per FLOP, direct 16-byte stores, no grouping):
+    // measured — at 10 crops the nominally 16 % cheaper 128x128 tiling was 30 % slower than the pair kernel
+    const long long c_256 = (it.N % 256 == 0) ? waves(t_256, sms) * kb * 512 * 14 / 10 : LLONG_MAX;
+    const long long c_128 = needs_256 ? LLONG_MAX : waves(t_128, sms) * kb * 256 * 14 / 10;
+    int choice;                                                               // 0 pair, 1 one-CTA 256, 2 one-CTA 128
+    if (pair_only || mode == 2 || mode == 3) choice = 0;
+    else if (mode == 1) choice = (it.N % 256 == 0) ? 1 : 2;
+    else if (c_pair <= c_256 && c_pair <= c_128) choice = 0;                  // ties go to the pair kernel (TMA stores, grouping)
+    else choice = (c_256 <= c_128) ? 1 : 2;
+    if (choice == 0 && !pair_ok) choice = (it.N % 256 == 0) ? 1 : 2;
+    if (choice == 0) {
       if (mode == 3) TP_TRY(launch_gemm_pair_group(&it, 1, sms, stream));
       else grouped[n_grouped++] = it;
-    } else if (it.N % 256 == 0) {
+    } else if (choice == 1) {
       TP_TRY(launch_gemm_t<256>(it, sms, stream));
     } else {
       TP_TRY(launch_gemm_t<128>(it, sms, stream));

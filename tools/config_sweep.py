@@ -49,7 +49,7 @@ for name, n, s in [("configs[1] N=64 s=2", 64, 2), ("configs[2] N=128 s=2", 128,
     del m, x0, xm
 
 # serving latency with the forward captured in a CUDA graph (removes Python / launch overhead)
-for n in (1, 10):
+for n in (1, 2, 4, 10, 16):
     m = module(2)
     sx0 = torch.randn(n, 576, 1024, device="cuda").bfloat16()
     sxm = torch.randn(n, 576, 4096, device="cuda").bfloat16()
