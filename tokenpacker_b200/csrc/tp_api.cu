@@ -274,11 +274,16 @@ int launch_gemms(const GemmItem* items, int count, int sms, cudaStream_t stream)
     // measured — at 10 crops the nominally 16 % cheaper 128x128 tiling was 30 % slower than the pair kernel
     const long long c_256 = (it.N % 256 == 0) ? waves(t_256, sms) * kb * 512 * 14 / 10 : LLONG_MAX;
     const long long c_128 = needs_256 ? LLONG_MAX : waves(t_128, sms) * kb * 256 * 14 / 10;
+    // a launch costs ~10k cycles of ramp and drain; pair-kernel items of one call share a single (grouped) launch
+    const long long launch = 10000;
+    const long long l_pair = pair_ok ? c_pair + launch / count : LLONG_MAX;
+    const long long l_256 = c_256 == LLONG_MAX ? LLONG_MAX : c_256 + launch;
+    const long long l_128 = c_128 == LLONG_MAX ? LLONG_MAX : c_128 + launch;
     int choice;                                                               // 0 pair, 1 one-CTA 256, 2 one-CTA 128
     if (pair_only || mode == 2 || mode == 3) choice = 0;
     else if (mode == 1) choice = (it.N % 256 == 0) ? 1 : 2;
-    else if (c_pair <= c_256 && c_pair <= c_128) choice = 0;                  // ties go to the pair kernel (TMA stores, grouping)
-    else choice = (c_256 <= c_128) ? 1 : 2;
+    else if (l_pair <= l_256 && l_pair <= l_128) choice = 0;                  // ties go to the pair kernel (TMA stores, grouping)
+    else choice = (l_256 <= l_128) ? 1 : 2;
     if (choice == 0 && !pair_ok) choice = (it.N % 256 == 0) ? 1 : 2;
     if (choice == 0) {
       if (mode == 3) TP_TRY(launch_gemm_pair_group(&it, 1, sms, stream));
