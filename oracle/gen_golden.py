@@ -201,8 +201,14 @@ def gen_splice():
         "ragged": ([[1, -200, 3, 4, -200, 7], [9, 13, 8, -200, 11, 12], [20, 21, 22, 23, 24, 25]], None, "pad", True),
         "infer": ([[1, 2, 3, -200, 4]], None, "pad", False),
         "slice": ([[1, -200, 3, 4], [9, 8, -200, 11]], [(2, 2), (1, 1)], "slice", True),
+        # tune_mm_mlp_adapter and mm_use_im_start_end (llava_arch.py:162-170): 30 / 31 stand for <im_start> / <im_end>
+        "startend": ([[1, 30, -200, 31, 4, 7], [30, -200, 31, 10, 11, 12]], None, "pad", True, True),
+        "startend_ragged": ([[1, 30, -200, 31, 30, -200, 31, 7], [9, 13, 8, 30, -200, 31, 11, 12], [20, 21, 22, 23, 24, 25, 26, 27]],
+                            None, "pad", True, True),
     }
-    for name, (ids, grids, mode, with_labels) in cases.items():
+    for name, case in cases.items():
+        ids, grids, mode, with_labels = case[:4]
+        start_end = len(case) > 4 and case[4]
         ids_t = torch.tensor(ids)
         n_tok = int((ids_t == -200).sum()) + sum(1 for row in ids if -200 not in row)
         if mode == "slice":
@@ -215,6 +221,7 @@ def gen_splice():
         labels = ids_t.clone() if with_labels else None
         mask = torch.ones_like(ids_t, dtype=torch.bool)
         fake = _Fake(torch.from_numpy(table), torch.from_numpy(feats))
+        fake.config = types.SimpleNamespace(tune_mm_mlp_adapter=start_end, mm_use_im_start_end=start_end)
         _, new_mask, _, embeds, new_labels = fake.prepare_inputs_labels_for_multimodal(ids_t, mask, None, labels, object(), mode, hb, wb)
         out[f"{name}_ids"] = np.asarray(ids, dtype=np.int64)
         out[f"{name}_feats"] = feats

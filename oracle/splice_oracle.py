@@ -1,10 +1,11 @@
 """CPU oracle for the text/vision splice  --  TEST INFRASTRUCTURE ONLY (see tokenpacker_oracle.py).
 
-numpy restatement of ``LlavaMetaForCausalLM.prepare_inputs_labels_for_multimodal`` (llava/model/llava_arch.py:100-233) for the
-configuration every released TokenPacker recipe uses (``mm_use_im_start_end = False``): each IMAGE_TOKEN_INDEX placeholder of a
-sample is replaced by the next image's visual rows, text tokens are embedded by table lookup, sequences are right-padded to
-the longest one.  Pinned by tests/golden/splice.npz, produced by calling the reference method itself on a stand-in model
-(oracle/gen_golden.py).
+numpy restatement of ``LlavaMetaForCausalLM.prepare_inputs_labels_for_multimodal`` (llava/model/llava_arch.py:100-233): each
+IMAGE_TOKEN_INDEX placeholder of a sample is replaced by the next image's visual rows, text tokens are embedded by table
+lookup, sequences are right-padded to the longest one.  ``im_start_end=True`` selects the branch taken when
+``tune_mm_mlp_adapter and mm_use_im_start_end`` (:162-170,176-177), whose label bookkeeping differs (the reference's slices are
+restated literally, including what they do when the placeholder is the first token).  Pinned by tests/golden/splice.npz,
+produced by calling the reference method itself on a stand-in model (oracle/gen_golden.py).
 """
 from __future__ import annotations
 
@@ -14,7 +15,7 @@ IGNORE_INDEX = -100        # llava/constants.py
 IMAGE_TOKEN_INDEX = -200
 
 
-def splice(input_ids, attention_mask, labels, image_seqs, embed_table):
+def splice(input_ids, attention_mask, labels, image_seqs, embed_table, im_start_end=False):
     """input_ids [B,L] int; attention_mask [B,L] bool or None; labels [B,L] int or None; image_seqs: list of [L_i,H] arrays,
     consumed in order (one per image token; a sample WITHOUT an image token still consumes one, llava_arch.py:121-134);
     embed_table [V,H].  Returns (attention_mask, inputs_embeds [B,Lmax,H], labels) like llava_arch.py:233."""
@@ -39,7 +40,19 @@ def splice(input_ids, attention_mask, labels, image_seqs, embed_table):
                 p = int(pos[0])
                 feat = image_seqs[img]
                 img += 1
-                parts.append(embed_table[ids[:p]])
+                if im_start_end:                                         # :162-170,176-177
+                    parts.append(embed_table[ids[:p - 1]])
+                    parts.append(embed_table[ids[p - 1:p]])
+                    parts.append(feat)
+                    parts.append(embed_table[ids[p + 1:p + 2]])
+                    if labels is not None:
+                        lparts.append(cur_labels[:p])
+                        lparts.append(np.full(feat.shape[0], IGNORE_INDEX, dtype=labels.dtype))
+                        lparts.append(cur_labels[p:p + 1])
+                        cur_labels = cur_labels[p + 2:]
+                    ids = ids[p + 2:]
+                    continue
+                parts.append(embed_table[ids[:p]])                       # :171-179
                 parts.append(feat)
                 if labels is not None:
                     lparts.append(cur_labels[:p])
