@@ -133,6 +133,13 @@ def test_splice_backward_matches_autograd(golden_dir, name):
     assert torch.equal(g_vis, v2.grad.bfloat16())
     torch.testing.assert_close(g_tab.float(), t2.grad.float(), rtol=1e-2, atol=1e-2)
     if start_end:
+        # only <im_start>/<im_end> rows (30, 31) — plus the ids of image-free samples, which llava_arch.py:121-134 embeds without
+        # .detach() — receive gradient
+        touched = {30, 31}
+        for row in ids.tolist():
+            if -200 not in row:
+                touched.update(row)
         untouched = torch.ones(table.shape[0], dtype=torch.bool)
-        untouched[[30, 31]] = False
+        untouched[sorted(touched)] = False
         assert torch.count_nonzero(g_tab[untouched.cuda()]) == 0
+        assert torch.count_nonzero(g_tab[30]) > 0 and torch.count_nonzero(g_tab[31]) > 0

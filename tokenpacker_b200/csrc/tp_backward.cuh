@@ -36,7 +36,7 @@ __device__ __forceinline__ float gelu_grad(float z) {
   p = fmaf(p, t, 0.0705230784f);
   p = fmaf(p, t, 1.0f);
   p *= p; p *= p; p *= p; p *= p;
-  const float e = 1.0f - __fdividef(1.0f, p);                 // erf(|z|/sqrt2)
+  const float e = 1.0f - rcp_approx(p);                 // erf(|z|/sqrt2)
   const float cdf = 0.5f * (1.0f + copysignf(e, z));
   const float pdf = 0.3989422804014327f * __expf(-0.5f * z * z);
   return fmaf(z, pdf, cdf);

@@ -20,8 +20,9 @@
 //
 // Fused epilogue (all optional, selected at run time, warp-uniform branches):
 //   v = acc
-//   v = rstd_r * (v - mu_r * col_a[c])           LayerNorm folded into the NEXT linear: (mu, rstd) from per-row sums
-//   v = v + col_b[c]                             bias (or the folded constant W.beta + b)
+//   v = fma(rstd_r, fma(-mu_r, col_a[c], v), col_b[c])    LayerNorm folded into the NEXT linear: (mu, rstd) from per-row sums,
+//                                                col_b = the folded constant W.beta + b    -- or, without a fold --
+//   v = v + col_b[c]                             bias
 //   v = gelu_erf(v)                              exact erf GELU (nn.GELU default)
 //   v = alpha * v                                1/sqrt(head_dim) query scaling
 //   y = bf16(v);  stats_out[r][slot] = (sum y, sum y*y) over this warp's columns  -> next LayerNorm fold (deterministic:
@@ -149,6 +150,9 @@ __device__ __forceinline__ void epilogue_tile(const GemmEpilogue& ep, int M, int
   const float* sb = s_col + kTileN + half * kColsPerWarp;
 
   float s1 = 0.f, s2 = 0.f;
+  const bool do_stats = ep.stats_out != nullptr;
+  const bool scale = ep.alpha != 1.0f;
+  const uint64_t rstd2 = pk2(rstd), nmu2 = pk2(-mu), alpha2 = pk2(ep.alpha);
   uint32_t r[2][32];
   tmem_ld_32x32b_x32(taddr, r[0]);
 #pragma unroll
@@ -164,36 +168,51 @@ __device__ __forceinline__ void epilogue_tile(const GemmEpilogue& ep, int M, int
     }
     if (col0 < N) {        // N is a multiple of 32 (checked on the host) -> whole chunk in or out
 #pragma unroll
-      for (int g8 = 0; g8 < 4; ++g8) {     // 8 columns = one 16-byte store
-        float v[8];
+      for (int g8 = 0; g8 < 4; ++g8) {     // 8 columns = one 16-byte store, computed as 4 packed-fp32 pairs
+        uint64_t v[4];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[chunk & 1][g8 * 8 + j]);
+        for (int j = 0; j < 4; ++j)
+          v[j] = pk2(__uint_as_float(r[chunk & 1][g8 * 8 + 2 * j]), __uint_as_float(r[chunk & 1][g8 * 8 + 2 * j + 1]));
         const int lc = chunk * 32 + g8 * 8;
-        if (ln_fold) {
-          const float4 a0 = *reinterpret_cast<const float4*>(sa + lc);
-          const float4 a1 = *reinterpret_cast<const float4*>(sa + lc + 4);
-          const float ca[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-#pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] = __fmul_rn(rstd, fmaf(-mu, ca[j], v[j]));
-        }
         {
+          // every multiply-add is an explicit fma (ptxas contracts adjacent mul.f32x2 / add.f32x2 pairs when it sees them,
+          // and not in every instantiation alike): v = fma(rstd, fma(-mu, col_a, v), col_b)   |   v = v + col_b
           const float4 b0 = *reinterpret_cast<const float4*>(sb + lc);
           const float4 b1 = *reinterpret_cast<const float4*>(sb + lc + 4);
-          const float cb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+          const uint64_t cb[4] = {pk2(b0.x, b0.y), pk2(b0.z, b0.w), pk2(b1.x, b1.y), pk2(b1.z, b1.w)};
+          if (ln_fold) {
+            const float4 a0 = *reinterpret_cast<const float4*>(sa + lc);
+            const float4 a1 = *reinterpret_cast<const float4*>(sa + lc + 4);
+            const uint64_t ca[4] = {pk2(a0.x, a0.y), pk2(a0.z, a0.w), pk2(a1.x, a1.y), pk2(a1.z, a1.w)};
 #pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] = __fadd_rn(v[j], cb[j]);
+            for (int j = 0; j < 4; ++j) v[j] = fma2(rstd2, fma2(nmu2, ca[j], v[j]), cb[j]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v[j] = add2(v[j], cb[j]);
+          }
         }
         if (ep.gelu) {
 #pragma unroll
-          for (int j = 0; j < 8; j += 2) gelu_erf_x2(v[j], v[j + 1]);      // packed fp32 pipe; same bits as gelu_erf
+          for (int j = 0; j < 4; ++j) v[j] = gelu_erf_pk(v[j]);
+        }
+        if (scale) {                       // alpha == 1 (every GEMM but in_proj_q): x * 1 is x, skip the multiply
+#pragma unroll
+          for (int j = 0; j < 4; ++j) v[j] = mul2(v[j], alpha2);
         }
         uint32_t pk[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          pk[j] = pack_bf16x2(__fmul_rn(v[2 * j], ep.alpha), __fmul_rn(v[2 * j + 1], ep.alpha));
-          const float y0 = bf16_lo(pk[j]), y1 = bf16_hi(pk[j]);
-          s1 = __fadd_rn(s1, __fadd_rn(y0, y1));
-          s2 = fmaf(y0, y0, fmaf(y1, y1, s2));
+          float lo, hi;
+          upk2(v[j], lo, hi);
+          pk[j] = pack_bf16x2(lo, hi);
+        }
+        if (do_stats) {                    // LayerNorm statistics of the ROUNDED values the next GEMM will read
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float y0 = bf16_lo(pk[j]), y1 = bf16_hi(pk[j]);
+            s1 = __fadd_rn(s1, __fadd_rn(y0, y1));
+            s2 = fmaf(y0, y0, fmaf(y1, y1, s2));
+          }
         }
         if (out.buf != nullptr) {
           // slab = 2 chunks; 16-byte chunk index inside the 128-byte row, XOR-swizzled with (row & 7) like TMA's SWIZZLE_128B

@@ -350,8 +350,16 @@ __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t threads) {
 // Exact-erf GELU (nn.GELU default, builder.py:63,69,81).  erf by Abramowitz & Stegun 7.1.28,
 //   erf(t) = 1 - (1 + a1 t + ... + a6 t^6)^-16,  |error| <= 3e-7 analytically, <= 2e-6 evaluated in fp32,
 // i.e. a GELU error below 1e-6 absolute — three orders of magnitude under the bf16 rounding of the stored result —
-// at ~17 instructions instead of libdevice erff's two divergent branches (~40): the epilogue of the K=1024 GEMMs
-// is instruction-bound, so this is on the critical path.
+// instead of libdevice erff's two divergent branches (~40 instructions): the epilogue of the K=1024 GEMMs is
+// instruction-bound, so this is on the critical path.
+// The reciprocal is ONE MUFU.RCP: p >= 1, so none of div.approx's range scaling (FSETP/FSEL/2xFMUL per element) is needed;
+// for p > 2^126 (|x| > ~14) both give 1 - tiny = 1.
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
 __device__ __forceinline__ float gelu_erf(float x) {
   const float t = __fmul_rn(fabsf(x), 0.70710678118654752440f);
   float p = 0.0000430638f;
@@ -362,18 +370,18 @@ __device__ __forceinline__ float gelu_erf(float x) {
   p = fmaf(p, t, 0.0705230784f);
   p = fmaf(p, t, 1.0f);
   p = __fmul_rn(p, p); p = __fmul_rn(p, p); p = __fmul_rn(p, p); p = __fmul_rn(p, p);   // ^16 (+inf for |x| > ~24 -> erf = 1)
-  const float e = __fsub_rn(1.0f, __fdividef(1.0f, p));   // erf(|x| / sqrt 2)
-  const float hx = __fmul_rn(0.5f, x);
-  return fmaf(fabsf(hx), e, hx);                        // 0.5 x (1 + sign(x) erf(|x|/sqrt 2)) = hx + |hx| e
+  const float e = __fsub_rn(1.0f, rcp_approx(p));       // erf(|x| / sqrt 2)
+  return __fmul_rn(0.5f, fmaf(fabsf(x), e, x));         // 0.5 x (1 + sign(x) erf(|x|/sqrt 2)) = 0.5 (x + |x| e)
 }
 
-// Two GELUs at once on Blackwell's packed-fp32 pipe (fma/mul .f32x2 = FFMA2/FMUL2: two independent IEEE operations per
-// instruction, so the results are bit-identical to two gelu_erf calls) — the polynomial is 11 of the 17 instructions.
+// Blackwell's packed-fp32 pipe (add/mul/fma .f32x2 = FADD2/FMUL2/FFMA2): two independent IEEE round-to-nearest operations
+// per instruction, so every result is bit-identical to the two scalar operations it replaces.
 __device__ __forceinline__ uint64_t pk2(float a, float b) {
   uint64_t r;
   asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
   return r;
 }
+__device__ __forceinline__ uint64_t pk2(float a) { return pk2(a, a); }
 __device__ __forceinline__ void upk2(uint64_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
 __device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
   uint64_t d;
@@ -385,25 +393,32 @@ __device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
   asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
   return d;
 }
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
 
-__device__ __forceinline__ void gelu_erf_x2(float& x0, float& x1) {
+// Two GELUs at once; same bits as two gelu_erf calls (1 - r = fma(r, -1, 1) exactly).
+__device__ __forceinline__ uint64_t gelu_erf_pk(uint64_t x) {
   constexpr uint64_t kAbs = 0x7fffffff7fffffffull;
-  const uint64_t x = pk2(x0, x1);
-  const uint64_t t = mul2(x & kAbs, pk2(0.70710678118654752440f, 0.70710678118654752440f));
-  uint64_t p = pk2(0.0000430638f, 0.0000430638f);
-  p = fma2(p, t, pk2(0.0002765672f, 0.0002765672f));
-  p = fma2(p, t, pk2(0.0001520143f, 0.0001520143f));
-  p = fma2(p, t, pk2(0.0092705272f, 0.0092705272f));
-  p = fma2(p, t, pk2(0.0422820123f, 0.0422820123f));
-  p = fma2(p, t, pk2(0.0705230784f, 0.0705230784f));
-  p = fma2(p, t, pk2(1.0f, 1.0f));
+  const uint64_t ax = x & kAbs;
+  const uint64_t t = mul2(ax, pk2(0.70710678118654752440f));
+  uint64_t p = pk2(0.0000430638f);
+  p = fma2(p, t, pk2(0.0002765672f));
+  p = fma2(p, t, pk2(0.0001520143f));
+  p = fma2(p, t, pk2(0.0092705272f));
+  p = fma2(p, t, pk2(0.0422820123f));
+  p = fma2(p, t, pk2(0.0705230784f));
+  p = fma2(p, t, pk2(1.0f));
   p = mul2(p, p); p = mul2(p, p); p = mul2(p, p); p = mul2(p, p);
   float p0, p1;
   upk2(p, p0, p1);
-  const uint64_t e = pk2(__fsub_rn(1.0f, __fdividef(1.0f, p0)), __fsub_rn(1.0f, __fdividef(1.0f, p1)));
-  const uint64_t hx = mul2(pk2(0.5f, 0.5f), x);
-  upk2(fma2(hx & kAbs, e, hx), x0, x1);
+  const uint64_t e = fma2(pk2(rcp_approx(p0), rcp_approx(p1)), pk2(-1.0f), pk2(1.0f));
+  return mul2(pk2(0.5f), fma2(ax, e, x));
 }
+
+__device__ __forceinline__ void gelu_erf_x2(float& x0, float& x1) { upk2(gelu_erf_pk(pk2(x0, x1)), x0, x1); }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
