@@ -58,8 +58,9 @@ def ref_projector(builder, params, s, hidden):
 
 def gen_projector(builder):
     torch.set_num_threads(os.cpu_count())
-    for s in (2, 3, 4):
-        hidden, n = 128, 2
+    # 2 / 3 / 4: the released models; 1 / 6 / 8 / 12 / 24: the other divisors of 24 the constructor accepts (builder.py:51-52)
+    for s in (2, 3, 4, 1, 6, 8, 12, 24):
+        hidden, n = 128, (2 if s > 1 else 1)
         params = tpo.make_params(hidden, seed=100 + s)
         x0, xm = tpo.make_inputs(n, seed=200 + s)
         with torch.no_grad():

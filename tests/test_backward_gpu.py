@@ -12,7 +12,7 @@ from oracle import torch_port
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("s,hidden,n", [(2, 256, 2), (3, 128, 3), (4, 256, 4)])
+@pytest.mark.parametrize("s,hidden,n", [(2, 256, 2), (3, 128, 3), (4, 256, 4), (6, 256, 2), (24, 256, 3)])
 def test_parameter_gradients_match_autograd_of_oracle(s, hidden, n):
     from tokenpacker_b200 import TokenPackerB200
     params = {k: tpo.round_bf16(v) for k, v in tpo.make_params(hidden, seed=21 + s).items()}

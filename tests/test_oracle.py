@@ -8,7 +8,10 @@ from oracle import hd_oracle as hdo
 from oracle import tokenpacker_oracle as tpo
 
 
-@pytest.mark.parametrize("s", [2, 3, 4])
+ALL_SCALE_FACTORS = [2, 3, 4, 1, 6, 8, 12, 24]      # every divisor of 24 the reference constructor accepts (builder.py:51-52)
+
+
+@pytest.mark.parametrize("s", ALL_SCALE_FACTORS)
 def test_projector_matches_reference_fp32(golden_dir, s):
     g = np.load(os.path.join(golden_dir, f"projector_s{s}_h128.npz"))
     hidden, n = int(g["hidden"]), int(g["n"])
@@ -119,7 +122,7 @@ def test_hd_assemble(golden_dir):
     assert hdo.hd_seq_len(3, 3, 144) == 1450 and hdo.hd_seq_len(1, 1, 144) == 145 and hdo.hd_seq_len(5, 5, 36) == 962
 
 
-@pytest.mark.parametrize("s", [2, 3, 4])
+@pytest.mark.parametrize("s", ALL_SCALE_FACTORS)
 def test_torch_port_matches_reference(golden_dir, s):
     """The PyTorch-CPU port that bench.py times as the CPU baseline reproduces the reference's own output."""
     import torch

@@ -31,7 +31,7 @@ def errors(out, ref):
     return float(np.sqrt(((out - ref) ** 2).mean()) / rms), float(np.abs(out - ref).max())
 
 
-@pytest.mark.parametrize("s", [2, 3, 4])
+@pytest.mark.parametrize("s", [2, 3, 4, 1, 6, 8, 12, 24])       # 2/3/4: released models; the rest: the other divisors of 24
 def test_against_oracle_small_hidden(s):
     hidden, n = 128, 3
     m, params = make_module(hidden, s, seed=100 + s)
@@ -58,6 +58,26 @@ def test_against_reference_golden_full_width(golden_dir, s):
     rel, mx = errors(sub, g["out_sub"])
     assert rel <= REL_RMS_TOL and mx <= MAX_ABS_TOL, (rel, mx)
     assert abs(float(np.sqrt((out.astype(np.float64) ** 2).mean())) - float(g["out_rms"])) < 2e-3 * float(g["out_rms"]) + 1e-4
+
+
+@pytest.mark.parametrize("s", [1, 6, 8, 12, 24])
+def test_against_reference_golden_other_scale_factors(golden_dir, s):
+    """The scale factors no released model uses but the reference constructor accepts (builder.py:51-52): streamed-window
+    attention kernel, generic point-query stencil; fixture = the REFERENCE module's fp32 output (fp32 weights and inputs, so the
+    gap includes the bf16 rounding of both: the reference's own bf16 gap, see the header)."""
+    g = np.load(os.path.join(golden_dir, f"projector_s{s}_h128.npz"))
+    hidden, n = int(g["hidden"]), int(g["n"])
+    from tokenpacker_b200 import TokenPackerB200
+    params = tpo.make_params(hidden, seed=int(g["param_seed"]))
+    m = TokenPackerB200(hidden_size=hidden, scale_factor=s)
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in params.items()}, strict=True)
+    m = m.to(device="cuda", dtype=torch.bfloat16).eval()
+    x0, xm = tpo.make_inputs(n, seed=int(g["input_seed"]))
+    with torch.no_grad():
+        out = m((torch.from_numpy(x0).cuda().bfloat16(), torch.from_numpy(xm).cuda().bfloat16()))
+    assert out.shape == (n, (24 // s) ** 2, hidden)
+    rel, mx = errors(out.float().cpu().numpy(), g["out"])
+    assert rel <= 1.2e-2 and mx <= 2e-2, (rel, mx)
 
 
 def test_batch_invariance_and_strided_views():

@@ -401,6 +401,37 @@ int launch_attn(const __nv_bfloat16* qp, const __nv_bfloat16* kp, const __nv_bfl
   return TP_OK;
 }
 
+// scale_factor dispatch: every divisor of 24 (builder.py:51-52).  2 / 3 / 4 (the released 144 / 64 / 36-token models) keep
+// the window in registers; the others stream it.
+int launch_front_s(int s, const __nv_bfloat16* x0, long long x0_stride, __nv_bfloat16* q, long long Q, cudaStream_t stream) {
+  switch (s) {
+    case 1: return launch_front<1>(x0, x0_stride, q, Q, stream);
+    case 2: return launch_front<2>(x0, x0_stride, q, Q, stream);
+    case 3: return launch_front<3>(x0, x0_stride, q, Q, stream);
+    case 4: return launch_front<4>(x0, x0_stride, q, Q, stream);
+    case 6: return launch_front<6>(x0, x0_stride, q, Q, stream);
+    case 8: return launch_front<8>(x0, x0_stride, q, Q, stream);
+    case 12: return launch_front<12>(x0, x0_stride, q, Q, stream);
+    case 24: return launch_front<24>(x0, x0_stride, q, Q, stream);
+    default: return TP_ERR_BAD_SCALE_FACTOR;
+  }
+}
+
+int launch_attn_s(int s, const __nv_bfloat16* qp, const __nv_bfloat16* kp, const __nv_bfloat16* vp, __nv_bfloat16* ctx, long long Q,
+                  cudaStream_t stream) {
+  switch (s) {
+    case 2: return launch_attn<2>(qp, kp, vp, ctx, Q, stream);
+    case 3: return launch_attn<3>(qp, kp, vp, ctx, Q, stream);
+    case 4: return launch_attn<4>(qp, kp, vp, ctx, Q, stream);
+    default: {
+      const long long threads = Q * 32;
+      TP_CUDA(launch_pdl(window_attn_stream_kernel, dim3(static_cast<unsigned>((threads + 255) / 256)), dim3(256), 0, stream, qp, kp, vp, ctx,
+                         Q, s));
+      return TP_OK;
+    }
+  }
+}
+
 }  // namespace
 
 // ==================================================================================================
@@ -508,7 +539,6 @@ int forward_impl(const void* packed, const void* x0, const void* xm, const void*
     xm = xm_layers[0];
   }
   if (scale_factor <= 0 || kGrid % scale_factor != 0) return TP_ERR_BAD_SCALE_FACTOR;          // builder.py:51-52
-  if (scale_factor < 2 || scale_factor > 4) return TP_ERR_INVALID_ARGUMENT;   // released configurations: 144/64/36 tokens
   if (packed == nullptr || x0 == nullptr || xm == nullptr || out == nullptr || workspace == nullptr || n_crops <= 0 ||
       !valid_hidden(hidden))
     return TP_ERR_INVALID_ARGUMENT;
@@ -545,9 +575,7 @@ int forward_impl(const void* packed, const void* x0, const void* xm, const void*
   //   [5] out = h_m W_m2^T + b_m2  -> final [N,M,H] (or packed HD) layout    :136
   {
     const __nv_bfloat16* x0p = static_cast<const __nv_bfloat16*>(x0);
-    if (s == 2) TP_TRY(launch_front<2>(x0p, x0_crop_stride, bf(W.q), Q, stream));
-    else if (s == 3) TP_TRY(launch_front<3>(x0p, x0_crop_stride, bf(W.q), Q, stream));
-    else TP_TRY(launch_front<4>(x0p, x0_crop_stride, bf(W.q), Q, stream));
+    TP_TRY(launch_front_s(s, x0p, x0_crop_stride, bf(W.q), Q, stream));
   }
   {
     AOperand a{xm, xm_width, 0, 0};
@@ -591,9 +619,7 @@ int forward_impl(const void* packed, const void* x0, const void* xm, const void*
     g[2].ep.alpha = 0.08838834764831845f;   // 1/sqrt(head_dim = 128): torch MHA scales q after the in-projection
     TP_TRY(launch_gemms(g, 3, dev.sms, stream));
   }
-  if (s == 2) TP_TRY(launch_attn<2>(bf(W.q_p), k_p, v_p, bf(W.ctx), Q, stream));
-  else if (s == 3) TP_TRY(launch_attn<3>(bf(W.q_p), k_p, v_p, bf(W.ctx), Q, stream));
-  else TP_TRY(launch_attn<4>(bf(W.q_p), k_p, v_p, bf(W.ctx), Q, stream));
+  TP_TRY(launch_attn_s(s, bf(W.q_p), k_p, v_p, bf(W.ctx), Q, stream));
   TP_TRY(launch_gemm(AOperand{bf(W.ctx), kC, 0, 0}, P + L.w_om, kC, Q, H, kC, plain_epilogue(bf(W.h_m), H, wf(L.b_om), 1), dev.sms, stream));
   {
     GemmEpilogue ep = plain_epilogue(out, H, wf(L.b_m2), 0);
@@ -701,7 +727,7 @@ int tp_forward_host(const void* packed, const void* x0_host, const void* xm_host
 
 #ifdef TP_GEMM_PROFILE
 // Profile builds only (libtokenpacker_b200_prof.so, not part of the public ABI): same as tp_gemm_bf16 plus a device
-// buffer [grid][8] of cycle counters: {producer wait-empty, producer total, mma wait-full, mma wait-tmem, mma total,
+// buffer [grid][16] of cycle counters: {producer wait-empty, producer total, mma wait-full, mma wait-tmem, mma total,
 // epilogue wait-accumulator, epilogue busy, -}.
 TP_API int tp_gemm_bf16_prof(const void* a, int64_t lda, const void* b, int64_t ldb, void* c, int64_t ldc, int64_t m, int64_t n, int64_t k,
                              const float* bias, int gelu, float alpha, long long* prof, void* stream) {

@@ -329,4 +329,102 @@ __global__ void __launch_bounds__(256) window_attn_bwd_kernel(const __nv_bfloat1
   for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(dqp + query * kC + i * 256 + lane * 8) = pack8(dq[i]);
 }
 
+// Backward for any window size (scale_factor 1, 6, 8, 12, 24): two passes over the window's keys.  Pass A streams
+// (s_j, dp_j) through an online softmax to get the row maximum, the denominator and sum_j p_j dp_j; pass B recomputes
+// p_j and emits dk'_j, dv'_j (written once: every fine token belongs to exactly one window) and accumulates dq'.
+__global__ void __launch_bounds__(256) window_attn_bwd_stream_kernel(const __nv_bfloat16* __restrict__ qp, const __nv_bfloat16* __restrict__ kp,
+                                                                     const __nv_bfloat16* __restrict__ vp, const __nv_bfloat16* __restrict__ dctx,
+                                                                     __nv_bfloat16* __restrict__ dqp, __nv_bfloat16* __restrict__ dkp,
+                                                                     __nv_bfloat16* __restrict__ dvp, long long n_queries, int s) {
+  const int G = kGrid / s;
+  const int M = G * G;
+  const int W = s * s;
+  const long long query = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (query >= n_queries) return;
+  const long long n = query / M;
+  const int m = static_cast<int>(query - n * M);
+  const int hb = m / G, wb = m - hb * G;
+  const long long tok0 = n * kTokens + static_cast<long long>(hb * s) * kGrid + wb * s;
+
+  float qf[4][8], dc[4][8];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    unpack8(__ldg(reinterpret_cast<const uint4*>(qp + query * kC + i * 256 + lane * 8)), qf[i]);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(dctx + query * kC + i * 256 + lane * 8)), dc[i]);
+  }
+  // (s_j, dp_j) for channel block i of key j, reduced over the head's 16 lanes
+  auto scores = [&](long long tok, int i, float& sc, float& dp) {
+    float kf[8], vf[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(kp + tok * kC + i * 256 + lane * 8)), kf);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(vp + tok * kC + i * 256 + lane * 8)), vf);
+    float d = 0.f, e = 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      d = fmaf(qf[i][c], kf[c], d);
+      e = fmaf(dc[i][c], vf[c], e);
+    }
+#pragma unroll
+    for (int off = 8; off > 0; off >>= 1) {
+      d += __shfl_xor_sync(0xffffffffu, d, off);
+      e += __shfl_xor_sync(0xffffffffu, e, off);
+    }
+    sc = d;
+    dp = e;
+  };
+  float mx[4], den[4], num[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    mx[i] = -INFINITY;
+    den[i] = 0.f;
+    num[i] = 0.f;
+  }
+  for (int j = 0; j < W; ++j) {
+    const int hi = j / s;
+    const long long tok = tok0 + static_cast<long long>(hi) * kGrid + (j - hi * s);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float sc, dp;
+      scores(tok, i, sc, dp);
+      const float m_new = fmaxf(mx[i], sc);
+      const float corr = __expf(mx[i] - m_new);
+      const float pj = __expf(sc - m_new);
+      den[i] = fmaf(den[i], corr, pj);
+      num[i] = fmaf(num[i], corr, pj * dp);
+      mx[i] = m_new;
+    }
+  }
+  float inv[4], dot[4], dq[4][8];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    inv[i] = 1.0f / den[i];
+    dot[i] = num[i] * inv[i];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) dq[i][c] = 0.f;
+  }
+  for (int j = 0; j < W; ++j) {
+    const int hi = j / s;
+    const long long tok = tok0 + static_cast<long long>(hi) * kGrid + (j - hi * s);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float sc, dp;
+      scores(tok, i, sc, dp);
+      const float pj = __expf(sc - mx[i]) * inv[i];
+      const float ds = pj * (dp - dot[i]);
+      float kf[8], dk[8], dv[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(kp + tok * kC + i * 256 + lane * 8)), kf);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        dq[i][c] = fmaf(ds, kf[c], dq[i][c]);
+        dk[c] = ds * qf[i][c];
+        dv[c] = pj * dc[i][c];
+      }
+      *reinterpret_cast<uint4*>(dkp + tok * kC + i * 256 + lane * 8) = pack8(dk);
+      *reinterpret_cast<uint4*>(dvp + tok * kC + i * 256 + lane * 8) = pack8(dv);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(dqp + query * kC + i * 256 + lane * 8) = pack8(dq[i]);
+}
+
 }  // namespace tp

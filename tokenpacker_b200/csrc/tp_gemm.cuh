@@ -52,6 +52,10 @@ struct GemmEpilogue {
   long long* prof;         // TP_GEMM_PROFILE builds only: [grid][8] cycle counters (nullptr otherwise)
 };
 
+#ifndef TP_EPI_SUB_PAIRS
+#define TP_EPI_SUB_PAIRS 8      // 4 / 8 / 16 measured: 8 = most interleaving that still fits the register budget without spills
+#endif
+
 #ifdef TP_GEMM_PROFILE
 #define TP_PROF_T0() const long long prof_t0__ = clock64()
 #define TP_PROF_ADD(var) (var) += clock64() - prof_t0__
@@ -119,7 +123,8 @@ constexpr int kOutSlabBytes = 128 * 128;   // 128 rows x 64 bf16
 
 template <int kTileN, typename ReleaseFn>
 __device__ __forceinline__ void epilogue_tile(const GemmEpilogue& ep, int M, int N, uint32_t tmem_acc, int row, int col_tile0,
-                                              int quarter, int half, const float* s_col, const OutStage& out, ReleaseFn release) {
+                                              int quarter, int half, const float* s_col, const OutStage& out, ReleaseFn release,
+                                              [[maybe_unused]] long long* pc = nullptr) {
   constexpr int kColsPerWarp = kTileN / 2;
   constexpr int kChunks = kColsPerWarp / 32;
   const bool ln_fold = ep.col_a != nullptr;
@@ -146,8 +151,8 @@ __device__ __forceinline__ void epilogue_tile(const GemmEpilogue& ep, int M, int
   }
   __nv_bfloat16* c_row = ep.c + dst_row * ep.ldc;
   const uint32_t taddr = tmem_acc + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(half * kColsPerWarp);
-  const float* sa = s_col + half * kColsPerWarp;
-  const float* sb = s_col + kTileN + half * kColsPerWarp;
+  const uint32_t sa_addr = smem_u32(s_col + half * kColsPerWarp), sb_addr = smem_u32(s_col + kTileN + half * kColsPerWarp);
+  const uint32_t out_addr = out.buf != nullptr ? smem_u32(out.buf) : 0u;
 
   float s1 = 0.f, s2 = 0.f;
   const bool do_stats = ep.stats_out != nullptr;
@@ -157,7 +162,11 @@ __device__ __forceinline__ void epilogue_tile(const GemmEpilogue& ep, int M, int
   tmem_ld_32x32b_x32(taddr, r[0]);
 #pragma unroll
   for (int chunk = 0; chunk < kChunks; ++chunk) {
-    tmem_ld_wait();
+    {
+      TP_PROF_T0();
+      tmem_ld_wait();
+      TP_PROF_ADD(pc[0]);
+    }
     if (chunk + 1 < kChunks) tmem_ld_32x32b_x32(taddr + static_cast<uint32_t>((chunk + 1) * 32), r[(chunk + 1) & 1]);
     else release();                                   // every TMEM read of this warp has landed in registers
     const int col0 = col_tile0 + half * kColsPerWarp + chunk * 32;
@@ -167,70 +176,86 @@ __device__ __forceinline__ void epilogue_tile(const GemmEpilogue& ep, int M, int
       named_bar_sync(out.barrier_id, 128);
     }
     if (col0 < N) {        // N is a multiple of 32 (checked on the host) -> whole chunk in or out
+      // kSubPairs packed pairs (2 columns each) go through every step together: each run-time option is ONE warp-uniform branch
+      // around a basic block of kSubPairs independent dependency chains for the scheduler to interleave.
+      constexpr int kSubPairs = TP_EPI_SUB_PAIRS;
+      const int rloc = quarter * 32 + static_cast<int>(lane_id());
 #pragma unroll
-      for (int g8 = 0; g8 < 4; ++g8) {     // 8 columns = one 16-byte store, computed as 4 packed-fp32 pairs
-        uint64_t v[4];
+      for (int sub = 0; sub < 16 / kSubPairs; ++sub) {
+        const int lc = chunk * 32 + sub * kSubPairs * 2;             // first column of this sub-block inside the warp's slice
+        uint64_t v[kSubPairs];
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-          v[j] = pk2(__uint_as_float(r[chunk & 1][g8 * 8 + 2 * j]), __uint_as_float(r[chunk & 1][g8 * 8 + 2 * j + 1]));
-        const int lc = chunk * 32 + g8 * 8;
-        {
-          // every multiply-add is an explicit fma (ptxas contracts adjacent mul.f32x2 / add.f32x2 pairs when it sees them,
-          // and not in every instantiation alike): v = fma(rstd, fma(-mu, col_a, v), col_b)   |   v = v + col_b
-          const float4 b0 = *reinterpret_cast<const float4*>(sb + lc);
-          const float4 b1 = *reinterpret_cast<const float4*>(sb + lc + 4);
-          const uint64_t cb[4] = {pk2(b0.x, b0.y), pk2(b0.z, b0.w), pk2(b1.x, b1.y), pk2(b1.z, b1.w)};
-          if (ln_fold) {
-            const float4 a0 = *reinterpret_cast<const float4*>(sa + lc);
-            const float4 a1 = *reinterpret_cast<const float4*>(sa + lc + 4);
-            const uint64_t ca[4] = {pk2(a0.x, a0.y), pk2(a0.z, a0.w), pk2(a1.x, a1.y), pk2(a1.z, a1.w)};
+        for (int j = 0; j < kSubPairs; ++j)
+          v[j] = pk2(__uint_as_float(r[chunk & 1][sub * kSubPairs * 2 + 2 * j]), __uint_as_float(r[chunk & 1][sub * kSubPairs * 2 + 2 * j + 1]));
+        const uint32_t sb4 = sb_addr + static_cast<uint32_t>(lc) * 4u;
+        if (ln_fold) {     // v = fma(rstd, fma(-mu, col_a, v), col_b): explicit fmas — ptxas contracts adjacent mul.f32x2 / add.f32x2
+          const uint32_t sa4 = sa_addr + static_cast<uint32_t>(lc) * 4u;    // pairs when it sees them, and not in every instantiation alike
 #pragma unroll
-            for (int j = 0; j < 4; ++j) v[j] = fma2(rstd2, fma2(nmu2, ca[j], v[j]), cb[j]);
-          } else {
+          for (int q = 0; q < kSubPairs / 2; ++q) {
+            const float4 a = lds_f4(sa4 + q * 16), b = lds_f4(sb4 + q * 16);
+            v[2 * q] = fma2(rstd2, fma2(nmu2, pk2(a.x, a.y), v[2 * q]), pk2(b.x, b.y));
+            v[2 * q + 1] = fma2(rstd2, fma2(nmu2, pk2(a.z, a.w), v[2 * q + 1]), pk2(b.z, b.w));
+          }
+        } else {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) v[j] = add2(v[j], cb[j]);
+          for (int q = 0; q < kSubPairs / 2; ++q) {
+            const float4 b = lds_f4(sb4 + q * 16);
+            v[2 * q] = add2(v[2 * q], pk2(b.x, b.y));
+            v[2 * q + 1] = add2(v[2 * q + 1], pk2(b.z, b.w));
           }
         }
         if (ep.gelu) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) v[j] = gelu_erf_pk(v[j]);
+          for (int j = 0; j < kSubPairs; ++j) v[j] = gelu_erf_pk(v[j]);
         }
-        if (scale) {                       // alpha == 1 (every GEMM but in_proj_q): x * 1 is x, skip the multiply
+        if (scale) {       // alpha == 1 (every GEMM but in_proj_q): x * 1 is x, skip the multiply
 #pragma unroll
-          for (int j = 0; j < 4; ++j) v[j] = mul2(v[j], alpha2);
+          for (int j = 0; j < kSubPairs; ++j) v[j] = mul2(v[j], alpha2);
         }
-        uint32_t pk[4];
+        uint32_t pk[kSubPairs];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < kSubPairs; ++j) {
           float lo, hi;
           upk2(v[j], lo, hi);
           pk[j] = pack_bf16x2(lo, hi);
         }
-        if (do_stats) {                    // LayerNorm statistics of the ROUNDED values the next GEMM will read
+        if (do_stats) {    // LayerNorm statistics of the ROUNDED values the next GEMM will read (column order: deterministic)
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
+          for (int j = 0; j < kSubPairs; ++j) {
             const float y0 = bf16_lo(pk[j]), y1 = bf16_hi(pk[j]);
             s1 = __fadd_rn(s1, __fadd_rn(y0, y1));
             s2 = fmaf(y0, y0, fmaf(y1, y1, s2));
           }
         }
         if (out.buf != nullptr) {
-          // slab = 2 chunks; 16-byte chunk index inside the 128-byte row, XOR-swizzled with (row & 7) like TMA's SWIZZLE_128B
-          const int rloc = quarter * 32 + static_cast<int>(lane_id());
-          const int ci = (chunk & 1) * 4 + g8;
-          uint8_t* dst = out.buf + ((chunk >> 1) & (out.n_bufs - 1)) * kOutSlabBytes + rloc * 128 + ((ci ^ (rloc & 7)) << 4);
-          *reinterpret_cast<uint4*>(dst) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          // slab = 2 chunks; 16-byte piece index inside the 128-byte row, XOR-swizzled with (row & 7) like TMA's SWIZZLE_128B
+          const uint32_t row_base = out_addr + static_cast<uint32_t>(((chunk >> 1) & (out.n_bufs - 1)) * kOutSlabBytes + rloc * 128);
+#pragma unroll
+          for (int g = 0; g < kSubPairs / 4; ++g) {
+            const int ci = (chunk & 1) * 4 + sub * (kSubPairs / 4) + g;
+            sts_u4(row_base + static_cast<uint32_t>((ci ^ (rloc & 7)) << 4), pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+          }
         } else if (row_ok) {
-          *reinterpret_cast<uint4*>(c_row + col0 + g8 * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+#pragma unroll
+          for (int g = 0; g < kSubPairs / 4; ++g)
+            *reinterpret_cast<uint4*>(c_row + col0 + sub * kSubPairs * 2 + g * 8) = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
         }
       }
     }
     if (out.buf != nullptr && (chunk & 1) == 1) {
       // slab complete: publish to the async proxy, make sure the previous store of this half has drained its buffer
       // (so the NEXT slab may overwrite it), then one thread issues the TMA store
-      fence_proxy_async_smem();
-      if (out.issuer && out.n_bufs == 2) bulk_wait_group_read<0>();
-      named_bar_sync(out.barrier_id, 128);
+      {
+        TP_PROF_T0();
+        fence_proxy_async_smem();
+        TP_PROF_ADD(pc[1]);
+      }
+      {
+        TP_PROF_T0();
+        if (out.issuer && out.n_bufs == 2) bulk_wait_group_read<0>();
+        named_bar_sync(out.barrier_id, 128);
+        TP_PROF_ADD(pc[2]);
+      }
       if (out.issuer) {
         const int slab = chunk >> 1;
         for (int p = 0; p < out.n_maps; ++p)
@@ -598,8 +623,8 @@ tp_gemm2_kernel(const __grid_constant__ GemmGroup grp, const __grid_constant__ P
     }
 #ifdef TP_GEMM_PROFILE
     if (grp.p[0].ep.prof != nullptr && lane == 0) {
-      grp.p[0].ep.prof[blockIdx.x * 8 + 0] = w_empty;
-      grp.p[0].ep.prof[blockIdx.x * 8 + 1] = clock64() - t_begin;
+      grp.p[0].ep.prof[blockIdx.x * 16 + 0] = w_empty;
+      grp.p[0].ep.prof[blockIdx.x * 16 + 1] = clock64() - t_begin;
     }
 #endif
   } else if (warp_idx == kMmaWarp) {
@@ -660,9 +685,9 @@ tp_gemm2_kernel(const __grid_constant__ GemmGroup grp, const __grid_constant__ P
       }
 #ifdef TP_GEMM_PROFILE
       if (grp.p[0].ep.prof != nullptr && lane == 0) {
-        grp.p[0].ep.prof[blockIdx.x * 8 + 2] = w_full;
-        grp.p[0].ep.prof[blockIdx.x * 8 + 3] = w_tmem;
-        grp.p[0].ep.prof[blockIdx.x * 8 + 4] = clock64() - t_begin;
+        grp.p[0].ep.prof[blockIdx.x * 16 + 2] = w_full;
+        grp.p[0].ep.prof[blockIdx.x * 16 + 3] = w_tmem;
+        grp.p[0].ep.prof[blockIdx.x * 16 + 4] = clock64() - t_begin;
       }
 #endif
     }
@@ -676,6 +701,7 @@ tp_gemm2_kernel(const __grid_constant__ GemmGroup grp, const __grid_constant__ P
     uint32_t acc_phase = 0;
     bool stored = false;
     [[maybe_unused]] long long w_acc = 0, t_work = 0;
+    [[maybe_unused]] long long pc[3] = {0, 0, 0};
     for (int tile = pair_idx; tile < num_tiles; tile += num_pairs) {
       const TileRef t = decode_tile(grp, tile);
       const GemmProblem& pr = *t.pr;
@@ -703,7 +729,7 @@ tp_gemm2_kernel(const __grid_constant__ GemmGroup grp, const __grid_constant__ P
                                 if (is_leader) mbar_arrive(release_bar);
                                 else mbar_arrive_cluster(release_bar, 0);
                               }
-                            });
+                            }, pc);
       TP_PROF_ADD(t_work);
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
@@ -713,8 +739,11 @@ tp_gemm2_kernel(const __grid_constant__ GemmGroup grp, const __grid_constant__ P
     }
 #ifdef TP_GEMM_PROFILE
     if (grp.p[0].ep.prof != nullptr && e == 0 && lane == 0) {
-      grp.p[0].ep.prof[blockIdx.x * 8 + 5] = w_acc;
-      grp.p[0].ep.prof[blockIdx.x * 8 + 6] = t_work;
+      grp.p[0].ep.prof[blockIdx.x * 16 + 5] = w_acc;
+      grp.p[0].ep.prof[blockIdx.x * 16 + 6] = t_work;
+      grp.p[0].ep.prof[blockIdx.x * 16 + 8] = pc[0];          // epilogue warp 0: cycles in tcgen05.wait::ld
+      grp.p[0].ep.prof[blockIdx.x * 16 + 9] = pc[1];         // ... in fence.proxy.async
+      grp.p[0].ep.prof[blockIdx.x * 16 + 10] = pc[2];          // ... in wait_group.read + named barrier
     }
 #endif
   }

@@ -24,8 +24,10 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 
 // ------------------------------------------------------------------------------------------------
 // Point queries (builder.py:117-118): bilinear 24x24 -> g x g with align_corners=False is a fixed stencil per
-// s x s window — s=2: mean of the 2x2; s=3: the centre token; s=4: mean of the centre 2x2 — computed in fp32
-// (the reference upcasts with .float()) and rounded once to bf16 (.to(x.dtype)).
+// s x s window: the source coordinate of output i is s*i + s/2 - 0.5, so an odd s reads the window's centre token
+// (weight exactly 1) and an even s the mean of its centre 2x2 (weights exactly 0.5 each) — s=2: mean of the 2x2;
+// s=3: the centre; s=4: mean of the centre 2x2; s=1: the token itself.  Computed in fp32 (the reference upcasts
+// with .float()) and rounded once to bf16 (.to(x.dtype)).
 // One thread per 8 channels of one query.
 // ------------------------------------------------------------------------------------------------
 template <int S>
@@ -45,11 +47,11 @@ __global__ void point_query_kernel(const __nv_bfloat16* __restrict__ x0, long lo
   const __nv_bfloat16* base = x0 + n * crop_stride + vec * 8;
   auto tok = [&](int r, int c) { return __ldg(reinterpret_cast<const uint4*>(base + static_cast<long long>(r * kGrid + c) * kC)); };
   uint4 out;
-  if (S == 3) {
-    out = tok(hb * 3 + 1, wb * 3 + 1);
+  if (S % 2 == 1) {
+    out = tok(hb * S + (S - 1) / 2, wb * S + (S - 1) / 2);
   } else {
-    const int r0 = hb * S + (S == 2 ? 0 : 1);
-    const int c0 = wb * S + (S == 2 ? 0 : 1);
+    const int r0 = hb * S + S / 2 - 1;
+    const int c0 = wb * S + S / 2 - 1;
     float a[8], b[8], c[8], d[8], o[8];
     unpack8(tok(r0, c0), a);
     unpack8(tok(r0, c0 + 1), b);
@@ -152,6 +154,71 @@ __global__ void __launch_bounds__(256) window_attn_kernel(const __nv_bfloat16* _
   }
 #pragma unroll
   for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(ctx + query * kC + i * 256 + lane * 8) = pack8(of[i]);
+}
+
+// Same computation for any window size (scale_factor 1, 6, 8, 12, 24: 1 ... 576 keys per query — constructor-valid upstream,
+// builder.py:51-52, though no released model uses them): the keys are streamed through an online softmax instead of being
+// held in registers.  Same warp / lane ownership as window_attn_kernel.
+__global__ void __launch_bounds__(256) window_attn_stream_kernel(const __nv_bfloat16* __restrict__ qp, const __nv_bfloat16* __restrict__ kp,
+                                                                 const __nv_bfloat16* __restrict__ vp, __nv_bfloat16* __restrict__ ctx,
+                                                                 long long n_queries, int s) {
+  const int G = kGrid / s;
+  const int M = G * G;
+  const int W = s * s;
+  grid_dependency_wait();
+  grid_launch_dependents();
+  const long long query = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (query >= n_queries) return;
+  const long long n = query / M;
+  const int m = static_cast<int>(query - n * M);
+  const int hb = m / G, wb = m - hb * G;
+  const long long tok0 = n * kTokens + static_cast<long long>(hb * s) * kGrid + wb * s;
+
+  float qf[4][8], of[4][8], mx[4], den[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    unpack8(__ldg(reinterpret_cast<const uint4*>(qp + query * kC + i * 256 + lane * 8)), qf[i]);
+    mx[i] = -INFINITY;
+    den[i] = 0.f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) of[i][e] = 0.f;
+  }
+  for (int j = 0; j < W; ++j) {
+    const int hi = j / s;
+    const long long tok = tok0 + static_cast<long long>(hi) * kGrid + (j - hi * s);
+    float sc[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float kf[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(kp + tok * kC + i * 256 + lane * 8)), kf);
+      float d = 0.f;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) d = fmaf(qf[i][e], kf[e], d);
+#pragma unroll
+      for (int off = 8; off > 0; off >>= 1) d += __shfl_xor_sync(0xffffffffu, d, off);
+      sc[i] = d;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float m_new = fmaxf(mx[i], sc[i]);
+      const float corr = __expf(mx[i] - m_new);       // 0 on the first key (mx = -inf)
+      const float pj = __expf(sc[i] - m_new);
+      den[i] = fmaf(den[i], corr, pj);
+      mx[i] = m_new;
+      float vf[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(vp + tok * kC + i * 256 + lane * 8)), vf);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) of[i][e] = fmaf(pj, vf[e], of[i][e] * corr);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float inv = 1.0f / den[i];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) of[i][e] *= inv;
+    *reinterpret_cast<uint4*>(ctx + query * kC + i * 256 + lane * 8) = pack8(of[i]);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------

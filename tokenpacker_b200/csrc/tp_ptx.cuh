@@ -420,6 +420,17 @@ __device__ __forceinline__ uint64_t gelu_erf_pk(uint64_t x) {
 
 __device__ __forceinline__ void gelu_erf_x2(float& x0, float& x1) { upk2(gelu_erf_pk(pk2(x0, x1)), x0, x1); }
 
+// Explicit shared-space vector accesses for the epilogue (pointers that travel through structs reach ptxas as generic
+// addresses: LD.E/ST.E with an address-space check instead of LDS/STS).  volatile: ordered with the barrier / mbarrier asm.
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts_u4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);

@@ -134,19 +134,18 @@ GemmItem plain_item(const void* a, long long lda, const void* b, long long ldb, 
 extern "C" {
 
 size_t tp_train_saved_bytes(int64_t n_crops, int scale_factor, int hidden) {
-  if (n_crops <= 0 || scale_factor < 2 || scale_factor > 4 || !valid_hidden(hidden)) return 0;
+  if (n_crops <= 0 || scale_factor <= 0 || kGrid % scale_factor != 0 || !valid_hidden(hidden)) return 0;
   return saved_layout(n_crops, scale_factor, hidden).total;
 }
 
 size_t tp_backward_workspace_bytes(int64_t n_crops, int scale_factor, int hidden) {
-  if (n_crops <= 0 || scale_factor < 2 || scale_factor > 4 || !valid_hidden(hidden)) return 0;
+  if (n_crops <= 0 || scale_factor <= 0 || kGrid % scale_factor != 0 || !valid_hidden(hidden)) return 0;
   return bwd_layout(n_crops, scale_factor, hidden).total;
 }
 
 int tp_forward_train(const void* packed, const void* x0, const void* xm, int64_t n_crops, int64_t x0_crop_stride, int64_t xm_crop_stride,
                      int scale_factor, int hidden, void* out, void* saved, size_t saved_bytes, void* stream_) {
   if (scale_factor <= 0 || kGrid % scale_factor != 0) return TP_ERR_BAD_SCALE_FACTOR;
-  if (scale_factor < 2 || scale_factor > 4) return TP_ERR_INVALID_ARGUMENT;
   if (packed == nullptr || x0 == nullptr || xm == nullptr || out == nullptr || saved == nullptr || n_crops <= 0 || !valid_hidden(hidden))
     return TP_ERR_INVALID_ARGUMENT;
   if (x0_crop_stride < static_cast<int64_t>(kTokens) * kC || xm_crop_stride < static_cast<int64_t>(kTokens) * kCm || x0_crop_stride % 8 != 0 ||
@@ -171,9 +170,7 @@ int tp_forward_train(const void* packed, const void* x0, const void* xm, int64_t
 
   {
     const __nv_bfloat16* x0p = static_cast<const __nv_bfloat16*>(x0);
-    if (s == 2) TP_TRY(launch_front<2>(x0p, x0_crop_stride, bf(S.q), Q, stream));
-    else if (s == 3) TP_TRY(launch_front<3>(x0p, x0_crop_stride, bf(S.q), Q, stream));
-    else TP_TRY(launch_front<4>(x0p, x0_crop_stride, bf(S.q), Q, stream));
+    TP_TRY(launch_front_s(s, x0p, x0_crop_stride, bf(S.q), Q, stream));
   }
   {
     AOperand a{xm, kCm, 0, 0};
@@ -202,9 +199,7 @@ int tp_forward_train(const void* packed, const void* x0, const void* xm, int64_t
     gi[2].ep.alpha = 0.08838834764831845f;
     TP_TRY(launch_gemms(gi, 3, dev.sms, stream));
   }
-  if (s == 2) TP_TRY(launch_attn<2>(bf(S.q_p), bf(S.k_p), bf(S.v_p), bf(S.ctx), Q, stream));
-  else if (s == 3) TP_TRY(launch_attn<3>(bf(S.q_p), bf(S.k_p), bf(S.v_p), bf(S.ctx), Q, stream));
-  else TP_TRY(launch_attn<4>(bf(S.q_p), bf(S.k_p), bf(S.v_p), bf(S.ctx), Q, stream));
+  TP_TRY(launch_attn_s(s, bf(S.q_p), bf(S.k_p), bf(S.v_p), bf(S.ctx), Q, stream));
   TP_TRY(launch_gemm(AOperand{bf(S.ctx), kC, 0, 0}, P + L.w_o, kC, Q, kC, kC, plain_epilogue(bf(S.o), kC, wf(L.b_o), 0), dev.sms, stream));
   TP_TRY(launch_gemm(AOperand{bf(S.o), kC, 0, 0}, P + L.w_m0, kC, Q, H, kC, plain_epilogue(bf(S.z_m), H, wf(L.b_m0), 0), dev.sms, stream));
   TP_TRY(launch_gelu_fwd(bf(S.z_m), bf(S.h_m), static_cast<size_t>(Q) * H, stream));
@@ -218,7 +213,6 @@ int tp_backward(const tp_weights* w, const void* xm, int64_t xm_crop_stride, int
       !valid_hidden(hidden))
     return TP_ERR_INVALID_ARGUMENT;
   if (scale_factor <= 0 || kGrid % scale_factor != 0) return TP_ERR_BAD_SCALE_FACTOR;
-  if (scale_factor < 2 || scale_factor > 4) return TP_ERR_INVALID_ARGUMENT;
   if (xm_crop_stride != static_cast<int64_t>(kTokens) * kCm) return TP_ERR_INVALID_ARGUMENT;   // backward takes contiguous xm
   {
     const void* const* f = reinterpret_cast<const void* const*>(w);
@@ -327,7 +321,8 @@ int tp_backward(const tp_weights* w, const void* xm, int64_t xm_crop_stride, int
     const unsigned blocks = static_cast<unsigned>((threads + 255) / 256);
     if (s == 2) window_attn_bwd_kernel<2><<<blocks, 256, 0, stream>>>(sb(S.q_p), sb(S.k_p), sb(S.v_p), wb(B.dctx), wb(B.dqp), wb(B.dkp), wb(B.dvp), Q);
     else if (s == 3) window_attn_bwd_kernel<3><<<blocks, 256, 0, stream>>>(sb(S.q_p), sb(S.k_p), sb(S.v_p), wb(B.dctx), wb(B.dqp), wb(B.dkp), wb(B.dvp), Q);
-    else window_attn_bwd_kernel<4><<<blocks, 256, 0, stream>>>(sb(S.q_p), sb(S.k_p), sb(S.v_p), wb(B.dctx), wb(B.dqp), wb(B.dkp), wb(B.dvp), Q);
+    else if (s == 4) window_attn_bwd_kernel<4><<<blocks, 256, 0, stream>>>(sb(S.q_p), sb(S.k_p), sb(S.v_p), wb(B.dctx), wb(B.dqp), wb(B.dkp), wb(B.dvp), Q);
+    else window_attn_bwd_stream_kernel<<<blocks, 256, 0, stream>>>(sb(S.q_p), sb(S.k_p), sb(S.v_p), wb(B.dctx), wb(B.dqp), wb(B.dkp), wb(B.dvp), Q, s);
     TP_CUDA(cudaGetLastError());
   }
   // ---- MHA in-projections:  q' = alpha (LN(y_q) W_iq^T + b),  k' = LN(y_k) W_ik^T + b,  v' likewise

@@ -88,8 +88,6 @@ class TokenPackerB200(nn.Module):
         if (raw_grid, embed_dim, num_heads, kv_dim) != (24, 1024, 8, 1024):
             raise NotImplementedError("the sm_100a kernels are specialised for CLIP-ViT-L/14-336: raw_grid=24, "
                                       "embed_dim=kv_dim=1024, num_heads=8 (the only configuration the reference builds)")
-        if scale_factor not in (2, 3, 4):
-            raise NotImplementedError("scale_factor must be 2, 3 or 4 (144 / 64 / 36 tokens)")
         if hidden_size % 32 != 0:
             raise NotImplementedError("hidden_size must be a multiple of 32")
         self.raw_grid = raw_grid

@@ -24,7 +24,7 @@ for name, m, n, k, gelu in shapes:
     b = (torch.randn(n, k, device="cuda") * 0.02).bfloat16()
     bias = torch.randn(n, device="cuda")
     c = torch.empty(m, n, device="cuda", dtype=torch.bfloat16)
-    prof = torch.zeros(148 * 8, dtype=torch.int64, device="cuda")
+    prof = torch.zeros(148 * 16, dtype=torch.int64, device="cuda")
     s = torch.cuda.current_stream().cuda_stream
     for _ in range(3):
         st = lib.tp_gemm_bf16_prof(a.data_ptr(), k, b.data_ptr(), k, c.data_ptr(), n, m, n, k, bias.data_ptr(), gelu, 1.0, prof.data_ptr(), s)
@@ -38,7 +38,7 @@ for name, m, n, k, gelu in shapes:
     torch.cuda.synchronize()
     us = e0.elapsed_time(e1) / 20 * 1e3
     print(f"   timed: {us:.1f} us  {2.0 * m * n * k / us / 1e6:.1f} TF/s")
-    p = prof.cpu().reshape(148, 8).double()
+    p = prof.cpu().reshape(148, 16).double()
     lead, peer = p[0::2], p[1::2]
     tiles = ((m + 255) // 256) * (n // 256)
     ideal = tiles / 74 * (k / 64) * 512
@@ -47,4 +47,6 @@ for name, m, n, k, gelu in shapes:
           f" | producer(peer): wait-empty {peer[:, 0].mean():9.0f} of {peer[:, 1].mean():9.0f}")
     print(f"   mma: wait-full {lead[:, 2].mean():9.0f} ({100 * lead[:, 2].mean() / lead[:, 4].mean():.0f}%)  wait-tmem {lead[:, 3].mean():9.0f} "
           f"({100 * lead[:, 3].mean() / lead[:, 4].mean():.0f}%)  total {lead[:, 4].mean():9.0f}  -> issue+other {lead[:, 4].mean() - lead[:, 2].mean() - lead[:, 3].mean():9.0f}")
-    print(f"   epilogue warp0: wait-acc {p[:, 5].mean():9.0f}  busy {p[:, 6].mean():9.0f}  busy/tile {p[:, 6].mean() / (tiles / 74):7.0f}")
+    print(f"   epilogue warp0: wait-acc {p[:, 5].mean():9.0f}  busy {p[:, 6].mean():9.0f}  busy/tile {p[:, 6].mean() / (tiles / 74):7.0f}"
+          f"  of which per tile: tcgen05.wait::ld {p[:, 8].mean() / (tiles / 74):6.0f}  fence.proxy.async {p[:, 9].mean() / (tiles / 74):6.0f}"
+          f"  wait_group.read+barrier {p[:, 10].mean() / (tiles / 74):6.0f}")
