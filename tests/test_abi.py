@@ -36,6 +36,10 @@ def test_strerror_and_size_queries():
     assert lib.tp_packed_bytes(4097) == 0
     assert lib.tp_workspace_bytes(64, 2, 4096) > 64 * 576 * 4096 * 2
     assert lib.tp_workspace_bytes(64, 5, 4096) == 0
+    for s in (1, 2, 3, 4, 6, 8, 12, 24):            # every divisor of 24 (builder.py:51-52), inference and training
+        assert lib.tp_workspace_bytes(2, s, 256) > 0 and lib.tp_train_saved_bytes(2, s, 256) > 0
+        assert lib.tp_backward_workspace_bytes(2, s, 256) > 0
+    assert lib.tp_train_saved_bytes(2, 7, 256) == 0
 
 
 def test_product_does_not_import_oracle():
