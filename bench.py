@@ -140,7 +140,14 @@ def cpu_reference_run(steps: int, warmup: int, crops: int):
         for _ in range(steps):
             torch_port.forward(params, x0, xm, SCALE)
         dt = (time.perf_counter() - t0) / steps
+        # BASELINE configs[0]: ONE image (576x1024 feats, s=2 -> 144 tokens), the reference forward on the CPU, fp32
+        torch_port.forward(params, x0[:1], xm[:1], SCALE)
+        t0 = time.perf_counter()
+        for _ in range(5):
+            torch_port.forward(params, x0[:1], xm[:1], SCALE)
+        single_ms = (time.perf_counter() - t0) / 5 * 1e3
     return {"value": crops * TOKENS_PER_CROP / dt, "unit": UNIT, "cores": int(torch.get_num_threads()), "kind": "port",
+            "configs0_single_image_ms": single_ms,
             "sample": f"{crops} crops/step x {steps} steps of the configs[1] workload (fp32, torch {torch.__version__} CPU ops, "
                       f"oracle/torch_port.py restatement of builder.py:107-137; best of pool sizes {cands} on {avail} visible cores), {dt * 1e3:.1f} ms/step"}, dt
 
@@ -402,6 +409,22 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu_baseline, _ = cpu_reference_run(steps=20, warmup=2, crops=8)
 
+    # ------------------------------------------------------------------ BASELINE configs[0]: one image through the public forward
+    single = None
+    if rank == 0:
+        with torch.no_grad():
+            for _ in range(5):
+                model((x0[:1], xm[:1]))
+            torch.cuda.synchronize()
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record()
+            for _ in range(50):
+                model((x0[:1], xm[:1]))
+            s1.record()
+            torch.cuda.synchronize()
+        single = {"gpu_ms": s0.elapsed_time(s1) / 50, "what": "configs[0]: 1 image, s=2 -> 144 tokens, TokenPackerB200.forward, 50 calls back to back",
+                  "cpu_reference_ms": None if cpu_baseline is None else cpu_baseline["configs0_single_image_ms"]}
+
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
@@ -411,7 +434,8 @@ def main():
                            "crops_per_gpu": N_CROPS, "tokens_per_step": tokens_per_step,
                            "l2": "inputs 377 MB/step per GPU exceed the 126 MB L2 (no explicit flush needed)",
                            "parallelism": f"dp{world} (crops sharded, weights replicated, no data-path collective)"},
-                "e2e": e2e, "gpu_launches": 7 * args.steps, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline, "gpu_eager_baseline": gpu_eager}
+                "e2e": e2e, "gpu_launches": 7 * args.steps, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline, "gpu_eager_baseline": gpu_eager,
+                "configs0_single_image": single}
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
