@@ -13,7 +13,7 @@ a = torch.randn(300, 200, device="cuda").bfloat16()
 b = torch.randn(512, 200, device="cuda").bfloat16()
 gemm_bf16(a, b, bias=torch.randn(512, device="cuda"), gelu=True)
 gemm_tn_bf16(torch.randn(200, 304, device="cuda").bfloat16(), torch.randn(200, 256, device="cuda").bfloat16())
-for s, hidden in ((2, 256), (3, 128)):
+for s, hidden in ((2, 256), (3, 128), (6, 128)):       # 6: the streamed-window attention kernels (forward + backward)
     m = TokenPackerB200(hidden_size=hidden, scale_factor=s).to("cuda", torch.bfloat16)
     x0 = torch.randn(2, 577, 1024, device="cuda").bfloat16()[:, 1:]
     xm = torch.randn(2, 577, 4096, device="cuda").bfloat16()[:, 1:]
