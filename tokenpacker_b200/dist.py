@@ -105,7 +105,8 @@ class FusedGatherTokenPacker:
         device = x_local[0].device
         buf, hdl = self._gathered_buffers(int(sum(counts)), device)[self._calls % 2]
         self._calls += 1
-        self.projector.forward_into_peers(x_local, list(hdl.buffer_ptrs), int(sum(counts[:rank])))
+        if counts[rank] > 0:            # a rank may own no crops of a small batch: it still takes part in the barrier
+            self.projector.forward_into_peers(x_local, list(hdl.buffer_ptrs), int(sum(counts[:rank])))
         hdl.barrier(channel=0)          # every rank's stores have landed everywhere
         return buf
 
