@@ -121,3 +121,24 @@ def test_argument_errors_are_status_codes_not_crashes():
         _lib.check(_lib.TP_ERR_BAD_PATCH_NUM, "x")
     with pytest.raises(_lib.TokenPackerError, match="workspace too small"):
         _lib.check(_lib.TP_ERR_WORKSPACE_TOO_SMALL, "x")
+
+
+def test_plain_c_consumer(tmp_path):
+    """include/tokenpacker_b200.h is C99, every declared entry point links from plain C, and size queries / argument validation /
+    the host-side grid selector run without a GPU (tests/abi_c/abi_check.c)."""
+    import shutil
+    import subprocess
+    from tokenpacker_b200 import _lib
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    exe = str(tmp_path / "abi_check")
+    src = os.path.join(ROOT, "tests", "abi_c", "abi_check.c")
+    text = open(src).read()
+    for name in header_functions():
+        assert f"&{name}" in text, f"{name} missing from abi_check.c"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), src, "-o", exe, "-L", libdir,
+                    "-l:libtokenpacker_b200.so", f"-Wl,-rpath,{libdir}"], check=True, capture_output=True, text=True)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
+    assert "abi ok" in r.stdout
