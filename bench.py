@@ -338,7 +338,7 @@ def main():
         assert torch.equal(hout, out.cpu()), "host-buffer path and device path disagree"
         e2e = {"value": tokens_per_step / (dt / args.steps), "unit": UNIT,
                "h2d_bytes_per_step": int(hx0.numel() * 2 + hxm.numel() * 2), "d2h_bytes_per_step": int(hout.numel() * 2),
-               "ms_per_step": dt / args.steps * 1e3, "steps_timed": e2e_steps, "api": "TokenPackerB200.forward_host -> tp_forward_host (pinned host buffers, 8-crop chunks)"}
+               "ms_per_step": dt / args.steps * 1e3, "steps_timed": e2e_steps, "api": "TokenPackerB200.forward_host -> tp_forward_host (pinned host buffers, 8-crop chunks with a tapered tail)"}
 
     # ------------------------------------------------------------------ roofline of the dominant kernel
     # tp_gemm2_kernel on its largest launch: h_kv = GELU(xm . [W_k0;W_v0]^T + b)  (M=36864, N=2048, K=4096), 56% of the

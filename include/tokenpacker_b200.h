@@ -105,7 +105,9 @@ TP_API int tp_forward_allgather(const void* packed, const void* x0, const void* 
                                 int64_t crop_offset, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Same call with HOST buffers (pinned recommended): copies inputs in, runs, copies the result out, pipelined over
- * chunks of crops on internal streams, and returns after the result is in ``out_host``.  d_* are caller-provided
+ * chunks of ``chunk_crops`` crops (the last few chunks shrink, so that the part not hidden behind the copies in — the final
+ * chunk's compute and copy out — is short) on internal streams, and returns after the result is in ``out_host``.  The workspace
+ * must cover tp_workspace_bytes(chunk_crops, ...).  d_* are caller-provided
  * device staging buffers of at least the sizes tp_forward needs for n_crops.  This is the end-to-end entry point
  * the benchmark times (host<->device traffic inside the call). */
 TP_API int tp_forward_host(const void* packed, const void* x0_host, const void* xm_host, int64_t n_crops, int scale_factor,

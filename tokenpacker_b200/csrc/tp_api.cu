@@ -689,10 +689,11 @@ int tp_forward_host(const void* packed, const void* x0_host, const void* xm_host
   cudaEventRecord(ev_start, stream);          // copies must not start before prior work on the caller's stream
   cudaStreamWaitEvent(s_in, ev_start, 0);
   cudaStreamWaitEvent(s_out, ev_start, 0);
-  const int64_t n_chunks = (n_crops + chunk_crops - 1) / chunk_crops;
-  for (int64_t c = 0; c < n_chunks && status == TP_OK; ++c) {
-    const int64_t c0 = c * chunk_crops;
-    const int64_t nc = (n_crops - c0) < chunk_crops ? (n_crops - c0) : chunk_crops;
+  // Full chunks, then a tapered tail (remaining/2, ..., 2, 1, 1): the copies in are the bottleneck (PCIe), so what is NOT hidden
+  // behind them is the last chunk's compute + copy out — keep that chunk small.
+  for (int64_t c0 = 0, nc = 0; c0 < n_crops && status == TP_OK; c0 += nc) {
+    const int64_t remaining = n_crops - c0;
+    nc = remaining > chunk_crops ? chunk_crops : (remaining > 1 ? (remaining + 1) / 2 : 1);
     cudaEvent_t ev_in = nullptr, ev_done = nullptr;
     cudaEventCreateWithFlags(&ev_in, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ev_done, cudaEventDisableTiming);
