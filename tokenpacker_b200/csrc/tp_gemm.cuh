@@ -10,13 +10,16 @@
 //   tp_gemm_kernel<BN>   one CTA per SM, 128 x BN tiles,  tcgen05.mma cta_group::1 (small problems, BN = 128 | 256)
 //   tp_gemm2_kernel      CTA pairs (cluster 2x1x1) on the two SMs of a TPC, 256 x 256 tiles, cta_group::2: each CTA
 //                        stages its own 128 rows of A and HALF of the B tile, so shared-memory fill traffic per FLOP
-//                        drops by a third and the mbarrier ring gets 6 stages deep instead of 4.
+//                        drops by a third; 4-stage mbarrier ring + double-buffered output slabs for the TMA stores.
+//                        Also the home of the TN form (MN-major operands, wgrad), multi-part A (four CLIP layers side by
+//                        side along K), grouped launches and the peer (all-gather) stores.
 //
-// CTA = 384 threads, persistent over output tiles:
-//   warp 0      TMA producer   (one lane): cp.async.bulk.tensor boxes, 128B swizzle, mbarrier ring
-//   warp 1      MMA issuer     (one lane, leader CTA only in pair mode): fp32 accumulators in TMEM
-//   warp 2      TMEM allocator (2 accumulator buffers: the epilogue of tile i overlaps tile i+1's MMAs)
-//   warps 4-11  epilogue: tcgen05.ld 32x32b (thread == output row), fused per-row / per-column math, 16-byte stores
+// CTA = 384 threads, persistent over output tiles (default role layout):
+//   warps 0-7   epilogue: tcgen05.ld 32x32b (thread == output row), fused per-row / per-column math on the packed fp32
+//               pipe, swizzled shared-memory slabs -> TMA stores (direct 16-byte stores in the one-CTA kernels / row scatter)
+//   warp 9      TMEM allocator (2 accumulator buffers: the epilogue of tile i overlaps tile i+1's MMAs)
+//   warp 10     TMA producer   (warp-uniform loop, elect.sync around the issue): cp.async.bulk.tensor boxes, 128B swizzle, mbarrier ring
+//   warp 11     MMA issuer     (leader CTA only in pair mode): fp32 accumulators in TMEM
 //
 // Fused epilogue (all optional, selected at run time, warp-uniform branches):
 //   v = acc
