@@ -55,12 +55,17 @@ def hd_grid(h: int, w: int, patch_num: int = 9, image_size: int = BLOCK):
 def _linear_taps(n_in: int, n_out: int):
     """ATen upsample_bilinear2d (align_corners=False, no antialias) taps in float32.
 
-    scale = n_in / n_out (float32); src = scale * (dst + 0.5) - 0.5, clamped below at 0;
+    scale = n_in / n_out (float32); src = fma(scale, dst + 0.5, -0.5), clamped below at 0;
     i0 = int(src); i1 = i0 + (i0 < n_in - 1); w1 = src - i0; w0 = 1 - w1.
+
+    The source coordinate is ONE fused multiply-add in ATen's CPU kernel as built (x86 vector code), not a rounded product
+    followed by a rounded subtraction: at ~1000-pixel extents one float32 ulp of the coordinate is 6e-5 of a pixel, so the two
+    differ by up to ~4e-5 in the output for O(1) pixel values.  Found by tests/test_reference_live.py on random sizes (the six
+    fixture cases happen to agree either way to 2e-6); emulated here exactly via float64 (24x24-bit product is exact).
     """
     scale = f32(n_in) / f32(n_out)
     dst = np.arange(n_out, dtype=f32)
-    src = scale * (dst + f32(0.5)) - f32(0.5)
+    src = (np.float64(scale) * (dst + f32(0.5)).astype(np.float64) - 0.5).astype(f32)
     src = np.maximum(src, f32(0)).astype(f32)
     i0 = src.astype(np.int64)
     i1 = np.minimum(i0 + 1, n_in - 1)

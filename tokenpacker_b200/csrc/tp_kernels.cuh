@@ -293,7 +293,7 @@ struct LinearTap {
 // ATen upsample_bilinear2d, align_corners=False, scales derived from sizes: src = (in/out)*(dst+0.5)-0.5 clamped at 0.
 __device__ __forceinline__ LinearTap linear_tap(int dst, int in_size, int out_size) {
   const float scale = static_cast<float>(in_size) / static_cast<float>(out_size);
-  float src = __fmaf_rn(scale, static_cast<float>(dst) + 0.5f, 0.f) - 0.5f;   // keep mul and sub separately rounded
+  float src = __fmaf_rn(scale, static_cast<float>(dst) + 0.5f, -0.5f);   // ONE fused multiply-add, like ATen's CPU kernel (see oracle/hd_oracle.py)
   src = fmaxf(src, 0.f);
   LinearTap t;
   t.i0 = min(static_cast<int>(src), in_size - 1);
