@@ -191,3 +191,74 @@ def test_tiling_block_vs_reference_source_random(ref_patch_divide):
         assert (hb, wb) == (int(ns["h_block"]), int(ns["w_block"]))
         assert crops.shape == want.shape, (crops.shape, want.shape)
         assert np.abs(crops - want).max() <= 2e-6, (h, w, patch_num, float(np.abs(crops - want).max()))
+
+
+@pytest.mark.parametrize("s,hidden,seed", [(2, 64, 911), (3, 32, 912), (4, 96, 913), (8, 32, 914)])
+def test_gradient_oracle_vs_reference_autograd(ref_builder, s, hidden, seed):
+    """tests/test_backward_gpu.py uses autograd over oracle/torch_port.py as the gradient oracle: pin THAT to autograd through the
+    reference module itself (fp32, CPU), every parameter."""
+    import torch
+    from oracle import tokenpacker_oracle as tpo
+    from oracle import torch_port
+    params = tpo.make_params(hidden, seed=seed)
+    x0, xm = tpo.make_inputs(2, seed=seed + 1000)
+    x0, xm = torch.from_numpy(x0), torch.from_numpy(xm)
+    gw = torch.from_numpy(np.random.default_rng(seed).standard_normal((2, (24 // s) ** 2, hidden)).astype(np.float32))
+    m = ref_builder.TokenPacker(hidden_size=hidden, scale_factor=s)
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in params.items()}, strict=True)
+    (m((x0, xm)) * gw).sum().backward()
+    p = {k: torch.from_numpy(v).clone().requires_grad_(True) for k, v in params.items()}
+    (torch_port.forward(p, x0, xm, s) * gw).sum().backward()
+    for name, ref_param in m.named_parameters():
+        g_ref, g = ref_param.grad, p[name].grad
+        scale = float(g_ref.abs().max()) + 1e-12
+        assert float((g - g_ref).abs().max()) <= 2e-5 * scale + 1e-7, (name, float((g - g_ref).abs().max()), scale)
+
+
+def test_slice_assembly_vs_reference_source_random():
+    """llava_arch.py:141-155 exec'd where it lies on random grids vs the oracle and the product's host plan (tp_hd_plan)."""
+    import textwrap
+    import torch
+    from oracle import hd_oracle as hdo
+    from tokenpacker_b200 import hd_plan
+    with open(os.path.join(REF, "llava/model/llava_arch.py")) as f:
+        src = textwrap.dedent("".join(f.readlines()[140:155]))
+    assert src.lstrip().startswith("image_feature_list = []")
+    rng = np.random.default_rng(606)
+    for trial in range(20):
+        m, hdim = int(rng.integers(1, 6)), 4
+        grids = [(int(rng.integers(1, 6)), int(rng.integers(1, 6))) for _ in range(int(rng.integers(1, 6)))]
+        sep_row = rng.standard_normal(hdim).astype(np.float32)
+        ret_row = rng.standard_normal(hdim).astype(np.float32)
+        total = sum(hdo.n_crops(a, b) for a, b in grids)
+        feats = rng.standard_normal((total, m, hdim)).astype(np.float32)
+
+        class _Model:
+            def embed_tokens(self, tok):
+                return torch.from_numpy(sep_row if int(tok[0]) == 0 else ret_row)[None]
+
+        class _Self:
+            def get_model(self):
+                return _Model()
+
+        ns = {"image_features": torch.from_numpy(feats), "h_block": [g[0] for g in grids], "w_block": [g[1] for g in grids],
+              "self": _Self(), "sep": torch.tensor([0]), "ret": torch.tensor([1]), "torch": torch, "cur_image_idx": 0}
+        want = []
+        for b in range(len(grids)):
+            ns["batch_idx"] = b
+            exec(src, ns)
+            want.append(ns["cur_image_features"].numpy())
+        want_cu = np.concatenate([[0], np.cumsum([q.shape[0] for q in want])])
+        want = np.concatenate(want, axis=0)
+        hb, wb = [g[0] for g in grids], [g[1] for g in grids]
+        packed, cu = hdo.hd_assemble(feats, hb, wb, sep_row, ret_row)
+        np.testing.assert_array_equal(packed, want)
+        np.testing.assert_array_equal(cu, want_cu)
+        plan = hd_plan(hb, wb, m)
+        np.testing.assert_array_equal(plan.cu_seqlens.numpy(), want_cu)
+        rebuilt = np.full_like(want, np.nan)
+        for c, r0 in enumerate(plan.seg_row_offset.tolist()):
+            rebuilt[r0:r0 + m] = feats[c]
+        rebuilt[plan.sep_rows.numpy()] = sep_row
+        rebuilt[plan.ret_rows.numpy()] = ret_row
+        np.testing.assert_array_equal(rebuilt, want)
