@@ -66,24 +66,27 @@ for n in (1, 2, 4, 10, 16):
     print(rows[-1], flush=True)
     del m, gr
 
-# configs[3]: HD patch_num=9, s=2, 32 images with seeded sizes -> grids via the grid selector, packed output
+# configs[3]: HD patch_num=9, s=2, 32 images, packed output — (a) seeded image sizes -> grids via the grid selector (231 crops),
+# (b) the all-1088x1088 variant: 32 x (3x3 + thumbnail) = 320 crops, 1450 tokens per image
 g = torch.Generator().manual_seed(0)
 hs = torch.randint(224, 1345, (32,), generator=g).tolist()
 ws_ = torch.randint(224, 1345, (32,), generator=g).tolist()
-grids = [hd_grid(h, w, 9) for h, w in zip(hs, ws_)]
-n = sum(n_crops(a, b) for a, b in grids)
-m = module(2)
-x0 = torch.randn(n, 576, 1024, device="cuda").bfloat16()
-xm = torch.randn(n, 576, 4096, device="cuda").bfloat16()
-sep = torch.randn(4096, device="cuda").bfloat16()
-ret = torch.randn(4096, device="cuda").bfloat16()
-hb, wb = [a for a, _ in grids], [b for _, b in grids]
-ms = timed(lambda: m.forward_packed((x0, xm), hb, wb, sep, ret))
-with torch.no_grad():
-    _, cu = m.forward_packed((x0, xm), hb, wb, sep, ret)
-tf = syn.flops_per_crop(2) * n / ms / 1e9
-rows.append({"config": f"configs[3] HD patch_num=9 s=2, 32 images -> {n} crops, packed {int(cu[-1])} rows ({int(cu[-1]) / 32:.0f} tok/img)",
-             "ms": round(ms, 4), "tokens_per_s": round(n * 144 / ms * 1e3), "tflops_alg": round(tf, 1), "frac_sustained_peak": round(tf / PEAK, 3)})
-print(rows[-1], flush=True)
+for label, sizes in (("seeded sizes", list(zip(hs, ws_))), ("all 1088x1088", [(1088, 1088)] * 32)):
+    grids = [hd_grid(h, w, 9) for h, w in sizes]
+    n = sum(n_crops(a, b) for a, b in grids)
+    m = module(2)
+    x0 = torch.randn(n, 576, 1024, device="cuda").bfloat16()
+    xm = torch.randn(n, 576, 4096, device="cuda").bfloat16()
+    sep = torch.randn(4096, device="cuda").bfloat16()
+    ret = torch.randn(4096, device="cuda").bfloat16()
+    hb, wb = [a for a, _ in grids], [b for _, b in grids]
+    ms = timed(lambda: m.forward_packed((x0, xm), hb, wb, sep, ret))
+    with torch.no_grad():
+        _, cu = m.forward_packed((x0, xm), hb, wb, sep, ret)
+    tf = syn.flops_per_crop(2) * n / ms / 1e9
+    rows.append({"config": f"configs[3] HD patch_num=9 s=2, 32 images ({label}) -> {n} crops, packed {int(cu[-1])} rows ({int(cu[-1]) / 32:.0f} tok/img)",
+                 "ms": round(ms, 4), "tokens_per_s": round(n * 144 / ms * 1e3), "tflops_alg": round(tf, 1), "frac_sustained_peak": round(tf / PEAK, 3)})
+    print(rows[-1], flush=True)
+    del m, x0, xm
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
 json.dump(rows, open(os.path.join(ROOT, "gpurun_out", "config_sweep.json"), "w"), indent=1)
