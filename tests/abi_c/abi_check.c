@@ -31,6 +31,23 @@ int main(void) {
     if (tp_hd_grid(1088, 1088, 10, 336, &hb, &wb) != TP_ERR_BAD_PATCH_NUM) return 8;
   }
   {
+    /* tiling sizes (train.py:701-708, :719-726): 1088 x 1088 on a 3 x 3 grid fills the 1008 canvas; thumbnail 336 x 336 */
+    int hr = 0, wr = 0, ht = 0, wt = 0;
+    if (tp_hd_fit(1088, 1088, 3, 3, &hr, &wr, &ht, &wt) != TP_OK || hr != 1008 || wr != 1008 || ht != 336 || wt != 336) return 11;
+    if (tp_hd_fit(500, 700, 2, 3, &hr, &wr, &ht, &wt) != TP_OK || hr != 672 || wr != 941 || ht != 240 || wt != 336) return 12;
+  }
+  {
+    /* slice assembly plan (llava_arch.py:139-155): a 3 x 3 image at 144 tokens per crop is 1450 rows, a 1 x 1 image 145 */
+    const int hb[2] = {3, 1}, wb[2] = {3, 1};
+    int64_t n_crops = 0, n_sep = 0, n_ret = 0;
+    int64_t seg[11], sep[6], ret[5], cu[3];
+    if (tp_hd_plan(hb, wb, 2, 144, NULL, NULL, NULL, NULL, &n_crops, &n_sep, &n_ret) != TP_OK) return 13;
+    if (n_crops != 11 || n_sep != 6 || n_ret != 5) return 14;
+    if (tp_hd_plan(hb, wb, 2, 144, seg, sep, ret, cu, &n_crops, &n_sep, &n_ret) != TP_OK) return 15;
+    if (cu[0] != 0 || cu[1] != 1450 || cu[2] != 1595) return 16;
+    if (seg[0] != 0 || seg[1] != 145 || seg[9] != 1305 || seg[10] != 1450) return 17;   /* thumbnail after the grid; next image */
+  }
+  {
     /* argument validation happens before any CUDA call */
     if (tp_forward(NULL, NULL, NULL, 1, 0, 0, 5, 4096, NULL, NULL, NULL, 0, NULL) != TP_ERR_BAD_SCALE_FACTOR) return 9;
     if (tp_forward(NULL, NULL, NULL, 1, 0, 0, 2, 4096, NULL, NULL, NULL, 0, NULL) != TP_ERR_INVALID_ARGUMENT) return 10;
