@@ -17,6 +17,13 @@ namespace {
 using namespace tp;
 
 thread_local char g_last_cuda_error[256] = "";
+#ifdef TP_B_PREFETCH
+thread_local bool g_weights_are_static = false;   // set for the duration of forward_impl: every B operand there is a packed weight
+struct StaticWeightsScope {
+  StaticWeightsScope() { g_weights_are_static = true; }
+  ~StaticWeightsScope() { g_weights_are_static = false; }
+};
+#endif
 
 #define TP_CUDA(call)                                                                                        \
   do {                                                                                                       \
@@ -152,6 +159,7 @@ struct GemmItem {
   void* const* peer_c = nullptr;   // fused all-gather: the same output slot in every peer's gathered buffer
   int n_peers = 0;
   int tn = 0;                      // 1: C[M,N] = A^T . B with A given as [K, M] (ld = a.ld) and B as [K, N] (ld = ldb), both row-major
+  int b_static = 0;                // B is a packed weight (not produced by the previous kernel): -DTP_B_PREFETCH experiment
 };
 
 int check_item(const GemmItem& it) {
@@ -225,6 +233,9 @@ int launch_gemm_pair_group(const GemmItem* items, int count, int sms, cudaStream
     p.num_n_blocks = static_cast<int>((it.N + Cfg::kTileN - 1) / Cfg::kTileN);
     p.num_tiles = static_cast<int>((it.M + Cfg::kTileM - 1) / Cfg::kTileM) * p.num_n_blocks;
     p.num_k_blocks = static_cast<int>((it.K + kBlockK - 1) / kBlockK);
+#ifdef TP_B_PREFETCH
+    p.b_static = (it.b_static != 0 || g_weights_are_static) ? 1 : 0;
+#endif
     p.ep = it.ep;
     total += p.num_tiles;
   }
@@ -549,6 +560,9 @@ int forward_impl(const void* packed, const void* x0, const void* xm, const void*
   if (n_crops * kTokens > 0x7fff0000ll) return TP_ERR_INVALID_ARGUMENT;
   DeviceInfo dev;
   TP_TRY(device_info(&dev));
+#ifdef TP_B_PREFETCH
+  StaticWeightsScope static_weights;
+#endif
   const int s = scale_factor, H = hidden;
   const int g = kGrid / s, Mq = g * g;
   const long long R = n_crops * kTokens, Q = n_crops * Mq;

@@ -489,6 +489,10 @@ struct GemmProblem {
   int num_n_blocks;
   int num_tiles;
   int num_k_blocks;
+#ifdef TP_B_PREFETCH
+  int b_static;          // B (weights) was not written by the previous kernel on the stream: its first tiles may be fetched before
+                         // griddepcontrol.wait (experiment, off by default: see the producer prologue)
+#endif
   GemmEpilogue ep;
 };
 
@@ -565,6 +569,30 @@ tp_gemm2_kernel(const __grid_constant__ GemmGroup grp, const __grid_constant__ P
   cluster_sync_all();                      // barriers of both CTAs initialised before any remote arrive / multicast commit
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_base_smem;
+#ifdef TP_B_PREFETCH
+  // EXPERIMENT (build with -DTP_B_PREFETCH; not validated on hardware yet): the B operand of every forward GEMM is a packed weight,
+  // written long before the previous kernel on the stream, so the first stages of this CTA's first tile can have their barriers
+  // armed and their B halves in flight BEFORE griddepcontrol.wait — the weight fetch then overlaps the previous kernel's tail
+  // (the single-crop latency is a chain of 7 dependent launches).  A joins after the wait; the barrier completes on the total bytes.
+  int prefetched = 0;
+  if (warp_idx == kTmaWarp && pair_idx < num_tiles) {
+    const TileRef t0 = decode_tile(grp, pair_idx);
+    const GemmProblem& pr0 = *t0.pr;
+    if (pr0.b_static != 0 && pr0.ab_mn_major == 0) {
+      prefetched = pr0.num_k_blocks < kStages ? pr0.num_k_blocks : kStages;
+      const int brow0 = t0.n_blk * kTileN + static_cast<int>(cta_rank) * (kTileN / 2);
+      for (int kb = 0; kb < prefetched; ++kb) {
+        if (elect_one()) {
+          uint8_t* sb = smem + kb * Cfg::kStageBytes + Cfg::kABytes;
+          if (is_leader) mbar_arrive_expect_tx(&full_bar[kb], 2 * Cfg::kStageBytes);
+          else mbar_arrive_cluster(&full_bar[kb], 0);
+          tma_load_2d_pair(sb, &pr0.tmap_b, &full_bar[kb], kb * kBlockK, brow0);
+        }
+        __syncwarp();
+      }
+    }
+  }
+#endif
   // Programmatic dependent launch: everything above overlapped the tail of the previous kernel on the stream; from here
   // on we read what it wrote.  (No-op when the launch carries no PDL attribute.)
   grid_dependency_wait();
@@ -596,11 +624,18 @@ tp_gemm2_kernel(const __grid_constant__ GemmGroup grp, const __grid_constant__ P
           mbar_wait(&empty_bar[stage], phase ^ 1u);
           TP_PROF_ADD(w_empty);
         }
+#ifdef TP_B_PREFETCH
+        const bool b_in_flight = tile == pair_idx && kb < prefetched;     // armed and B issued in the prologue
+#else
+        constexpr bool b_in_flight = false;
+#endif
         if (elect_one()) {
           uint8_t* sa = smem + stage * Cfg::kStageBytes;
           uint8_t* sb = sa + Cfg::kABytes;
-          if (is_leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
-          else mbar_arrive_cluster(&full_bar[stage], 0);
+          if (!b_in_flight) {
+            if (is_leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
+            else mbar_arrive_cluster(&full_bar[stage], 0);
+          }
           if (pr.ab_mn_major) {
             // boxes of [64 K-rows x 64 MN-elements]: coordinates (mn, k); two MN atoms per operand per CTA
             tma_load_2d_pair(sa, &pr.tmap_a, &full_bar[stage], row0, kb * kBlockK);
@@ -618,7 +653,7 @@ tp_gemm2_kernel(const __grid_constant__ GemmGroup grp, const __grid_constant__ P
               tma_load_3d_pair(sa + Cfg::kABytes / 2, ta, &full_bar[stage], ka, srow1, seg1);
             }
           }
-          if (!pr.ab_mn_major) tma_load_2d_pair(sb, &pr.tmap_b, &full_bar[stage], kb * kBlockK, brow0);
+          if (!pr.ab_mn_major && !b_in_flight) tma_load_2d_pair(sb, &pr.tmap_b, &full_bar[stage], kb * kBlockK, brow0);
         }
         __syncwarp();
         if (++stage == kStages) { stage = 0; phase ^= 1u; }
