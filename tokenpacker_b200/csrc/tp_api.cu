@@ -185,8 +185,12 @@ int launch_gemm_t(const GemmItem& it, int sms, cudaStream_t stream) {
   TP_CUDA(cudaFuncSetAttribute(tp_gemm_kernel<kBlockN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
   const long long tiles = ((it.M + kBlockM - 1) / kBlockM) * ((it.N + kBlockN - 1) / kBlockN);
   const int grid = static_cast<int>(tiles < sms ? tiles : sms);
+  GemmEpilogue ep = it.ep;
+#ifdef TP_B_PREFETCH
+  ep.b_static = (it.b_static != 0 || g_weights_are_static) ? 1 : 0;
+#endif
   TP_CUDA(launch_pdl(tp_gemm_kernel<kBlockN>, dim3(grid), dim3(kGemmThreads), Cfg::kSmemBytes, stream, map_a, map_b, static_cast<int>(it.M),
-                     static_cast<int>(it.N), static_cast<int>(it.K), static_cast<int>(it.a.seg_rows), it.ep));
+                     static_cast<int>(it.N), static_cast<int>(it.K), static_cast<int>(it.a.seg_rows), ep));
   return TP_OK;
 }
 

@@ -52,7 +52,10 @@ struct GemmEpilogue {
   float ln_eps;
   float alpha;
   int gelu;
-  long long* prof;         // TP_GEMM_PROFILE builds only: [grid][8] cycle counters (nullptr otherwise)
+  long long* prof;         // TP_GEMM_PROFILE builds only: [grid][16] cycle counters (nullptr otherwise)
+#ifdef TP_B_PREFETCH
+  int b_static;            // one-CTA kernels: see GemmProblem::b_static
+#endif
 };
 
 #ifndef TP_EPI_SUB_PAIRS
@@ -347,6 +350,18 @@ tp_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_base_smem;
+#ifdef TP_B_PREFETCH
+  // EXPERIMENT (see tp_gemm2_kernel): weight tiles of this CTA's first output tile in flight before griddepcontrol.wait
+  int prefetched = 0;
+  if (warp_idx == kTmaWarp && lane == 0 && ep.b_static != 0 && static_cast<int>(blockIdx.x) < num_tiles) {
+    const int n_blk0 = static_cast<int>(blockIdx.x) % num_n_blocks;
+    prefetched = num_k_blocks < kStages ? num_k_blocks : kStages;
+    for (int kb = 0; kb < prefetched; ++kb) {
+      mbar_arrive_expect_tx(&full_bar[kb], Cfg::kStageBytes);
+      tma_load_2d(smem + kb * Cfg::kStageBytes + Cfg::kABytes, &tmap_b, &full_bar[kb], kb * kBlockK, n_blk0 * kBlockN);
+    }
+  }
+#endif
   grid_dependency_wait();                  // PDL: the prologue above overlapped the previous kernel's tail
   grid_launch_dependents();
 
@@ -362,7 +377,12 @@ tp_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           mbar_wait(&empty_bar[stage], phase ^ 1u);
           uint8_t* sa = smem + stage * Cfg::kStageBytes;
           uint8_t* sb = sa + Cfg::kABytes;
-          mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+#ifdef TP_B_PREFETCH
+          const bool b_in_flight = tile == static_cast<int>(blockIdx.x) && kb < prefetched;
+#else
+          constexpr bool b_in_flight = false;
+#endif
+          if (!b_in_flight) mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
           if (a_seg_rows == 0) {
             tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * kBlockK, m_blk * kBlockM);
           } else {
@@ -374,7 +394,7 @@ tp_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               tma_load_3d(sa + h * (Cfg::kABytes / 2), &tmap_a, &full_bar[stage], kb * kBlockK, g - seg * a_seg_rows, seg);
             }
           }
-          tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * kBlockK, n_blk * kBlockN);
+          if (!b_in_flight) tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * kBlockK, n_blk * kBlockN);
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
       }
