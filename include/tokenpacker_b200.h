@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define TP_ABI_VERSION 1
+#define TP_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define TP_API __attribute__((visibility("default")))
@@ -45,6 +45,8 @@ TP_API const char* tp_strerror(int status);
 TP_API int tp_abi_version(void);
 /* Name of the last failing CUDA call on this thread ("" if none); diagnostic only. */
 TP_API const char* tp_last_cuda_error(void);
+/* Number of kernels this library has launched from the calling host thread so far (diagnostic: the benchmark's gpu_launches). */
+TP_API uint64_t tp_launch_count(void);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Parameters.  Raw module parameters exactly as the reference state_dict holds them (builder.py:59-83), bf16,
@@ -86,6 +88,15 @@ TP_API int tp_forward(const void* packed, const void* x0, const void* xm, int64_
                int64_t xm_crop_stride, int scale_factor, int hidden, void* out, const int64_t* seg_row_offset,
                void* workspace, size_t workspace_bytes, void* stream);
 
+/* Same forward with the HD packed layout as a UNIFORM row stride: crop i's M rows go to rows i*out_crop_rows .. +M-1 of ``out``
+ * (row stride H).  llava_arch.py:139-155 follows every crop's tokens with exactly one separator row (',' between columns, '\n'
+ * at the end of a grid row and after the thumbnail), so the packed sequence of any batch of images is this layout with
+ * out_crop_rows = M + 1 and the separator rows (tp_hd_fill_separators) in the gaps.  Unlike the seg_row_offset form the output
+ * stays on the TMA-store path: each 128-row slab leaves as one clipped 3-D box per crop it touches.  out_crop_rows = 0 or M: dense. */
+TP_API int tp_forward_packed(const void* packed, const void* x0, const void* xm, int64_t n_crops, int64_t x0_crop_stride,
+                             int64_t xm_crop_stride, int scale_factor, int hidden, void* out, int64_t out_crop_rows,
+                             void* workspace, size_t workspace_bytes, void* stream);
+
 /* Same forward, taking the multi-level stack as its FOUR layers instead of their concatenation: layers[0..3] are the CLIP
  * hidden states 12 / 16 / 22 / 23 that CLIPVisionTower.feature_select concatenates (clip_encoder.py:28-44), each
  * [n_crops, 576, 1024] bf16 with row stride 1024 and crop stride ``crop_stride`` (577*1024 for the [:,1:] views of the raw
@@ -94,15 +105,17 @@ TP_API int tp_forward(const void* packed, const void* x0, const void* xm, int64_
 TP_API int tp_forward_layers(const void* packed, const void* const* layers, int64_t n_crops, int64_t crop_stride, int scale_factor,
                              int hidden, void* out, const int64_t* seg_row_offset, void* workspace, size_t workspace_bytes, void* stream);
 
-/* Multi-GPU form with the all-gather FUSED into the last GEMM's epilogue.  peer_out[p] (p < n_peers <= 8) is the base of a
- * gathered buffer [total_crops, M, H] bf16 on GPU p, mapped into this process (CUDA IPC / symmetric memory; own buffer
- * included).  This rank's n_crops crops are written to rows [crop_offset*M, (crop_offset+n_crops)*M) of EVERY peer buffer by
- * TMA stores over NVLink, tile by tile as the GEMM produces them — no separate collective kernel and no staging copy.
- * The caller must run a cross-rank barrier after the stream reaches this call before any rank reads its gathered buffer.
+/* Multi-GPU form with the all-gather FUSED into the last GEMM's epilogue.  peer_out[p] (p < n_peers <= 8) is the base of an
+ * output buffer [total_crops * R, H] bf16 on GPU p (R = out_crop_rows, or M when out_crop_rows is 0: the dense gathered
+ * [total_crops, M, H] form), mapped into this process (CUDA IPC / symmetric memory; own buffer included).  This rank's n_crops
+ * crops are written to rows (crop_offset + i)*R .. +M-1 of EVERY peer buffer by TMA stores over NVLink, tile by tile as the GEMM
+ * produces them — no separate collective kernel, no staging copy and, with R = M + 1, no assembly pass either: the stores land
+ * in the packed per-image sequences of llava_arch.py:139-155 directly (separator rows: tp_hd_fill_separators on each rank).
+ * The caller must run a cross-rank barrier after the stream reaches this call before any rank reads its buffer.
  * Needs hidden % 256 == 0.  Replaces: encode_images on sharded crops + the cross-rank reassembly of llava_arch.py:139-155. */
 TP_API int tp_forward_allgather(const void* packed, const void* x0, const void* xm, int64_t n_crops, int64_t x0_crop_stride,
                                 int64_t xm_crop_stride, int scale_factor, int hidden, void* const* peer_out, int n_peers,
-                                int64_t crop_offset, void* workspace, size_t workspace_bytes, void* stream);
+                                int64_t crop_offset, int64_t out_crop_rows, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Same call with HOST buffers (pinned recommended): copies inputs in, runs, copies the result out, pipelined over
  * chunks of ``chunk_crops`` crops (the last few chunks shrink, so that the part not hidden behind the copies in — the final
@@ -155,6 +168,24 @@ TP_API int tp_hd_fit(int64_t h, int64_t w, int h_block, int w_block, int* h_resi
  * zero-padded 336*hb x 336*wb canvas, row-major 336x336 crops, plus — when hb*wb > 1 — the thumbnail resized
  * from the PADDED canvas.  crops: [hb*wb (+1), 3, 336, 336] fp32.  All device pointers. */
 TP_API int tp_hd_tile(const float* image, int64_t h, int64_t w, int h_block, int w_block, float* crops, void* stream);
+
+/* Batched form of the tiling block: the collator concatenates the crops of a batch (train.py:797-800), so the front end of a
+ * batch is ONE launch over variable-size images, thumbnails included.
+ *   tp_hd_tile_batch_plan  host function: per image grid selection (tp_hd_grid) + fitted sizes (tp_hd_fit), fills
+ *                          images_host[n_images] (image = images[b], a DEVICE pointer to [3,h,w] fp32), crop_table_host[3*n_crops]
+ *                          = (image, grid row, grid column; column -1 = the thumbnail), h_block / w_block, *n_crops.  Any output
+ *                          pointer may be NULL (count only).  Crop order = the reference's: image by image, row-major, thumbnail last.
+ *   tp_hd_tile_batch       the launch: images_dev / crop_table_dev are device copies of the two tables; crops [n_crops,3,336,336] fp32. */
+typedef struct tp_hd_image {
+  const float* image;
+  int32_t h, w, hb, wb;
+  int32_t h_r, w_r;
+  int32_t h_t, w_t;
+  int64_t crop0;
+} tp_hd_image;
+TP_API int tp_hd_tile_batch_plan(const int64_t* h, const int64_t* w, const void* const* images, int64_t n_images, int patch_num,
+                                 tp_hd_image* images_host, int32_t* crop_table_host, int* h_block, int* w_block, int64_t* n_crops);
+TP_API int tp_hd_tile_batch(const tp_hd_image* images_dev, const int32_t* crop_table_dev, int64_t n_crops, float* crops, void* stream);
 
 /* Slice assembly (llava_arch.py:139-155).  Host helper: fills seg_row_offset_host[n_crops] (destination row of each
  * crop's first token), sep_rows / ret_rows (destination rows of the ',' and '\n' embedding rows; capacities are the

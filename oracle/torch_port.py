@@ -24,8 +24,12 @@ def _divide(x, kernel_size, token_num, n, c):
     return x.permute(2, 0, 1, 3, 4).reshape(k * k, -1, c)
 
 
-def forward(p: dict, x0: torch.Tensor, xm: torch.Tensor, scale_factor: int) -> torch.Tensor:
-    """p: reference state_dict (torch tensors, any float dtype); x0 [N,576,1024]; xm [N,576,4096] -> [N,M,H]."""
+def forward(p: dict, x0: torch.Tensor, xm: torch.Tensor, scale_factor: int, pre_ln=None) -> torch.Tensor:
+    """p: reference state_dict (torch tensors, any float dtype); x0 [N,576,1024]; xm [N,576,4096] -> [N,M,H].
+    ``pre_ln`` (tests only): applied to the inputs of the three LayerNorms, e.g. a bf16 round trip to model a bf16 module's
+    storage of those activations; None = the reference's arithmetic in the tensors' own dtype."""
+    if pre_ln is None:
+        pre_ln = lambda t: t                                                             # noqa: E731
     if RAW_GRID % scale_factor != 0:
         raise ValueError("scale_factor must be divisible by grid size")
     g = RAW_GRID // scale_factor
@@ -37,12 +41,12 @@ def forward(p: dict, x0: torch.Tensor, xm: torch.Tensor, scale_factor: int) -> t
     def ln(x, name):
         return F.layer_norm(x, (1024,), p[f"{name}.weight"], p[f"{name}.bias"], 1e-6)
 
-    key = ln(two_layer(xm, "k_proj_1"), "ln_k_1").permute(1, 0, 2)                       # :112
-    value = ln(two_layer(xm, "v_proj_1"), "ln_v_1").permute(1, 0, 2)                     # :113
+    key = ln(pre_ln(two_layer(xm, "k_proj_1")), "ln_k_1").permute(1, 0, 2)               # :112
+    value = ln(pre_ln(two_layer(xm, "v_proj_1")), "ln_v_1").permute(1, 0, 2)             # :113
     token_num, n, c = key.shape
     q = F.interpolate(x0.reshape(n, RAW_GRID, RAW_GRID, -1).float().permute(0, 3, 1, 2), size=(g, g), mode="bilinear")
     q = q.permute(0, 2, 3, 1).reshape(n, -1, c).to(x0.dtype)                             # :117-118
-    query = ln(F.linear(q, p["q_proj_1.weight"]), "ln_q_1").permute(1, 0, 2)             # :120
+    query = ln(pre_ln(F.linear(q, p["q_proj_1.weight"])), "ln_q_1").permute(1, 0, 2)     # :120
     rq = _divide(query, 1, m, n, c)                                                      # :122-124
     rk = _divide(key, scale_factor, token_num, n, c)
     rv = _divide(value, scale_factor, token_num, n, c)

@@ -16,11 +16,12 @@ int main(void) {
       (const void*)&tp_forward_train,     (const void*)&tp_backward,          (const void*)&tp_gemm_bf16,
       (const void*)&tp_gemm_tn_bf16,      (const void*)&tp_hd_grid,           (const void*)&tp_hd_fit,
       (const void*)&tp_hd_tile,           (const void*)&tp_hd_plan,           (const void*)&tp_hd_scatter_crops,
-      (const void*)&tp_gather_rows,       (const void*)&tp_hd_fill_separators};
+      (const void*)&tp_gather_rows,       (const void*)&tp_hd_fill_separators, (const void*)&tp_forward_packed,
+      (const void*)&tp_launch_count,      (const void*)&tp_hd_tile_batch_plan, (const void*)&tp_hd_tile_batch};
   size_t i;
   for (i = 0; i < sizeof(entry) / sizeof(entry[0]); ++i)
     if (entry[i] == NULL) return 2;
-  if (tp_abi_version() != 1) return 3;
+  if (tp_abi_version() != 2) return 3;
   if (strcmp(tp_strerror(TP_ERR_BAD_SCALE_FACTOR), "scale_factor must be divisible by grid size") != 0) return 4;
   if (tp_packed_bytes(4096) == 0 || tp_packed_bytes(4097) != 0) return 5;
   if (tp_workspace_bytes(64, 2, 4096) == 0 || tp_workspace_bytes(64, 5, 4096) != 0) return 6;

@@ -23,7 +23,7 @@ def test_library_exports_header_symbols():
     for n in names:
         assert hasattr(raw, n), f"{n} declared in the header but not exported"
     assert sorted(_lib.SIGNATURES) == names, "ctypes binding and header disagree"
-    assert _lib.lib.tp_abi_version() == 1
+    assert _lib.lib.tp_abi_version() == 2
 
 
 def test_strerror_and_size_queries():

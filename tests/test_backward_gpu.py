@@ -1,7 +1,7 @@
 """Backward of the projector (tp_forward_train / tp_backward through autograd) against PyTorch autograd over the oracle's
 torch port (the reference's op sequence, fp32) on identical bf16-rounded weights and inputs.
 Tolerance: every parameter gradient within 3e-2 relative RMS error (bf16 activations and bf16 gradient storage through a
-chain of ~10 GEMMs; the forward's own gate is 6e-3)."""
+chain of ~10 GEMMs; the forward's own gate is 3e-3)."""
 import numpy as np
 import pytest
 import torch
@@ -32,7 +32,7 @@ def test_parameter_gradients_match_autograd_of_oracle(s, hidden, n):
     ref_out = torch_port.forward(ref_p, x0, xm, s)
     (ref_out * gw.bfloat16().float()).sum().backward()
 
-    assert (out.float() - ref_out).pow(2).mean().sqrt() / ref_out.pow(2).mean().sqrt() < 6e-3
+    assert (out.float() - ref_out).pow(2).mean().sqrt() / ref_out.pow(2).mean().sqrt() < 3e-3
     worst = {}
     for name, p in m.named_parameters():
         g, r = p.grad.float(), ref_p[name].grad

@@ -5,6 +5,15 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
+def _assert_close(out, ref):
+    """Elementwise: bf16 rounding of the stored result is at most half an ulp = 2^-9 |ref| (gate 2^-8 |ref|), plus a floor of
+    2e-4 of the matrix scale for fp32 accumulation-order differences between the two GEMMs (K up to 36864)."""
+    err = (out.float() - ref).abs()
+    bound = ref.abs() * 2.0 ** -8 + 2e-4 * ref.abs().max()
+    worst = (err - bound).max().item()
+    assert worst <= 0, (worst, err.max().item(), ref.abs().max().item())
+
+
 def _ref(a, b, bias, gelu, alpha):
     y = a.float() @ b.float().t()
     if bias is not None:
@@ -24,9 +33,7 @@ def test_gemm_shapes(m, n, k):
     b = (torch.randn(n, k, device="cuda", generator=g) * 0.05).to(torch.bfloat16)
     out = gemm_bf16(a, b)
     ref = _ref(a, b, None, False, 1.0)
-    err = (out.float() - ref).abs().max().item()
-    scale = ref.abs().max().item()
-    assert err <= 1e-2 * scale + 1e-3, (err, scale)     # bf16 output rounding: 2^-9 relative
+    _assert_close(out, ref)
 
 
 @pytest.mark.parametrize("gelu", [False, True])
@@ -38,7 +45,7 @@ def test_gemm_epilogue_bias_gelu_alpha(gelu):
     bias = torch.randn(512, device="cuda", generator=g)
     out = gemm_bf16(a, b, bias=bias, gelu=gelu, alpha=0.5)
     ref = _ref(a, b, bias, gelu, 0.5)
-    assert (out.float() - ref).abs().max().item() <= 1e-2 * ref.abs().max().item() + 1e-3
+    _assert_close(out, ref)
 
 
 def test_gemm_strided_operands_and_identity():
@@ -70,8 +77,7 @@ def test_gemm_tn_wgrad_form(m, n, k):
     b = (torch.randn(k, n, device="cuda", generator=g) * 0.05).to(torch.bfloat16)
     out = gemm_tn_bf16(a, b)
     ref = a.float().t() @ b.float()
-    err = (out.float() - ref).abs().max().item()
-    assert err <= 1e-2 * ref.abs().max().item() + 1e-3, (err, ref.abs().max().item())
+    _assert_close(out, ref)
 
 
 def test_gemm_tn_exact_small_integers():

@@ -2,7 +2,7 @@
 makes — k/v first layers as one GEMM, LayerNorm folded into the following linear with statistics taken from the ROUNDED
 activations, 1/sqrt(128) applied in the in-projection epilogue, out_proj folded into mlp.0 — with a bf16 rounding at every point
 where the device stores bf16 and float32 arithmetic in between.  Held to the float64 oracle at the same gates the GPU parity
-tests use (rel-RMS <= 6e-3, max-abs <= 1.5e-2): the algebra and the rounding plan meet the tolerance by construction, whatever
+tests use (rel-RMS <= 3e-3, max-abs <= 5e-3): the algebra and the rounding plan meet the tolerance by construction, whatever
 the kernels do.  (The kernels themselves are held to the oracle on the GPU: tests/test_projector_gpu.py.)"""
 import numpy as np
 import pytest
@@ -77,5 +77,5 @@ def test_device_plan_meets_the_gpu_gates(s):
     out = device_plan_forward(params, x0, xm, s).astype(np.float64)
     rel = float(np.sqrt(((out - ref) ** 2).mean()) / np.sqrt((ref ** 2).mean()))
     mx = float(np.abs(out - ref).max())
-    assert rel <= 6e-3 and mx <= 1.5e-2, (rel, mx)
+    assert rel <= 3e-3 and mx <= 5e-3, (rel, mx)
     assert rel >= 2e-4          # sanity: the model really rounds to bf16 (a pure-fp32 pipeline would sit at ~1e-6)

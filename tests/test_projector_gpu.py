@@ -1,6 +1,6 @@
 """Parity of the CUDA projector (through the nn.Module -> C ABI -> sm_100a kernels) with the oracle and the
 reference-generated golden fixtures.  Tolerances (stated per SURVEY.md §8c): bf16 storage / fp32 accumulation vs the
-fp32|fp64 oracle on identical bf16-rounded weights and inputs: rel-RMS <= 6e-3 and max-abs <= 1.5e-2 at output
+fp32|fp64 oracle on identical bf16-rounded weights and inputs: rel-RMS <= 3e-3 and max-abs <= 5e-3 (measured 1.8e-3 / 1.2e-3) at output
 RMS ~0.1 (the reference's own bf16-vs-fp32 gap at these inputs is rel-RMS 4.6e-3..5.3e-3, max-abs up to 4.9e-3)."""
 import os
 
@@ -12,8 +12,8 @@ from oracle import tokenpacker_oracle as tpo
 
 pytestmark = pytest.mark.gpu
 
-REL_RMS_TOL = 6e-3
-MAX_ABS_TOL = 1.5e-2
+REL_RMS_TOL = 3e-3
+MAX_ABS_TOL = 5e-3
 
 
 def make_module(hidden, s, seed):

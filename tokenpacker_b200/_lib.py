@@ -42,20 +42,29 @@ class TpWeights(C.Structure):
     _fields_ = [(name, C.c_void_p) for name, _ in WEIGHT_FIELDS]
 
 
+class TpHdImage(C.Structure):
+    """tp_hd_image: one row of the batched tiling plan."""
+    _fields_ = [("image", C.c_void_p), ("h", C.c_int32), ("w", C.c_int32), ("hb", C.c_int32), ("wb", C.c_int32),
+                ("h_r", C.c_int32), ("w_r", C.c_int32), ("h_t", C.c_int32), ("w_t", C.c_int32), ("crop0", C.c_int64)]
+
+
 # name -> (restype, argtypes); kept as data so tests can check the header and the binding agree
 SIGNATURES = {
     "tp_strerror": (C.c_char_p, [C.c_int]),
     "tp_abi_version": (C.c_int, []),
     "tp_last_cuda_error": (C.c_char_p, []),
+    "tp_launch_count": (C.c_uint64, []),
     "tp_packed_bytes": (C.c_size_t, [C.c_int]),
     "tp_pack_weights": (C.c_int, [C.POINTER(TpWeights), C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
     "tp_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int, C.c_int]),
     "tp_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_int,
                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "tp_forward_packed": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_int,
+                                    C.c_void_p, C.c_int64, C.c_void_p, C.c_size_t, C.c_void_p]),
     "tp_forward_layers": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_size_t, C.c_void_p]),
     "tp_forward_allgather": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_int,
-                                       C.POINTER(C.c_void_p), C.c_int, C.c_int64, C.c_void_p, C.c_size_t, C.c_void_p]),
+                                       C.POINTER(C.c_void_p), C.c_int, C.c_int64, C.c_int64, C.c_void_p, C.c_size_t, C.c_void_p]),
     "tp_forward_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int64, C.c_void_p]),
     "tp_train_saved_bytes": (C.c_size_t, [C.c_int64, C.c_int, C.c_int]),
@@ -72,6 +81,10 @@ SIGNATURES = {
     "tp_hd_fit": (C.c_int, [C.c_int64, C.c_int64, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
                             C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "tp_hd_tile": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "tp_hd_tile_batch_plan": (C.c_int, [C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_void_p), C.c_int64, C.c_int,
+                                        C.POINTER(TpHdImage), C.POINTER(C.c_int32), C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                        C.POINTER(C.c_int64)]),
+    "tp_hd_tile_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "tp_hd_plan": (C.c_int, [C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int64, C.c_int, C.POINTER(C.c_int64),
                              C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64),
                              C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),

@@ -17,13 +17,7 @@ namespace {
 using namespace tp;
 
 thread_local char g_last_cuda_error[256] = "";
-#ifdef TP_B_PREFETCH
-thread_local bool g_weights_are_static = false;   // set for the duration of forward_impl: every B operand there is a packed weight
-struct StaticWeightsScope {
-  StaticWeightsScope() { g_weights_are_static = true; }
-  ~StaticWeightsScope() { g_weights_are_static = false; }
-};
-#endif
+thread_local unsigned long long g_launch_count = 0;   // kernels launched from this host thread (tp_launch_count, diagnostic)
 
 #define TP_CUDA(call)                                                                                        \
   do {                                                                                                       \
@@ -85,7 +79,7 @@ int make_map_2d(CUtensorMap* map, const void* ptr, long long rows, long long col
 
 // bf16 tensor [segs, seg_rows, cols] with row stride ld and segment stride seg_stride (elements); box 64 x 64 x 1.
 int make_map_3d(CUtensorMap* map, const void* ptr, long long segs, long long seg_rows, long long cols, long long ld,
-                long long seg_stride) {
+                long long seg_stride, int box_rows = 64) {
   EncodeTiledFn fn = encode_tiled_fn();
   if (fn == nullptr) {
     snprintf(g_last_cuda_error, sizeof(g_last_cuda_error), "cuTensorMapEncodeTiled entry point not found");
@@ -94,7 +88,7 @@ int make_map_3d(CUtensorMap* map, const void* ptr, long long segs, long long seg
   if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0 || (ld * 2) % 16 != 0 || (seg_stride * 2) % 16 != 0) return TP_ERR_INVALID_ARGUMENT;
   cuuint64_t dims[3] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(seg_rows), static_cast<cuuint64_t>(segs)};
   cuuint64_t strides[2] = {static_cast<cuuint64_t>(ld) * 2, static_cast<cuuint64_t>(seg_stride) * 2};
-  cuuint32_t box[3] = {static_cast<cuuint32_t>(kBlockK), 64, 1};
+  cuuint32_t box[3] = {static_cast<cuuint32_t>(kBlockK), static_cast<cuuint32_t>(box_rows), 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -146,7 +140,9 @@ cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t s
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = getenv("TP_NO_PDL") != nullptr ? 0 : 1;   // debugging aid: plain stream serialization
+  static const bool no_pdl = getenv("TP_NO_PDL") != nullptr;   // debugging aid: plain stream serialization
+  cfg.numAttrs = no_pdl ? 0 : 1;
+  ++g_launch_count;
   return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
@@ -159,7 +155,6 @@ struct GemmItem {
   void* const* peer_c = nullptr;   // fused all-gather: the same output slot in every peer's gathered buffer
   int n_peers = 0;
   int tn = 0;                      // 1: C[M,N] = A^T . B with A given as [K, M] (ld = a.ld) and B as [K, N] (ld = ldb), both row-major
-  int b_static = 0;                // B is a packed weight (not produced by the previous kernel): -DTP_B_PREFETCH experiment
 };
 
 int check_item(const GemmItem& it) {
@@ -182,13 +177,18 @@ int launch_gemm_t(const GemmItem& it, int sms, cudaStream_t stream) {
   CUtensorMap map_a, map_b;
   TP_TRY(make_a_map(&map_a, it.a, it.M, it.K));
   TP_TRY(make_map_2d(&map_b, it.b, it.N, it.K, it.ldb, kBlockN));
-  TP_CUDA(cudaFuncSetAttribute(tp_gemm_kernel<kBlockN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+  {
+    static thread_local unsigned attr_done = 0;        // bit per device: the attribute is per (function, device)
+    int dev = 0;
+    TP_CUDA(cudaGetDevice(&dev));
+    if (dev >= 32 || !(attr_done & (1u << dev))) {
+      TP_CUDA(cudaFuncSetAttribute(tp_gemm_kernel<kBlockN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+      if (dev < 32) attr_done |= 1u << dev;
+    }
+  }
   const long long tiles = ((it.M + kBlockM - 1) / kBlockM) * ((it.N + kBlockN - 1) / kBlockN);
   const int grid = static_cast<int>(tiles < sms ? tiles : sms);
   GemmEpilogue ep = it.ep;
-#ifdef TP_B_PREFETCH
-  ep.b_static = (it.b_static != 0 || g_weights_are_static) ? 1 : 0;
-#endif
   TP_CUDA(launch_pdl(tp_gemm_kernel<kBlockN>, dim3(grid), dim3(kGemmThreads), Cfg::kSmemBytes, stream, map_a, map_b, static_cast<int>(it.M),
                      static_cast<int>(it.N), static_cast<int>(it.K), static_cast<int>(it.a.seg_rows), ep));
   return TP_OK;
@@ -227,9 +227,18 @@ int launch_gemm_pair_group(const GemmItem* items, int count, int sms, cudaStream
       TP_TRY(make_map_2d(&p.tmap_b, it.b, it.N, it.K, it.ldb, Cfg::kTileN / 2));
     }
     if (p.a_parts == 0) { p.a_parts = 1; p.a_kblocks_per_part = static_cast<int>((it.K + kBlockK - 1) / kBlockK); }
-    // C goes out through TMA stores (64-col x 128-row swizzled slabs) unless rows are scattered to segment offsets
-    TP_TRY(make_map_2d(&p.tmap_c, it.ep.c, it.M, it.N, it.ep.ldc, kBlockM));
+    // C goes out through TMA stores (64-col x 128-row swizzled slabs) unless rows are scattered to ARBITRARY segment offsets;
+    // uniformly strided segments (the HD packed layout) stay on the TMA path through a 3-D (cols, row in segment, segment) map
     p.use_tma_store = it.ep.seg_row_offset == nullptr ? 1 : 0;
+    const bool c_segmented = p.use_tma_store && it.ep.seg_stride != 0 && it.ep.seg_stride != it.ep.seg_len;
+    if (c_segmented) {
+      if (it.ep.seg_len <= 0 || it.M % it.ep.seg_len != 0 || it.ep.seg_stride < it.ep.seg_len) return TP_ERR_INVALID_ARGUMENT;
+      p.c_seg_len = it.ep.seg_len;
+      TP_TRY(make_map_3d(&p.tmap_c, it.ep.c, it.M / it.ep.seg_len, it.ep.seg_len, it.N, it.ep.ldc, it.ep.seg_stride * it.ep.ldc,
+                         it.ep.seg_len < kBlockM ? it.ep.seg_len : kBlockM));
+    } else {
+      TP_TRY(make_map_2d(&p.tmap_c, it.ep.c, it.M, it.N, it.ep.ldc, kBlockM));
+    }
     p.M = static_cast<int>(it.M);
     p.N = static_cast<int>(it.N);
     p.K = static_cast<int>(it.K);
@@ -237,9 +246,6 @@ int launch_gemm_pair_group(const GemmItem* items, int count, int sms, cudaStream
     p.num_n_blocks = static_cast<int>((it.N + Cfg::kTileN - 1) / Cfg::kTileN);
     p.num_tiles = static_cast<int>((it.M + Cfg::kTileM - 1) / Cfg::kTileM) * p.num_n_blocks;
     p.num_k_blocks = static_cast<int>((it.K + kBlockK - 1) / kBlockK);
-#ifdef TP_B_PREFETCH
-    p.b_static = (it.b_static != 0 || g_weights_are_static) ? 1 : 0;
-#endif
     p.ep = it.ep;
     total += p.num_tiles;
   }
@@ -249,11 +255,25 @@ int launch_gemm_pair_group(const GemmItem* items, int count, int sms, cudaStream
   memset(&peers, 0, sizeof(peers));
   if (items[0].n_peers > 0) {
     if (count != 1 || items[0].n_peers > kMaxPeers || items[0].ep.seg_row_offset != nullptr) return TP_ERR_INVALID_ARGUMENT;
-    for (int p = 0; p < items[0].n_peers; ++p)
-      TP_TRY(make_map_2d(&peers.m[p], items[0].peer_c[p], items[0].M, items[0].N, items[0].ep.ldc, kBlockM));
+    const GemmItem& it0 = items[0];
+    for (int p = 0; p < it0.n_peers; ++p) {
+      if (g.p[0].c_seg_len != 0)
+        TP_TRY(make_map_3d(&peers.m[p], it0.peer_c[p], it0.M / it0.ep.seg_len, it0.ep.seg_len, it0.N, it0.ep.ldc, it0.ep.seg_stride * it0.ep.ldc,
+                           it0.ep.seg_len < kBlockM ? it0.ep.seg_len : kBlockM));
+      else
+        TP_TRY(make_map_2d(&peers.m[p], it0.peer_c[p], it0.M, it0.N, it0.ep.ldc, kBlockM));
+    }
     peers.count = items[0].n_peers;
   }
-  TP_CUDA(cudaFuncSetAttribute(tp_gemm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+  {
+    static thread_local unsigned attr_done = 0;
+    int dev = 0;
+    TP_CUDA(cudaGetDevice(&dev));
+    if (dev >= 32 || !(attr_done & (1u << dev))) {
+      TP_CUDA(cudaFuncSetAttribute(tp_gemm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+      if (dev < 32) attr_done |= 1u << dev;
+    }
+  }
   const long long max_pairs = sms / 2;
   const int grid = 2 * static_cast<int>(total < max_pairs ? total : max_pairs);
   TP_CUDA(launch_pdl(tp_gemm2_kernel, dim3(grid), dim3(kGemmThreads), Cfg::kSmemBytes, stream, g, peers));
@@ -372,12 +392,12 @@ PackedLayout packed_layout(int H) {
 // ------------------------------------------------------------------------------------------------
 // Workspace layout (per call; all intermediates bf16 unless noted)
 // ------------------------------------------------------------------------------------------------
-constexpr int kStatSlots = kC / 128;   // one (sum, sumsq) slot per 128 output columns of a 1024-wide linear
+constexpr int kStatSlots = kC / 128;   // one (mean, M2) slot per 128 output columns of a 1024-wide linear
 
 struct WorkLayout {
   size_t h_kv;      // [R,2048]  GELU(W0 xm + b) for k|v ; reused as k' | v' ([R,1024] each) once consumed
   size_t y_k, y_v;  // [R,1024]  second linear outputs (pre-LayerNorm)
-  size_t stats;     // f32 [2R + Q, 8, 2]  per-row partial (sum, sumsq) per 128-column block: k rows, v rows, q rows
+  size_t stats;     // f32 [2R + Q, 8, 2]  per-row (mean, M2) of each 128-column block: k rows, v rows, q rows
   size_t q, y_q, q_p, ctx, h_m;      // [Q,1024] x4, [Q,H]
   size_t total;
 };
@@ -471,6 +491,8 @@ int tp_abi_version(void) { return TP_ABI_VERSION; }
 
 const char* tp_last_cuda_error(void) { return g_last_cuda_error; }
 
+uint64_t tp_launch_count(void) { return g_launch_count; }
+
 size_t tp_packed_bytes(int hidden) { return valid_hidden(hidden) ? packed_layout(hidden).total : 0; }
 
 int tp_pack_weights(const tp_weights* w, int hidden, void* packed, size_t packed_bytes, void* stream_) {
@@ -518,13 +540,13 @@ int tp_pack_weights(const tp_weights* w, int hidden, void* packed, size_t packed
     TP_TRY(device_info(&dev));
     transpose_bf16_kernel<<<dim3(kC / 32, kC / 32), dim3(32, 8), 0, stream>>>(static_cast<const __nv_bfloat16*>(w->out_proj_w),
                                                                               reinterpret_cast<__nv_bfloat16*>(P + L.w_ot), kC);
-    TP_CUDA(cudaGetLastError());
+    TP_CUDA(cudaGetLastError()); ++g_launch_count;
     TP_TRY(launch_gemm(AOperand{w->mlp_0_w, kC, 0, 0}, P + L.w_ot, kC, hidden, kC, kC, plain_epilogue(P + L.w_om, kC, nullptr, 0), dev.sms, stream));
     matvec_bias_kernel<<<(hidden * 32 + 255) / 256, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(w->mlp_0_w),
                                                                       static_cast<const __nv_bfloat16*>(w->out_proj_b),
                                                                       static_cast<const __nv_bfloat16*>(w->mlp_0_b),
                                                                       reinterpret_cast<float*>(P + L.b_om), hidden, kC);
-    TP_CUDA(cudaGetLastError());
+    TP_CUDA(cudaGetLastError()); ++g_launch_count;
   }
   TP_CUDA(copy(L.w_o, w->out_proj_w, mat));
   TP_CUDA(bias(L.b_o, w->out_proj_b, kC));
@@ -546,8 +568,8 @@ namespace {
 // xm_layers != nullptr: the multi-level stack is given as its four [n_crops, 576, 1024] layers (row stride 1024, crop stride
 // xm_crop_stride) instead of one [n_crops, 576, 4096] tensor; ``xm`` is then ignored.
 int forward_impl(const void* packed, const void* x0, const void* xm, const void* const* xm_layers, int64_t n_crops, int64_t x0_crop_stride,
-                 int64_t xm_crop_stride, int scale_factor, int hidden, void* out, const int64_t* seg_row_offset, void* const* peer_out,
-                 int n_peers, void* workspace, size_t workspace_bytes, void* stream_) {
+                 int64_t xm_crop_stride, int scale_factor, int hidden, void* out, const int64_t* seg_row_offset, int64_t out_crop_rows,
+                 void* const* peer_out, int n_peers, void* workspace, size_t workspace_bytes, void* stream_) {
   if (xm_layers != nullptr) {
     for (int i = 0; i < 4; ++i)
       if (xm_layers[i] == nullptr) return TP_ERR_INVALID_ARGUMENT;
@@ -564,9 +586,6 @@ int forward_impl(const void* packed, const void* x0, const void* xm, const void*
   if (n_crops * kTokens > 0x7fff0000ll) return TP_ERR_INVALID_ARGUMENT;
   DeviceInfo dev;
   TP_TRY(device_info(&dev));
-#ifdef TP_B_PREFETCH
-  StaticWeightsScope static_weights;
-#endif
   const int s = scale_factor, H = hidden;
   const int g = kGrid / s, Mq = g * g;
   const long long R = n_crops * kTokens, Q = n_crops * Mq;
@@ -644,6 +663,10 @@ int forward_impl(const void* packed, const void* x0, const void* xm, const void*
     if (seg_row_offset != nullptr) {
       ep.seg_row_offset = reinterpret_cast<const long long*>(seg_row_offset);
       ep.seg_len = Mq;
+    } else if (out_crop_rows != 0 && out_crop_rows != Mq) {
+      if (out_crop_rows < Mq || out_crop_rows > 0x7fffffffll / H) return TP_ERR_INVALID_ARGUMENT;
+      ep.seg_len = Mq;
+      ep.seg_stride = static_cast<int>(out_crop_rows);
     }
     GemmItem it{AOperand{bf(W.h_m), H, 0, 0}, P + L.w_m2, H, Q, H, H, ep};
     it.peer_c = peer_out;
@@ -659,32 +682,72 @@ extern "C" {
 int tp_forward(const void* packed, const void* x0, const void* xm, int64_t n_crops, int64_t x0_crop_stride, int64_t xm_crop_stride,
                int scale_factor, int hidden, void* out, const int64_t* seg_row_offset, void* workspace, size_t workspace_bytes,
                void* stream) {
-  return forward_impl(packed, x0, xm, nullptr, n_crops, x0_crop_stride, xm_crop_stride, scale_factor, hidden, out, seg_row_offset, nullptr, 0,
+  return forward_impl(packed, x0, xm, nullptr, n_crops, x0_crop_stride, xm_crop_stride, scale_factor, hidden, out, seg_row_offset, 0, nullptr, 0,
                       workspace, workspace_bytes, stream);
+}
+
+int tp_forward_packed(const void* packed, const void* x0, const void* xm, int64_t n_crops, int64_t x0_crop_stride, int64_t xm_crop_stride,
+                      int scale_factor, int hidden, void* out, int64_t out_crop_rows, void* workspace, size_t workspace_bytes, void* stream) {
+  return forward_impl(packed, x0, xm, nullptr, n_crops, x0_crop_stride, xm_crop_stride, scale_factor, hidden, out, nullptr, out_crop_rows, nullptr,
+                      0, workspace, workspace_bytes, stream);
 }
 
 int tp_forward_layers(const void* packed, const void* const* layers, int64_t n_crops, int64_t crop_stride, int scale_factor, int hidden,
                       void* out, const int64_t* seg_row_offset, void* workspace, size_t workspace_bytes, void* stream) {
   if (layers == nullptr) return TP_ERR_INVALID_ARGUMENT;
-  return forward_impl(packed, layers[3], nullptr, layers, n_crops, crop_stride, crop_stride, scale_factor, hidden, out, seg_row_offset,
+  return forward_impl(packed, layers[3], nullptr, layers, n_crops, crop_stride, crop_stride, scale_factor, hidden, out, seg_row_offset, 0,
                       nullptr, 0, workspace, workspace_bytes, stream);
 }
 
 int tp_forward_allgather(const void* packed, const void* x0, const void* xm, int64_t n_crops, int64_t x0_crop_stride,
                          int64_t xm_crop_stride, int scale_factor, int hidden, void* const* peer_out, int n_peers, int64_t crop_offset,
-                         void* workspace, size_t workspace_bytes, void* stream) {
+                         int64_t out_crop_rows, void* workspace, size_t workspace_bytes, void* stream) {
   if (peer_out == nullptr || n_peers <= 0 || n_peers > kMaxPeers || crop_offset < 0 || hidden % 256 != 0) return TP_ERR_INVALID_ARGUMENT;
   if (scale_factor <= 0 || kGrid % scale_factor != 0) return TP_ERR_BAD_SCALE_FACTOR;
   const int g = kGrid / scale_factor;
-  const size_t slot = static_cast<size_t>(crop_offset) * g * g * hidden * 2;      // this rank's first row in every gathered buffer
+  if (out_crop_rows != 0 && out_crop_rows < g * g) return TP_ERR_INVALID_ARGUMENT;
+  const size_t crop_rows = out_crop_rows != 0 ? static_cast<size_t>(out_crop_rows) : static_cast<size_t>(g) * g;
+  const size_t slot = static_cast<size_t>(crop_offset) * crop_rows * hidden * 2;   // this rank's first row in every peer's output buffer
   void* dst[kMaxPeers];
   for (int p = 0; p < n_peers; ++p) {
     if (peer_out[p] == nullptr) return TP_ERR_INVALID_ARGUMENT;
     dst[p] = static_cast<uint8_t*>(peer_out[p]) + slot;
   }
-  return forward_impl(packed, x0, xm, nullptr, n_crops, x0_crop_stride, xm_crop_stride, scale_factor, hidden, dst[0], nullptr, dst, n_peers,
-                      workspace, workspace_bytes, stream);
+  return forward_impl(packed, x0, xm, nullptr, n_crops, x0_crop_stride, xm_crop_stride, scale_factor, hidden, dst[0], nullptr, out_crop_rows, dst,
+                      n_peers, workspace, workspace_bytes, stream);
 }
+
+namespace {
+// Copy streams and events of the host-buffer path: created once per (host thread, device) and kept for the life of the thread —
+// creating and destroying two streams and 2 events per chunk on every call cost more host time than the launches themselves.
+// (The only state the library keeps; it holds no memory and never outlives its thread's CUDA context use.)
+constexpr int kHostEvents = 64;      // ring of (copy-in done, compute done) event pairs; a 64-crop call uses ~12
+struct HostPipe {
+  int device = -1;
+  cudaStream_t s_in = nullptr, s_out = nullptr;
+  cudaEvent_t ev_start = nullptr, ev_in[kHostEvents] = {}, ev_done[kHostEvents] = {};
+};
+thread_local HostPipe g_host_pipe[16];
+
+int host_pipe(HostPipe** out) {
+  int dev = 0;
+  TP_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 16) return TP_ERR_INVALID_ARGUMENT;
+  HostPipe& hp = g_host_pipe[dev];
+  if (hp.device != dev) {
+    TP_CUDA(cudaStreamCreateWithFlags(&hp.s_in, cudaStreamNonBlocking));
+    TP_CUDA(cudaStreamCreateWithFlags(&hp.s_out, cudaStreamNonBlocking));
+    TP_CUDA(cudaEventCreateWithFlags(&hp.ev_start, cudaEventDisableTiming));
+    for (int i = 0; i < kHostEvents; ++i) {
+      TP_CUDA(cudaEventCreateWithFlags(&hp.ev_in[i], cudaEventDisableTiming));
+      TP_CUDA(cudaEventCreateWithFlags(&hp.ev_done[i], cudaEventDisableTiming));
+    }
+    hp.device = dev;
+  }
+  *out = &hp;
+  return TP_OK;
+}
+}  // namespace
 
 int tp_forward_host(const void* packed, const void* x0_host, const void* xm_host, int64_t n_crops, int scale_factor, int hidden,
                     void* out_host, void* d_x0, void* d_xm, void* d_out, void* workspace, size_t workspace_bytes, int64_t chunk_crops,
@@ -698,46 +761,57 @@ int tp_forward_host(const void* packed, const void* x0_host, const void* xm_host
   const int g = kGrid / scale_factor;
   const size_t x0_b = static_cast<size_t>(kTokens) * kC * 2, xm_b = static_cast<size_t>(kTokens) * kCm * 2;
   const size_t out_b = static_cast<size_t>(g) * g * hidden * 2;
-  cudaStream_t s_in = nullptr, s_out = nullptr;
-  TP_CUDA(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
-  TP_CUDA(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
+  HostPipe* hp = nullptr;
+  TP_TRY(host_pipe(&hp));
   int status = TP_OK;
-  cudaEvent_t ev_start = nullptr;
-  cudaEventCreateWithFlags(&ev_start, cudaEventDisableTiming);
-  cudaEventRecord(ev_start, stream);          // copies must not start before prior work on the caller's stream
-  cudaStreamWaitEvent(s_in, ev_start, 0);
-  cudaStreamWaitEvent(s_out, ev_start, 0);
+  cudaError_t err = cudaSuccess;
+  const char* where = "";
+  // every CUDA call of the pipeline is checked; the first failure stops issuing and is reported after the common drain below
+#define TP_HOST_STEP(call)                                   \
+  do {                                                       \
+    if (err == cudaSuccess && status == TP_OK) {             \
+      err = (call);                                          \
+      if (err != cudaSuccess) where = #call;                 \
+    }                                                        \
+  } while (0)
+  TP_HOST_STEP(cudaEventRecord(hp->ev_start, stream));          // copies must not start before prior work on the caller's stream
+  TP_HOST_STEP(cudaStreamWaitEvent(hp->s_in, hp->ev_start, 0));
+  TP_HOST_STEP(cudaStreamWaitEvent(hp->s_out, hp->ev_start, 0));
   // Full chunks, then a tapered tail (remaining/2, ..., 2, 1, 1): the copies in are the bottleneck (PCIe), so what is NOT hidden
   // behind them is the last chunk's compute + copy out — keep that chunk small.
-  for (int64_t c0 = 0, nc = 0; c0 < n_crops && status == TP_OK; c0 += nc) {
+  int slot = 0;
+  for (int64_t c0 = 0, nc = 0; c0 < n_crops && status == TP_OK && err == cudaSuccess; c0 += nc, ++slot) {
     const int64_t remaining = n_crops - c0;
     nc = remaining > chunk_crops ? chunk_crops : (remaining > 1 ? (remaining + 1) / 2 : 1);
-    cudaEvent_t ev_in = nullptr, ev_done = nullptr;
-    cudaEventCreateWithFlags(&ev_in, cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&ev_done, cudaEventDisableTiming);
-    cudaMemcpyAsync(static_cast<uint8_t*>(d_x0) + c0 * x0_b, static_cast<const uint8_t*>(x0_host) + c0 * x0_b, nc * x0_b,
-                    cudaMemcpyHostToDevice, s_in);
-    cudaMemcpyAsync(static_cast<uint8_t*>(d_xm) + c0 * xm_b, static_cast<const uint8_t*>(xm_host) + c0 * xm_b, nc * xm_b,
-                    cudaMemcpyHostToDevice, s_in);
-    cudaEventRecord(ev_in, s_in);
-    cudaStreamWaitEvent(stream, ev_in, 0);
-    status = tp_forward(packed, static_cast<uint8_t*>(d_x0) + c0 * x0_b, static_cast<uint8_t*>(d_xm) + c0 * xm_b, nc,
-                        static_cast<int64_t>(kTokens) * kC, static_cast<int64_t>(kTokens) * kCm, scale_factor, hidden,
-                        static_cast<uint8_t*>(d_out) + c0 * out_b, nullptr, workspace, workspace_bytes, stream);
-    cudaEventRecord(ev_done, stream);
-    cudaStreamWaitEvent(s_out, ev_done, 0);
-    cudaMemcpyAsync(static_cast<uint8_t*>(out_host) + c0 * out_b, static_cast<uint8_t*>(d_out) + c0 * out_b, nc * out_b,
-                    cudaMemcpyDeviceToHost, s_out);
-    cudaEventDestroy(ev_in);
-    cudaEventDestroy(ev_done);
+    if (slot == kHostEvents) {          // ring exhausted (very long calls): drain before reusing the events
+      TP_HOST_STEP(cudaStreamSynchronize(hp->s_out));
+      slot = 0;
+    }
+    TP_HOST_STEP(cudaMemcpyAsync(static_cast<uint8_t*>(d_x0) + c0 * x0_b, static_cast<const uint8_t*>(x0_host) + c0 * x0_b, nc * x0_b,
+                                 cudaMemcpyHostToDevice, hp->s_in));
+    TP_HOST_STEP(cudaMemcpyAsync(static_cast<uint8_t*>(d_xm) + c0 * xm_b, static_cast<const uint8_t*>(xm_host) + c0 * xm_b, nc * xm_b,
+                                 cudaMemcpyHostToDevice, hp->s_in));
+    TP_HOST_STEP(cudaEventRecord(hp->ev_in[slot], hp->s_in));
+    TP_HOST_STEP(cudaStreamWaitEvent(stream, hp->ev_in[slot], 0));
+    if (err == cudaSuccess)
+      status = tp_forward(packed, static_cast<uint8_t*>(d_x0) + c0 * x0_b, static_cast<uint8_t*>(d_xm) + c0 * xm_b, nc,
+                          static_cast<int64_t>(kTokens) * kC, static_cast<int64_t>(kTokens) * kCm, scale_factor, hidden,
+                          static_cast<uint8_t*>(d_out) + c0 * out_b, nullptr, workspace, workspace_bytes, stream);
+    TP_HOST_STEP(cudaEventRecord(hp->ev_done[slot], stream));
+    TP_HOST_STEP(cudaStreamWaitEvent(hp->s_out, hp->ev_done[slot], 0));
+    TP_HOST_STEP(cudaMemcpyAsync(static_cast<uint8_t*>(out_host) + c0 * out_b, static_cast<uint8_t*>(d_out) + c0 * out_b, nc * out_b,
+                                 cudaMemcpyDeviceToHost, hp->s_out));
   }
-  cudaError_t e1 = cudaStreamSynchronize(s_out);
-  cudaError_t e2 = cudaStreamSynchronize(stream);
-  cudaError_t e3 = cudaStreamSynchronize(s_in);
-  cudaEventDestroy(ev_start);
-  cudaStreamDestroy(s_in);
-  cudaStreamDestroy(s_out);
+#undef TP_HOST_STEP
+  // common drain: whatever was issued completes before the caller's buffers may be touched again
+  const cudaError_t e1 = cudaStreamSynchronize(hp->s_out);
+  const cudaError_t e2 = cudaStreamSynchronize(stream);
+  const cudaError_t e3 = cudaStreamSynchronize(hp->s_in);
   if (status != TP_OK) return status;
+  if (err != cudaSuccess) {
+    snprintf(g_last_cuda_error, sizeof(g_last_cuda_error), "%s: %s", where, cudaGetErrorString(err));
+    return TP_ERR_CUDA;
+  }
   TP_CUDA(e1);
   TP_CUDA(e2);
   TP_CUDA(e3);
@@ -881,13 +955,57 @@ int tp_hd_tile(const float* image, int64_t h, int64_t w, int h_block, int w_bloc
   const long long total = 3ll * h_block * kBlockPx * w_block * kBlockPx;
   hd_tile_main_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(image, static_cast<int>(h), static_cast<int>(w),
                                                                                       h_block, w_block, h_r, w_r, crops);
-  TP_CUDA(cudaGetLastError());
+  TP_CUDA(cudaGetLastError()); ++g_launch_count;
   if (h_block * w_block > 1) {
     if (h_t <= 0 || w_t <= 0) return TP_ERR_INVALID_ARGUMENT;
     const int t = 3 * kBlockPx * kBlockPx;
     hd_tile_thumb_kernel<<<(t + 255) / 256, 256, 0, stream>>>(h_block, w_block, h_t, w_t, crops);
-    TP_CUDA(cudaGetLastError());
+    TP_CUDA(cudaGetLastError()); ++g_launch_count;
   }
+  return TP_OK;
+}
+
+int tp_hd_tile_batch_plan(const int64_t* h, const int64_t* w, const void* const* images, int64_t n_images, int patch_num,
+                          tp_hd_image* images_host, int32_t* crop_table_host, int* h_block, int* w_block, int64_t* n_crops) {
+  if (h == nullptr || w == nullptr || n_images < 0 || n_crops == nullptr) return TP_ERR_INVALID_ARGUMENT;
+  if (patch_num != 9 && patch_num != 16 && patch_num != 25) return TP_ERR_BAD_PATCH_NUM;
+  int64_t crop = 0;
+  for (int64_t b = 0; b < n_images; ++b) {
+    if (h[b] <= 0 || w[b] <= 0 || h[b] > 32768 || w[b] > 32768) return TP_ERR_INVALID_ARGUMENT;
+    int hb = 0, wb = 0, h_r = 0, w_r = 0, h_t = 0, w_t = 0;
+    TP_TRY(tp_hd_grid(h[b], w[b], patch_num, kBlockPx, &hb, &wb));
+    TP_TRY(tp_hd_fit(h[b], w[b], hb, wb, &h_r, &w_r, &h_t, &w_t));
+    if (h_r <= 0 || w_r <= 0 || (hb * wb > 1 && (h_t <= 0 || w_t <= 0))) return TP_ERR_INVALID_ARGUMENT;
+    if (h_block) h_block[b] = hb;
+    if (w_block) w_block[b] = wb;
+    if (images_host) {
+      tp_hd_image& im = images_host[b];
+      im.image = images ? static_cast<const float*>(images[b]) : nullptr;
+      im.h = static_cast<int>(h[b]); im.w = static_cast<int>(w[b]); im.hb = hb; im.wb = wb;
+      im.h_r = h_r; im.w_r = w_r; im.h_t = hb * wb > 1 ? h_t : 0; im.w_t = hb * wb > 1 ? w_t : 0;
+      im.crop0 = crop;
+    }
+    for (int i = 0; i < hb; ++i)
+      for (int j = 0; j < wb; ++j, ++crop)
+        if (crop_table_host) { crop_table_host[crop * 3] = static_cast<int32_t>(b); crop_table_host[crop * 3 + 1] = i; crop_table_host[crop * 3 + 2] = j; }
+    if (hb * wb > 1) {       // train.py:718: the thumbnail is appended only when the image was split
+      if (crop_table_host) { crop_table_host[crop * 3] = static_cast<int32_t>(b); crop_table_host[crop * 3 + 1] = 0; crop_table_host[crop * 3 + 2] = -1; }
+      ++crop;
+    }
+  }
+  *n_crops = crop;
+  return TP_OK;
+}
+
+int tp_hd_tile_batch(const tp_hd_image* images_dev, const int32_t* crop_table_dev, int64_t n_crops, float* crops, void* stream_) {
+  static_assert(sizeof(tp_hd_image) == sizeof(HdImage), "tp_hd_image and the kernel's HdImage must have the same layout");
+  if (images_dev == nullptr || crop_table_dev == nullptr || crops == nullptr || n_crops < 0) return TP_ERR_INVALID_ARGUMENT;
+  if (n_crops == 0) return TP_OK;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const long long total = n_crops * 3 * kBlockPx * (kBlockPx / 4);
+  hd_tile_batch_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(reinterpret_cast<const HdImage*>(images_dev), crop_table_dev,
+                                                                                       n_crops, crops);
+  TP_CUDA(cudaGetLastError()); ++g_launch_count;
   return TP_OK;
 }
 
@@ -941,7 +1059,7 @@ int tp_hd_scatter_crops(const void* feats, int64_t n_crops, int tokens_per_crop,
   scatter_crops_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, stream>>>(
       static_cast<const __nv_bfloat16*>(feats), n_crops, tokens_per_crop, hidden, reinterpret_cast<const long long*>(seg_row_offset),
       static_cast<__nv_bfloat16*>(out));
-  TP_CUDA(cudaGetLastError());
+  TP_CUDA(cudaGetLastError()); ++g_launch_count;
   return TP_OK;
 }
 
@@ -953,7 +1071,7 @@ int tp_gather_rows(const void* table, const void* visual, int hidden, const int6
   gather_rows_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, stream>>>(
       static_cast<const __nv_bfloat16*>(table), static_cast<const __nv_bfloat16*>(visual), hidden, reinterpret_cast<const long long*>(src_index),
       n_rows, static_cast<__nv_bfloat16*>(out));
-  TP_CUDA(cudaGetLastError());
+  TP_CUDA(cudaGetLastError()); ++g_launch_count;
   return TP_OK;
 }
 
@@ -966,13 +1084,13 @@ int tp_hd_fill_separators(void* out, int hidden, const int64_t* sep_rows, int64_
     if (sep_rows == nullptr || sep_row == nullptr) return TP_ERR_INVALID_ARGUMENT;
     fill_rows_kernel<<<static_cast<unsigned>((n_sep * vecs + 255) / 256), 256, 0, stream>>>(
         static_cast<__nv_bfloat16*>(out), hidden, reinterpret_cast<const long long*>(sep_rows), n_sep, static_cast<const __nv_bfloat16*>(sep_row));
-    TP_CUDA(cudaGetLastError());
+    TP_CUDA(cudaGetLastError()); ++g_launch_count;
   }
   if (n_ret > 0) {
     if (ret_rows == nullptr || ret_row == nullptr) return TP_ERR_INVALID_ARGUMENT;
     fill_rows_kernel<<<static_cast<unsigned>((n_ret * vecs + 255) / 256), 256, 0, stream>>>(
         static_cast<__nv_bfloat16*>(out), hidden, reinterpret_cast<const long long*>(ret_rows), n_ret, static_cast<const __nv_bfloat16*>(ret_row));
-    TP_CUDA(cudaGetLastError());
+    TP_CUDA(cudaGetLastError()); ++g_launch_count;
   }
   return TP_OK;
 }

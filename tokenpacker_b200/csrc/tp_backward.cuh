@@ -11,17 +11,25 @@ namespace tp {
 
 constexpr int kStatSlotsBwd = kC / 128;
 
+// per-row LayerNorm statistics from the per-128-column (mean, M2) pairs the forward GEMM epilogue left (same combination, same
+// order, same bits as the folded LayerNorm in tp_gemm.cuh)
 __device__ __forceinline__ void row_mean_rstd(const float* stats, long long row, float& mu, float& rstd) {
   const float2* st = reinterpret_cast<const float2*>(stats) + row * kStatSlotsBwd;
-  float t1 = 0.f, t2 = 0.f;
+  float t1 = 0.f, m2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < kStatSlotsBwd; ++i) t1 = __fadd_rn(t1, st[i].x);
+  const float inv_slots = __frcp_rn(static_cast<float>(kStatSlotsBwd));
+  mu = __fmul_rn(t1, inv_slots);
+  float between = 0.f;
 #pragma unroll
   for (int i = 0; i < kStatSlotsBwd; ++i) {
     const float2 v = st[i];
-    t1 = __fadd_rn(t1, v.x);
-    t2 = __fadd_rn(t2, v.y);
+    const float d = __fsub_rn(v.x, mu);
+    between = fmaf(d, d, between);
+    m2 = __fadd_rn(m2, v.y);
   }
-  mu = __fmul_rn(t1, 1.0f / kC);
-  const float var = fmaxf(fmaf(-mu, mu, __fmul_rn(t2, 1.0f / kC)), 0.f);
+  const float inv_dim = 1.0f / kC;
+  const float var = __fmul_rn(fmaf(between, __fmul_rn(inv_slots, __frcp_rn(inv_dim)), m2), inv_dim);
   rstd = rsqrtf(__fadd_rn(var, 1e-6f));
 }
 

@@ -28,8 +28,8 @@
 //   v = v + col_b[c]                             bias
 //   v = gelu_erf(v)                              exact erf GELU (nn.GELU default)
 //   v = alpha * v                                1/sqrt(head_dim) query scaling
-//   y = bf16(v);  stats_out[r][slot] = (sum y, sum y*y) over this warp's columns  -> next LayerNorm fold (deterministic:
-//                                                one slot per 128-column block, summed in fixed order by the consumer)
+//   y = bf16(v);  stats_out[r][slot] = (mean, M2) of y over this warp's 128 columns  -> next LayerNorm fold (deterministic:
+//                                                one slot per 128-column block, combined Chan-style in fixed order by the consumer)
 //   C[dst_row(r), c] = y                         optional segment scatter (HD packed output)
 #pragma once
 
@@ -42,10 +42,13 @@ struct GemmEpilogue {
   long long ldc;           // elements between output rows
   const float* col_a;      // [N]  LN fold: row-sum of the gamma-folded weight      (nullptr: no LN fold)
   const float* col_b;      // [N]  bias                                             (nullptr: none)
-  const float* stats_in;   // [M, stats_in_slots, 2] partial (sum, sumsq) of the A rows (required with col_a)
+  const float* stats_in;   // [M, stats_in_slots, 2] per-block (mean, M2) of the A rows (required with col_a)
   float* stats_out;        // [M, stats_out_slots, 2]                               (nullptr: none)
-  const long long* seg_row_offset;  // [M / seg_len] destination row of each segment's first row (nullptr: identity)
-  int seg_len;
+  const long long* seg_row_offset;  // [M / seg_len] destination row of each segment's first row (nullptr: identity / uniform stride)
+  int seg_len;             // rows per segment (one crop's tokens)
+  int seg_stride;          // uniform-stride form (seg_row_offset == nullptr): segment i starts at output row i * seg_stride
+                           // (0: contiguous).  The HD packed layout (llava_arch.py:139-155) is exactly this with stride = seg_len + 1:
+                           // every crop is followed by ONE separator row (',' or '\n').  Kept on the TMA-store path (3-D C map).
   int stats_in_slots;
   int stats_out_slots;     // = N / 128 (host-checked; statistics need 256-column tiles): slot = col / 128
   float ln_inv_dim;        // 1 / ln_dim
@@ -53,9 +56,6 @@ struct GemmEpilogue {
   float alpha;
   int gelu;
   long long* prof;         // TP_GEMM_PROFILE builds only: [grid][16] cycle counters (nullptr otherwise)
-#ifdef TP_B_PREFETCH
-  int b_static;            // one-CTA kernels: see GemmProblem::b_static
-#endif
 };
 
 #ifndef TP_EPI_SUB_PAIRS
@@ -118,7 +118,10 @@ struct PeerStores {
 
 struct OutStage {
   uint8_t* buf;              // this half's 2 x 16 KiB staging buffers (nullptr: direct 16-byte global stores)
-  const CUtensorMap* tmap;   // C tensor map(s), box = 64 cols x 128 rows, SWIZZLE_128B
+  const CUtensorMap* tmap;   // C tensor map(s), box = 64 cols x 128 rows, SWIZZLE_128B  (3-D, box 64 x seg_box x 1, when seg_len != 0)
+  int seg_len;               // 0: plain 2-D output; else rows per segment of the 3-D (cols, row in segment, segment) map
+  int seg_box;               // box rows of the 3-D map = min(seg_len, 128)
+  int n_segs;
   int n_maps;                // 1, or the number of peer maps (consecutive CUtensorMaps starting at tmap)
   int row_tile0;             // first global row of this CTA's 128-row tile
   int n_bufs;                // 2: slabs alternate buffers (one barrier per slab); 1: single buffer (two barriers per slab)
@@ -137,30 +140,39 @@ __device__ __forceinline__ void epilogue_tile(const GemmEpilogue& ep, int M, int
   const bool row_ok = row < M;
   float mu = 0.f, rstd = 1.f;
   if (ln_fold && row_ok) {
-    float t1 = 0.f, t2 = 0.f;
+    // Row statistics arrive as one (mean_i, M2_i) pair per 128-column block (M2 = sum of squared deviations from the block's own
+    // mean) and are combined Chan-style in a fixed order: no E[y^2] - mu^2 cancellation when |mean| >> std, bitwise reproducible.
     const float2* st = reinterpret_cast<const float2*>(ep.stats_in) + static_cast<long long>(row) * ep.stats_in_slots;
-    for (int i = 0; i < ep.stats_in_slots; ++i) {     // fixed order -> bitwise reproducible LayerNorm statistics
+    float t1 = 0.f, m2 = 0.f;
+    for (int i = 0; i < ep.stats_in_slots; ++i) t1 = __fadd_rn(t1, st[i].x);
+    const float inv_slots = __frcp_rn(static_cast<float>(ep.stats_in_slots));
+    mu = __fmul_rn(t1, inv_slots);
+    float between = 0.f;
+    for (int i = 0; i < ep.stats_in_slots; ++i) {
       const float2 v = st[i];
-      t1 = __fadd_rn(t1, v.x);
-      t2 = __fadd_rn(t2, v.y);
+      const float d = __fsub_rn(v.x, mu);
+      between = fmaf(d, d, between);
+      m2 = __fadd_rn(m2, v.y);
     }
     // explicit intrinsics throughout the epilogue math: no FMA-contraction freedom for the compiler, so the one-CTA and
     // CTA-pair instantiations (and any future one) produce the same bits for the same row
-    mu = __fmul_rn(t1, ep.ln_inv_dim);
-    const float var = fmaxf(fmaf(-mu, mu, __fmul_rn(t2, ep.ln_inv_dim)), 0.f);
+    const float var = __fmul_rn(fmaf(between, __fmul_rn(inv_slots, __frcp_rn(ep.ln_inv_dim)), m2), ep.ln_inv_dim);
     rstd = rsqrtf(__fadd_rn(var, ep.ln_eps));
   }
   long long dst_row = row;
   if (ep.seg_row_offset != nullptr && row_ok) {
     const int seg = row / ep.seg_len;
     dst_row = ep.seg_row_offset[seg] + (row - seg * ep.seg_len);
+  } else if (ep.seg_stride != 0 && row_ok) {
+    const int seg = row / ep.seg_len;
+    dst_row = static_cast<long long>(seg) * ep.seg_stride + (row - seg * ep.seg_len);
   }
   __nv_bfloat16* c_row = ep.c + dst_row * ep.ldc;
   const uint32_t taddr = tmem_acc + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(half * kColsPerWarp);
   const uint32_t sa_addr = smem_u32(s_col + half * kColsPerWarp), sb_addr = smem_u32(s_col + kTileN + half * kColsPerWarp);
   const uint32_t out_addr = out.buf != nullptr ? smem_u32(out.buf) : 0u;
 
-  float s1 = 0.f, s2 = 0.f;
+  float s1 = 0.f, s2 = 0.f, shift = 0.f;     // statistics of (y - shift), shift = the block's first value: sums stay small
   const bool do_stats = ep.stats_out != nullptr;
   const bool scale = ep.alpha != 1.0f;
   const uint64_t rstd2 = pk2(rstd), nmu2 = pk2(-mu), alpha2 = pk2(ep.alpha);
@@ -226,9 +238,10 @@ __device__ __forceinline__ void epilogue_tile(const GemmEpilogue& ep, int M, int
           pk[j] = pack_bf16x2(lo, hi);
         }
         if (do_stats) {    // LayerNorm statistics of the ROUNDED values the next GEMM will read (column order: deterministic)
+          if (chunk == 0 && sub == 0) shift = bf16_lo(pk[0]);
 #pragma unroll
           for (int j = 0; j < kSubPairs; ++j) {
-            const float y0 = bf16_lo(pk[j]), y1 = bf16_hi(pk[j]);
+            const float y0 = __fsub_rn(bf16_lo(pk[j]), shift), y1 = __fsub_rn(bf16_hi(pk[j]), shift);
             s1 = __fadd_rn(s1, __fadd_rn(y0, y1));
             s2 = fmaf(y0, y0, fmaf(y1, y1, s2));
           }
@@ -264,17 +277,35 @@ __device__ __forceinline__ void epilogue_tile(const GemmEpilogue& ep, int M, int
       }
       if (out.issuer) {
         const int slab = chunk >> 1;
-        for (int p = 0; p < out.n_maps; ++p)
-          tma_store_2d(out.tmap + p, out.buf + (slab & (out.n_bufs - 1)) * kOutSlabBytes, col_tile0 + half * kColsPerWarp + slab * 64,
-                       out.row_tile0);
+        const uint8_t* src = out.buf + (slab & (out.n_bufs - 1)) * kOutSlabBytes;
+        const int col = col_tile0 + half * kColsPerWarp + slab * 64;
+        if (out.seg_len == 0) {
+          for (int p = 0; p < out.n_maps; ++p) tma_store_2d(out.tmap + p, src, col, out.row_tile0);
+        } else {
+          // Segmented output rows (global row g = seg * seg_len + r  ->  map coordinate (col, r, seg)): the slab's 128 rows are
+          // cut at segment boundaries and each piece leaves through the SAME fixed-size box.  A piece that starts before the slab
+          // or ends after it is positioned so that the surplus box rows fall outside [0, seg_len) of its segment, where TMA clips
+          // them (signed coordinates): src_row = clamp(a, 0, 128 - box), r0 = src_row - a, a = slab row of the segment's row 0.
+          // The 128B swizzle is a function of the absolute shared-memory address, so any 128-byte-aligned source row works.
+          int seg = out.row_tile0 / out.seg_len;
+          for (int a = seg * out.seg_len - out.row_tile0; a < kBlockM && seg < out.n_segs; a += out.seg_len, ++seg) {
+            const int src_row = min(max(a, 0), kBlockM - out.seg_box);
+            for (int p = 0; p < out.n_maps; ++p) tma_store_3d(out.tmap + p, src + src_row * 128, col, src_row - a, seg);
+          }
+        }
         bulk_commit_group();
       }
     }
   }
   if (ep.stats_out != nullptr && row_ok) {
     const int slot = (col_tile0 + half * kColsPerWarp) / kColsPerWarp;
-    if (slot < ep.stats_out_slots)
-      reinterpret_cast<float2*>(ep.stats_out)[static_cast<long long>(row) * ep.stats_out_slots + slot] = make_float2(s1, s2);
+    if (slot < ep.stats_out_slots) {
+      // (mean, M2) of this 128-column block: mean = shift + s1/n, M2 = s2 - s1^2/n  (deviations from `shift` are O(std): no cancellation)
+      constexpr float inv_n = 1.0f / kColsPerWarp;
+      const float dm = __fmul_rn(s1, inv_n);
+      reinterpret_cast<float2*>(ep.stats_out)[static_cast<long long>(row) * ep.stats_out_slots + slot] =
+          make_float2(__fadd_rn(shift, dm), fmaxf(fmaf(-s1, dm, s2), 0.f));
+    }
   }
 }
 
@@ -350,18 +381,6 @@ tp_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_base_smem;
-#ifdef TP_B_PREFETCH
-  // EXPERIMENT (see tp_gemm2_kernel): weight tiles of this CTA's first output tile in flight before griddepcontrol.wait
-  int prefetched = 0;
-  if (warp_idx == kTmaWarp && lane == 0 && ep.b_static != 0 && static_cast<int>(blockIdx.x) < num_tiles) {
-    const int n_blk0 = static_cast<int>(blockIdx.x) % num_n_blocks;
-    prefetched = num_k_blocks < kStages ? num_k_blocks : kStages;
-    for (int kb = 0; kb < prefetched; ++kb) {
-      mbar_arrive_expect_tx(&full_bar[kb], Cfg::kStageBytes);
-      tma_load_2d(smem + kb * Cfg::kStageBytes + Cfg::kABytes, &tmap_b, &full_bar[kb], kb * kBlockK, n_blk0 * kBlockN);
-    }
-  }
-#endif
   grid_dependency_wait();                  // PDL: the prologue above overlapped the previous kernel's tail
   grid_launch_dependents();
 
@@ -377,12 +396,7 @@ tp_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           mbar_wait(&empty_bar[stage], phase ^ 1u);
           uint8_t* sa = smem + stage * Cfg::kStageBytes;
           uint8_t* sb = sa + Cfg::kABytes;
-#ifdef TP_B_PREFETCH
-          const bool b_in_flight = tile == static_cast<int>(blockIdx.x) && kb < prefetched;
-#else
-          constexpr bool b_in_flight = false;
-#endif
-          if (!b_in_flight) mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
           if (a_seg_rows == 0) {
             tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * kBlockK, m_blk * kBlockM);
           } else {
@@ -394,7 +408,7 @@ tp_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               tma_load_3d(sa + h * (Cfg::kABytes / 2), &tmap_a, &full_bar[stage], kb * kBlockK, g - seg * a_seg_rows, seg);
             }
           }
-          if (!b_in_flight) tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * kBlockK, n_blk * kBlockN);
+          tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * kBlockK, n_blk * kBlockN);
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
       }
@@ -448,7 +462,7 @@ tp_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tcgen05_fence_after();
       uint64_t* release_bar = &tmem_empty_bar[acc];
-      const OutStage no_stage{nullptr, nullptr, 0, 0, 0, 0, false};
+      const OutStage no_stage{nullptr, nullptr, 0, 0, 0, 0, 0, 0, 0, false};
       epilogue_tile<kBlockN>(ep, M, N, tmem_base + static_cast<uint32_t>(acc * kBlockN),
                              m_blk * kBlockM + quarter * 32 + static_cast<int>(lane), n_blk * kBlockN, quarter, half, s_col, no_stage, [&]() {
                                tcgen05_fence_before();
@@ -505,14 +519,11 @@ struct GemmProblem {
   int M, N, K;
   int a_seg_rows;        // 0: plain 2-D A; else rows per segment of the 3-D (crop-strided) A map
   int ab_mn_major;       // 1: BOTH operands are given as row-major [K, M] / [K, N] matrices (wgrad: C = A^T . B, contraction over rows)
-  int use_tma_store;     // C through TMA stores (0 when rows are scattered to segment offsets)
+  int use_tma_store;     // C through TMA stores (0 when rows are scattered to arbitrary segment offsets)
+  int c_seg_len;         // != 0: tmap_c (and the peer maps) are 3-D (cols, row in segment, segment): uniform-stride segmented output
   int num_n_blocks;
   int num_tiles;
   int num_k_blocks;
-#ifdef TP_B_PREFETCH
-  int b_static;          // B (weights) was not written by the previous kernel on the stream: its first tiles may be fetched before
-                         // griddepcontrol.wait (experiment, off by default: see the producer prologue)
-#endif
   GemmEpilogue ep;
 };
 
@@ -589,30 +600,6 @@ tp_gemm2_kernel(const __grid_constant__ GemmGroup grp, const __grid_constant__ P
   cluster_sync_all();                      // barriers of both CTAs initialised before any remote arrive / multicast commit
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_base_smem;
-#ifdef TP_B_PREFETCH
-  // EXPERIMENT (build with -DTP_B_PREFETCH; not validated on hardware yet): the B operand of every forward GEMM is a packed weight,
-  // written long before the previous kernel on the stream, so the first stages of this CTA's first tile can have their barriers
-  // armed and their B halves in flight BEFORE griddepcontrol.wait — the weight fetch then overlaps the previous kernel's tail
-  // (the single-crop latency is a chain of 7 dependent launches).  A joins after the wait; the barrier completes on the total bytes.
-  int prefetched = 0;
-  if (warp_idx == kTmaWarp && pair_idx < num_tiles) {
-    const TileRef t0 = decode_tile(grp, pair_idx);
-    const GemmProblem& pr0 = *t0.pr;
-    if (pr0.b_static != 0 && pr0.ab_mn_major == 0) {
-      prefetched = pr0.num_k_blocks < kStages ? pr0.num_k_blocks : kStages;
-      const int brow0 = t0.n_blk * kTileN + static_cast<int>(cta_rank) * (kTileN / 2);
-      for (int kb = 0; kb < prefetched; ++kb) {
-        if (elect_one()) {
-          uint8_t* sb = smem + kb * Cfg::kStageBytes + Cfg::kABytes;
-          if (is_leader) mbar_arrive_expect_tx(&full_bar[kb], 2 * Cfg::kStageBytes);
-          else mbar_arrive_cluster(&full_bar[kb], 0);
-          tma_load_2d_pair(sb, &pr0.tmap_b, &full_bar[kb], kb * kBlockK, brow0);
-        }
-        __syncwarp();
-      }
-    }
-  }
-#endif
   // Programmatic dependent launch: everything above overlapped the tail of the previous kernel on the stream; from here
   // on we read what it wrote.  (No-op when the launch carries no PDL attribute.)
   grid_dependency_wait();
@@ -644,18 +631,11 @@ tp_gemm2_kernel(const __grid_constant__ GemmGroup grp, const __grid_constant__ P
           mbar_wait(&empty_bar[stage], phase ^ 1u);
           TP_PROF_ADD(w_empty);
         }
-#ifdef TP_B_PREFETCH
-        const bool b_in_flight = tile == pair_idx && kb < prefetched;     // armed and B issued in the prologue
-#else
-        constexpr bool b_in_flight = false;
-#endif
         if (elect_one()) {
           uint8_t* sa = smem + stage * Cfg::kStageBytes;
           uint8_t* sb = sa + Cfg::kABytes;
-          if (!b_in_flight) {
-            if (is_leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
-            else mbar_arrive_cluster(&full_bar[stage], 0);
-          }
+          if (is_leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
+          else mbar_arrive_cluster(&full_bar[stage], 0);
           if (pr.ab_mn_major) {
             // boxes of [64 K-rows x 64 MN-elements]: coordinates (mn, k); two MN atoms per operand per CTA
             tma_load_2d_pair(sa, &pr.tmap_a, &full_bar[stage], row0, kb * kBlockK);
@@ -673,7 +653,7 @@ tp_gemm2_kernel(const __grid_constant__ GemmGroup grp, const __grid_constant__ P
               tma_load_3d_pair(sa + Cfg::kABytes / 2, ta, &full_bar[stage], ka, srow1, seg1);
             }
           }
-          if (!pr.ab_mn_major && !b_in_flight) tma_load_2d_pair(sb, &pr.tmap_b, &full_bar[stage], kb * kBlockK, brow0);
+          if (!pr.ab_mn_major) tma_load_2d_pair(sb, &pr.tmap_b, &full_bar[stage], kb * kBlockK, brow0);
         }
         __syncwarp();
         if (++stage == kStages) { stage = 0; phase ^= 1u; }
@@ -776,6 +756,7 @@ tp_gemm2_kernel(const __grid_constant__ GemmGroup grp, const __grid_constant__ P
       const int row_tile0 = t.m_blk * Cfg::kTileM + static_cast<int>(cta_rank) * kBlockM;
       const int row = row_tile0 + quarter * 32 + static_cast<int>(lane);
       const OutStage out{pr.use_tma_store ? s_out + half * Cfg::kOutBufs * kOutSlabBytes : nullptr, peers.count > 0 ? &peers.m[0] : &pr.tmap_c,
+                         pr.c_seg_len, pr.c_seg_len < kBlockM ? pr.c_seg_len : kBlockM, pr.c_seg_len != 0 ? pr.M / pr.c_seg_len : 0,
                          peers.count > 0 ? peers.count : 1, row_tile0, Cfg::kOutBufs, static_cast<uint32_t>(2 + half),
                          quarter == 0 && lane == 0};
       stored = stored || pr.use_tma_store;

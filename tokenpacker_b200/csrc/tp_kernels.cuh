@@ -353,6 +353,65 @@ __global__ void hd_tile_thumb_kernel(int hb, int wb, int h_t, int w_t, float* __
   crops[((static_cast<long long>(hb * wb) * 3 + ch) * kBlockPx + y) * kBlockPx + x] = v;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Batched form of the tiling block: ONE launch tiles a whole batch of variable-size images (the collator concatenates the
+// crops of a batch, train.py:797-800), thumbnails included, float4 stores.  Every thread produces 4 consecutive pixels of one
+// crop row.  The thumbnail is resized from the PADDED canvas (train.py:710,718-730); instead of reading pass-1 output back, each
+// canvas tap is recomputed from the source image with exactly the arithmetic the main crops use, so the bits are those of
+// the two-pass kernels above.
+// ------------------------------------------------------------------------------------------------
+struct HdImage {            // mirrors tp_hd_image (include/tokenpacker_b200.h)
+  const float* image;       // [3, h, w] fp32, normalised
+  int h, w, hb, wb;
+  int h_r, w_r;             // resized content of the main canvas
+  int h_t, w_t;             // resized content of the thumbnail (0 when hb*wb == 1)
+  long long crop0;          // index of this image's first crop in the batch output
+};
+
+__device__ __forceinline__ float hd_canvas_value(const HdImage& im, const float* __restrict__ plane, int Y, int X) {
+  if (Y >= im.h_r || X >= im.w_r) return 0.f;
+  const LinearTap ty = linear_tap(Y, im.h, im.h_r), tx = linear_tap(X, im.w, im.w_r);
+  const float* r0 = plane + static_cast<long long>(ty.i0) * im.w;
+  const float* r1 = plane + static_cast<long long>(ty.i1) * im.w;
+  return bilerp(__ldg(r0 + tx.i0), __ldg(r0 + tx.i1), __ldg(r1 + tx.i0), __ldg(r1 + tx.i1), ty, tx);
+}
+
+// crop_table[c] = (image index, grid row, grid column); grid column -1 marks the image's thumbnail
+__global__ void __launch_bounds__(256) hd_tile_batch_kernel(const HdImage* __restrict__ images, const int* __restrict__ crop_table,
+                                                            long long n_crops, float* __restrict__ crops) {
+  constexpr int kVecPerRow = kBlockPx / 4;                     // 84 float4 per crop row
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = n_crops * 3 * kBlockPx * kVecPerRow;
+  if (idx >= total) return;
+  const int xv = static_cast<int>(idx % kVecPerRow);
+  const int y = static_cast<int>((idx / kVecPerRow) % kBlockPx);
+  const int ch = static_cast<int>((idx / (static_cast<long long>(kVecPerRow) * kBlockPx)) % 3);
+  const long long crop = idx / (static_cast<long long>(kVecPerRow) * kBlockPx * 3);
+  const int img = crop_table[crop * 3], ci = crop_table[crop * 3 + 1], cj = crop_table[crop * 3 + 2];
+  const HdImage im = images[img];
+  const float* plane = im.image + static_cast<long long>(ch) * im.h * im.w;
+  float v[4];
+  if (cj >= 0) {
+    const int Y = ci * kBlockPx + y;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] = hd_canvas_value(im, plane, Y, cj * kBlockPx + xv * 4 + k);
+  } else {
+    const int ch_h = im.hb * kBlockPx, ch_w = im.wb * kBlockPx;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int x = xv * 4 + k;
+      float out = 0.f;
+      if (y < im.h_t && x < im.w_t) {
+        const LinearTap ty = linear_tap(y, ch_h, im.h_t), tx = linear_tap(x, ch_w, im.w_t);
+        out = bilerp(hd_canvas_value(im, plane, ty.i0, tx.i0), hd_canvas_value(im, plane, ty.i0, tx.i1),
+                     hd_canvas_value(im, plane, ty.i1, tx.i0), hd_canvas_value(im, plane, ty.i1, tx.i1), ty, tx);
+      }
+      v[k] = out;
+    }
+  }
+  *reinterpret_cast<float4*>(crops + ((crop * 3 + ch) * kBlockPx + y) * kBlockPx + xv * 4) = make_float4(v[0], v[1], v[2], v[3]);
+}
+
 // out[seg_row_offset[c] + m, :] = feats[c, m, :]  (bf16; one thread per 8 channels): crop token blocks -> packed rows.
 __global__ void scatter_crops_kernel(const __nv_bfloat16* __restrict__ feats, long long n_crops, int tokens, int hidden,
                                      const long long* __restrict__ seg_row_offset, __nv_bfloat16* __restrict__ out) {

@@ -133,6 +133,14 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* s
                "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
                : "memory");
 }
+// 3-D form: (c0 = column, c1 = row inside a segment, c2 = segment).  Coordinates are SIGNED and the box is clipped against the
+// tensor bounds on both sides: rows with c1 + i < 0 or >= dim1 are simply not written (their shared-memory rows are skipped),
+// which is what lets one fixed-size box store the head or the tail of a segment (see the packed-row stores in tp_gemm.cuh).
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* smem_src, int32_t c0, int32_t c1, int32_t c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
 __device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // wait until at most kPending of this thread's bulk groups still READ their shared-memory source
 template <int kPending>

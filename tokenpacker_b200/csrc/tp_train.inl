@@ -91,7 +91,7 @@ int launch_transpose(const void* in, long long ld_in, void* out, long long ld_ou
   const dim3 grid(static_cast<unsigned>((cols + 31) / 32), static_cast<unsigned>((rows + 31) / 32));
   transpose_kernel<<<grid, dim3(32, 8), 0, stream>>>(static_cast<const __nv_bfloat16*>(in), ld_in, static_cast<__nv_bfloat16*>(out), ld_out, rows,
                                                       cols);
-  TP_CUDA(cudaGetLastError());
+  TP_CUDA(cudaGetLastError()); ++g_launch_count;
   return TP_OK;
 }
 
@@ -99,7 +99,7 @@ int launch_gelu_fwd(const void* z, void* h, size_t elems, cudaStream_t stream) {
   const long long n8 = static_cast<long long>(elems / 8);
   gelu_fwd_kernel<<<static_cast<unsigned>((n8 + 255) / 256), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(z),
                                                                                 static_cast<__nv_bfloat16*>(h), n8);
-  TP_CUDA(cudaGetLastError());
+  TP_CUDA(cudaGetLastError()); ++g_launch_count;
   return TP_OK;
 }
 
@@ -107,7 +107,7 @@ int launch_gelu_bwd(void* dh, const void* z, size_t elems, cudaStream_t stream) 
   const long long n8 = static_cast<long long>(elems / 8);
   gelu_bwd_kernel<<<static_cast<unsigned>((n8 + 255) / 256), 256, 0, stream>>>(static_cast<__nv_bfloat16*>(dh),
                                                                                 static_cast<const __nv_bfloat16*>(z), n8);
-  TP_CUDA(cudaGetLastError());
+  TP_CUDA(cudaGetLastError()); ++g_launch_count;
   return TP_OK;
 }
 
@@ -115,10 +115,10 @@ int launch_ln_bwd(const void* g, const void* y, const float* stats, const void* 
                   void* dgamma, void* dbeta, cudaStream_t stream) {
   ln_bwd_kernel<<<kLnBlocks, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(g), static_cast<const __nv_bfloat16*>(y), stats,
                                                static_cast<const __nv_bfloat16*>(gamma), static_cast<__nv_bfloat16*>(dy), partial, rows);
-  TP_CUDA(cudaGetLastError());
+  TP_CUDA(cudaGetLastError()); ++g_launch_count;
   ln_param_reduce_kernel<<<kC / 256, 256, 0, stream>>>(partial, kLnBlocks, static_cast<__nv_bfloat16*>(dgamma),
                                                        static_cast<__nv_bfloat16*>(dbeta));
-  TP_CUDA(cudaGetLastError());
+  TP_CUDA(cudaGetLastError()); ++g_launch_count;
   return TP_OK;
 }
 
@@ -278,15 +278,15 @@ int tp_backward(const tp_weights* w, const void* xm, int64_t xm_crop_stride, int
     const int chunks = static_cast<int>(rows < kColChunks ? rows : kColChunks);
     colsum_partial_kernel<<<dim3((cols + 1023) / 1024, chunks), 128, 0, stream>>>(static_cast<const __nv_bfloat16*>(dy), ld_dy, rows, cols,
                                                                                   chunks, col_part);
-    TP_CUDA(cudaGetLastError());
+    TP_CUDA(cudaGetLastError()); ++g_launch_count;
     colsum_reduce_kernel<<<(cols + 255) / 256, 256, 0, stream>>>(col_part, chunks, cols, scale, static_cast<__nv_bfloat16*>(out));
-    TP_CUDA(cudaGetLastError());
+    TP_CUDA(cudaGetLastError()); ++g_launch_count;
     return TP_OK;
   };
   auto ln_apply = [&](const __nv_bfloat16* y, const float* stats, const void* gamma, const void* beta, __nv_bfloat16* out, long long rows) -> int {
     ln_apply_kernel<<<static_cast<unsigned>((rows * 32 + 255) / 256), 256, 0, stream>>>(y, stats, static_cast<const __nv_bfloat16*>(gamma),
                                                                                         static_cast<const __nv_bfloat16*>(beta), out, rows);
-    TP_CUDA(cudaGetLastError());
+    TP_CUDA(cudaGetLastError()); ++g_launch_count;
     return TP_OK;
   };
 
@@ -323,7 +323,7 @@ int tp_backward(const tp_weights* w, const void* xm, int64_t xm_crop_stride, int
     else if (s == 3) window_attn_bwd_kernel<3><<<blocks, 256, 0, stream>>>(sb(S.q_p), sb(S.k_p), sb(S.v_p), wb(B.dctx), wb(B.dqp), wb(B.dkp), wb(B.dvp), Q);
     else if (s == 4) window_attn_bwd_kernel<4><<<blocks, 256, 0, stream>>>(sb(S.q_p), sb(S.k_p), sb(S.v_p), wb(B.dctx), wb(B.dqp), wb(B.dkp), wb(B.dvp), Q);
     else window_attn_bwd_stream_kernel<<<blocks, 256, 0, stream>>>(sb(S.q_p), sb(S.k_p), sb(S.v_p), wb(B.dctx), wb(B.dqp), wb(B.dkp), wb(B.dvp), Q, s);
-    TP_CUDA(cudaGetLastError());
+    TP_CUDA(cudaGetLastError()); ++g_launch_count;
   }
   // ---- MHA in-projections:  q' = alpha (LN(y_q) W_iq^T + b),  k' = LN(y_k) W_ik^T + b,  v' likewise
   TP_TRY(ln_apply(sb(S.y_q), stats_q, w->ln_q_w, w->ln_q_b, wb(B.lnq_t), Q));      // LN outputs, [rows,1024] as stored (not transposed)

@@ -72,44 +72,70 @@ class ShardedTokenPacker:
 
 
 class FusedGatherTokenPacker:
-    """Projector whose last GEMM stores straight into every rank's gathered buffer over NVLink (TMA stores to peer-mapped
+    """Projector whose last GEMM stores straight into every rank's output buffer over NVLink (TMA stores to peer-mapped
     memory from ``torch.distributed._symmetric_memory``): compute and the all-gather are ONE kernel, transfers overlap the
-    remaining tiles' math.  CUDA + NCCL-capable ranks of one NVLink domain only.
+    remaining tiles' math.  ``forward_hd`` goes one step further: the stores land in the PACKED per-image rows of
+    llava_arch.py:139-155 on every rank (uniform crop stride M + 1, see ``tp_forward_packed``), so there is no gathered
+    intermediate and no assembly pass — each rank only fills the separator rows of its own copy.  CUDA + NCCL-capable ranks of
+    one NVLink domain only; inference only.
 
-    Two gathered buffers alternate between calls, so ONE cross-rank barrier per call is enough: the barrier of call i+1 (which
+    Two buffers alternate between calls, so ONE cross-rank barrier per call is enough: the barrier of call i+1 (which
     every rank reaches only after its stream has consumed call i's buffer) is what licenses call i+2 to overwrite that buffer."""
 
     def __init__(self, projector, group=None):
         self.projector = projector
         self.group = group if group is not None else dist.group.WORLD
-        self._bufs = None
-        self._shape = None
-        self._calls = 0
+        self._bufs = {}
+        self._calls = {}
 
-    def _gathered_buffers(self, total_crops: int, device):
+    def _buffers(self, shape, device):
         import torch.distributed._symmetric_memory as symm_mem
-        shape = (total_crops, self.projector.num_queries, self.projector.hidden_size)
-        if self._bufs is None or self._shape != shape:
+        if shape not in self._bufs:
             bufs = []
             for _ in range(2):
                 t = symm_mem.empty(shape, dtype=torch.bfloat16, device=device)
                 bufs.append((t, symm_mem.rendezvous(t, self.group)))
             bufs[0][1].barrier(channel=0)        # nobody starts writing before everybody has mapped the buffers
-            self._bufs, self._shape, self._calls = bufs, shape, 0
-        return self._bufs
+            self._bufs[shape], self._calls[shape] = bufs, 0
+        i = self._calls[shape]
+        self._calls[shape] = i + 1
+        return self._bufs[shape][i % 2]
 
     def forward_gathered(self, x_local, counts: Sequence[int]):
         """Returns the gathered [sum(counts), M, H] crop blocks — a view of a symmetric buffer that stays valid until the call
         after next."""
         rank = dist.get_rank(self.group)
         device = x_local[0].device
-        buf, hdl = self._gathered_buffers(int(sum(counts)), device)[self._calls % 2]
-        self._calls += 1
+        buf, hdl = self._buffers((int(sum(counts)), self.projector.num_queries, self.projector.hidden_size), device)
         if counts[rank] > 0:            # a rank may own no crops of a small batch: it still takes part in the barrier
             self.projector.forward_into_peers(x_local, list(hdl.buffer_ptrs), int(sum(counts[:rank])))
         hdl.barrier(channel=0)          # every rank's stores have landed everywhere
         return buf
 
     def forward_hd(self, x_local, counts: Sequence[int], h_block, w_block, sep_row, ret_row):
-        from .hd import hd_assemble
-        return hd_assemble(self.forward_gathered(x_local, counts), h_block, w_block, sep_row, ret_row)
+        """HD path across ranks in ONE pass: returns (packed [sum(L_i), H], cu_seqlens) — the packed tensor is a view of a
+        symmetric buffer that stays valid until the call after next."""
+        from ._lib import lib, check
+        from .hd import hd_plan_device
+        proj = self.projector
+        rank = dist.get_rank(self.group)
+        device = x_local[0].device
+        m, hidden = proj.num_queries, proj.hidden_size
+        plan, _, sep_rows, ret_rows = hd_plan_device(h_block, w_block, m, device)
+        total_crops = int(sum(counts))
+        if plan.n_crops != total_crops:
+            raise ValueError(f"grids describe {plan.n_crops} crops but the ranks hold {total_crops}")
+        total_rows = int(plan.cu_seqlens[-1])
+        assert total_rows == total_crops * (m + 1)
+        buf, hdl = self._buffers((total_rows, hidden), device)
+        with torch.cuda.device(device):
+            # separator rows of MY copy (local stores; peers only ever write crop rows)
+            sep_b = sep_row.to(device=device, dtype=torch.bfloat16).contiguous()
+            ret_b = ret_row.to(device=device, dtype=torch.bfloat16).contiguous()
+            stream = torch.cuda.current_stream(device).cuda_stream
+            check(lib.tp_hd_fill_separators(buf.data_ptr(), hidden, sep_rows.data_ptr(), sep_rows.numel(), sep_b.data_ptr(),
+                                            ret_rows.data_ptr(), ret_rows.numel(), ret_b.data_ptr(), stream), "tp_hd_fill_separators")
+        if counts[rank] > 0:
+            proj.forward_into_peers(x_local, list(hdl.buffer_ptrs), int(sum(counts[:rank])), out_crop_rows=m + 1)
+        hdl.barrier(channel=0)          # every rank's stores have landed everywhere
+        return buf, plan.cu_seqlens

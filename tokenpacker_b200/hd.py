@@ -12,6 +12,7 @@ from dataclasses import dataclass
 
 import torch
 
+from . import _lib
 from ._lib import lib, check
 
 BLOCK = 336
@@ -69,6 +70,50 @@ def hd_tile(image: torch.Tensor, patch_num: int = 9):
         stream = torch.cuda.current_stream(image.device).cuda_stream
         check(lib.tp_hd_tile(image.data_ptr(), h, w, hb, wb, crops.data_ptr(), stream), "tp_hd_tile")
     return crops, hb, wb
+
+
+def hd_tile_batch(images, patch_num: int = 9):
+    """The tiling block for a whole batch in ONE launch (the collator cats the crops of a batch, train.py:797-800).
+
+    images: sequence of float32 CUDA tensors [3,h,w] or [1,3,h,w] (already normalised), sizes may differ.
+    Returns (crops [sum_i n_crops_i, 3, 336, 336] float32 in the reference's order — image by image, grid row-major, thumbnail
+    last —, h_block list, w_block list)."""
+    imgs = []
+    for im in images:
+        if im.dim() == 4:
+            if im.shape[0] != 1:
+                raise ValueError("each image is [3,h,w] or [1,3,h,w]")
+            im = im[0]
+        if im.dim() != 3 or im.shape[0] != 3:
+            raise ValueError("each image is [3,h,w] or [1,3,h,w]")
+        if not im.is_cuda:
+            raise RuntimeError("tokenpacker_b200 has no CPU path: images must be CUDA tensors")
+        imgs.append(im.to(torch.float32).contiguous())
+    b = len(imgs)
+    if b == 0:
+        raise ValueError("empty batch")
+    device = imgs[0].device
+    hs = (C.c_int64 * b)(*[int(im.shape[1]) for im in imgs])
+    ws = (C.c_int64 * b)(*[int(im.shape[2]) for im in imgs])
+    ptrs = (C.c_void_p * b)(*[im.data_ptr() for im in imgs])
+    hb, wb = (C.c_int * b)(), (C.c_int * b)()
+    nc = C.c_int64(0)
+    check(lib.tp_hd_tile_batch_plan(hs, ws, ptrs, b, int(patch_num), None, None, hb, wb, C.byref(nc)), "tp_hd_tile_batch_plan")
+    table = torch.empty((max(nc.value, 1), 3), dtype=torch.int32)
+    desc = (_lib.TpHdImage * b)()
+    check(lib.tp_hd_tile_batch_plan(hs, ws, ptrs, b, int(patch_num), desc, C.cast(table.data_ptr(), C.POINTER(C.c_int32)), hb, wb,
+                                    C.byref(nc)), "tp_hd_tile_batch_plan")
+    desc_t = torch.frombuffer(bytearray(bytes(desc)), dtype=torch.uint8)
+    with torch.cuda.device(device):
+        desc_d = desc_t.to(device)
+        table_d = table.to(device)
+        crops = torch.empty((nc.value, 3, BLOCK, BLOCK), dtype=torch.float32, device=device)
+        stream = torch.cuda.current_stream(device).cuda_stream
+        check(lib.tp_hd_tile_batch(desc_d.data_ptr(), table_d.data_ptr(), nc.value, crops.data_ptr(), stream), "tp_hd_tile_batch")
+        # the sources and tables must outlive the asynchronous launch: tie them to the stream
+        for t in imgs + [desc_d, table_d]:
+            t.record_stream(torch.cuda.current_stream(device))
+    return crops, list(hb), list(wb)
 
 
 def hd_seq_len(hb: int, wb: int, m: int) -> int:
@@ -133,6 +178,11 @@ def hd_assemble(feats: torch.Tensor, h_block, w_block, sep_row: torch.Tensor, re
     plan, seg, sep_rows, ret_rows = hd_plan_device(h_block, w_block, m, device)
     if plan.n_crops != feats.shape[0]:
         raise ValueError(f"grids describe {plan.n_crops} crops but {feats.shape[0]} were given")
+    if torch.is_grad_enabled() and (feats.requires_grad or sep_row.requires_grad or ret_row.requires_grad):
+        from .projector import _PackedScatterFunction      # training: differentiable scatter (gradient = one row gather)
+        with torch.cuda.device(device):
+            out = _PackedScatterFunction.apply(feats.to(torch.bfloat16), sep_row, ret_row, seg, sep_rows, ret_rows, int(plan.cu_seqlens[-1]))
+        return (out if feats.dtype == torch.bfloat16 else out.to(feats.dtype)), plan.cu_seqlens
     fb = feats.to(torch.bfloat16).contiguous()
     with torch.cuda.device(device):
         out = torch.empty((int(plan.cu_seqlens[-1]), hdim), dtype=torch.bfloat16, device=device)

@@ -10,6 +10,7 @@ parameter containers only — their ``forward`` is never called.
 from __future__ import annotations
 
 import ctypes as C
+import warnings
 from functools import partial
 
 import torch
@@ -45,7 +46,10 @@ class _ProjectorFunction(torch.autograd.Function):
     def forward(ctx, module, x0b, s0, xmb, sm, *params):
         device = x0b.device
         n = x0b.shape[0]
-        packed = module._packed_weights(device)
+        # training: ALWAYS repack from the live parameters.  Optimizers that update through a ``.data`` alias (DeepSpeed ZeRO-2's
+        # bit16 flat buffer: every reference recipe, scripts/v1_5/*.sh) change neither data_ptr nor _version, so no key can tell
+        # that the weights moved; they change every step anyway and the pack is small next to forward + backward.
+        packed = module._packed_weights(device, fresh=True)
         out = torch.empty((n, module.num_queries, module.hidden_size), dtype=torch.bfloat16, device=device)
         nbytes = lib.tp_train_saved_bytes(n, module.scale_factor, module.hidden_size)
         saved = torch.empty(nbytes, dtype=torch.uint8, device=device)
@@ -77,6 +81,42 @@ class _ProjectorFunction(torch.autograd.Function):
                                   g.data_ptr(), ctx.saved.data_ptr(), C.byref(g_struct), ws.data_ptr(), ws_bytes, stream), "tp_backward")
         out = [gr.to(dt) if need else None for gr, (dt, need) in zip(grads, ctx.param_meta)]
         return (None, None, None, None, None) + tuple(out)
+
+
+class _PackedScatterFunction(torch.autograd.Function):
+    """Differentiable slice assembly (llava_arch.py:139-155) for the training path: crop blocks [N,M,H] -> packed rows, with the
+    ',' / '\\n' rows filled in.  Forward = tp_hd_scatter_crops + tp_hd_fill_separators; backward = one row gather
+    (tp_gather_rows with the forward's destination rows as source index) plus the column sums of the separator rows' gradients."""
+
+    @staticmethod
+    def forward(ctx, feats, sep_row, ret_row, seg, sep_rows, ret_rows, total_rows):
+        n, m, h = feats.shape
+        fb = feats.contiguous()
+        out = torch.empty((total_rows, h), dtype=torch.bfloat16, device=feats.device)
+        sep_b = sep_row.detach().to(device=feats.device, dtype=torch.bfloat16).contiguous()
+        ret_b = ret_row.detach().to(device=feats.device, dtype=torch.bfloat16).contiguous()
+        stream = torch.cuda.current_stream(feats.device).cuda_stream
+        check(lib.tp_hd_scatter_crops(fb.data_ptr(), n, m, h, seg.data_ptr(), out.data_ptr(), stream), "tp_hd_scatter_crops")
+        check(lib.tp_hd_fill_separators(out.data_ptr(), h, sep_rows.data_ptr(), sep_rows.numel(), sep_b.data_ptr(),
+                                        ret_rows.data_ptr(), ret_rows.numel(), ret_b.data_ptr(), stream), "tp_hd_fill_separators")
+        ctx.shape = (n, m, h)
+        ctx.meta = (sep_row.dtype, ret_row.dtype)
+        ctx.save_for_backward(seg, sep_rows, ret_rows)
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        seg, sep_rows, ret_rows = ctx.saved_tensors
+        n, m, h = ctx.shape
+        g = g.to(torch.bfloat16).contiguous()
+        src = (seg.view(n, 1) + torch.arange(m, device=g.device, dtype=torch.int64).view(1, m)).reshape(-1).contiguous()
+        gf = torch.empty((n * m, h), dtype=torch.bfloat16, device=g.device)
+        stream = torch.cuda.current_stream(g.device).cuda_stream
+        check(lib.tp_gather_rows(g.data_ptr(), g.data_ptr(), h, src.data_ptr(), n * m, gf.data_ptr(), stream), "tp_gather_rows")
+        g_sep = g.index_select(0, sep_rows).float().sum(0).to(ctx.meta[0]) if ctx.needs_input_grad[1] else None
+        g_ret = g.index_select(0, ret_rows).float().sum(0).to(ctx.meta[1]) if ctx.needs_input_grad[2] else None
+        return gf.view(n, m, h), g_sep, g_ret, None, None, None, None
 
 
 class TokenPackerB200(nn.Module):
@@ -112,6 +152,9 @@ class TokenPackerB200(nn.Module):
         self.apply(self._init_weights)
         self._packed = None
         self._packed_key = None
+        self._keepalive = None
+        self._warned_dtype = False
+        self.register_load_state_dict_post_hook(lambda module, incompatible: module.invalidate_packed())
 
     @staticmethod
     def _init_weights(m):
@@ -132,10 +175,25 @@ class TokenPackerB200(nn.Module):
         sd = dict(self.named_parameters())
         return [sd[key] for _, key in _lib.WEIGHT_FIELDS]
 
-    def _packed_weights(self, device):
+    def invalidate_packed(self):
+        """Drop the derived weight cache.  Called automatically by load_state_dict, .to() / .cuda() / .half() (``_apply``),
+        ``train()`` / ``eval()`` switches and after every training forward; call it yourself after writing parameters through a
+        ``.data`` alias outside of training (such writes change neither ``data_ptr`` nor ``_version``, so no cache key sees them)."""
+        self._packed = None
+        self._packed_key = None
+
+    def _apply(self, fn, *args, **kwargs):
+        self.invalidate_packed()
+        return super()._apply(fn, *args, **kwargs)
+
+    def train(self, mode: bool = True):
+        self.invalidate_packed()
+        return super().train(mode)
+
+    def _packed_weights(self, device, fresh: bool = False):
         params = self._raw_params()
         key = (str(device),) + tuple((p.data_ptr(), p._version, p.dtype) for p in params)
-        if self._packed is not None and self._packed_key == key:
+        if not fresh and self._packed is not None and self._packed_key == key:
             return self._packed
         bf = [p.detach().to(device=device, dtype=torch.bfloat16).contiguous() for p in params]
         w = _lib.TpWeights(*[t.data_ptr() for t in bf])
@@ -144,7 +202,8 @@ class TokenPackerB200(nn.Module):
         stream = torch.cuda.current_stream(device).cuda_stream
         check(lib.tp_pack_weights(C.byref(w), self.hidden_size, packed.data_ptr(), nbytes, stream), "tp_pack_weights")
         self._keepalive = bf     # sources must outlive the asynchronous packing kernels
-        self._packed, self._packed_key = packed, key
+        # a pack made for a training forward is never reused (see _ProjectorFunction.forward): the next call repacks
+        self._packed, self._packed_key = packed, (None if fresh else key)
         return packed
 
     # ------------------------------------------------------------------------------------------------------------
@@ -170,6 +229,11 @@ class TokenPackerB200(nn.Module):
             raise ValueError(f"expected feat [N,576,1024] and feat_multi [N,576,4096], got {tuple(x0.shape)} {tuple(xm.shape)}")
         if not (x0.is_cuda and xm.is_cuda):
             raise RuntimeError("tokenpacker_b200 has no CPU path: inputs must be CUDA tensors on a B200")
+        if not self._warned_dtype and (x0.dtype != torch.bfloat16 or next(self.parameters()).dtype != torch.bfloat16):
+            self._warned_dtype = True
+            warnings.warn("tokenpacker_b200 computes with bf16 storage and fp32 accumulation: fp16 / fp32 inputs and parameters are cast to "
+                          "bf16 at the boundary and the result is cast back (every released TokenPacker recipe runs bf16; an fp16 or "
+                          "fp32 module gets bf16-precision results)", stacklevel=3)
         if torch.is_grad_enabled() and (x0.requires_grad or xm.requires_grad):
             raise NotImplementedError("gradients w.r.t. the CLIP features are not implemented (the vision tower is frozen in every "
                                       "released TokenPacker recipe): detach the features or run under torch.no_grad()")
@@ -193,13 +257,18 @@ class TokenPackerB200(nn.Module):
                 self._launch(x0b, s0, xmb, sm, out, None)
         return out if out_dtype == torch.bfloat16 else out.to(out_dtype)
 
-    def _launch(self, x0b, s0, xmb, sm, out, seg_row_offset):
+    def _launch(self, x0b, s0, xmb, sm, out, seg_row_offset, out_crop_rows: int = 0):
         device = x0b.device
         n = x0b.shape[0]
         packed = self._packed_weights(device)
         ws_bytes = lib.tp_workspace_bytes(n, self.scale_factor, self.hidden_size)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=device)
         stream = torch.cuda.current_stream(device).cuda_stream
+        if out_crop_rows:
+            check(lib.tp_forward_packed(packed.data_ptr(), x0b.data_ptr(), xmb.data_ptr(), n, s0, sm, self.scale_factor,
+                                        self.hidden_size, out.data_ptr(), int(out_crop_rows), ws.data_ptr(), ws_bytes, stream),
+                  "tp_forward_packed")
+            return
         seg_ptr = seg_row_offset.data_ptr() if seg_row_offset is not None else None
         check(lib.tp_forward(packed.data_ptr(), x0b.data_ptr(), xmb.data_ptr(), n, s0, sm, self.scale_factor,
                              self.hidden_size, out.data_ptr(), seg_ptr, ws.data_ptr(), ws_bytes, stream), "tp_forward")
@@ -208,6 +277,7 @@ class TokenPackerB200(nn.Module):
         """Forward from the four CLIP hidden states (layers 12, 16, 22, 23; each [N,577,1024] with the CLS token, or [N,576,1024])
         WITHOUT materialising their concatenation: replaces ``feature_select`` + ``torch.cat`` (clip_encoder.py:28-44) followed by
         ``forward``; the last layer doubles as the single-level feature (select_layer = -2).  Inference only."""
+        self._require_inference("forward_layers")
         if len(layers) != 4:
             raise ValueError("expected the 4 hidden states (12, 16, 22, 23)")
         views = []
@@ -236,10 +306,18 @@ class TokenPackerB200(nn.Module):
                                         ws.data_ptr(), ws_bytes, stream), "tp_forward_layers")
         return out
 
-    def forward_into_peers(self, x, peer_ptrs, crop_offset: int):
-        """Fused projector + all-gather: this rank's crops are written by the last GEMM's TMA stores into the gathered buffer of
-        every peer GPU (``peer_ptrs``: device pointers of the [total_crops, M, H] bf16 buffers, one per rank, mapped into this
-        process — e.g. ``torch.distributed._symmetric_memory`` ``buffer_ptrs``).  Asynchronous; a cross-rank barrier must follow."""
+    def _require_inference(self, what: str):
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            raise NotImplementedError(f"{what} is an inference path (its kernels keep no intermediates): call it under torch.no_grad(), "
+                                      "or use forward() / forward_packed(), which are differentiable")
+
+    def forward_into_peers(self, x, peer_ptrs, crop_offset: int, out_crop_rows: int = 0):
+        """Fused projector + all-gather: this rank's crops are written by the last GEMM's TMA stores into the output buffer of
+        every peer GPU (``peer_ptrs``: device pointers of the bf16 buffers, one per rank, mapped into this process — e.g.
+        ``torch.distributed._symmetric_memory`` ``buffer_ptrs``).  ``out_crop_rows`` = 0: dense gathered [total_crops, M, H];
+        = M + 1: the packed HD rows of llava_arch.py:139-155 directly (separator rows are the caller's).  Asynchronous; a cross-rank
+        barrier must follow.  Inference only."""
+        self._require_inference("forward_into_peers")
         x0, xm = self._check_inputs(x, None)
         device = x0.device
         with torch.cuda.device(device):
@@ -252,7 +330,8 @@ class TokenPackerB200(nn.Module):
             stream = torch.cuda.current_stream(device).cuda_stream
             arr = (C.c_void_p * len(peer_ptrs))(*[int(p) for p in peer_ptrs])
             check(lib.tp_forward_allgather(packed.data_ptr(), x0b.data_ptr(), xmb.data_ptr(), n, s0, sm, self.scale_factor,
-                                           self.hidden_size, arr, len(peer_ptrs), int(crop_offset), ws.data_ptr(), ws_bytes, stream),
+                                           self.hidden_size, arr, len(peer_ptrs), int(crop_offset), int(out_crop_rows), ws.data_ptr(),
+                                           ws_bytes, stream),
                   "tp_forward_allgather")
 
     def forward_host(self, x, out: torch.Tensor | None = None, chunk_crops: int = 8, device=None):
@@ -289,27 +368,37 @@ class TokenPackerB200(nn.Module):
         """Projector + HD slice assembly (llava_arch.py:139-155) in one pass.
 
         x as in forward(), crops ordered image by image (grid row-major, then the thumbnail); h_block / w_block:
-        per-image grids; sep_row / ret_row: the ',' and '\\n' embedding rows [hidden].  The last GEMM's epilogue writes
-        every crop's tokens straight to its place in the packed sequence; separator rows are filled by a tiny kernel.
-        Returns (packed [sum(L_i), hidden], cu_seqlens int64 [B+1] on the host)."""
+        per-image grids; sep_row / ret_row: the ',' and '\\n' embedding rows [hidden].  Every crop of the packed sequence is
+        followed by exactly one separator row, so crop i's tokens start at row i*(M+1): the last GEMM's TMA stores write them
+        there directly (tp_forward_packed); the separator rows are filled by a tiny kernel.  Under autograd (training,
+        pretrain_hd.sh / finetune_hd.sh use mode='slice') the same result comes from the differentiable forward plus a
+        differentiable scatter.  Returns (packed [sum(L_i), hidden], cu_seqlens int64 [B+1] on the host)."""
         from .hd import hd_plan_device
         x0, xm = self._check_inputs(x, None)
         device = x0.device
         plan, seg, sep_rows, ret_rows = hd_plan_device(h_block, w_block, self.num_queries, device)
         if plan.n_crops != x0.shape[0]:
             raise ValueError(f"grids describe {plan.n_crops} crops but {x0.shape[0]} were given")
+        total = int(plan.cu_seqlens[-1])
+        crop_rows = self.num_queries + 1
+        assert total == plan.n_crops * crop_rows      # one separator row per crop: the uniform stride the kernel relies on
+        training = torch.is_grad_enabled() and (any(p.requires_grad for p in self.parameters()) or sep_row.requires_grad
+                                                or ret_row.requires_grad)
         with torch.cuda.device(device):
-            x0b, s0 = self._as_crop_strided(x0.to(torch.bfloat16), 1024)
-            xmb, sm = self._as_crop_strided(xm.to(torch.bfloat16), 4096)
-            total = int(plan.cu_seqlens[-1])
-            out = torch.empty((total, self.hidden_size), dtype=torch.bfloat16, device=device)
-            self._launch(x0b, s0, xmb, sm, out, seg)
-            sep_b = sep_row.to(device=device, dtype=torch.bfloat16).contiguous()
-            ret_b = ret_row.to(device=device, dtype=torch.bfloat16).contiguous()
-            stream = torch.cuda.current_stream(device).cuda_stream
-            check(lib.tp_hd_fill_separators(out.data_ptr(), self.hidden_size, sep_rows.data_ptr(), sep_rows.numel(),
-                                            sep_b.data_ptr(), ret_rows.data_ptr(), ret_rows.numel(), ret_b.data_ptr(), stream),
-                  "tp_hd_fill_separators")
+            if training:
+                feats = self.forward((x0, xm)).to(torch.bfloat16)
+                out = _PackedScatterFunction.apply(feats, sep_row, ret_row, seg, sep_rows, ret_rows, total)
+            else:
+                x0b, s0 = self._as_crop_strided(x0.to(torch.bfloat16), 1024)
+                xmb, sm = self._as_crop_strided(xm.to(torch.bfloat16), 4096)
+                out = torch.empty((total, self.hidden_size), dtype=torch.bfloat16, device=device)
+                self._launch(x0b, s0, xmb, sm, out, None, out_crop_rows=crop_rows)
+                sep_b = sep_row.to(device=device, dtype=torch.bfloat16).contiguous()
+                ret_b = ret_row.to(device=device, dtype=torch.bfloat16).contiguous()
+                stream = torch.cuda.current_stream(device).cuda_stream
+                check(lib.tp_hd_fill_separators(out.data_ptr(), self.hidden_size, sep_rows.data_ptr(), sep_rows.numel(),
+                                                sep_b.data_ptr(), ret_rows.data_ptr(), ret_rows.numel(), ret_b.data_ptr(), stream),
+                      "tp_hd_fill_separators")
         return (out if x0.dtype == torch.bfloat16 else out.to(x0.dtype)), plan.cu_seqlens
 
     def extra_repr(self):
