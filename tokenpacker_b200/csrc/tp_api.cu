@@ -155,11 +155,20 @@ struct GemmItem {
   void* const* peer_c = nullptr;   // fused all-gather: the same output slot in every peer's gathered buffer
   int n_peers = 0;
   int tn = 0;                      // 1: C[M,N] = A^T . B with A given as [K, M] (ld = a.ld) and B as [K, N] (ld = ldb), both row-major
+  int k_splits = 1;                // > 1: split-K; ep.c must then be a float buffer [k_splits][M, ldc] (ep.out_f32 = 1, pair kernel only)
+  // chains (launch_chain): GEMMs of consecutive stages in ONE persistent launch, ordered by per-row-block tile counters
+  int stage = 0;                   // items of equal stage are independent of each other
+  int dep = -1;                    // index (in the chain) of the item whose C is this item's A: same M, plain 2-D A
+  int* done_counter = nullptr;     // filled by launch_chain
+  const int* dep_counter = nullptr;
+  int dep_target = 0;
 };
 
 int check_item(const GemmItem& it) {
   if (it.M <= 0 || it.N <= 0 || it.K <= 0 || it.N % 32 != 0 || it.M > 0x7fffff00ll) return TP_ERR_INVALID_ARGUMENT;   // K: any (TMA zero-fills)
   if ((reinterpret_cast<uintptr_t>(it.ep.c) & 15) != 0 || (it.ep.ldc * 2) % 16 != 0) return TP_ERR_INVALID_ARGUMENT;
+  if (it.k_splits < 1 || (it.k_splits > 1 && !it.ep.out_f32) || (it.ep.out_f32 && (it.ep.seg_row_offset != nullptr || it.ep.seg_stride != 0)))
+    return TP_ERR_INVALID_ARGUMENT;
   if (it.ep.stats_out != nullptr && (it.N % 256 != 0 || it.ep.stats_out_slots != it.N / 128)) return TP_ERR_INVALID_ARGUMENT;
   if (it.ep.col_a != nullptr && (it.ep.stats_in == nullptr || it.ep.stats_in_slots <= 0)) return TP_ERR_INVALID_ARGUMENT;
   return TP_OK;
@@ -229,7 +238,7 @@ int launch_gemm_pair_group(const GemmItem* items, int count, int sms, cudaStream
     if (p.a_parts == 0) { p.a_parts = 1; p.a_kblocks_per_part = static_cast<int>((it.K + kBlockK - 1) / kBlockK); }
     // C goes out through TMA stores (64-col x 128-row swizzled slabs) unless rows are scattered to ARBITRARY segment offsets;
     // uniformly strided segments (the HD packed layout) stay on the TMA path through a 3-D (cols, row in segment, segment) map
-    p.use_tma_store = it.ep.seg_row_offset == nullptr ? 1 : 0;
+    p.use_tma_store = (it.ep.seg_row_offset == nullptr && !it.ep.out_f32) ? 1 : 0;
     const bool c_segmented = p.use_tma_store && it.ep.seg_stride != 0 && it.ep.seg_stride != it.ep.seg_len;
     if (c_segmented) {
       if (it.ep.seg_len <= 0 || it.M % it.ep.seg_len != 0 || it.ep.seg_stride < it.ep.seg_len) return TP_ERR_INVALID_ARGUMENT;
@@ -244,26 +253,43 @@ int launch_gemm_pair_group(const GemmItem* items, int count, int sms, cudaStream
     p.K = static_cast<int>(it.K);
     p.a_seg_rows = static_cast<int>(it.a.seg_rows);
     p.num_n_blocks = static_cast<int>((it.N + Cfg::kTileN - 1) / Cfg::kTileN);
-    p.num_tiles = static_cast<int>((it.M + Cfg::kTileM - 1) / Cfg::kTileM) * p.num_n_blocks;
     p.num_k_blocks = static_cast<int>((it.K + kBlockK - 1) / kBlockK);
+    p.tiles_mn = static_cast<int>((it.M + Cfg::kTileM - 1) / Cfg::kTileM) * p.num_n_blocks;
+    p.k_splits = it.k_splits;
+    p.kb_per_split = (p.num_k_blocks + p.k_splits - 1) / p.k_splits;
+    if (static_cast<long long>(p.k_splits - 1) * p.kb_per_split >= p.num_k_blocks) return TP_ERR_INVALID_ARGUMENT;   // no empty split
+    p.c_split_stride = it.M * it.ep.ldc;
+    p.num_tiles = p.tiles_mn * p.k_splits;
     p.ep = it.ep;
+    p.done_counter = it.done_counter;
+    p.dep_counter = it.dep_counter;
+    p.dep_target = it.dep_target;
+    if ((p.done_counter != nullptr && !p.use_tma_store) || (p.dep_counter != nullptr && (it.tn || it.a.seg_rows != 0)))
+      return TP_ERR_INVALID_ARGUMENT;          // tile counters are published by the store warps / index plain 256-row blocks of A
+    p.peer_out = it.n_peers > 0 ? 1 : 0;
     total += p.num_tiles;
   }
   if (total > 0x7fffffffll) return TP_ERR_INVALID_ARGUMENT;
   g.total_tiles = static_cast<int>(total);
   PeerStores peers;
   memset(&peers, 0, sizeof(peers));
-  if (items[0].n_peers > 0) {
-    if (count != 1 || items[0].n_peers > kMaxPeers || items[0].ep.seg_row_offset != nullptr) return TP_ERR_INVALID_ARGUMENT;
-    const GemmItem& it0 = items[0];
+  int peer_item = -1;
+  for (int i = 0; i < count; ++i)
+    if (items[i].n_peers > 0) {
+      if (peer_item >= 0) return TP_ERR_INVALID_ARGUMENT;      // one set of peer maps per launch
+      peer_item = i;
+    }
+  if (peer_item >= 0) {
+    const GemmItem& it0 = items[peer_item];
+    if (it0.n_peers > kMaxPeers || it0.ep.seg_row_offset != nullptr) return TP_ERR_INVALID_ARGUMENT;
     for (int p = 0; p < it0.n_peers; ++p) {
-      if (g.p[0].c_seg_len != 0)
+      if (g.p[peer_item].c_seg_len != 0)
         TP_TRY(make_map_3d(&peers.m[p], it0.peer_c[p], it0.M / it0.ep.seg_len, it0.ep.seg_len, it0.N, it0.ep.ldc, it0.ep.seg_stride * it0.ep.ldc,
                            it0.ep.seg_len < kBlockM ? it0.ep.seg_len : kBlockM));
       else
         TP_TRY(make_map_2d(&peers.m[p], it0.peer_c[p], it0.M, it0.N, it0.ep.ldc, kBlockM));
     }
-    peers.count = items[0].n_peers;
+    peers.count = it0.n_peers;
   }
   {
     static thread_local unsigned attr_done = 0;
@@ -283,43 +309,55 @@ int launch_gemm_pair_group(const GemmItem* items, int count, int sms, cudaStream
 // Kernel selection: CTA-pair 256x256 tiles whenever the problem fills them (independent problems of one stage share a
 // launch), else one-CTA 128 x {256,128} tiles.  TP_GEMM_MODE=1 forces the one-CTA kernels, =2 forces the pair kernel,
 // =3 pair kernel without grouping (A/B experiments; read per call, no caching).
+// Returns 0 pair, 1 one-CTA 256, 2 one-CTA 128, or -1 (invalid).
+int choose_kernel(const GemmItem& it, int count, int sms, int mode) {
+  const bool pair_ok = (it.N % 256 == 0) && sms >= 2;
+  const bool pair_only = it.n_peers > 0 || it.tn || it.a.parts > 1 || it.k_splits > 1 || it.ep.out_f32;   // pair-kernel-only features
+  if (pair_only && !pair_ok) return -1;
+  const bool needs_256 = it.ep.stats_out != nullptr;                        // statistics slots assume 256-column tiles
+  // Estimated tensor-pipe cycles of each candidate = waves x k-blocks x cycles per k-block.  Large problems always land
+  // on the pair kernel; small ones (single crops: the serving latency case) get the tile shape that fills more SMs.  All
+  // kernels produce identical bits, so the choice never changes results.
+  const long long kb = (it.K + kBlockK - 1) / kBlockK;
+  auto waves = [](long long tiles, long long units) { return (tiles + units - 1) / units; };
+  const long long t_pair = ((it.M + 255) / 256) * ((it.N + 255) / 256);
+  const long long t_256 = ((it.M + 127) / 128) * ((it.N + 255) / 256);
+  const long long t_128 = ((it.M + 127) / 128) * ((it.N + 127) / 128);
+  const long long c_pair = pair_ok ? waves(t_pair, sms / 2) * kb * 512 : LLONG_MAX;
+  // one-CTA kernels pay ~40 % over their nominal MMA time (more operand traffic per FLOP, direct 16-byte stores, no grouping):
+  // measured — at 10 crops the nominally 16 % cheaper 128x128 tiling was 30 % slower than the pair kernel
+  const long long c_256 = (it.N % 256 == 0) ? waves(t_256, sms) * kb * 512 * 14 / 10 : LLONG_MAX;
+  const long long c_128 = needs_256 ? LLONG_MAX : waves(t_128, sms) * kb * 256 * 14 / 10;
+  // a launch costs ~10k cycles of ramp and drain; pair-kernel items of one call share a single (grouped) launch
+  const long long launch = 10000;
+  const long long l_pair = pair_ok ? c_pair + launch / count : LLONG_MAX;
+  const long long l_256 = c_256 == LLONG_MAX ? LLONG_MAX : c_256 + launch;
+  const long long l_128 = c_128 == LLONG_MAX ? LLONG_MAX : c_128 + launch;
+  int choice;
+  if (pair_only || mode == 2 || mode == 3) choice = 0;
+  else if (mode == 1) choice = (it.N % 256 == 0) ? 1 : 2;
+  else if (l_pair <= l_256 && l_pair <= l_128) choice = 0;                  // ties go to the pair kernel (TMA stores, grouping)
+  else choice = (l_256 <= l_128) ? 1 : 2;
+  if (choice == 0 && !pair_ok) choice = (it.N % 256 == 0) ? 1 : 2;
+  return choice;
+}
+
+int gemm_mode() {
+  const char* mode_env = getenv("TP_GEMM_MODE");
+  return mode_env != nullptr ? atoi(mode_env) : 0;
+}
+
 int launch_gemms(const GemmItem* items, int count, int sms, cudaStream_t stream) {
   if (count <= 0 || count > kMaxGroup) return TP_ERR_INVALID_ARGUMENT;
-  const char* mode_env = getenv("TP_GEMM_MODE");
-  const int mode = mode_env != nullptr ? atoi(mode_env) : 0;
+  const int mode = gemm_mode();
   GemmItem grouped[kMaxGroup];
   int n_grouped = 0;
   for (int i = 0; i < count; ++i) {
     TP_TRY(check_item(items[i]));
     const GemmItem& it = items[i];
-    const bool pair_ok = (it.N % 256 == 0) && sms >= 2;
-    const bool pair_only = it.n_peers > 0 || it.tn || it.a.parts > 1;        // features that live in the pair kernel only
-    if (pair_only && (!pair_ok || (it.n_peers > 0 && count != 1))) return TP_ERR_INVALID_ARGUMENT;
-    const bool needs_256 = it.ep.stats_out != nullptr;                        // statistics slots assume 256-column tiles
-    // Estimated tensor-pipe cycles of each candidate = waves x k-blocks x cycles per k-block.  Large problems always land
-    // on the pair kernel; small ones (single crops: the serving latency case) get the tile shape that fills more SMs.  All
-    // kernels produce identical bits, so the choice never changes results.
-    const long long kb = (it.K + kBlockK - 1) / kBlockK;
-    auto waves = [](long long tiles, long long units) { return (tiles + units - 1) / units; };
-    const long long t_pair = ((it.M + 255) / 256) * ((it.N + 255) / 256);
-    const long long t_256 = ((it.M + 127) / 128) * ((it.N + 255) / 256);
-    const long long t_128 = ((it.M + 127) / 128) * ((it.N + 127) / 128);
-    const long long c_pair = pair_ok ? waves(t_pair, sms / 2) * kb * 512 : LLONG_MAX;
-    // one-CTA kernels pay ~40 % over their nominal MMA time (more operand traffic per FLOP, direct 16-byte stores, no grouping):
-    // measured — at 10 crops the nominally 16 % cheaper 128x128 tiling was 30 % slower than the pair kernel
-    const long long c_256 = (it.N % 256 == 0) ? waves(t_256, sms) * kb * 512 * 14 / 10 : LLONG_MAX;
-    const long long c_128 = needs_256 ? LLONG_MAX : waves(t_128, sms) * kb * 256 * 14 / 10;
-    // a launch costs ~10k cycles of ramp and drain; pair-kernel items of one call share a single (grouped) launch
-    const long long launch = 10000;
-    const long long l_pair = pair_ok ? c_pair + launch / count : LLONG_MAX;
-    const long long l_256 = c_256 == LLONG_MAX ? LLONG_MAX : c_256 + launch;
-    const long long l_128 = c_128 == LLONG_MAX ? LLONG_MAX : c_128 + launch;
-    int choice;                                                               // 0 pair, 1 one-CTA 256, 2 one-CTA 128
-    if (pair_only || mode == 2 || mode == 3) choice = 0;
-    else if (mode == 1) choice = (it.N % 256 == 0) ? 1 : 2;
-    else if (l_pair <= l_256 && l_pair <= l_128) choice = 0;                  // ties go to the pair kernel (TMA stores, grouping)
-    else choice = (l_256 <= l_128) ? 1 : 2;
-    if (choice == 0 && !pair_ok) choice = (it.N % 256 == 0) ? 1 : 2;
+    if (it.n_peers > 0 && count != 1) return TP_ERR_INVALID_ARGUMENT;
+    const int choice = choose_kernel(it, count, sms, mode);
+    if (choice < 0) return TP_ERR_INVALID_ARGUMENT;
     if (choice == 0) {
       if (mode == 3) TP_TRY(launch_gemm_pair_group(&it, 1, sms, stream));
       else grouped[n_grouped++] = it;
@@ -330,6 +368,50 @@ int launch_gemms(const GemmItem* items, int count, int sms, cudaStream_t stream)
     }
   }
   if (n_grouped > 0) TP_TRY(launch_gemm_pair_group(grouped, n_grouped, sms, stream));
+  return TP_OK;
+}
+
+// A chain of dependent GEMM stages (items sorted by stage; items[i].dep names the producer of items[i]'s A operand).
+// When every item lands on the CTA-pair kernel the whole chain is ONE persistent launch: tiles are numbered stage after stage,
+// consumers wait on per-row-block tile counters (``flags``, zeroed by the caller earlier on the stream) instead of on kernel
+// boundaries, so there is no ramp, drain or partial last wave between the linears.  Otherwise (small problems on one-CTA
+// tiles, TP_CHAIN=0, forced modes) the stages run as separate launches exactly as before; either way the bits are the same.
+int launch_chain(GemmItem* items, int count, int* flags, long long flag_capacity, int sms, cudaStream_t stream) {
+  if (count <= 0 || count > kMaxGroup) return TP_ERR_INVALID_ARGUMENT;
+  const int mode = gemm_mode();
+  static const bool chain_off = [] { const char* e = getenv("TP_CHAIN"); return e != nullptr && atoi(e) == 0; }();
+  bool chain = !chain_off && flags != nullptr && (mode == 0 || mode == 2);
+  for (int i = 0; i < count && chain; ++i) {
+    // the chain is one launch: its ramp / drain is shared by all `count` items
+    if (check_item(items[i]) != TP_OK || choose_kernel(items[i], count, sms, mode) != 0 || items[i].ep.seg_row_offset != nullptr) chain = false;
+    const int d = items[i].dep;
+    if (d >= 0 && (d >= i || items[d].stage >= items[i].stage || items[d].M != items[i].M || items[i].a.seg_rows != 0)) return TP_ERR_INVALID_ARGUMENT;
+  }
+  if (chain) {
+    long long used = 0;
+    for (int i = 0; i < count; ++i) {
+      bool produces = false;
+      for (int j = 0; j < count; ++j) produces = produces || items[j].dep == i;
+      if (!produces) continue;
+      const long long blocks = (items[i].M + 255) / 256;
+      if (used + blocks > flag_capacity) return TP_ERR_WORKSPACE_TOO_SMALL;
+      items[i].done_counter = flags + used;
+      used += blocks;
+    }
+    for (int i = 0; i < count; ++i) {
+      const int d = items[i].dep;
+      if (d < 0) continue;
+      items[i].dep_counter = items[d].done_counter;
+      items[i].dep_target = 4 * static_cast<int>((items[d].N + 255) / 256);     // 2 CTAs x 2 column halves per producer tile
+    }
+    return launch_gemm_pair_group(items, count, sms, stream);
+  }
+  for (int first = 0; first < count;) {
+    int last = first;
+    while (last + 1 < count && items[last + 1].stage == items[first].stage) ++last;
+    TP_TRY(launch_gemms(items + first, last - first + 1, sms, stream));
+    first = last + 1;
+  }
   return TP_OK;
 }
 
@@ -395,10 +477,13 @@ PackedLayout packed_layout(int H) {
 constexpr int kStatSlots = kC / 128;   // one (mean, M2) slot per 128 output columns of a 1024-wide linear
 
 struct WorkLayout {
-  size_t h_kv;      // [R,2048]  GELU(W0 xm + b) for k|v ; reused as k' | v' ([R,1024] each) once consumed
+  size_t h_kv;      // [R,2048]  GELU(W0 xm + b) for k|v
   size_t y_k, y_v;  // [R,1024]  second linear outputs (pre-LayerNorm)
+  size_t k_p, v_p;  // [R,1024]  MHA in-projections of the keys / values
   size_t stats;     // f32 [2R + Q, 8, 2]  per-row (mean, M2) of each 128-column block: k rows, v rows, q rows
   size_t q, y_q, q_p, ctx, h_m;      // [Q,1024] x4, [Q,H]
+  size_t flags;     // int32 [n_flags]  per-row-block tile counters of the chained GEMM launches (zeroed by the point-query kernel)
+  long long n_flags;
   size_t total;
 };
 
@@ -412,9 +497,13 @@ WorkLayout work_layout(long long n_crops, int s, int H) {
   L.h_kv = take(R * 2 * kC * 2);
   L.y_k = take(R * kC * 2);
   L.y_v = take(R * kC * 2);
+  L.k_p = take(R * kC * 2);
+  L.v_p = take(R * kC * 2);
   L.stats = take((2 * R + Q) * kStatSlots * 2 * 4);
   L.q = take(Q * kC * 2); L.y_q = take(Q * kC * 2); L.q_p = take(Q * kC * 2); L.ctx = take(Q * kC * 2);
   L.h_m = take(Q * static_cast<size_t>(H) * 2);
+  L.n_flags = 3 * static_cast<long long>((R + 255) / 256) + 2 * static_cast<long long>((Q + 255) / 256);
+  L.flags = take(static_cast<size_t>(L.n_flags) * 4);
   L.total = off;
   return L;
 }
@@ -422,9 +511,10 @@ WorkLayout work_layout(long long n_crops, int s, int H) {
 bool valid_hidden(int H) { return H >= 32 && H % 32 == 0 && H <= 65536; }
 
 template <int S>
-int launch_front(const __nv_bfloat16* x0, long long x0_stride, __nv_bfloat16* q, long long Q, cudaStream_t stream) {
+int launch_front(const __nv_bfloat16* x0, long long x0_stride, __nv_bfloat16* q, long long Q, int* flags, int n_flags, cudaStream_t stream) {
   const long long threads = Q * 128;
-  TP_CUDA(launch_pdl(point_query_kernel<S>, dim3(static_cast<unsigned>((threads + 255) / 256)), dim3(256), 0, stream, x0, x0_stride, q, Q));
+  TP_CUDA(launch_pdl(point_query_kernel<S>, dim3(static_cast<unsigned>((threads + 255) / 256)), dim3(256), 0, stream, x0, x0_stride, q, Q, flags,
+                     n_flags));
   return TP_OK;
 }
 
@@ -438,16 +528,17 @@ int launch_attn(const __nv_bfloat16* qp, const __nv_bfloat16* kp, const __nv_bfl
 
 // scale_factor dispatch: every divisor of 24 (builder.py:51-52).  2 / 3 / 4 (the released 144 / 64 / 36-token models) keep
 // the window in registers; the others stream it.
-int launch_front_s(int s, const __nv_bfloat16* x0, long long x0_stride, __nv_bfloat16* q, long long Q, cudaStream_t stream) {
+int launch_front_s(int s, const __nv_bfloat16* x0, long long x0_stride, __nv_bfloat16* q, long long Q, int* flags, int n_flags,
+                   cudaStream_t stream) {
   switch (s) {
-    case 1: return launch_front<1>(x0, x0_stride, q, Q, stream);
-    case 2: return launch_front<2>(x0, x0_stride, q, Q, stream);
-    case 3: return launch_front<3>(x0, x0_stride, q, Q, stream);
-    case 4: return launch_front<4>(x0, x0_stride, q, Q, stream);
-    case 6: return launch_front<6>(x0, x0_stride, q, Q, stream);
-    case 8: return launch_front<8>(x0, x0_stride, q, Q, stream);
-    case 12: return launch_front<12>(x0, x0_stride, q, Q, stream);
-    case 24: return launch_front<24>(x0, x0_stride, q, Q, stream);
+    case 1: return launch_front<1>(x0, x0_stride, q, Q, flags, n_flags, stream);
+    case 2: return launch_front<2>(x0, x0_stride, q, Q, flags, n_flags, stream);
+    case 3: return launch_front<3>(x0, x0_stride, q, Q, flags, n_flags, stream);
+    case 4: return launch_front<4>(x0, x0_stride, q, Q, flags, n_flags, stream);
+    case 6: return launch_front<6>(x0, x0_stride, q, Q, flags, n_flags, stream);
+    case 8: return launch_front<8>(x0, x0_stride, q, Q, flags, n_flags, stream);
+    case 12: return launch_front<12>(x0, x0_stride, q, Q, flags, n_flags, stream);
+    case 24: return launch_front<24>(x0, x0_stride, q, Q, flags, n_flags, stream);
     default: return TP_ERR_BAD_SCALE_FACTOR;
   }
 }
@@ -602,63 +693,71 @@ int forward_impl(const void* packed, const void* x0, const void* xm, const void*
   float* stats_v = stats_k + 2 * kStatSlots * R;
   float* stats_q = stats_v + 2 * kStatSlots * R;     // every slot is written by the producing GEMM: no memset needed
 
-  // Launch plan (7 kernels; independent GEMMs of a stage share one grouped launch of the CTA-pair kernel):
-  //   [S] point queries            builder.py:117-118
+  // Launch plan.  Large batches: 4 launches — [S], chain A = {[1], [2], [3]} and chain B = {[4], [5]} as ONE persistent CTA-pair
+  // launch each (stages ordered by per-row-block tile counters instead of kernel boundaries), [A] in between.  Small batches
+  // (one-CTA tiles win): the same stages as separate launches.
+  //   [S] point queries            builder.py:117-118   (+ resets the tile counters)
   //   [1] h_kv = GELU(xm [W_k0;W_v0]^T + b)                                 :112-113 first linears, xm read once
-  //   [2] y_k | y_v | y_q   = second linears k/v + q_proj_1 (+ row sums for the LayerNorms)   :112-113, :120
+  //   [2] y_k | y_v | y_q   = second linears k/v + q_proj_1 (+ row statistics for the LayerNorms)   :112-113, :120
   //   [3] k'  | v'  | q'    = LayerNorm folded into the MHA in-projections (q' scaled by 1/sqrt 128)   MHA in_proj
   //   [A] window attention core                                              :122-130
   //   [4] h_m = GELU(ctx (W_m0 W_o)^T + (W_m0 b_o + b_m0))                   out_proj folded into mlp.0  (:130,:136)
   //   [5] out = h_m W_m2^T + b_m2  -> final [N,M,H] (or packed HD) layout    :136
+  int* flags = reinterpret_cast<int*>(ws + W.flags);
+  const long long flags_a = 3 * ((R + 255) / 256);          // chain A: [1], [2]k, [2]v produce for later stages ([2]q: Q rows, below)
   {
     const __nv_bfloat16* x0p = static_cast<const __nv_bfloat16*>(x0);
-    TP_TRY(launch_front_s(s, x0p, x0_crop_stride, bf(W.q), Q, stream));
+    TP_TRY(launch_front_s(s, x0p, x0_crop_stride, bf(W.q), Q, flags, static_cast<int>(W.n_flags), stream));
   }
+  // k' / v' have buffers of their own: in a chained launch [3] runs while other row blocks of [2] still read h_kv, so the
+  // round-1 trick of writing them over the dead h_kv buffer is no longer legal
+  __nv_bfloat16* k_p = bf(W.k_p);
+  __nv_bfloat16* v_p = bf(W.v_p);
   {
+    GemmItem g[7];
     AOperand a{xm, xm_width, 0, 0};
     if (xm_crop_stride != static_cast<int64_t>(kTokens) * xm_width) a = AOperand{xm, xm_width, kTokens, xm_crop_stride};
     if (xm_layers != nullptr) {
       a.parts = 4;
       for (int i = 1; i < 4; ++i) a.more[i - 1] = xm_layers[i];
     }
-    TP_TRY(launch_gemm(a, P + L.w_kv0, kCm, R, 2 * kC, kCm, plain_epilogue(bf(W.h_kv), 2 * kC, wf(L.b_kv0), 1), dev.sms, stream));
-  }
-  {
-    GemmItem g[3];
-    g[0] = GemmItem{AOperand{bf(W.h_kv), 2 * kC, 0, 0}, P + L.w_k2, kC, R, kC, kC, plain_epilogue(bf(W.y_k), kC, wf(L.b_k2), 0)};
-    g[0].ep.stats_out = stats_k;
-    g[0].ep.stats_out_slots = kStatSlots;
-    g[1] = GemmItem{AOperand{bf(W.h_kv) + kC, 2 * kC, 0, 0}, P + L.w_v2, kC, R, kC, kC, plain_epilogue(bf(W.y_v), kC, wf(L.b_v2), 0)};
-    g[1].ep.stats_out = stats_v;
+    g[0] = GemmItem{a, P + L.w_kv0, kCm, R, 2 * kC, kCm, plain_epilogue(bf(W.h_kv), 2 * kC, wf(L.b_kv0), 1)};
+    g[0].stage = 0;
+    g[1] = GemmItem{AOperand{bf(W.h_kv), 2 * kC, 0, 0}, P + L.w_k2, kC, R, kC, kC, plain_epilogue(bf(W.y_k), kC, wf(L.b_k2), 0)};
+    g[1].ep.stats_out = stats_k;
     g[1].ep.stats_out_slots = kStatSlots;
-    g[2] = GemmItem{AOperand{bf(W.q), kC, 0, 0}, P + L.w_q, kC, Q, kC, kC, plain_epilogue(bf(W.y_q), kC, nullptr, 0)};
-    g[2].ep.stats_out = stats_q;
+    g[2] = GemmItem{AOperand{bf(W.h_kv) + kC, 2 * kC, 0, 0}, P + L.w_v2, kC, R, kC, kC, plain_epilogue(bf(W.y_v), kC, wf(L.b_v2), 0)};
+    g[2].ep.stats_out = stats_v;
     g[2].ep.stats_out_slots = kStatSlots;
-    TP_TRY(launch_gemms(g, 3, dev.sms, stream));
-  }
-  // k' / v' are written over the dead h_kv buffer
-  __nv_bfloat16* k_p = bf(W.h_kv);
-  __nv_bfloat16* v_p = bf(W.h_kv) + static_cast<size_t>(R) * kC;
-  {
-    GemmItem g[3];
-    g[0] = GemmItem{AOperand{bf(W.y_k), kC, 0, 0}, P + L.w_ik, kC, R, kC, kC, plain_epilogue(k_p, kC, wf(L.c_k), 0)};
-    g[0].ep.col_a = wf(L.wsum_k);
-    g[0].ep.stats_in = stats_k;
-    g[0].ep.stats_in_slots = kStatSlots;
-    g[1] = GemmItem{AOperand{bf(W.y_v), kC, 0, 0}, P + L.w_iv, kC, R, kC, kC, plain_epilogue(v_p, kC, wf(L.c_v), 0)};
-    g[1].ep.col_a = wf(L.wsum_v);
-    g[1].ep.stats_in = stats_v;
-    g[1].ep.stats_in_slots = kStatSlots;
-    g[2] = GemmItem{AOperand{bf(W.y_q), kC, 0, 0}, P + L.w_iq, kC, Q, kC, kC, plain_epilogue(bf(W.q_p), kC, wf(L.c_q), 0)};
-    g[2].ep.col_a = wf(L.wsum_q);
-    g[2].ep.stats_in = stats_q;
-    g[2].ep.stats_in_slots = kStatSlots;
-    g[2].ep.alpha = 0.08838834764831845f;   // 1/sqrt(head_dim = 128): torch MHA scales q after the in-projection
-    TP_TRY(launch_gemms(g, 3, dev.sms, stream));
+    g[3] = GemmItem{AOperand{bf(W.q), kC, 0, 0}, P + L.w_q, kC, Q, kC, kC, plain_epilogue(bf(W.y_q), kC, nullptr, 0)};
+    g[3].ep.stats_out = stats_q;
+    g[3].ep.stats_out_slots = kStatSlots;
+    g[1].stage = g[2].stage = g[3].stage = 1;
+    g[1].dep = g[2].dep = 0;
+    g[4] = GemmItem{AOperand{bf(W.y_k), kC, 0, 0}, P + L.w_ik, kC, R, kC, kC, plain_epilogue(k_p, kC, wf(L.c_k), 0)};
+    g[4].ep.col_a = wf(L.wsum_k);
+    g[4].ep.stats_in = stats_k;
+    g[4].ep.stats_in_slots = kStatSlots;
+    g[5] = GemmItem{AOperand{bf(W.y_v), kC, 0, 0}, P + L.w_iv, kC, R, kC, kC, plain_epilogue(v_p, kC, wf(L.c_v), 0)};
+    g[5].ep.col_a = wf(L.wsum_v);
+    g[5].ep.stats_in = stats_v;
+    g[5].ep.stats_in_slots = kStatSlots;
+    g[6] = GemmItem{AOperand{bf(W.y_q), kC, 0, 0}, P + L.w_iq, kC, Q, kC, kC, plain_epilogue(bf(W.q_p), kC, wf(L.c_q), 0)};
+    g[6].ep.col_a = wf(L.wsum_q);
+    g[6].ep.stats_in = stats_q;
+    g[6].ep.stats_in_slots = kStatSlots;
+    g[6].ep.alpha = 0.08838834764831845f;   // 1/sqrt(head_dim = 128): torch MHA scales q after the in-projection
+    g[4].stage = g[5].stage = g[6].stage = 2;
+    g[4].dep = 1;
+    g[5].dep = 2;
+    g[6].dep = 3;
+    TP_TRY(launch_chain(g, 7, flags, flags_a + (Q + 255) / 256, dev.sms, stream));
   }
   TP_TRY(launch_attn_s(s, bf(W.q_p), k_p, v_p, bf(W.ctx), Q, stream));
-  TP_TRY(launch_gemm(AOperand{bf(W.ctx), kC, 0, 0}, P + L.w_om, kC, Q, H, kC, plain_epilogue(bf(W.h_m), H, wf(L.b_om), 1), dev.sms, stream));
   {
+    GemmItem g[2];
+    g[0] = GemmItem{AOperand{bf(W.ctx), kC, 0, 0}, P + L.w_om, kC, Q, H, kC, plain_epilogue(bf(W.h_m), H, wf(L.b_om), 1)};
+    g[0].stage = 0;
     GemmEpilogue ep = plain_epilogue(out, H, wf(L.b_m2), 0);
     if (seg_row_offset != nullptr) {
       ep.seg_row_offset = reinterpret_cast<const long long*>(seg_row_offset);
@@ -668,10 +767,13 @@ int forward_impl(const void* packed, const void* x0, const void* xm, const void*
       ep.seg_len = Mq;
       ep.seg_stride = static_cast<int>(out_crop_rows);
     }
-    GemmItem it{AOperand{bf(W.h_m), H, 0, 0}, P + L.w_m2, H, Q, H, H, ep};
-    it.peer_c = peer_out;
-    it.n_peers = n_peers;
-    TP_TRY(launch_gemms(&it, 1, dev.sms, stream));
+    g[1] = GemmItem{AOperand{bf(W.h_m), H, 0, 0}, P + L.w_m2, H, Q, H, H, ep};
+    g[1].peer_c = peer_out;
+    g[1].n_peers = n_peers;
+    g[1].stage = 1;
+    g[1].dep = 0;
+    int* flags_b = flags + flags_a + (Q + 255) / 256;
+    TP_TRY(launch_chain(g, 2, flags_b, (Q + 255) / 256, dev.sms, stream));
   }
   return TP_OK;
 }

@@ -16,9 +16,13 @@
 //
 // CTA = 384 threads, persistent over output tiles (default role layout):
 //   warps 0-7   epilogue: tcgen05.ld 32x32b (thread == output row), fused per-row / per-column math on the packed fp32
-//               pipe, swizzled shared-memory slabs -> TMA stores (direct 16-byte stores in the one-CTA kernels / row scatter)
-//   warp 9      TMEM allocator (2 accumulator buffers: the epilogue of tile i overlaps tile i+1's MMAs)
-//   warp 10     TMA producer   (warp-uniform loop, elect.sync around the issue): cp.async.bulk.tensor boxes, 128B swizzle, mbarrier ring
+//               pipe, swizzled shared-memory slabs (direct 16-byte stores in the one-CTA kernels / arbitrary row scatter)
+//   warps 8, 9  store warps of the pair kernel (one per column half): wait for a finished slab on an mbarrier, issue its TMA
+//               store(s), hand the buffer back, and — for GEMMs that other GEMMs of the same launch depend on — publish each
+//               finished tile to a global counter.  The epilogue warps never wait for a store.  Warp 9 also allocates TMEM
+//               (2 accumulator buffers: the epilogue of tile i overlaps tile i+1's MMAs)
+//   warp 10     TMA producer   (warp-uniform loop, elect.sync around the issue): cp.async.bulk.tensor boxes, 128B swizzle, mbarrier
+//               ring; spins on the producer GEMM's tile counter before the first load of a dependent tile
 //   warp 11     MMA issuer     (leader CTA only in pair mode): fp32 accumulators in TMEM
 //
 // Fused epilogue (all optional, selected at run time, warp-uniform branches):
@@ -55,6 +59,7 @@ struct GemmEpilogue {
   float ln_eps;
   float alpha;
   int gelu;
+  int out_f32;             // 1: C is float [M, ldc] (split-K partial sums of the wgrads): fp32 direct stores, no bf16 rounding
   long long* prof;         // TP_GEMM_PROFILE builds only: [grid][16] cycle counters (nullptr otherwise)
 };
 
@@ -78,20 +83,11 @@ constexpr int kGemmThreads = 384;
 // the single-lane TMA / MMA warps must never lose an issue slot to the (instruction-heavy) epilogue warps: they get
 // the HIGHEST ids.  Epilogue warp w reads TMEM lanes 32*(w % 4)..+31 (hardware restriction), so 8 epilogue warps =
 // 4 lane quarters x 2 column halves.
-#ifndef TP_ROLE_LAYOUT
-#define TP_ROLE_LAYOUT 1
-#endif
-#if TP_ROLE_LAYOUT == 1
 constexpr int kEpiWarp0 = 0;
 constexpr int kTmaWarp = 10;
 constexpr int kMmaWarp = 11;
 constexpr int kAllocWarp = 9;
-#else
-constexpr int kEpiWarp0 = 4;
-constexpr int kTmaWarp = 0;
-constexpr int kMmaWarp = 1;
-constexpr int kAllocWarp = 2;
-#endif
+constexpr int kStoreWarp0 = 8;      // pair kernel: warps 8 and 9 issue the TMA stores of column half 0 / 1 (role layout 1 only)
 constexpr int kNumEpiWarps = 8;
 constexpr int kEpiThreads = kNumEpiWarps * 32;
 constexpr int kEpiBarrierId = 1;
@@ -117,23 +113,18 @@ struct PeerStores {
 };
 
 struct OutStage {
-  uint8_t* buf;              // this half's 2 x 16 KiB staging buffers (nullptr: direct 16-byte global stores)
-  const CUtensorMap* tmap;   // C tensor map(s), box = 64 cols x 128 rows, SWIZZLE_128B  (3-D, box 64 x seg_box x 1, when seg_len != 0)
-  int seg_len;               // 0: plain 2-D output; else rows per segment of the 3-D (cols, row in segment, segment) map
-  int seg_box;               // box rows of the 3-D map = min(seg_len, 128)
-  int n_segs;
-  int n_maps;                // 1, or the number of peer maps (consecutive CUtensorMaps starting at tmap)
-  int row_tile0;             // first global row of this CTA's 128-row tile
-  int n_bufs;                // 2: slabs alternate buffers (one barrier per slab); 1: single buffer (two barriers per slab)
-  uint32_t barrier_id;       // named barrier shared by the 4 warps (128 threads) of this half
-  bool issuer;               // this thread issues (and tracks) the half's TMA stores
+  uint8_t* buf;              // this half's n_bufs x 16 KiB staging buffers (nullptr: direct 16-byte global stores)
+  uint64_t* full_bar;        // [n_bufs] slab written (count 4: one arrive per epilogue warp of the half) -> store warp
+  uint64_t* empty_bar;       // [n_bufs] slab's TMA store has finished reading the buffer (count 1, store warp) -> epilogue warps
+  int n_bufs;                // 2: slabs alternate buffers; 1: single buffer
+  uint32_t slab_seq;         // running slab number of this half (buffer = seq % n_bufs, mbarrier phase = seq / n_bufs)
 };
 constexpr int kOutSlabBytes = 128 * 128;   // 128 rows x 64 bf16
 
 template <int kTileN, typename ReleaseFn>
 __device__ __forceinline__ void epilogue_tile(const GemmEpilogue& ep, int M, int N, uint32_t tmem_acc, int row, int col_tile0,
                                               int quarter, int half, const float* s_col, const OutStage& out, ReleaseFn release,
-                                              [[maybe_unused]] long long* pc = nullptr) {
+                                              [[maybe_unused]] long long* pc = nullptr, long long c_extra = 0) {
   constexpr int kColsPerWarp = kTileN / 2;
   constexpr int kChunks = kColsPerWarp / 32;
   const bool ln_fold = ep.col_a != nullptr;
@@ -168,6 +159,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmEpilogue& ep, int M, int
     dst_row = static_cast<long long>(seg) * ep.seg_stride + (row - seg * ep.seg_len);
   }
   __nv_bfloat16* c_row = ep.c + dst_row * ep.ldc;
+  float* c_row32 = reinterpret_cast<float*>(ep.c) + c_extra + dst_row * ep.ldc;     // out_f32 only (c_extra: split-K slice)
   const uint32_t taddr = tmem_acc + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(half * kColsPerWarp);
   const uint32_t sa_addr = smem_u32(s_col + half * kColsPerWarp), sb_addr = smem_u32(s_col + kTileN + half * kColsPerWarp);
   const uint32_t out_addr = out.buf != nullptr ? smem_u32(out.buf) : 0u;
@@ -188,10 +180,13 @@ __device__ __forceinline__ void epilogue_tile(const GemmEpilogue& ep, int M, int
     if (chunk + 1 < kChunks) tmem_ld_32x32b_x32(taddr + static_cast<uint32_t>((chunk + 1) * 32), r[(chunk + 1) & 1]);
     else release();                                   // every TMEM read of this warp has landed in registers
     const int col0 = col_tile0 + half * kColsPerWarp + chunk * 32;
-    if (out.buf != nullptr && out.n_bufs == 1 && (chunk & 1) == 0) {
-      // single staging buffer: the previous slab's TMA store must have finished READING it before anyone overwrites it
-      if (out.issuer) bulk_wait_group_read<0>();
-      named_bar_sync(out.barrier_id, 128);
+    const uint32_t slab_q = out.slab_seq + static_cast<uint32_t>(chunk >> 1);
+    const uint32_t slab_buf = slab_q & static_cast<uint32_t>(out.n_bufs - 1);
+    if (out.buf != nullptr && (chunk & 1) == 0) {
+      // the TMA store that last used this staging buffer must have finished READING it (signalled by the store warp)
+      TP_PROF_T0();
+      mbar_wait(&out.empty_bar[slab_buf], ((slab_q >> (out.n_bufs - 1)) & 1u) ^ 1u);
+      TP_PROF_ADD(pc[2]);
     }
     if (col0 < N) {        // N is a multiple of 32 (checked on the host) -> whole chunk in or out
       // kSubPairs packed pairs (2 columns each) go through every step together: each run-time option is ONE warp-uniform branch
@@ -248,63 +243,48 @@ __device__ __forceinline__ void epilogue_tile(const GemmEpilogue& ep, int M, int
         }
         if (out.buf != nullptr) {
           // slab = 2 chunks; 16-byte piece index inside the 128-byte row, XOR-swizzled with (row & 7) like TMA's SWIZZLE_128B
-          const uint32_t row_base = out_addr + static_cast<uint32_t>(((chunk >> 1) & (out.n_bufs - 1)) * kOutSlabBytes + rloc * 128);
+          const uint32_t row_base = out_addr + static_cast<uint32_t>(slab_buf * kOutSlabBytes + rloc * 128);
 #pragma unroll
           for (int g = 0; g < kSubPairs / 4; ++g) {
             const int ci = (chunk & 1) * 4 + sub * (kSubPairs / 4) + g;
             sts_u4(row_base + static_cast<uint32_t>((ci ^ (rloc & 7)) << 4), pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
           }
         } else if (row_ok) {
+          if (ep.out_f32) {
 #pragma unroll
-          for (int g = 0; g < kSubPairs / 4; ++g)
-            *reinterpret_cast<uint4*>(c_row + col0 + sub * kSubPairs * 2 + g * 8) = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+            for (int g = 0; g < kSubPairs / 2; ++g) {
+              float4 f;
+              upk2(v[2 * g], f.x, f.y);
+              upk2(v[2 * g + 1], f.z, f.w);
+              *reinterpret_cast<float4*>(c_row32 + col0 + sub * kSubPairs * 2 + g * 4) = f;
+            }
+          } else {
+#pragma unroll
+            for (int g = 0; g < kSubPairs / 4; ++g)
+              *reinterpret_cast<uint4*>(c_row + col0 + sub * kSubPairs * 2 + g * 8) = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+          }
         }
+      }
+    }
+    if (chunk == kChunks - 1 && ep.stats_out != nullptr && row_ok) {
+      // statistics are final once the last chunk's values exist; written BEFORE the last slab is handed over so that the store
+      // warp's tile-done release (dependent GEMMs of the same launch read them) covers these stores too
+      const int slot = (col_tile0 + half * kColsPerWarp) / kColsPerWarp;
+      if (slot < ep.stats_out_slots) {
+        // (mean, M2) of this 128-column block: mean = shift + s1/n, M2 = s2 - s1^2/n  (deviations from `shift` are O(std): no cancellation)
+        constexpr float inv_n = 1.0f / kColsPerWarp;
+        const float dm = __fmul_rn(s1, inv_n);
+        reinterpret_cast<float2*>(ep.stats_out)[static_cast<long long>(row) * ep.stats_out_slots + slot] =
+            make_float2(__fadd_rn(shift, dm), fmaxf(fmaf(-s1, dm, s2), 0.f));
       }
     }
     if (out.buf != nullptr && (chunk & 1) == 1) {
-      // slab complete: publish to the async proxy, make sure the previous store of this half has drained its buffer
-      // (so the NEXT slab may overwrite it), then one thread issues the TMA store
-      {
-        TP_PROF_T0();
-        fence_proxy_async_smem();
-        TP_PROF_ADD(pc[1]);
-      }
-      {
-        TP_PROF_T0();
-        if (out.issuer && out.n_bufs == 2) bulk_wait_group_read<0>();
-        named_bar_sync(out.barrier_id, 128);
-        TP_PROF_ADD(pc[2]);
-      }
-      if (out.issuer) {
-        const int slab = chunk >> 1;
-        const uint8_t* src = out.buf + (slab & (out.n_bufs - 1)) * kOutSlabBytes;
-        const int col = col_tile0 + half * kColsPerWarp + slab * 64;
-        if (out.seg_len == 0) {
-          for (int p = 0; p < out.n_maps; ++p) tma_store_2d(out.tmap + p, src, col, out.row_tile0);
-        } else {
-          // Segmented output rows (global row g = seg * seg_len + r  ->  map coordinate (col, r, seg)): the slab's 128 rows are
-          // cut at segment boundaries and each piece leaves through the SAME fixed-size box.  A piece that starts before the slab
-          // or ends after it is positioned so that the surplus box rows fall outside [0, seg_len) of its segment, where TMA clips
-          // them (signed coordinates): src_row = clamp(a, 0, 128 - box), r0 = src_row - a, a = slab row of the segment's row 0.
-          // The 128B swizzle is a function of the absolute shared-memory address, so any 128-byte-aligned source row works.
-          int seg = out.row_tile0 / out.seg_len;
-          for (int a = seg * out.seg_len - out.row_tile0; a < kBlockM && seg < out.n_segs; a += out.seg_len, ++seg) {
-            const int src_row = min(max(a, 0), kBlockM - out.seg_box);
-            for (int p = 0; p < out.n_maps; ++p) tma_store_3d(out.tmap + p, src + src_row * 128, col, src_row - a, seg);
-          }
-        }
-        bulk_commit_group();
-      }
-    }
-  }
-  if (ep.stats_out != nullptr && row_ok) {
-    const int slot = (col_tile0 + half * kColsPerWarp) / kColsPerWarp;
-    if (slot < ep.stats_out_slots) {
-      // (mean, M2) of this 128-column block: mean = shift + s1/n, M2 = s2 - s1^2/n  (deviations from `shift` are O(std): no cancellation)
-      constexpr float inv_n = 1.0f / kColsPerWarp;
-      const float dm = __fmul_rn(s1, inv_n);
-      reinterpret_cast<float2*>(ep.stats_out)[static_cast<long long>(row) * ep.stats_out_slots + slot] =
-          make_float2(__fadd_rn(shift, dm), fmaxf(fmaf(-s1, dm, s2), 0.f));
+      // slab complete: make the generic-proxy writes visible to the async proxy, then one arrive per warp hands it to the store warp
+      TP_PROF_T0();
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane_id() == 0) mbar_arrive(&out.full_bar[slab_buf]);
+      TP_PROF_ADD(pc[1]);
     }
   }
 }
@@ -462,7 +442,7 @@ tp_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tcgen05_fence_after();
       uint64_t* release_bar = &tmem_empty_bar[acc];
-      const OutStage no_stage{nullptr, nullptr, 0, 0, 0, 0, 0, 0, 0, false};
+      const OutStage no_stage{nullptr, nullptr, nullptr, 1, 0u};
       epilogue_tile<kBlockN>(ep, M, N, tmem_base + static_cast<uint32_t>(acc * kBlockN),
                              m_blk * kBlockM + quarter * 32 + static_cast<int>(lane), n_blk * kBlockN, quarter, half, s_col, no_stage, [&]() {
                                tcgen05_fence_before();
@@ -501,11 +481,11 @@ struct Gemm2Config {
   static constexpr int kTmemCols = 2 * kTileN;
   static constexpr int kOutBytes = 2 * kOutBufs * kOutSlabBytes; // [2 column halves][kOutBufs] output slabs for TMA stores
   static constexpr int kColStageBytes = 2 * 2 * kTileN * 4;
-  static constexpr int kBarrierBytes = (2 * kStages + 4) * 8 + 16;
+  static constexpr int kBarrierBytes = (2 * kStages + 4 + 4 * kOutBufs) * 8 + 16;   // ring + accumulators + slab full/empty per half
   static constexpr int kSmemBytes = kStages * kStageBytes + kOutBytes + kColStageBytes + kBarrierBytes + 1024;
 };
 
-constexpr int kMaxGroup = 3;
+constexpr int kMaxGroup = 8;
 
 constexpr int kMaxAParts = 4;
 
@@ -522,8 +502,22 @@ struct GemmProblem {
   int use_tma_store;     // C through TMA stores (0 when rows are scattered to arbitrary segment offsets)
   int c_seg_len;         // != 0: tmap_c (and the peer maps) are 3-D (cols, row in segment, segment): uniform-stride segmented output
   int num_n_blocks;
-  int num_tiles;
+  int num_tiles;         // = tiles_mn * k_splits
   int num_k_blocks;
+  // split-K (wgrads whose output is a few tiles but whose contraction runs over every row of the batch): tile = (split, m, n),
+  // split s covers k-blocks [s * kb_per_split, (s+1) * kb_per_split) and writes its fp32 partial to slice s of C (ep.out_f32)
+  int k_splits;          // >= 1
+  int kb_per_split;
+  int tiles_mn;
+  long long c_split_stride;   // floats between consecutive split slices of C
+  // Dependencies between GEMMs of ONE launch (a chain of linears runs as a single persistent kernel: no ramp / drain / partial
+  // last wave per layer).  Tiles are numbered problem after problem and every CTA pair walks its tiles in increasing order, so a
+  // tile only ever waits for lower-numbered tiles: no deadlock as long as all pairs are co-resident (grid <= 74 pairs).
+  int* done_counter;     // != nullptr: [ceil(M/256)] tile counter of THIS problem's output row blocks, +1 per (CTA, column half)
+                         //             once that part of a tile is in global memory (bumped by the store warps)
+  const int* dep_counter;// != nullptr: the A operand's row block m_blk is ready when dep_counter[m_blk] >= dep_target
+  int dep_target;        //             (= 4 * num_n_blocks of the producing problem: 2 CTAs x 2 column halves per tile)
+  int peer_out;          // C of this problem goes to the PeerStores maps (fused all-gather) instead of tmap_c
   GemmEpilogue ep;
 };
 
@@ -536,6 +530,8 @@ struct GemmGroup {
 struct TileRef {
   const GemmProblem* pr;
   int m_blk, n_blk;
+  int kb0, kb1;          // k-block range of this tile (the whole K unless the problem is split)
+  int split;
 };
 
 __device__ __forceinline__ TileRef decode_tile(const GemmGroup& g, int tile) {
@@ -546,8 +542,15 @@ __device__ __forceinline__ TileRef decode_tile(const GemmGroup& g, int tile) {
   }
   TileRef t;
   t.pr = &g.p[p];
+  t.split = 0;
+  if (t.pr->k_splits > 1) {
+    t.split = tile / t.pr->tiles_mn;
+    tile -= t.split * t.pr->tiles_mn;
+  }
   t.m_blk = tile / t.pr->num_n_blocks;
   t.n_blk = tile - t.m_blk * t.pr->num_n_blocks;
+  t.kb0 = t.split * t.pr->kb_per_split;
+  t.kb1 = t.kb0 + t.pr->kb_per_split < t.pr->num_k_blocks ? t.kb0 + t.pr->kb_per_split : t.pr->num_k_blocks;
   return t;
 }
 
@@ -566,7 +569,9 @@ tp_gemm2_kernel(const __grid_constant__ GemmGroup grp, const __grid_constant__ P
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tmem_full_bar = empty_bar + kStages;
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;
-  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  uint64_t* slab_full_bar = tmem_empty_bar + 2;                 // [2 halves][kOutBufs]
+  uint64_t* slab_empty_bar = slab_full_bar + 2 * Cfg::kOutBufs; // [2 halves][kOutBufs]
+  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(slab_empty_bar + 2 * Cfg::kOutBufs);
 
   const int warp_idx = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
   const uint32_t lane = lane_id();
@@ -591,6 +596,10 @@ tp_gemm2_kernel(const __grid_constant__ GemmGroup grp, const __grid_constant__ P
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full_bar[i], 1);                   // multicast tcgen05.commit from the leader
       mbar_init(&tmem_empty_bar[i], 2 * kNumEpiWarps);   // epilogue warps of BOTH CTAs (waited on in the leader only)
+    }
+    for (int i = 0; i < 2 * Cfg::kOutBufs; ++i) {
+      mbar_init(&slab_full_bar[i], kNumEpiWarps / 2);    // one arrive per epilogue warp of the column half
+      mbar_init(&slab_empty_bar[i], 1);                  // the half's store warp
     }
     fence_barrier_init();
   } else if (warp_idx == kAllocWarp) {
@@ -618,6 +627,12 @@ tp_gemm2_kernel(const __grid_constant__ GemmGroup grp, const __grid_constant__ P
       const int row0 = t.m_blk * Cfg::kTileM + static_cast<int>(cta_rank) * kBlockM;          // my 128 rows of A
       const int brow0 = t.n_blk * kTileN + static_cast<int>(cta_rank) * (kTileN / 2);        // my half of the B tile
       // segmented A (3-D map, 64-row boxes): global row g -> (segment g / seg_rows, row g % seg_rows); hoisted per tile
+      if (pr.dep_counter != nullptr) {
+        // A's row block is written by an earlier GEMM of this launch: wait until all its tiles have been published (acquire), then
+        // order the TMA (async proxy) reads after the acquire
+        wait_counter_at_least(pr.dep_counter + t.m_blk, pr.dep_target);
+        fence_proxy_async_all();
+      }
       int seg0 = 0, srow0 = 0, seg1 = 0, srow1 = 0;
       if (pr.a_seg_rows != 0) {
         seg0 = row0 / pr.a_seg_rows;
@@ -625,7 +640,7 @@ tp_gemm2_kernel(const __grid_constant__ GemmGroup grp, const __grid_constant__ P
         seg1 = (row0 + 64) / pr.a_seg_rows;
         srow1 = row0 + 64 - seg1 * pr.a_seg_rows;
       }
-      for (int kb = 0; kb < pr.num_k_blocks; ++kb) {
+      for (int kb = t.kb0; kb < t.kb1; ++kb) {
         {
           TP_PROF_T0();
           mbar_wait(&empty_bar[stage], phase ^ 1u);
@@ -675,8 +690,8 @@ tp_gemm2_kernel(const __grid_constant__ GemmGroup grp, const __grid_constant__ P
       [[maybe_unused]] long long w_full = 0, w_tmem = 0;
       [[maybe_unused]] const long long t_begin = clock64();
       for (int tile = pair_idx; tile < num_tiles; tile += num_pairs) {
-        const GemmProblem& mpr = *decode_tile(grp, tile).pr;
-        const int num_k_blocks = mpr.num_k_blocks;
+        const TileRef mt = decode_tile(grp, tile);
+        const GemmProblem& mpr = *mt.pr;
         const bool mn_major = mpr.ab_mn_major != 0;
         const uint32_t idesc = mn_major ? make_idesc_bf16_f32(Cfg::kTileM, kTileN, 1, 1) : make_idesc_bf16_f32(Cfg::kTileM, kTileN);
         {
@@ -686,7 +701,7 @@ tp_gemm2_kernel(const __grid_constant__ GemmGroup grp, const __grid_constant__ P
         }
         tcgen05_fence_after();
         const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * kTileN);
-        for (int kb = 0; kb < num_k_blocks; ++kb) {
+        for (int kb = mt.kb0; kb < mt.kb1; ++kb) {
           {
             TP_PROF_T0();
             mbar_wait(&full_bar[stage], phase);              // both CTAs' boxes have landed
@@ -701,7 +716,7 @@ tp_gemm2_kernel(const __grid_constant__ GemmGroup grp, const __grid_constant__ P
 #pragma unroll
               for (int k = 0; k < kBlockK / kUmmaK; ++k) {
                 umma_bf16_pair(tmem_d, desc_a + static_cast<uint64_t>(k * 2), desc_b + static_cast<uint64_t>(k * 2), idesc,
-                               static_cast<uint32_t>((kb | k) != 0));
+                               static_cast<uint32_t>(((kb - mt.kb0) | k) != 0));
               }
             } else {
               // MN-major tiles: two 64-wide MN atoms 8 KiB apart per operand; one UMMA (K = 16) consumes two 8-row K groups = 2 KiB
@@ -710,11 +725,11 @@ tp_gemm2_kernel(const __grid_constant__ GemmGroup grp, const __grid_constant__ P
 #pragma unroll
               for (int k = 0; k < kBlockK / kUmmaK; ++k) {
                 umma_bf16_pair(tmem_d, desc_a + static_cast<uint64_t>(k * (2048 >> 4)), desc_b + static_cast<uint64_t>(k * (2048 >> 4)), idesc,
-                               static_cast<uint32_t>((kb | k) != 0));
+                               static_cast<uint32_t>(((kb - mt.kb0) | k) != 0));
               }
             }
             umma_commit_pair(&empty_bar[stage], 0x3);        // frees the slot in BOTH CTAs
-            if (kb == num_k_blocks - 1) umma_commit_pair(&tmem_full_bar[acc], 0x3);   // accumulator complete -> both epilogues
+            if (kb == mt.kb1 - 1) umma_commit_pair(&tmem_full_bar[acc], 0x3);   // accumulator complete -> both epilogues
           }
           __syncwarp();
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
@@ -737,7 +752,7 @@ tp_gemm2_kernel(const __grid_constant__ GemmGroup grp, const __grid_constant__ P
     const int epi_tid = e * 32 + static_cast<int>(lane);
     int acc = 0;
     uint32_t acc_phase = 0;
-    bool stored = false;
+    uint32_t slab_seq = 0;
     [[maybe_unused]] long long w_acc = 0, t_work = 0;
     [[maybe_unused]] long long pc[3] = {0, 0, 0};
     for (int tile = pair_idx; tile < num_tiles; tile += num_pairs) {
@@ -755,11 +770,9 @@ tp_gemm2_kernel(const __grid_constant__ GemmGroup grp, const __grid_constant__ P
       uint64_t* release_bar = &tmem_empty_bar[acc];
       const int row_tile0 = t.m_blk * Cfg::kTileM + static_cast<int>(cta_rank) * kBlockM;
       const int row = row_tile0 + quarter * 32 + static_cast<int>(lane);
-      const OutStage out{pr.use_tma_store ? s_out + half * Cfg::kOutBufs * kOutSlabBytes : nullptr, peers.count > 0 ? &peers.m[0] : &pr.tmap_c,
-                         pr.c_seg_len, pr.c_seg_len < kBlockM ? pr.c_seg_len : kBlockM, pr.c_seg_len != 0 ? pr.M / pr.c_seg_len : 0,
-                         peers.count > 0 ? peers.count : 1, row_tile0, Cfg::kOutBufs, static_cast<uint32_t>(2 + half),
-                         quarter == 0 && lane == 0};
-      stored = stored || pr.use_tma_store;
+      const OutStage out{pr.use_tma_store ? s_out + half * Cfg::kOutBufs * kOutSlabBytes : nullptr, slab_full_bar + half * Cfg::kOutBufs,
+                         slab_empty_bar + half * Cfg::kOutBufs, Cfg::kOutBufs, slab_seq};
+      if (pr.use_tma_store) slab_seq += kTileN / 2 / 64;            // slabs per tile and column half
       epilogue_tile<kTileN>(pr.ep, pr.M, pr.N, tmem_base + static_cast<uint32_t>(acc * kTileN), row, t.n_blk * kTileN, quarter, half, s_col,
                             out, [&]() {
                               tcgen05_fence_before();
@@ -768,13 +781,9 @@ tp_gemm2_kernel(const __grid_constant__ GemmGroup grp, const __grid_constant__ P
                                 if (is_leader) mbar_arrive(release_bar);
                                 else mbar_arrive_cluster(release_bar, 0);
                               }
-                            }, pc);
+                            }, pc, static_cast<long long>(t.split) * pr.c_split_stride);
       TP_PROF_ADD(t_work);
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
-    }
-    if (stored && quarter == 0 && lane == 0) {
-      bulk_wait_group<0>();                      // my half's last TMA stores have been performed
-      if (peers.count > 0) __threadfence_system();   // ... and are ordered before the cross-GPU barrier that follows the kernel
     }
 #ifdef TP_GEMM_PROFILE
     if (grp.p[0].ep.prof != nullptr && e == 0 && lane == 0) {
@@ -785,6 +794,68 @@ tp_gemm2_kernel(const __grid_constant__ GemmGroup grp, const __grid_constant__ P
       grp.p[0].ep.prof[blockIdx.x * 16 + 10] = pc[2];          // ... in wait_group.read + named barrier
     }
 #endif
+  }
+
+  if (warp_idx == kStoreWarp0 || warp_idx == kStoreWarp0 + 1) {
+    // ======================================= store warps (both CTAs, one per column half) =========
+    // Walks the same tile sequence as the epilogue warps of its half.  Per slab: wait until the 4 epilogue warps have written
+    // it (mbarrier), issue the TMA store(s) — plain 2-D box, clipped 3-D boxes for segmented rows, one per peer GPU for the
+    // fused all-gather —, wait until the copy engine has READ the buffer and hand it back.  Per tile of a GEMM that others in
+    // this launch depend on: wait for the stores to be PERFORMED, then publish the tile (release) on its row block's counter.
+    const int half = warp_idx - kStoreWarp0;
+    uint64_t* full = slab_full_bar + half * Cfg::kOutBufs;
+    uint64_t* empty = slab_empty_bar + half * Cfg::kOutBufs;
+    uint32_t q = 0;
+    for (int tile = pair_idx; tile < num_tiles; tile += num_pairs) {
+      const TileRef t = decode_tile(grp, tile);
+      const GemmProblem& pr = *t.pr;
+      if (!pr.use_tma_store) continue;
+      const int row_tile0 = t.m_blk * Cfg::kTileM + static_cast<int>(cta_rank) * kBlockM;
+      const bool to_peers = pr.peer_out != 0 && peers.count > 0;
+      const CUtensorMap* maps = to_peers ? &peers.m[0] : &pr.tmap_c;
+      const int n_maps = to_peers ? peers.count : 1;
+      for (int slab = 0; slab < kTileN / 2 / 64; ++slab, ++q) {
+        const uint32_t buf = q & static_cast<uint32_t>(Cfg::kOutBufs - 1);
+        mbar_wait(&full[buf], (q >> (Cfg::kOutBufs - 1)) & 1u);
+        if (elect_one()) {
+          const uint8_t* src = s_out + (half * Cfg::kOutBufs + static_cast<int>(buf)) * kOutSlabBytes;
+          const int col = t.n_blk * kTileN + half * (kTileN / 2) + slab * 64;
+          if (pr.c_seg_len == 0) {
+            for (int p = 0; p < n_maps; ++p) tma_store_2d(maps + p, src, col, row_tile0);
+          } else {
+            // Segmented output rows (global row g = seg * seg_len + r  ->  map coordinate (col, r, seg)): the slab's 128 rows are
+            // cut at segment boundaries and each piece leaves through the SAME fixed-size box.  A piece that starts before the slab
+            // or ends after it is positioned so that the surplus box rows fall outside [0, seg_len) of its segment, where TMA clips
+            // them (signed coordinates): src_row = clamp(a, 0, 128 - box), r0 = src_row - a, a = slab row of the segment's row 0.
+            // The 128B swizzle is a function of the absolute shared-memory address, so any 128-byte-aligned source row works.
+            const int seg_box = pr.c_seg_len < kBlockM ? pr.c_seg_len : kBlockM;
+            const int n_segs = pr.M / pr.c_seg_len;
+            int seg = row_tile0 / pr.c_seg_len;
+            for (int a = seg * pr.c_seg_len - row_tile0; a < kBlockM && seg < n_segs; a += pr.c_seg_len, ++seg) {
+              const int src_row = min(max(a, 0), kBlockM - seg_box);
+              for (int p = 0; p < n_maps; ++p) tma_store_3d(maps + p, src + src_row * 128, col, src_row - a, seg);
+            }
+          }
+          bulk_commit_group();
+          bulk_wait_group_read<0>();               // the buffer has been read: the epilogue warps may overwrite it
+          mbar_arrive(&empty[buf]);
+        }
+        __syncwarp();
+      }
+      if (pr.done_counter != nullptr) {
+        if (elect_one()) {
+          bulk_wait_group<0>();                    // this CTA-half's part of the tile is in global memory ...
+          fence_proxy_async_all();                 // ... (async-proxy writes) ordered before the generic-proxy release below
+          red_release_gpu_add(pr.done_counter + t.m_blk, 1);
+        }
+        __syncwarp();
+      }
+    }
+    if (elect_one()) {
+      bulk_wait_group<0>();                        // my half's last TMA stores have been performed
+      if (peers.count > 0) __threadfence_system(); // ... and are ordered before the cross-GPU barrier that follows the kernel
+    }
+    __syncwarp();
   }
 
   tcgen05_fence_before();

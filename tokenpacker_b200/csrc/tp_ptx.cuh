@@ -348,6 +348,35 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar, uint16_t cta_mas
 __device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void grid_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+// ------------------------------------------------------------------------------------------------
+// Cross-CTA tile counters in global memory (dependencies between GEMMs of one persistent launch)
+// ------------------------------------------------------------------------------------------------
+// Orders async-proxy accesses (TMA loads / stores) with the generic-proxy ones around it, all state spaces.
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+__device__ __forceinline__ void red_release_gpu_add(int* p, int v) {
+  asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// Bounded like every other spin of the library: a protocol bug must trap, never hang the GPU.
+__device__ __forceinline__ void wait_counter_at_least(const int* p, int target) {
+  if (ld_acquire_gpu(p) >= target) return;
+  const long long t0 = clock64();
+  while (ld_acquire_gpu(p) < target) {
+    __nanosleep(64);
+    if (clock64() - t0 > TP_SPIN_LIMIT_CYCLES) {
+      printf("tokenpacker_b200: tile-counter wait timed out (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
+      __trap();
+    }
+  }
+}
+
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
