@@ -162,7 +162,9 @@ struct GemmItem {
   int* done_counter = nullptr;     // filled by launch_chain
   const int* dep_counter = nullptr;
   int dep_target = 0;
+  int dep_shift = 0;
 };
+constexpr int kDepFront = -2;      // GemmItem::dep: the A operand is the point-query output of the launch's front work
 
 int check_item(const GemmItem& it) {
   if (it.M <= 0 || it.N <= 0 || it.K <= 0 || it.N % 32 != 0 || it.M > 0x7fffff00ll) return TP_ERR_INVALID_ARGUMENT;   // K: any (TMA zero-fills)
@@ -204,7 +206,7 @@ int launch_gemm_t(const GemmItem& it, int sms, cudaStream_t stream) {
 }
 
 // Up to kMaxGroup independent problems in ONE launch of the CTA-pair kernel.
-int launch_gemm_pair_group(const GemmItem* items, int count, int sms, cudaStream_t stream) {
+int launch_gemm_pair_group(const GemmItem* items, int count, int sms, cudaStream_t stream, const FrontWork* front = nullptr) {
   using Cfg = Gemm2Config;
   GemmGroup g;
   memset(&g, 0, sizeof(g));
@@ -264,6 +266,7 @@ int launch_gemm_pair_group(const GemmItem* items, int count, int sms, cudaStream
     p.done_counter = it.done_counter;
     p.dep_counter = it.dep_counter;
     p.dep_target = it.dep_target;
+    p.dep_shift = it.dep_shift;
     if ((p.done_counter != nullptr && !p.use_tma_store) || (p.dep_counter != nullptr && (it.tn || it.a.seg_rows != 0)))
       return TP_ERR_INVALID_ARGUMENT;          // tile counters are published by the store warps / index plain 256-row blocks of A
     p.peer_out = it.n_peers > 0 ? 1 : 0;
@@ -271,6 +274,7 @@ int launch_gemm_pair_group(const GemmItem* items, int count, int sms, cudaStream
   }
   if (total > 0x7fffffffll) return TP_ERR_INVALID_ARGUMENT;
   g.total_tiles = static_cast<int>(total);
+  if (front != nullptr) g.front = *front;
   PeerStores peers;
   memset(&peers, 0, sizeof(peers));
   int peer_item = -1;
@@ -302,6 +306,8 @@ int launch_gemm_pair_group(const GemmItem* items, int count, int sms, cudaStream
   }
   const long long max_pairs = sms / 2;
   const int grid = 2 * static_cast<int>(total < max_pairs ? total : max_pairs);
+  for (int i = 0; i < count; ++i)
+    if (g.p[i].dep_shift == 31) g.p[i].dep_target = grid;        // front work: one arrival per CTA of this launch
   TP_CUDA(launch_pdl(tp_gemm2_kernel, dim3(grid), dim3(kGemmThreads), Cfg::kSmemBytes, stream, g, peers));
   return TP_OK;
 }
@@ -371,24 +377,39 @@ int launch_gemms(const GemmItem* items, int count, int sms, cudaStream_t stream)
   return TP_OK;
 }
 
-// A chain of dependent GEMM stages (items sorted by stage; items[i].dep names the producer of items[i]'s A operand).
-// When every item lands on the CTA-pair kernel the whole chain is ONE persistent launch: tiles are numbered stage after stage,
-// consumers wait on per-row-block tile counters (``flags``, zeroed by the caller earlier on the stream) instead of on kernel
-// boundaries, so there is no ramp, drain or partial last wave between the linears.  Otherwise (small problems on one-CTA
-// tiles, TP_CHAIN=0, forced modes) the stages run as separate launches exactly as before; either way the bits are the same.
-int launch_chain(GemmItem* items, int count, int* flags, long long flag_capacity, int sms, cudaStream_t stream) {
+int launch_front_s(int s, const __nv_bfloat16* x0, long long x0_stride, __nv_bfloat16* q, long long Q, cudaStream_t stream);
+
+// A chain of dependent GEMM stages (items sorted by stage; items[i].dep names the producer of items[i]'s A operand, kDepFront =
+// the point queries described by ``front``).  When every item lands on the CTA-pair kernel the whole chain is ONE persistent
+// launch: tiles are numbered stage after stage, consumers wait on per-row-block tile counters (``flags``, zeroed earlier on the
+// stream) instead of on kernel boundaries — no ramp, drain or partial last wave between the linears — and the point queries are
+// computed by the epilogue warps while the first accumulators are still being produced.  Otherwise (small problems on one-CTA
+// tiles, TP_CHAIN=0, forced modes) the point queries and the stages run as separate launches exactly as before; either way the
+// bits are the same.
+int launch_chain(GemmItem* items, int count, int* flags, long long flag_capacity, const FrontWork* front, int sms, cudaStream_t stream) {
   if (count <= 0 || count > kMaxGroup) return TP_ERR_INVALID_ARGUMENT;
   const int mode = gemm_mode();
   static const bool chain_off = [] { const char* e = getenv("TP_CHAIN"); return e != nullptr && atoi(e) == 0; }();
   bool chain = !chain_off && flags != nullptr && (mode == 0 || mode == 2);
-  for (int i = 0; i < count && chain; ++i) {
-    // the chain is one launch: its ramp / drain is shared by all `count` items
-    if (check_item(items[i]) != TP_OK || choose_kernel(items[i], count, sms, mode) != 0 || items[i].ep.seg_row_offset != nullptr) chain = false;
+  for (int i = 0; i < count; ++i) {
     const int d = items[i].dep;
-    if (d >= 0 && (d >= i || items[d].stage >= items[i].stage || items[d].M != items[i].M || items[i].a.seg_rows != 0)) return TP_ERR_INVALID_ARGUMENT;
+    if (d == kDepFront ? front == nullptr
+                       : (d >= 0 && (d >= i || items[d].stage >= items[i].stage || items[d].M != items[i].M || items[i].a.seg_rows != 0)))
+      return TP_ERR_INVALID_ARGUMENT;
+    // the chain is one launch: its ramp / drain is shared by all `count` items
+    if (chain && (check_item(items[i]) != TP_OK || choose_kernel(items[i], count, sms, mode) != 0 || items[i].ep.seg_row_offset != nullptr))
+      chain = false;
   }
   if (chain) {
     long long used = 0;
+    FrontWork fw;
+    memset(&fw, 0, sizeof(fw));
+    if (front != nullptr) {
+      if (used + 1 > flag_capacity) return TP_ERR_WORKSPACE_TOO_SMALL;
+      fw = *front;
+      fw.done_counter = flags + used;
+      used += 1;
+    }
     for (int i = 0; i < count; ++i) {
       bool produces = false;
       for (int j = 0; j < count; ++j) produces = produces || items[j].dep == i;
@@ -400,12 +421,17 @@ int launch_chain(GemmItem* items, int count, int* flags, long long flag_capacity
     }
     for (int i = 0; i < count; ++i) {
       const int d = items[i].dep;
-      if (d < 0) continue;
-      items[i].dep_counter = items[d].done_counter;
-      items[i].dep_target = 4 * static_cast<int>((items[d].N + 255) / 256);     // 2 CTAs x 2 column halves per producer tile
+      if (d == kDepFront) {
+        items[i].dep_counter = fw.done_counter;
+        items[i].dep_shift = 31;                                                 // one launch-wide counter; target = grid size
+      } else if (d >= 0) {
+        items[i].dep_counter = items[d].done_counter;
+        items[i].dep_target = 4 * static_cast<int>((items[d].N + 255) / 256);   // 2 CTAs x 2 column halves per producer tile
+      }
     }
-    return launch_gemm_pair_group(items, count, sms, stream);
+    return launch_gemm_pair_group(items, count, sms, stream, front != nullptr ? &fw : nullptr);
   }
+  if (front != nullptr) TP_TRY(launch_front_s(front->s, front->x0, front->crop_stride, front->q, front->n_queries, stream));
   for (int first = 0; first < count;) {
     int last = first;
     while (last + 1 < count && items[last + 1].stage == items[first].stage) ++last;
@@ -502,7 +528,7 @@ WorkLayout work_layout(long long n_crops, int s, int H) {
   L.stats = take((2 * R + Q) * kStatSlots * 2 * 4);
   L.q = take(Q * kC * 2); L.y_q = take(Q * kC * 2); L.q_p = take(Q * kC * 2); L.ctx = take(Q * kC * 2);
   L.h_m = take(Q * static_cast<size_t>(H) * 2);
-  L.n_flags = 3 * static_cast<long long>((R + 255) / 256) + 2 * static_cast<long long>((Q + 255) / 256);
+  L.n_flags = 3 * static_cast<long long>((R + 255) / 256) + 2 * static_cast<long long>((Q + 255) / 256) + 1;
   L.flags = take(static_cast<size_t>(L.n_flags) * 4);
   L.total = off;
   return L;
@@ -511,10 +537,9 @@ WorkLayout work_layout(long long n_crops, int s, int H) {
 bool valid_hidden(int H) { return H >= 32 && H % 32 == 0 && H <= 65536; }
 
 template <int S>
-int launch_front(const __nv_bfloat16* x0, long long x0_stride, __nv_bfloat16* q, long long Q, int* flags, int n_flags, cudaStream_t stream) {
+int launch_front(const __nv_bfloat16* x0, long long x0_stride, __nv_bfloat16* q, long long Q, cudaStream_t stream) {
   const long long threads = Q * 128;
-  TP_CUDA(launch_pdl(point_query_kernel<S>, dim3(static_cast<unsigned>((threads + 255) / 256)), dim3(256), 0, stream, x0, x0_stride, q, Q, flags,
-                     n_flags));
+  TP_CUDA(launch_pdl(point_query_kernel<S>, dim3(static_cast<unsigned>((threads + 255) / 256)), dim3(256), 0, stream, x0, x0_stride, q, Q));
   return TP_OK;
 }
 
@@ -528,17 +553,16 @@ int launch_attn(const __nv_bfloat16* qp, const __nv_bfloat16* kp, const __nv_bfl
 
 // scale_factor dispatch: every divisor of 24 (builder.py:51-52).  2 / 3 / 4 (the released 144 / 64 / 36-token models) keep
 // the window in registers; the others stream it.
-int launch_front_s(int s, const __nv_bfloat16* x0, long long x0_stride, __nv_bfloat16* q, long long Q, int* flags, int n_flags,
-                   cudaStream_t stream) {
+int launch_front_s(int s, const __nv_bfloat16* x0, long long x0_stride, __nv_bfloat16* q, long long Q, cudaStream_t stream) {
   switch (s) {
-    case 1: return launch_front<1>(x0, x0_stride, q, Q, flags, n_flags, stream);
-    case 2: return launch_front<2>(x0, x0_stride, q, Q, flags, n_flags, stream);
-    case 3: return launch_front<3>(x0, x0_stride, q, Q, flags, n_flags, stream);
-    case 4: return launch_front<4>(x0, x0_stride, q, Q, flags, n_flags, stream);
-    case 6: return launch_front<6>(x0, x0_stride, q, Q, flags, n_flags, stream);
-    case 8: return launch_front<8>(x0, x0_stride, q, Q, flags, n_flags, stream);
-    case 12: return launch_front<12>(x0, x0_stride, q, Q, flags, n_flags, stream);
-    case 24: return launch_front<24>(x0, x0_stride, q, Q, flags, n_flags, stream);
+    case 1: return launch_front<1>(x0, x0_stride, q, Q, stream);
+    case 2: return launch_front<2>(x0, x0_stride, q, Q, stream);
+    case 3: return launch_front<3>(x0, x0_stride, q, Q, stream);
+    case 4: return launch_front<4>(x0, x0_stride, q, Q, stream);
+    case 6: return launch_front<6>(x0, x0_stride, q, Q, stream);
+    case 8: return launch_front<8>(x0, x0_stride, q, Q, stream);
+    case 12: return launch_front<12>(x0, x0_stride, q, Q, stream);
+    case 24: return launch_front<24>(x0, x0_stride, q, Q, stream);
     default: return TP_ERR_BAD_SCALE_FACTOR;
   }
 }
@@ -696,7 +720,7 @@ int forward_impl(const void* packed, const void* x0, const void* xm, const void*
   // Launch plan.  Large batches: 4 launches — [S], chain A = {[1], [2], [3]} and chain B = {[4], [5]} as ONE persistent CTA-pair
   // launch each (stages ordered by per-row-block tile counters instead of kernel boundaries), [A] in between.  Small batches
   // (one-CTA tiles win): the same stages as separate launches.
-  //   [S] point queries            builder.py:117-118   (+ resets the tile counters)
+  //   [S] point queries            builder.py:117-118   (inside chain A: done by the epilogue warps before their first tile)
   //   [1] h_kv = GELU(xm [W_k0;W_v0]^T + b)                                 :112-113 first linears, xm read once
   //   [2] y_k | y_v | y_q   = second linears k/v + q_proj_1 (+ row statistics for the LayerNorms)   :112-113, :120
   //   [3] k'  | v'  | q'    = LayerNorm folded into the MHA in-projections (q' scaled by 1/sqrt 128)   MHA in_proj
@@ -705,10 +729,14 @@ int forward_impl(const void* packed, const void* x0, const void* xm, const void*
   //   [5] out = h_m W_m2^T + b_m2  -> final [N,M,H] (or packed HD) layout    :136
   int* flags = reinterpret_cast<int*>(ws + W.flags);
   const long long flags_a = 3 * ((R + 255) / 256);          // chain A: [1], [2]k, [2]v produce for later stages ([2]q: Q rows, below)
-  {
-    const __nv_bfloat16* x0p = static_cast<const __nv_bfloat16*>(x0);
-    TP_TRY(launch_front_s(s, x0p, x0_crop_stride, bf(W.q), Q, flags, static_cast<int>(W.n_flags), stream));
-  }
+  TP_CUDA(cudaMemsetAsync(flags, 0, static_cast<size_t>(W.n_flags) * 4, stream));      // tile counters of the chained launches
+  FrontWork front;
+  memset(&front, 0, sizeof(front));
+  front.x0 = static_cast<const __nv_bfloat16*>(x0);
+  front.q = bf(W.q);
+  front.crop_stride = x0_crop_stride;
+  front.n_queries = Q;
+  front.s = s;
   // k' / v' have buffers of their own: in a chained launch [3] runs while other row blocks of [2] still read h_kv, so the
   // round-1 trick of writing them over the dead h_kv buffer is no longer legal
   __nv_bfloat16* k_p = bf(W.k_p);
@@ -734,6 +762,7 @@ int forward_impl(const void* packed, const void* x0, const void* xm, const void*
     g[3].ep.stats_out_slots = kStatSlots;
     g[1].stage = g[2].stage = g[3].stage = 1;
     g[1].dep = g[2].dep = 0;
+    g[3].dep = kDepFront;
     g[4] = GemmItem{AOperand{bf(W.y_k), kC, 0, 0}, P + L.w_ik, kC, R, kC, kC, plain_epilogue(k_p, kC, wf(L.c_k), 0)};
     g[4].ep.col_a = wf(L.wsum_k);
     g[4].ep.stats_in = stats_k;
@@ -751,7 +780,7 @@ int forward_impl(const void* packed, const void* x0, const void* xm, const void*
     g[4].dep = 1;
     g[5].dep = 2;
     g[6].dep = 3;
-    TP_TRY(launch_chain(g, 7, flags, flags_a + (Q + 255) / 256, dev.sms, stream));
+    TP_TRY(launch_chain(g, 7, flags, flags_a + (Q + 255) / 256 + 1, &front, dev.sms, stream));
   }
   TP_TRY(launch_attn_s(s, bf(W.q_p), k_p, v_p, bf(W.ctx), Q, stream));
   {
@@ -772,8 +801,8 @@ int forward_impl(const void* packed, const void* x0, const void* xm, const void*
     g[1].n_peers = n_peers;
     g[1].stage = 1;
     g[1].dep = 0;
-    int* flags_b = flags + flags_a + (Q + 255) / 256;
-    TP_TRY(launch_chain(g, 2, flags_b, (Q + 255) / 256, dev.sms, stream));
+    int* flags_b = flags + flags_a + (Q + 255) / 256 + 1;
+    TP_TRY(launch_chain(g, 2, flags_b, (Q + 255) / 256, nullptr, dev.sms, stream));
   }
   return TP_OK;
 }

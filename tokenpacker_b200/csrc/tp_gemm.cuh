@@ -515,16 +515,33 @@ struct GemmProblem {
   // tile only ever waits for lower-numbered tiles: no deadlock as long as all pairs are co-resident (grid <= 74 pairs).
   int* done_counter;     // != nullptr: [ceil(M/256)] tile counter of THIS problem's output row blocks, +1 per (CTA, column half)
                          //             once that part of a tile is in global memory (bumped by the store warps)
-  const int* dep_counter;// != nullptr: the A operand's row block m_blk is ready when dep_counter[m_blk] >= dep_target
+  const int* dep_counter;// != nullptr: the A operand's row block m_blk is ready when dep_counter[m_blk >> dep_shift] >= dep_target
   int dep_target;        //             (= 4 * num_n_blocks of the producing problem: 2 CTAs x 2 column halves per tile)
+  int dep_shift;         //             0 for GEMM -> GEMM (same row blocks); 31 for a single launch-wide counter (front work)
   int peer_out;          // C of this problem goes to the PeerStores maps (fused all-gather) instead of tmap_c
   GemmEpilogue ep;
+};
+
+// Optional prologue work of a chained launch: the point queries (builder.py:117-118: bilinear 24x24 -> g x g, align_corners=False
+// == a fixed stencil per s x s window: the centre token for odd s, the mean of the centre 2x2 for even s; fp32, one bf16 rounding).
+// Done by the epilogue warps of every CTA BEFORE their first tile — that time is otherwise idle (the first accumulator of the
+// K=4096 GEMM takes ~33k cycles to appear), so the stencil costs nothing and needs no launch of its own.  Every CTA handles a
+// strided share of the (query, 8-channel vector) items and then bumps done_counter once; the GEMM that reads q waits for
+// gridDim.x arrivals.
+struct FrontWork {
+  const __nv_bfloat16* x0;   // nullptr: no front work in this launch
+  __nv_bfloat16* q;          // [n_queries, 1024]
+  long long crop_stride;     // elements between crops of x0
+  long long n_queries;
+  int s;                     // scale factor
+  int* done_counter;
 };
 
 struct GemmGroup {
   GemmProblem p[kMaxGroup];
   int count;
   int total_tiles;
+  FrontWork front;
 };
 
 struct TileRef {
@@ -630,7 +647,7 @@ tp_gemm2_kernel(const __grid_constant__ GemmGroup grp, const __grid_constant__ P
       if (pr.dep_counter != nullptr) {
         // A's row block is written by an earlier GEMM of this launch: wait until all its tiles have been published (acquire), then
         // order the TMA (async proxy) reads after the acquire
-        wait_counter_at_least(pr.dep_counter + t.m_blk, pr.dep_target);
+        wait_counter_at_least(pr.dep_counter + (t.m_blk >> pr.dep_shift), pr.dep_target);
         fence_proxy_async_all();
       }
       int seg0 = 0, srow0 = 0, seg1 = 0, srow1 = 0;
@@ -755,6 +772,39 @@ tp_gemm2_kernel(const __grid_constant__ GemmGroup grp, const __grid_constant__ P
     uint32_t slab_seq = 0;
     [[maybe_unused]] long long w_acc = 0, t_work = 0;
     [[maybe_unused]] long long pc[3] = {0, 0, 0};
+    if (grp.front.x0 != nullptr) {
+      // point queries: this CTA's share of the (query, 8-channel vector) items, 128 vectors per query
+      const FrontWork& fw = grp.front;
+      const int g = 24 / fw.s, mq = g * g;
+      const int lo = (fw.s & 1) ? (fw.s - 1) / 2 : fw.s / 2 - 1;          // first tap inside the window (row and column)
+      const long long items = fw.n_queries * 128;
+      for (long long idx = static_cast<long long>(blockIdx.x) * kEpiThreads + epi_tid; idx < items; idx += static_cast<long long>(gridDim.x) * kEpiThreads) {
+        const long long query = idx >> 7;
+        const int vec = static_cast<int>(idx & 127);
+        const long long n = query / mq;
+        const int m = static_cast<int>(query - n * mq);
+        const int hb = m / g, wb = m - hb * g;
+        const __nv_bfloat16* base = fw.x0 + n * fw.crop_stride + vec * 8 + static_cast<long long>((hb * fw.s + lo) * 24 + wb * fw.s + lo) * 1024;
+        uint4 o = __ldg(reinterpret_cast<const uint4*>(base));
+        if (!(fw.s & 1)) {
+          const uint4 b = __ldg(reinterpret_cast<const uint4*>(base + 1024)), c = __ldg(reinterpret_cast<const uint4*>(base + 24 * 1024)),
+                      d = __ldg(reinterpret_cast<const uint4*>(base + 25 * 1024));
+          // 0.25 * ((a + b) + (c + d)): the association of point_query_kernel (bit-identical; power-of-two scaling is exact)
+          auto mean4 = [](uint32_t a_, uint32_t b_, uint32_t c_, uint32_t d_) {
+            const float l = 0.25f * ((bf16_lo(a_) + bf16_lo(b_)) + (bf16_lo(c_) + bf16_lo(d_)));
+            const float h = 0.25f * ((bf16_hi(a_) + bf16_hi(b_)) + (bf16_hi(c_) + bf16_hi(d_)));
+            return pack_bf16x2(l, h);
+          };
+          o = make_uint4(mean4(o.x, b.x, c.x, d.x), mean4(o.y, b.y, c.y, d.y), mean4(o.z, b.z, c.z, d.z), mean4(o.w, b.w, c.w, d.w));
+        }
+        *reinterpret_cast<uint4*>(fw.q + query * 1024 + vec * 8) = o;
+      }
+      named_bar_sync(kEpiBarrierId, kEpiThreads);           // every epilogue thread's stores are issued ...
+      if (epi_tid == 0) {
+        __threadfence();                                     // ... and ordered (cumulatively) before the release below
+        red_release_gpu_add(fw.done_counter, 1);
+      }
+    }
     for (int tile = pair_idx; tile < num_tiles; tile += num_pairs) {
       const TileRef t = decode_tile(grp, tile);
       const GemmProblem& pr = *t.pr;

@@ -32,15 +32,11 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 // ------------------------------------------------------------------------------------------------
 template <int S>
 __global__ void point_query_kernel(const __nv_bfloat16* __restrict__ x0, long long crop_stride, __nv_bfloat16* __restrict__ q,
-                                   long long n_queries, int* __restrict__ flags, int n_flags) {
+                                   long long n_queries) {
   constexpr int G = kGrid / S;
   constexpr int M = G * G;
   grid_dependency_wait();        // PDL: inputs may come from the previous kernel on the stream
   grid_launch_dependents();
-  // first kernel of every forward: also resets the tile counters of the chained GEMM launches that follow on the stream (they read
-  // them only after their own griddepcontrol.wait, i.e. after this grid has completed)
-  if (blockIdx.x == 0 && flags != nullptr)
-    for (int i = threadIdx.x; i < n_flags; i += blockDim.x) flags[i] = 0;
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long long query = idx >> 7;          // 128 vectors of 8 channels per query
   const int vec = static_cast<int>(idx & 127);

@@ -173,7 +173,7 @@ int tp_forward_train(const void* packed, const void* x0, const void* xm, int64_t
 
   {
     const __nv_bfloat16* x0p = static_cast<const __nv_bfloat16*>(x0);
-    TP_TRY(launch_front_s(s, x0p, x0_crop_stride, bf(S.q), Q, nullptr, 0, stream));
+    TP_TRY(launch_front_s(s, x0p, x0_crop_stride, bf(S.q), Q, stream));
   }
   {
     AOperand a{xm, kCm, 0, 0};
