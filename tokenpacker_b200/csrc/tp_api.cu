@@ -100,6 +100,31 @@ int make_map_3d(CUtensorMap* map, const void* ptr, long long segs, long long seg
   return TP_OK;
 }
 
+// Window-major destination of a raster-ordered [crops * 576, cols] bf16 matrix (scale factor s, g = 24 / s): dims
+// (channel, wi, wb, hi, crop-and-hb), box = 64 channels x s x g x 1 x 1 = one token row of 24 tokens.
+int make_map_wm(CUtensorMap* map, const void* ptr, long long rows, long long cols, long long ld, int s) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (fn == nullptr) {
+    snprintf(g_last_cuda_error, sizeof(g_last_cuda_error), "cuTensorMapEncodeTiled entry point not found");
+    return TP_ERR_CUDA;
+  }
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0 || (ld * 2) % 16 != 0 || rows % 576 != 0 || (s != 2 && s != 4 && s != 8)) return TP_ERR_INVALID_ARGUMENT;
+  const int g = 24 / s;
+  cuuint64_t dims[5] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(s), static_cast<cuuint64_t>(g), static_cast<cuuint64_t>(s),
+                        static_cast<cuuint64_t>(rows / 576 * g)};
+  const cuuint64_t row_b = static_cast<cuuint64_t>(ld) * 2;
+  cuuint64_t strides[4] = {row_b, row_b * s * s, row_b * s, row_b * s * s * g};
+  cuuint32_t box[5] = {static_cast<cuuint32_t>(kBlockK), static_cast<cuuint32_t>(s), static_cast<cuuint32_t>(g), 1, 1};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    snprintf(g_last_cuda_error, sizeof(g_last_cuda_error), "cuTensorMapEncodeTiled(5d) failed: %d", static_cast<int>(r));
+    return TP_ERR_CUDA;
+  }
+  return TP_OK;
+}
+
 struct DeviceInfo {
   int sms;
 };
@@ -155,6 +180,13 @@ struct GemmItem {
   void* const* peer_c = nullptr;   // fused all-gather: the same output slot in every peer's gathered buffer
   int n_peers = 0;
   int tn = 0;                      // 1: C[M,N] = A^T . B with A given as [K, M] (ld = a.ld) and B as [K, N] (ld = ldb), both row-major
+  // kind 1 (KV-attention, pair kernel only): a / b = y_k (window-major rows) and the gamma-folded W_ik; a2 / b2 = y_v and W_iv;
+  // M = rows of y_k, N = K = 1024; attn holds everything else; dep / dep2 / dep3 = the producers of y_k, y_v and q'
+  int kind = 0;
+  const void* a2 = nullptr;
+  const void* b2 = nullptr;
+  AttnParams attn = {};
+  int dep2 = -1, dep3 = -1;
   int k_splits = 1;                // > 1: split-K; ep.c must then be a float buffer [k_splits][M, ldc] (ep.out_f32 = 1, pair kernel only)
   // chains (launch_chain): GEMMs of consecutive stages in ONE persistent launch, ordered by per-row-block tile counters
   int stage = 0;                   // items of equal stage are independent of each other
@@ -163,10 +195,12 @@ struct GemmItem {
   const int* dep_counter = nullptr;
   int dep_target = 0;
   int dep_shift = 0;
+  int dep_span = 0, dep_src_blocks = 0, dep_per = 0;     // producer is a KV-attention item (see GemmProblem)
 };
 constexpr int kDepFront = -2;      // GemmItem::dep: the A operand is the point-query output of the launch's front work
 
 int check_item(const GemmItem& it) {
+  if (it.kind == 1) return (it.M > 0 && it.M % 16 == 0 && it.attn.qp != nullptr && it.attn.ctx != nullptr) ? TP_OK : TP_ERR_INVALID_ARGUMENT;
   if (it.M <= 0 || it.N <= 0 || it.K <= 0 || it.N % 32 != 0 || it.M > 0x7fffff00ll) return TP_ERR_INVALID_ARGUMENT;   // K: any (TMA zero-fills)
   if ((reinterpret_cast<uintptr_t>(it.ep.c) & 15) != 0 || (it.ep.ldc * 2) % 16 != 0) return TP_ERR_INVALID_ARGUMENT;
   if (it.k_splits < 1 || (it.k_splits > 1 && !it.ep.out_f32) || (it.ep.out_f32 && (it.ep.seg_row_offset != nullptr || it.ep.seg_stride != 0)))
@@ -215,6 +249,28 @@ int launch_gemm_pair_group(const GemmItem* items, int count, int sms, cudaStream
   for (int i = 0; i < count; ++i) {
     const GemmItem& it = items[i];
     GemmProblem& p = g.p[i];
+    if (it.kind == 1) {
+      if (it.N != kC || it.K != kC || it.a2 == nullptr || it.b2 == nullptr || (it.attn.s != 2 && it.attn.s != 4)) return TP_ERR_INVALID_ARGUMENT;
+      TP_TRY(make_map_2d(&p.tmap_a, it.a.ptr, it.M, it.K, it.a.ld, kBlockM));
+      TP_TRY(make_map_2d(&p.tmap_a2, it.a2, it.M, it.K, it.a.ld, kBlockM));
+      TP_TRY(make_map_2d(&p.tmap_b, it.b, it.N, it.K, it.ldb, 64));           // 64 of the head's 128 weight rows per CTA
+      TP_TRY(make_map_2d(&p.tmap_b2, it.b2, it.N, it.K, it.ldb, 64));
+      p.kind = 1;
+      p.attn = it.attn;
+      p.a_parts = 1;
+      p.M = static_cast<int>(it.M);
+      p.N = static_cast<int>(it.N);
+      p.K = static_cast<int>(it.K);
+      p.num_n_blocks = 8;                                                      // one tile column per head
+      p.num_k_blocks = static_cast<int>(it.K / kBlockK);
+      p.tiles_mn = static_cast<int>((it.M + Cfg::kTileM - 1) / Cfg::kTileM) * p.num_n_blocks;
+      p.k_splits = 1;
+      p.kb_per_split = p.num_k_blocks;
+      p.num_tiles = p.tiles_mn;
+      p.dep_counter = nullptr;                                                 // its dependencies live in attn.{k,v,q}_counter
+      total += p.num_tiles;
+      continue;
+    }
     if (it.tn) {
       // row-major [K, M] / [K, N] operands: box = 64 MN-elements x 64 K-rows
       TP_TRY(make_map_2d(&p.tmap_a, it.a.ptr, it.K, it.M, it.a.ld, 64));
@@ -242,7 +298,11 @@ int launch_gemm_pair_group(const GemmItem* items, int count, int sms, cudaStream
     // uniformly strided segments (the HD packed layout) stay on the TMA path through a 3-D (cols, row in segment, segment) map
     p.use_tma_store = (it.ep.seg_row_offset == nullptr && !it.ep.out_f32) ? 1 : 0;
     const bool c_segmented = p.use_tma_store && it.ep.seg_stride != 0 && it.ep.seg_stride != it.ep.seg_len;
-    if (c_segmented) {
+    if (it.ep.wm_s != 0) {
+      if (!p.use_tma_store || c_segmented || it.n_peers > 0) return TP_ERR_INVALID_ARGUMENT;
+      p.c_wm_s = it.ep.wm_s;
+      TP_TRY(make_map_wm(&p.tmap_c, it.ep.c, it.M, it.N, it.ep.ldc, it.ep.wm_s));
+    } else if (c_segmented) {
       if (it.ep.seg_len <= 0 || it.M % it.ep.seg_len != 0 || it.ep.seg_stride < it.ep.seg_len) return TP_ERR_INVALID_ARGUMENT;
       p.c_seg_len = it.ep.seg_len;
       TP_TRY(make_map_3d(&p.tmap_c, it.ep.c, it.M / it.ep.seg_len, it.ep.seg_len, it.N, it.ep.ldc, it.ep.seg_stride * it.ep.ldc,
@@ -267,6 +327,9 @@ int launch_gemm_pair_group(const GemmItem* items, int count, int sms, cudaStream
     p.dep_counter = it.dep_counter;
     p.dep_target = it.dep_target;
     p.dep_shift = it.dep_shift;
+    p.dep_span = it.dep_span;
+    p.dep_src_blocks = it.dep_src_blocks;
+    p.dep_per = it.dep_per;
     if ((p.done_counter != nullptr && !p.use_tma_store) || (p.dep_counter != nullptr && (it.tn || it.a.seg_rows != 0)))
       return TP_ERR_INVALID_ARGUMENT;          // tile counters are published by the store warps / index plain 256-row blocks of A
     p.peer_out = it.n_peers > 0 ? 1 : 0;
@@ -318,7 +381,7 @@ int launch_gemm_pair_group(const GemmItem* items, int count, int sms, cudaStream
 // Returns 0 pair, 1 one-CTA 256, 2 one-CTA 128, or -1 (invalid).
 int choose_kernel(const GemmItem& it, int count, int sms, int mode) {
   const bool pair_ok = (it.N % 256 == 0) && sms >= 2;
-  const bool pair_only = it.n_peers > 0 || it.tn || it.a.parts > 1 || it.k_splits > 1 || it.ep.out_f32;   // pair-kernel-only features
+  const bool pair_only = it.n_peers > 0 || it.tn || it.a.parts > 1 || it.k_splits > 1 || it.ep.out_f32 || it.kind == 1 || it.ep.wm_s != 0;   // pair-kernel-only features
   if (pair_only && !pair_ok) return -1;
   const bool needs_256 = it.ep.stats_out != nullptr;                        // statistics slots assume 256-column tiles
   // Estimated tensor-pipe cycles of each candidate = waves x k-blocks x cycles per k-block.  Large problems always land
@@ -386,20 +449,39 @@ int launch_front_s(int s, const __nv_bfloat16* x0, long long x0_stride, __nv_bfl
 // computed by the epilogue warps while the first accumulators are still being produced.  Otherwise (small problems on one-CTA
 // tiles, TP_CHAIN=0, forced modes) the point queries and the stages run as separate launches exactly as before; either way the
 // bits are the same.
+bool chain_enabled(int mode) {
+  const char* e = getenv("TP_CHAIN");                // A/B aid, read per call: TP_CHAIN=0 -> one launch per stage
+  const bool chain_off = e != nullptr && atoi(e) == 0;
+  return !chain_off && (mode == 0 || mode == 2);
+}
+
+// Can these items run as one chained launch of the pair kernel?  (every item on 256-row pair tiles, nothing scattered to arbitrary
+// rows).  by_cost: additionally require that the size-based kernel choice lands on the pair kernel for every item (chains whose
+// unchained form computes the same bits); without it the chain is taken whenever the pair kernel CAN run it (the fused-attention
+// plan: its results must not depend on the batch size, so neither may the decision).
+bool chain_feasible(const GemmItem* items, int count, int sms, bool by_cost = true) {
+  const int mode = gemm_mode();
+  if (!chain_enabled(mode) || count <= 0 || count > kMaxGroup || sms < 2) return false;
+  for (int i = 0; i < count; ++i) {
+    if (check_item(items[i]) != TP_OK || items[i].ep.seg_row_offset != nullptr || items[i].N % 256 != 0) return false;
+    if (by_cost && choose_kernel(items[i], count, sms, mode) != 0) return false;
+  }
+  return true;
+}
+
 int launch_chain(GemmItem* items, int count, int* flags, long long flag_capacity, const FrontWork* front, int sms, cudaStream_t stream) {
   if (count <= 0 || count > kMaxGroup) return TP_ERR_INVALID_ARGUMENT;
-  const int mode = gemm_mode();
-  static const bool chain_off = [] { const char* e = getenv("TP_CHAIN"); return e != nullptr && atoi(e) == 0; }();
-  bool chain = !chain_off && flags != nullptr && (mode == 0 || mode == 2);
   for (int i = 0; i < count; ++i) {
-    const int d = items[i].dep;
-    if (d == kDepFront ? front == nullptr
-                       : (d >= 0 && (d >= i || items[d].stage >= items[i].stage || items[d].M != items[i].M || items[i].a.seg_rows != 0)))
-      return TP_ERR_INVALID_ARGUMENT;
-    // the chain is one launch: its ramp / drain is shared by all `count` items
-    if (chain && (check_item(items[i]) != TP_OK || choose_kernel(items[i], count, sms, mode) != 0 || items[i].ep.seg_row_offset != nullptr))
-      chain = false;
+    const int deps[3] = {items[i].dep, items[i].dep2, items[i].dep3};
+    for (int d : deps) {
+      if (d == kDepFront ? front == nullptr : (d >= 0 && (d >= i || items[d].stage >= items[i].stage))) return TP_ERR_INVALID_ARGUMENT;
+      // GEMM -> GEMM: the consumer's A row blocks are the producer's C row blocks
+      if (d >= 0 && items[i].kind == 0 && items[d].kind == 0 && (items[d].M != items[i].M || items[i].a.seg_rows != 0)) return TP_ERR_INVALID_ARGUMENT;
+    }
   }
+  bool fused_items = false;
+  for (int i = 0; i < count; ++i) fused_items = fused_items || items[i].kind == 1 || items[i].ep.wm_s != 0;
+  const bool chain = flags != nullptr && chain_feasible(items, count, sms, !fused_items);
   if (chain) {
     long long used = 0;
     FrontWork fw;
@@ -412,25 +494,50 @@ int launch_chain(GemmItem* items, int count, int* flags, long long flag_capacity
     }
     for (int i = 0; i < count; ++i) {
       bool produces = false;
-      for (int j = 0; j < count; ++j) produces = produces || items[j].dep == i;
+      for (int j = 0; j < count; ++j) produces = produces || items[j].dep == i || items[j].dep2 == i || items[j].dep3 == i;
       if (!produces) continue;
-      const long long blocks = (items[i].M + 255) / 256;
+      // a KV-attention item produces ctx: one counter per block of 256 queries; a GEMM: one per block of 256 output rows
+      const long long out_rows = items[i].kind == 1 ? items[i].M / (items[i].attn.s * items[i].attn.s) : items[i].M;
+      const long long blocks = (out_rows + 255) / 256;
       if (used + blocks > flag_capacity) return TP_ERR_WORKSPACE_TOO_SMALL;
       items[i].done_counter = flags + used;
+      if (items[i].kind == 1) {
+        items[i].attn.done_counter = items[i].done_counter;
+        items[i].done_counter = nullptr;            // published by the epilogue warps, not by the store warps
+      }
       used += blocks;
     }
+    auto counter_of = [&](int d) { return items[d].kind == 1 ? items[d].attn.done_counter : items[d].done_counter; };
+    auto gemm_target = [&](int d) { return 4 * static_cast<int>((items[d].N + 255) / 256); };   // 2 CTAs x 2 column halves per tile
     for (int i = 0; i < count; ++i) {
-      const int d = items[i].dep;
+      GemmItem& it = items[i];
+      if (it.kind == 1) {
+        if (it.dep < 0 || it.dep2 < 0 || it.dep3 < 0 || items[it.dep].M != it.M || items[it.dep2].M != it.M) return TP_ERR_INVALID_ARGUMENT;
+        it.attn.k_counter = counter_of(it.dep);
+        it.attn.v_counter = counter_of(it.dep2);
+        it.attn.kv_target = gemm_target(it.dep);
+        it.attn.q_counter = counter_of(it.dep3);
+        it.attn.q_target = gemm_target(it.dep3);
+        continue;
+      }
+      const int d = it.dep;
       if (d == kDepFront) {
-        items[i].dep_counter = fw.done_counter;
-        items[i].dep_shift = 31;                                                 // one launch-wide counter; target = grid size
+        it.dep_counter = fw.done_counter;
+        it.dep_shift = 31;                                                 // one launch-wide counter; target = grid size
+      } else if (d >= 0 && items[d].kind == 1) {
+        it.dep_counter = counter_of(d);
+        it.dep_span = items[d].attn.s * items[d].attn.s;                   // KV tiles per block of 256 queries
+        it.dep_src_blocks = static_cast<int>((items[d].M + 255) / 256);
+        it.dep_per = 16;                                                   // 8 heads x 2 CTAs per KV tile
       } else if (d >= 0) {
-        items[i].dep_counter = items[d].done_counter;
-        items[i].dep_target = 4 * static_cast<int>((items[d].N + 255) / 256);   // 2 CTAs x 2 column halves per producer tile
+        it.dep_counter = counter_of(d);
+        it.dep_target = gemm_target(d);
       }
     }
     return launch_gemm_pair_group(items, count, sms, stream, front != nullptr ? &fw : nullptr);
   }
+  for (int i = 0; i < count; ++i)
+    if (items[i].kind == 1 || items[i].ep.wm_s != 0) return TP_ERR_INVALID_ARGUMENT;      // fused-attention items exist only inside a chain
   if (front != nullptr) TP_TRY(launch_front_s(front->s, front->x0, front->crop_stride, front->q, front->n_queries, stream));
   for (int first = 0; first < count;) {
     int last = first;
@@ -528,7 +635,7 @@ WorkLayout work_layout(long long n_crops, int s, int H) {
   L.stats = take((2 * R + Q) * kStatSlots * 2 * 4);
   L.q = take(Q * kC * 2); L.y_q = take(Q * kC * 2); L.q_p = take(Q * kC * 2); L.ctx = take(Q * kC * 2);
   L.h_m = take(Q * static_cast<size_t>(H) * 2);
-  L.n_flags = 3 * static_cast<long long>((R + 255) / 256) + 2 * static_cast<long long>((Q + 255) / 256) + 1;
+  L.n_flags = 3 * static_cast<long long>((R + 255) / 256) + 4 * static_cast<long long>((Q + 255) / 256) + 2;
   L.flags = take(static_cast<size_t>(L.n_flags) * 4);
   L.total = off;
   return L;
@@ -737,6 +844,77 @@ int forward_impl(const void* packed, const void* x0, const void* xm, const void*
   front.crop_stride = x0_crop_stride;
   front.n_queries = Q;
   front.s = s;
+  // ---- fully fused plan (scale factors 2 and 4, batches large enough for pair tiles): ONE launch for the whole forward.
+  //   [2] stores y_k / y_v WINDOW-MAJOR (the s x s keys of a window become consecutive rows: divide_feature done by the TMA store),
+  //   and the K / V in-projections run as KV-attention tiles whose epilogue is the window attention itself: k', v' never reach memory.
+  //   Stages: [1] | [2]k [2]v [2]q | [3]q | KV-attention | [4] | [5], ordered by tile counters; point queries as front work.
+  const char* fuse_env = getenv("TP_FUSE_ATTN");       // A/B aid, read per call: TP_FUSE_ATTN=0 -> separate attention kernel
+  const bool fuse_off = fuse_env != nullptr && atoi(fuse_env) == 0;
+  if ((s == 2 || s == 4) && !fuse_off && seg_row_offset == nullptr) {
+    GemmItem g[8];
+    AOperand a{xm, xm_width, 0, 0};
+    if (xm_crop_stride != static_cast<int64_t>(kTokens) * xm_width) a = AOperand{xm, xm_width, kTokens, xm_crop_stride};
+    if (xm_layers != nullptr) {
+      a.parts = 4;
+      for (int i = 1; i < 4; ++i) a.more[i - 1] = xm_layers[i];
+    }
+    g[0] = GemmItem{a, P + L.w_kv0, kCm, R, 2 * kC, kCm, plain_epilogue(bf(W.h_kv), 2 * kC, wf(L.b_kv0), 1)};
+    g[1] = GemmItem{AOperand{bf(W.h_kv), 2 * kC, 0, 0}, P + L.w_k2, kC, R, kC, kC, plain_epilogue(bf(W.y_k), kC, wf(L.b_k2), 0)};
+    g[1].ep.stats_out = stats_k;
+    g[2] = GemmItem{AOperand{bf(W.h_kv) + kC, 2 * kC, 0, 0}, P + L.w_v2, kC, R, kC, kC, plain_epilogue(bf(W.y_v), kC, wf(L.b_v2), 0)};
+    g[2].ep.stats_out = stats_v;
+    g[3] = GemmItem{AOperand{bf(W.q), kC, 0, 0}, P + L.w_q, kC, Q, kC, kC, plain_epilogue(bf(W.y_q), kC, nullptr, 0)};
+    g[3].ep.stats_out = stats_q;
+    for (int i = 1; i <= 3; ++i) {
+      g[i].ep.stats_out_slots = kStatSlots;
+      g[i].stage = 1;
+    }
+    g[1].ep.wm_s = g[2].ep.wm_s = s;
+    g[1].dep = g[2].dep = 0;
+    g[3].dep = kDepFront;
+    g[4] = GemmItem{AOperand{bf(W.y_q), kC, 0, 0}, P + L.w_iq, kC, Q, kC, kC, plain_epilogue(bf(W.q_p), kC, wf(L.c_q), 0)};
+    g[4].ep.col_a = wf(L.wsum_q);
+    g[4].ep.stats_in = stats_q;
+    g[4].ep.stats_in_slots = kStatSlots;
+    g[4].ep.alpha = 0.08838834764831845f;   // 1/sqrt(head_dim = 128): torch MHA scales q after the in-projection
+    g[4].stage = 2;
+    g[4].dep = 3;
+    g[5] = GemmItem{AOperand{bf(W.y_k), kC, 0, 0}, P + L.w_ik, kC, R, kC, kC, plain_epilogue(nullptr, kC, nullptr, 0)};
+    g[5].kind = 1;
+    g[5].a2 = bf(W.y_v);
+    g[5].b2 = P + L.w_iv;
+    g[5].attn.qp = bf(W.q_p);
+    g[5].attn.ctx = bf(W.ctx);
+    g[5].attn.stats_k = stats_k;
+    g[5].attn.stats_v = stats_v;
+    g[5].attn.wsum_k = wf(L.wsum_k);
+    g[5].attn.cst_k = wf(L.c_k);
+    g[5].attn.wsum_v = wf(L.wsum_v);
+    g[5].attn.cst_v = wf(L.c_v);
+    g[5].attn.s = s;
+    g[5].attn.stats_slots = kStatSlots;
+    g[5].attn.ln_inv_dim = 1.0f / kC;
+    g[5].attn.ln_eps = 1e-6f;
+    g[5].stage = 3;
+    g[5].dep = 1;
+    g[5].dep2 = 2;
+    g[5].dep3 = 4;
+    g[6] = GemmItem{AOperand{bf(W.ctx), kC, 0, 0}, P + L.w_om, kC, Q, H, kC, plain_epilogue(bf(W.h_m), H, wf(L.b_om), 1)};
+    g[6].stage = 4;
+    g[6].dep = 5;
+    GemmEpilogue ep = plain_epilogue(out, H, wf(L.b_m2), 0);
+    if (out_crop_rows != 0 && out_crop_rows != Mq) {
+      if (out_crop_rows < Mq || out_crop_rows > 0x7fffffffll / H) return TP_ERR_INVALID_ARGUMENT;
+      ep.seg_len = Mq;
+      ep.seg_stride = static_cast<int>(out_crop_rows);
+    }
+    g[7] = GemmItem{AOperand{bf(W.h_m), H, 0, 0}, P + L.w_m2, H, Q, H, H, ep};
+    g[7].peer_c = peer_out;
+    g[7].n_peers = n_peers;
+    g[7].stage = 5;
+    g[7].dep = 6;
+    if (chain_feasible(g, 8, dev.sms, false)) return launch_chain(g, 8, flags, W.n_flags, &front, dev.sms, stream);
+  }
   // k' / v' have buffers of their own: in a chained launch [3] runs while other row blocks of [2] still read h_kv, so the
   // round-1 trick of writing them over the dead h_kv buffer is no longer legal
   __nv_bfloat16* k_p = bf(W.k_p);
