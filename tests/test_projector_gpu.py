@@ -157,6 +157,7 @@ def test_kernel_variants_agree_bitwise(monkeypatch):
     through the whole forward (explicit-intrinsic epilogue math), so the automatic size-based selection cannot make a
     crop's result depend on how many crops share its call."""
     s, hidden, n = 4, 256, 10
+    monkeypatch.setenv("TP_FUSE_ATTN", "0")          # this test is about the GEMM kernels: keep the attention core a kernel of its own
     m, _ = make_module(hidden, s, seed=3)
     g = torch.Generator(device="cuda").manual_seed(7)
     x0 = torch.randn(n, 576, 1024, device="cuda", generator=g).bfloat16()
@@ -171,6 +172,38 @@ def test_kernel_variants_agree_bitwise(monkeypatch):
         assert torch.equal(outs["0"], outs[mode]), mode
         assert torch.equal(outs["0"][5:], outs["half" + mode]), mode
     assert torch.equal(outs["0"][5:], outs["half0"])       # Q=180 (one-CTA kernels) vs Q=360 (pair kernels) under auto selection
+
+
+@pytest.mark.parametrize("s,hidden,n", [(2, 256, 5), (4, 512, 9), (2, 4096, 3)])
+def test_fused_single_launch_vs_separate_kernels(s, hidden, n, monkeypatch):
+    """scale_factor 2 / 4 with hidden % 256 == 0 run as ONE persistent launch (window-major y_k / y_v, K/V in-projections fused with
+    the window attention: k', v' stay in fp32 registers).  TP_FUSE_ATTN=0 / TP_CHAIN=0 select the separate-kernel plans: same
+    math, k' / v' additionally rounded to bf16 — the two must agree to rounding, and each must meet the oracle gate; the fused
+    plan must not depend on the batch (row n of a batched call == the single-crop call, bit for bit)."""
+    from tokenpacker_b200._lib import lib
+    m, params = make_module(hidden, s, seed=21)
+    x0, xm = tpo.make_inputs(n, seed=22)
+    x0, xm = tpo.round_bf16(x0), tpo.round_bf16(xm)
+    ref = tpo.tokenpacker_forward(params, x0, xm, s, dtype=np.float32)
+    t0, tm = torch.from_numpy(x0).cuda().bfloat16(), torch.from_numpy(xm).cuda().bfloat16()
+    with torch.no_grad():
+        l0 = lib.tp_launch_count()
+        fused = m((t0, tm)).clone()
+        assert lib.tp_launch_count() - l0 == 1                      # the whole forward is one kernel
+        single = m((t0[n - 1:], tm[n - 1:])).clone()
+        monkeypatch.setenv("TP_FUSE_ATTN", "0")
+        chained = m((t0, tm)).clone()
+        monkeypatch.setenv("TP_CHAIN", "0")
+        l0 = lib.tp_launch_count()
+        plain = m((t0, tm)).clone()
+        assert lib.tp_launch_count() - l0 >= 7                      # [S] + 5 GEMM stages + attention, one launch each (or more)
+    assert torch.equal(fused[n - 1:], single)
+    assert torch.equal(chained, plain)                              # chaining changes scheduling, never bits
+    for name, out in (("fused", fused), ("plain", plain)):
+        rel, mx = errors(out.float().cpu().numpy(), ref)
+        assert rel <= REL_RMS_TOL and mx <= MAX_ABS_TOL, (name, rel, mx)
+    d = (fused.float() - plain.float())
+    assert float(d.pow(2).mean().sqrt() / plain.float().pow(2).mean().sqrt()) < 2e-3
 
 
 @pytest.mark.parametrize("n,s,hidden", [(1, 2, 5120), (3, 3, 5120), (7, 4, 4096)])

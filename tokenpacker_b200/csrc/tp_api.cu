@@ -100,6 +100,31 @@ int make_map_3d(CUtensorMap* map, const void* ptr, long long segs, long long seg
   return TP_OK;
 }
 
+// Window-major destination of a raster-ordered [crops * 576, cols] bf16 matrix (scale factor s, g = 24 / s): dims
+// (channel, wi, wb, hi, crop-and-hb), box = 64 channels x s x g x 1 x 1 = one token row of 24 tokens.
+int make_map_wm(CUtensorMap* map, const void* ptr, long long rows, long long cols, long long ld, int s) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (fn == nullptr) {
+    snprintf(g_last_cuda_error, sizeof(g_last_cuda_error), "cuTensorMapEncodeTiled entry point not found");
+    return TP_ERR_CUDA;
+  }
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0 || (ld * 2) % 16 != 0 || rows % 576 != 0 || (s != 2 && s != 4 && s != 8)) return TP_ERR_INVALID_ARGUMENT;
+  const int g = 24 / s;
+  cuuint64_t dims[5] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(s), static_cast<cuuint64_t>(g), static_cast<cuuint64_t>(s),
+                        static_cast<cuuint64_t>(rows / 576 * g)};
+  const cuuint64_t row_b = static_cast<cuuint64_t>(ld) * 2;
+  cuuint64_t strides[4] = {row_b, row_b * s * s, row_b * s, row_b * s * s * g};
+  cuuint32_t box[5] = {static_cast<cuuint32_t>(kBlockK), static_cast<cuuint32_t>(s), static_cast<cuuint32_t>(g), 1, 1};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    snprintf(g_last_cuda_error, sizeof(g_last_cuda_error), "cuTensorMapEncodeTiled(5d) failed: %d", static_cast<int>(r));
+    return TP_ERR_CUDA;
+  }
+  return TP_OK;
+}
+
 struct DeviceInfo {
   int sms;
 };
@@ -155,11 +180,31 @@ struct GemmItem {
   void* const* peer_c = nullptr;   // fused all-gather: the same output slot in every peer's gathered buffer
   int n_peers = 0;
   int tn = 0;                      // 1: C[M,N] = A^T . B with A given as [K, M] (ld = a.ld) and B as [K, N] (ld = ldb), both row-major
+  // kind 1 (KV-attention, pair kernel only): a / b = y_k (window-major rows) and the gamma-folded W_ik; a2 / b2 = y_v and W_iv;
+  // M = rows of y_k, N = K = 1024; attn holds everything else; dep / dep2 / dep3 = the producers of y_k, y_v and q'
+  int kind = 0;
+  const void* a2 = nullptr;
+  const void* b2 = nullptr;
+  AttnParams attn = {};
+  int dep2 = -1, dep3 = -1;
+  int k_splits = 1;                // > 1: split-K; ep.c must then be a float buffer [k_splits][M, ldc] (ep.out_f32 = 1, pair kernel only)
+  // chains (launch_chain): GEMMs of consecutive stages in ONE persistent launch, ordered by per-row-block tile counters
+  int stage = 0;                   // items of equal stage are independent of each other
+  int dep = -1;                    // index (in the chain) of the item whose C is this item's A: same M, plain 2-D A
+  int* done_counter = nullptr;     // filled by launch_chain
+  const int* dep_counter = nullptr;
+  int dep_target = 0;
+  int dep_shift = 0;
+  int dep_span = 0, dep_src_blocks = 0, dep_per = 0;     // producer is a KV-attention item (see GemmProblem)
 };
+constexpr int kDepFront = -2;      // GemmItem::dep: the A operand is the point-query output of the launch's front work
 
 int check_item(const GemmItem& it) {
+  if (it.kind == 1) return (it.M > 0 && it.M % 16 == 0 && it.attn.qp != nullptr && it.attn.ctx != nullptr) ? TP_OK : TP_ERR_INVALID_ARGUMENT;
   if (it.M <= 0 || it.N <= 0 || it.K <= 0 || it.N % 32 != 0 || it.M > 0x7fffff00ll) return TP_ERR_INVALID_ARGUMENT;   // K: any (TMA zero-fills)
   if ((reinterpret_cast<uintptr_t>(it.ep.c) & 15) != 0 || (it.ep.ldc * 2) % 16 != 0) return TP_ERR_INVALID_ARGUMENT;
+  if (it.k_splits < 1 || (it.k_splits > 1 && !it.ep.out_f32) || (it.ep.out_f32 && (it.ep.seg_row_offset != nullptr || it.ep.seg_stride != 0)))
+    return TP_ERR_INVALID_ARGUMENT;
   if (it.ep.stats_out != nullptr && (it.N % 256 != 0 || it.ep.stats_out_slots != it.N / 128)) return TP_ERR_INVALID_ARGUMENT;
   if (it.ep.col_a != nullptr && (it.ep.stats_in == nullptr || it.ep.stats_in_slots <= 0)) return TP_ERR_INVALID_ARGUMENT;
   return TP_OK;
@@ -195,7 +240,7 @@ int launch_gemm_t(const GemmItem& it, int sms, cudaStream_t stream) {
 }
 
 // Up to kMaxGroup independent problems in ONE launch of the CTA-pair kernel.
-int launch_gemm_pair_group(const GemmItem* items, int count, int sms, cudaStream_t stream) {
+int launch_gemm_pair_group(const GemmItem* items, int count, int sms, cudaStream_t stream, const FrontWork* front = nullptr) {
   using Cfg = Gemm2Config;
   GemmGroup g;
   memset(&g, 0, sizeof(g));
@@ -204,6 +249,28 @@ int launch_gemm_pair_group(const GemmItem* items, int count, int sms, cudaStream
   for (int i = 0; i < count; ++i) {
     const GemmItem& it = items[i];
     GemmProblem& p = g.p[i];
+    if (it.kind == 1) {
+      if (it.N != kC || it.K != kC || it.a2 == nullptr || it.b2 == nullptr || (it.attn.s != 2 && it.attn.s != 4)) return TP_ERR_INVALID_ARGUMENT;
+      TP_TRY(make_map_2d(&p.tmap_a, it.a.ptr, it.M, it.K, it.a.ld, kBlockM));
+      TP_TRY(make_map_2d(&p.tmap_a2, it.a2, it.M, it.K, it.a.ld, kBlockM));
+      TP_TRY(make_map_2d(&p.tmap_b, it.b, it.N, it.K, it.ldb, 64));           // 64 of the head's 128 weight rows per CTA
+      TP_TRY(make_map_2d(&p.tmap_b2, it.b2, it.N, it.K, it.ldb, 64));
+      p.kind = 1;
+      p.attn = it.attn;
+      p.a_parts = 1;
+      p.M = static_cast<int>(it.M);
+      p.N = static_cast<int>(it.N);
+      p.K = static_cast<int>(it.K);
+      p.num_n_blocks = 8;                                                      // one tile column per head
+      p.num_k_blocks = static_cast<int>(it.K / kBlockK);
+      p.tiles_mn = static_cast<int>((it.M + Cfg::kTileM - 1) / Cfg::kTileM) * p.num_n_blocks;
+      p.k_splits = 1;
+      p.kb_per_split = p.num_k_blocks;
+      p.num_tiles = p.tiles_mn;
+      p.dep_counter = nullptr;                                                 // its dependencies live in attn.{k,v,q}_counter
+      total += p.num_tiles;
+      continue;
+    }
     if (it.tn) {
       // row-major [K, M] / [K, N] operands: box = 64 MN-elements x 64 K-rows
       TP_TRY(make_map_2d(&p.tmap_a, it.a.ptr, it.K, it.M, it.a.ld, 64));
@@ -229,9 +296,13 @@ int launch_gemm_pair_group(const GemmItem* items, int count, int sms, cudaStream
     if (p.a_parts == 0) { p.a_parts = 1; p.a_kblocks_per_part = static_cast<int>((it.K + kBlockK - 1) / kBlockK); }
     // C goes out through TMA stores (64-col x 128-row swizzled slabs) unless rows are scattered to ARBITRARY segment offsets;
     // uniformly strided segments (the HD packed layout) stay on the TMA path through a 3-D (cols, row in segment, segment) map
-    p.use_tma_store = it.ep.seg_row_offset == nullptr ? 1 : 0;
+    p.use_tma_store = (it.ep.seg_row_offset == nullptr && !it.ep.out_f32) ? 1 : 0;
     const bool c_segmented = p.use_tma_store && it.ep.seg_stride != 0 && it.ep.seg_stride != it.ep.seg_len;
-    if (c_segmented) {
+    if (it.ep.wm_s != 0) {
+      if (!p.use_tma_store || c_segmented || it.n_peers > 0) return TP_ERR_INVALID_ARGUMENT;
+      p.c_wm_s = it.ep.wm_s;
+      TP_TRY(make_map_wm(&p.tmap_c, it.ep.c, it.M, it.N, it.ep.ldc, it.ep.wm_s));
+    } else if (c_segmented) {
       if (it.ep.seg_len <= 0 || it.M % it.ep.seg_len != 0 || it.ep.seg_stride < it.ep.seg_len) return TP_ERR_INVALID_ARGUMENT;
       p.c_seg_len = it.ep.seg_len;
       TP_TRY(make_map_3d(&p.tmap_c, it.ep.c, it.M / it.ep.seg_len, it.ep.seg_len, it.N, it.ep.ldc, it.ep.seg_stride * it.ep.ldc,
@@ -244,26 +315,48 @@ int launch_gemm_pair_group(const GemmItem* items, int count, int sms, cudaStream
     p.K = static_cast<int>(it.K);
     p.a_seg_rows = static_cast<int>(it.a.seg_rows);
     p.num_n_blocks = static_cast<int>((it.N + Cfg::kTileN - 1) / Cfg::kTileN);
-    p.num_tiles = static_cast<int>((it.M + Cfg::kTileM - 1) / Cfg::kTileM) * p.num_n_blocks;
     p.num_k_blocks = static_cast<int>((it.K + kBlockK - 1) / kBlockK);
+    p.tiles_mn = static_cast<int>((it.M + Cfg::kTileM - 1) / Cfg::kTileM) * p.num_n_blocks;
+    p.k_splits = it.k_splits;
+    p.kb_per_split = (p.num_k_blocks + p.k_splits - 1) / p.k_splits;
+    if (static_cast<long long>(p.k_splits - 1) * p.kb_per_split >= p.num_k_blocks) return TP_ERR_INVALID_ARGUMENT;   // no empty split
+    p.c_split_stride = it.M * it.ep.ldc;
+    p.num_tiles = p.tiles_mn * p.k_splits;
     p.ep = it.ep;
+    p.done_counter = it.done_counter;
+    p.dep_counter = it.dep_counter;
+    p.dep_target = it.dep_target;
+    p.dep_shift = it.dep_shift;
+    p.dep_span = it.dep_span;
+    p.dep_src_blocks = it.dep_src_blocks;
+    p.dep_per = it.dep_per;
+    if ((p.done_counter != nullptr && !p.use_tma_store) || (p.dep_counter != nullptr && (it.tn || it.a.seg_rows != 0)))
+      return TP_ERR_INVALID_ARGUMENT;          // tile counters are published by the store warps / index plain 256-row blocks of A
+    p.peer_out = it.n_peers > 0 ? 1 : 0;
     total += p.num_tiles;
   }
   if (total > 0x7fffffffll) return TP_ERR_INVALID_ARGUMENT;
   g.total_tiles = static_cast<int>(total);
+  if (front != nullptr) g.front = *front;
   PeerStores peers;
   memset(&peers, 0, sizeof(peers));
-  if (items[0].n_peers > 0) {
-    if (count != 1 || items[0].n_peers > kMaxPeers || items[0].ep.seg_row_offset != nullptr) return TP_ERR_INVALID_ARGUMENT;
-    const GemmItem& it0 = items[0];
+  int peer_item = -1;
+  for (int i = 0; i < count; ++i)
+    if (items[i].n_peers > 0) {
+      if (peer_item >= 0) return TP_ERR_INVALID_ARGUMENT;      // one set of peer maps per launch
+      peer_item = i;
+    }
+  if (peer_item >= 0) {
+    const GemmItem& it0 = items[peer_item];
+    if (it0.n_peers > kMaxPeers || it0.ep.seg_row_offset != nullptr) return TP_ERR_INVALID_ARGUMENT;
     for (int p = 0; p < it0.n_peers; ++p) {
-      if (g.p[0].c_seg_len != 0)
+      if (g.p[peer_item].c_seg_len != 0)
         TP_TRY(make_map_3d(&peers.m[p], it0.peer_c[p], it0.M / it0.ep.seg_len, it0.ep.seg_len, it0.N, it0.ep.ldc, it0.ep.seg_stride * it0.ep.ldc,
                            it0.ep.seg_len < kBlockM ? it0.ep.seg_len : kBlockM));
       else
         TP_TRY(make_map_2d(&peers.m[p], it0.peer_c[p], it0.M, it0.N, it0.ep.ldc, kBlockM));
     }
-    peers.count = items[0].n_peers;
+    peers.count = it0.n_peers;
   }
   {
     static thread_local unsigned attr_done = 0;
@@ -276,6 +369,8 @@ int launch_gemm_pair_group(const GemmItem* items, int count, int sms, cudaStream
   }
   const long long max_pairs = sms / 2;
   const int grid = 2 * static_cast<int>(total < max_pairs ? total : max_pairs);
+  for (int i = 0; i < count; ++i)
+    if (g.p[i].dep_shift == 31) g.p[i].dep_target = grid;        // front work: one arrival per CTA of this launch
   TP_CUDA(launch_pdl(tp_gemm2_kernel, dim3(grid), dim3(kGemmThreads), Cfg::kSmemBytes, stream, g, peers));
   return TP_OK;
 }
@@ -283,43 +378,55 @@ int launch_gemm_pair_group(const GemmItem* items, int count, int sms, cudaStream
 // Kernel selection: CTA-pair 256x256 tiles whenever the problem fills them (independent problems of one stage share a
 // launch), else one-CTA 128 x {256,128} tiles.  TP_GEMM_MODE=1 forces the one-CTA kernels, =2 forces the pair kernel,
 // =3 pair kernel without grouping (A/B experiments; read per call, no caching).
+// Returns 0 pair, 1 one-CTA 256, 2 one-CTA 128, or -1 (invalid).
+int choose_kernel(const GemmItem& it, int count, int sms, int mode) {
+  const bool pair_ok = (it.N % 256 == 0) && sms >= 2;
+  const bool pair_only = it.n_peers > 0 || it.tn || it.a.parts > 1 || it.k_splits > 1 || it.ep.out_f32 || it.kind == 1 || it.ep.wm_s != 0;   // pair-kernel-only features
+  if (pair_only && !pair_ok) return -1;
+  const bool needs_256 = it.ep.stats_out != nullptr;                        // statistics slots assume 256-column tiles
+  // Estimated tensor-pipe cycles of each candidate = waves x k-blocks x cycles per k-block.  Large problems always land
+  // on the pair kernel; small ones (single crops: the serving latency case) get the tile shape that fills more SMs.  All
+  // kernels produce identical bits, so the choice never changes results.
+  const long long kb = (it.K + kBlockK - 1) / kBlockK;
+  auto waves = [](long long tiles, long long units) { return (tiles + units - 1) / units; };
+  const long long t_pair = ((it.M + 255) / 256) * ((it.N + 255) / 256);
+  const long long t_256 = ((it.M + 127) / 128) * ((it.N + 255) / 256);
+  const long long t_128 = ((it.M + 127) / 128) * ((it.N + 127) / 128);
+  const long long c_pair = pair_ok ? waves(t_pair, sms / 2) * kb * 512 : LLONG_MAX;
+  // one-CTA kernels pay ~40 % over their nominal MMA time (more operand traffic per FLOP, direct 16-byte stores, no grouping):
+  // measured — at 10 crops the nominally 16 % cheaper 128x128 tiling was 30 % slower than the pair kernel
+  const long long c_256 = (it.N % 256 == 0) ? waves(t_256, sms) * kb * 512 * 14 / 10 : LLONG_MAX;
+  const long long c_128 = needs_256 ? LLONG_MAX : waves(t_128, sms) * kb * 256 * 14 / 10;
+  // a launch costs ~10k cycles of ramp and drain; pair-kernel items of one call share a single (grouped) launch
+  const long long launch = 10000;
+  const long long l_pair = pair_ok ? c_pair + launch / count : LLONG_MAX;
+  const long long l_256 = c_256 == LLONG_MAX ? LLONG_MAX : c_256 + launch;
+  const long long l_128 = c_128 == LLONG_MAX ? LLONG_MAX : c_128 + launch;
+  int choice;
+  if (pair_only || mode == 2 || mode == 3) choice = 0;
+  else if (mode == 1) choice = (it.N % 256 == 0) ? 1 : 2;
+  else if (l_pair <= l_256 && l_pair <= l_128) choice = 0;                  // ties go to the pair kernel (TMA stores, grouping)
+  else choice = (l_256 <= l_128) ? 1 : 2;
+  if (choice == 0 && !pair_ok) choice = (it.N % 256 == 0) ? 1 : 2;
+  return choice;
+}
+
+int gemm_mode() {
+  const char* mode_env = getenv("TP_GEMM_MODE");
+  return mode_env != nullptr ? atoi(mode_env) : 0;
+}
+
 int launch_gemms(const GemmItem* items, int count, int sms, cudaStream_t stream) {
   if (count <= 0 || count > kMaxGroup) return TP_ERR_INVALID_ARGUMENT;
-  const char* mode_env = getenv("TP_GEMM_MODE");
-  const int mode = mode_env != nullptr ? atoi(mode_env) : 0;
+  const int mode = gemm_mode();
   GemmItem grouped[kMaxGroup];
   int n_grouped = 0;
   for (int i = 0; i < count; ++i) {
     TP_TRY(check_item(items[i]));
     const GemmItem& it = items[i];
-    const bool pair_ok = (it.N % 256 == 0) && sms >= 2;
-    const bool pair_only = it.n_peers > 0 || it.tn || it.a.parts > 1;        // features that live in the pair kernel only
-    if (pair_only && (!pair_ok || (it.n_peers > 0 && count != 1))) return TP_ERR_INVALID_ARGUMENT;
-    const bool needs_256 = it.ep.stats_out != nullptr;                        // statistics slots assume 256-column tiles
-    // Estimated tensor-pipe cycles of each candidate = waves x k-blocks x cycles per k-block.  Large problems always land
-    // on the pair kernel; small ones (single crops: the serving latency case) get the tile shape that fills more SMs.  All
-    // kernels produce identical bits, so the choice never changes results.
-    const long long kb = (it.K + kBlockK - 1) / kBlockK;
-    auto waves = [](long long tiles, long long units) { return (tiles + units - 1) / units; };
-    const long long t_pair = ((it.M + 255) / 256) * ((it.N + 255) / 256);
-    const long long t_256 = ((it.M + 127) / 128) * ((it.N + 255) / 256);
-    const long long t_128 = ((it.M + 127) / 128) * ((it.N + 127) / 128);
-    const long long c_pair = pair_ok ? waves(t_pair, sms / 2) * kb * 512 : LLONG_MAX;
-    // one-CTA kernels pay ~40 % over their nominal MMA time (more operand traffic per FLOP, direct 16-byte stores, no grouping):
-    // measured — at 10 crops the nominally 16 % cheaper 128x128 tiling was 30 % slower than the pair kernel
-    const long long c_256 = (it.N % 256 == 0) ? waves(t_256, sms) * kb * 512 * 14 / 10 : LLONG_MAX;
-    const long long c_128 = needs_256 ? LLONG_MAX : waves(t_128, sms) * kb * 256 * 14 / 10;
-    // a launch costs ~10k cycles of ramp and drain; pair-kernel items of one call share a single (grouped) launch
-    const long long launch = 10000;
-    const long long l_pair = pair_ok ? c_pair + launch / count : LLONG_MAX;
-    const long long l_256 = c_256 == LLONG_MAX ? LLONG_MAX : c_256 + launch;
-    const long long l_128 = c_128 == LLONG_MAX ? LLONG_MAX : c_128 + launch;
-    int choice;                                                               // 0 pair, 1 one-CTA 256, 2 one-CTA 128
-    if (pair_only || mode == 2 || mode == 3) choice = 0;
-    else if (mode == 1) choice = (it.N % 256 == 0) ? 1 : 2;
-    else if (l_pair <= l_256 && l_pair <= l_128) choice = 0;                  // ties go to the pair kernel (TMA stores, grouping)
-    else choice = (l_256 <= l_128) ? 1 : 2;
-    if (choice == 0 && !pair_ok) choice = (it.N % 256 == 0) ? 1 : 2;
+    if (it.n_peers > 0 && count != 1) return TP_ERR_INVALID_ARGUMENT;
+    const int choice = choose_kernel(it, count, sms, mode);
+    if (choice < 0) return TP_ERR_INVALID_ARGUMENT;
     if (choice == 0) {
       if (mode == 3) TP_TRY(launch_gemm_pair_group(&it, 1, sms, stream));
       else grouped[n_grouped++] = it;
@@ -330,6 +437,114 @@ int launch_gemms(const GemmItem* items, int count, int sms, cudaStream_t stream)
     }
   }
   if (n_grouped > 0) TP_TRY(launch_gemm_pair_group(grouped, n_grouped, sms, stream));
+  return TP_OK;
+}
+
+int launch_front_s(int s, const __nv_bfloat16* x0, long long x0_stride, __nv_bfloat16* q, long long Q, cudaStream_t stream);
+
+// A chain of dependent GEMM stages (items sorted by stage; items[i].dep names the producer of items[i]'s A operand, kDepFront =
+// the point queries described by ``front``).  When every item lands on the CTA-pair kernel the whole chain is ONE persistent
+// launch: tiles are numbered stage after stage, consumers wait on per-row-block tile counters (``flags``, zeroed earlier on the
+// stream) instead of on kernel boundaries — no ramp, drain or partial last wave between the linears — and the point queries are
+// computed by the epilogue warps while the first accumulators are still being produced.  Otherwise (small problems on one-CTA
+// tiles, TP_CHAIN=0, forced modes) the point queries and the stages run as separate launches exactly as before; either way the
+// bits are the same.
+bool chain_enabled(int mode) {
+  const char* e = getenv("TP_CHAIN");                // A/B aid, read per call: TP_CHAIN=0 -> one launch per stage
+  const bool chain_off = e != nullptr && atoi(e) == 0;
+  return !chain_off && (mode == 0 || mode == 2);
+}
+
+// Can these items run as one chained launch of the pair kernel?  (every item on 256-row pair tiles, nothing scattered to arbitrary
+// rows).  by_cost: additionally require that the size-based kernel choice lands on the pair kernel for every item (chains whose
+// unchained form computes the same bits); without it the chain is taken whenever the pair kernel CAN run it (the fused-attention
+// plan: its results must not depend on the batch size, so neither may the decision).
+bool chain_feasible(const GemmItem* items, int count, int sms, bool by_cost = true) {
+  const int mode = gemm_mode();
+  if (!chain_enabled(mode) || count <= 0 || count > kMaxGroup || sms < 2) return false;
+  for (int i = 0; i < count; ++i) {
+    if (check_item(items[i]) != TP_OK || items[i].ep.seg_row_offset != nullptr || items[i].N % 256 != 0) return false;
+    if (by_cost && choose_kernel(items[i], count, sms, mode) != 0) return false;
+  }
+  return true;
+}
+
+int launch_chain(GemmItem* items, int count, int* flags, long long flag_capacity, const FrontWork* front, int sms, cudaStream_t stream) {
+  if (count <= 0 || count > kMaxGroup) return TP_ERR_INVALID_ARGUMENT;
+  for (int i = 0; i < count; ++i) {
+    const int deps[3] = {items[i].dep, items[i].dep2, items[i].dep3};
+    for (int d : deps) {
+      if (d == kDepFront ? front == nullptr : (d >= 0 && (d >= i || items[d].stage >= items[i].stage))) return TP_ERR_INVALID_ARGUMENT;
+      // GEMM -> GEMM: the consumer's A row blocks are the producer's C row blocks
+      if (d >= 0 && items[i].kind == 0 && items[d].kind == 0 && (items[d].M != items[i].M || items[i].a.seg_rows != 0)) return TP_ERR_INVALID_ARGUMENT;
+    }
+  }
+  bool fused_items = false;
+  for (int i = 0; i < count; ++i) fused_items = fused_items || items[i].kind == 1 || items[i].ep.wm_s != 0;
+  const bool chain = flags != nullptr && chain_feasible(items, count, sms, !fused_items);
+  if (chain) {
+    long long used = 0;
+    FrontWork fw;
+    memset(&fw, 0, sizeof(fw));
+    if (front != nullptr) {
+      if (used + 1 > flag_capacity) return TP_ERR_WORKSPACE_TOO_SMALL;
+      fw = *front;
+      fw.done_counter = flags + used;
+      used += 1;
+    }
+    for (int i = 0; i < count; ++i) {
+      bool produces = false;
+      for (int j = 0; j < count; ++j) produces = produces || items[j].dep == i || items[j].dep2 == i || items[j].dep3 == i;
+      if (!produces) continue;
+      // a KV-attention item produces ctx: one counter per block of 256 queries; a GEMM: one per block of 256 output rows
+      const long long out_rows = items[i].kind == 1 ? items[i].M / (items[i].attn.s * items[i].attn.s) : items[i].M;
+      const long long blocks = (out_rows + 255) / 256;
+      if (used + blocks > flag_capacity) return TP_ERR_WORKSPACE_TOO_SMALL;
+      items[i].done_counter = flags + used;
+      if (items[i].kind == 1) {
+        items[i].attn.done_counter = items[i].done_counter;
+        items[i].done_counter = nullptr;            // published by the epilogue warps, not by the store warps
+      }
+      used += blocks;
+    }
+    auto counter_of = [&](int d) { return items[d].kind == 1 ? items[d].attn.done_counter : items[d].done_counter; };
+    auto gemm_target = [&](int d) { return 4 * static_cast<int>((items[d].N + 255) / 256); };   // 2 CTAs x 2 column halves per tile
+    for (int i = 0; i < count; ++i) {
+      GemmItem& it = items[i];
+      if (it.kind == 1) {
+        if (it.dep < 0 || it.dep2 < 0 || it.dep3 < 0 || items[it.dep].M != it.M || items[it.dep2].M != it.M) return TP_ERR_INVALID_ARGUMENT;
+        it.attn.k_counter = counter_of(it.dep);
+        it.attn.v_counter = counter_of(it.dep2);
+        it.attn.kv_target = gemm_target(it.dep);
+        it.attn.q_counter = counter_of(it.dep3);
+        it.attn.q_target = gemm_target(it.dep3);
+        continue;
+      }
+      const int d = it.dep;
+      if (d == kDepFront) {
+        it.dep_counter = fw.done_counter;
+        it.dep_shift = 31;                                                 // one launch-wide counter; target = grid size
+      } else if (d >= 0 && items[d].kind == 1) {
+        it.dep_counter = counter_of(d);
+        it.dep_span = items[d].attn.s * items[d].attn.s;                   // KV tiles per block of 256 queries
+        it.dep_src_blocks = static_cast<int>((items[d].M + 255) / 256);
+        it.dep_per = 16;                                                   // 8 heads x 2 CTAs per KV tile
+      } else if (d >= 0) {
+        it.dep_counter = counter_of(d);
+        it.dep_target = gemm_target(d);
+      }
+    }
+    return launch_gemm_pair_group(items, count, sms, stream, front != nullptr ? &fw : nullptr);
+  }
+  for (int i = 0; i < count; ++i)
+    if (items[i].kind == 1 || items[i].ep.wm_s != 0) return TP_ERR_INVALID_ARGUMENT;      // fused-attention items exist only inside a chain
+  if (front != nullptr) TP_TRY(launch_front_s(front->s, front->x0, front->crop_stride, front->q, front->n_queries, stream));
+  for (int first = 0; first < count;) {
+    int last = first;
+    while (last + 1 < count && items[last + 1].stage == items[first].stage) ++last;
+    TP_TRY(launch_gemms(items + first, last - first + 1, sms, stream));
+    first = last + 1;
+  }
   return TP_OK;
 }
 
@@ -395,10 +610,13 @@ PackedLayout packed_layout(int H) {
 constexpr int kStatSlots = kC / 128;   // one (mean, M2) slot per 128 output columns of a 1024-wide linear
 
 struct WorkLayout {
-  size_t h_kv;      // [R,2048]  GELU(W0 xm + b) for k|v ; reused as k' | v' ([R,1024] each) once consumed
+  size_t h_kv;      // [R,2048]  GELU(W0 xm + b) for k|v
   size_t y_k, y_v;  // [R,1024]  second linear outputs (pre-LayerNorm)
+  size_t k_p, v_p;  // [R,1024]  MHA in-projections of the keys / values
   size_t stats;     // f32 [2R + Q, 8, 2]  per-row (mean, M2) of each 128-column block: k rows, v rows, q rows
   size_t q, y_q, q_p, ctx, h_m;      // [Q,1024] x4, [Q,H]
+  size_t flags;     // int32 [n_flags]  per-row-block tile counters of the chained GEMM launches (zeroed by the point-query kernel)
+  long long n_flags;
   size_t total;
 };
 
@@ -412,9 +630,13 @@ WorkLayout work_layout(long long n_crops, int s, int H) {
   L.h_kv = take(R * 2 * kC * 2);
   L.y_k = take(R * kC * 2);
   L.y_v = take(R * kC * 2);
+  L.k_p = take(R * kC * 2);
+  L.v_p = take(R * kC * 2);
   L.stats = take((2 * R + Q) * kStatSlots * 2 * 4);
   L.q = take(Q * kC * 2); L.y_q = take(Q * kC * 2); L.q_p = take(Q * kC * 2); L.ctx = take(Q * kC * 2);
   L.h_m = take(Q * static_cast<size_t>(H) * 2);
+  L.n_flags = 3 * static_cast<long long>((R + 255) / 256) + 4 * static_cast<long long>((Q + 255) / 256) + 2;
+  L.flags = take(static_cast<size_t>(L.n_flags) * 4);
   L.total = off;
   return L;
 }
@@ -602,63 +824,147 @@ int forward_impl(const void* packed, const void* x0, const void* xm, const void*
   float* stats_v = stats_k + 2 * kStatSlots * R;
   float* stats_q = stats_v + 2 * kStatSlots * R;     // every slot is written by the producing GEMM: no memset needed
 
-  // Launch plan (7 kernels; independent GEMMs of a stage share one grouped launch of the CTA-pair kernel):
-  //   [S] point queries            builder.py:117-118
+  // Launch plan.  Large batches: 4 launches — [S], chain A = {[1], [2], [3]} and chain B = {[4], [5]} as ONE persistent CTA-pair
+  // launch each (stages ordered by per-row-block tile counters instead of kernel boundaries), [A] in between.  Small batches
+  // (one-CTA tiles win): the same stages as separate launches.
+  //   [S] point queries            builder.py:117-118   (inside chain A: done by the epilogue warps before their first tile)
   //   [1] h_kv = GELU(xm [W_k0;W_v0]^T + b)                                 :112-113 first linears, xm read once
-  //   [2] y_k | y_v | y_q   = second linears k/v + q_proj_1 (+ row sums for the LayerNorms)   :112-113, :120
+  //   [2] y_k | y_v | y_q   = second linears k/v + q_proj_1 (+ row statistics for the LayerNorms)   :112-113, :120
   //   [3] k'  | v'  | q'    = LayerNorm folded into the MHA in-projections (q' scaled by 1/sqrt 128)   MHA in_proj
   //   [A] window attention core                                              :122-130
   //   [4] h_m = GELU(ctx (W_m0 W_o)^T + (W_m0 b_o + b_m0))                   out_proj folded into mlp.0  (:130,:136)
   //   [5] out = h_m W_m2^T + b_m2  -> final [N,M,H] (or packed HD) layout    :136
-  {
-    const __nv_bfloat16* x0p = static_cast<const __nv_bfloat16*>(x0);
-    TP_TRY(launch_front_s(s, x0p, x0_crop_stride, bf(W.q), Q, stream));
-  }
-  {
+  int* flags = reinterpret_cast<int*>(ws + W.flags);
+  const long long flags_a = 3 * ((R + 255) / 256);          // chain A: [1], [2]k, [2]v produce for later stages ([2]q: Q rows, below)
+  TP_CUDA(cudaMemsetAsync(flags, 0, static_cast<size_t>(W.n_flags) * 4, stream));      // tile counters of the chained launches
+  FrontWork front;
+  memset(&front, 0, sizeof(front));
+  front.x0 = static_cast<const __nv_bfloat16*>(x0);
+  front.q = bf(W.q);
+  front.crop_stride = x0_crop_stride;
+  front.n_queries = Q;
+  front.s = s;
+  // ---- fully fused plan (scale factors 2 and 4, batches large enough for pair tiles): ONE launch for the whole forward.
+  //   [2] stores y_k / y_v WINDOW-MAJOR (the s x s keys of a window become consecutive rows: divide_feature done by the TMA store),
+  //   and the K / V in-projections run as KV-attention tiles whose epilogue is the window attention itself: k', v' never reach memory.
+  //   Stages: [1] | [2]k [2]v [2]q | [3]q | KV-attention | [4] | [5], ordered by tile counters; point queries as front work.
+  const char* fuse_env = getenv("TP_FUSE_ATTN");       // A/B aid, read per call: TP_FUSE_ATTN=0 -> separate attention kernel
+  const bool fuse_off = fuse_env != nullptr && atoi(fuse_env) == 0;
+  if ((s == 2 || s == 4) && !fuse_off && seg_row_offset == nullptr) {
+    GemmItem g[8];
     AOperand a{xm, xm_width, 0, 0};
     if (xm_crop_stride != static_cast<int64_t>(kTokens) * xm_width) a = AOperand{xm, xm_width, kTokens, xm_crop_stride};
     if (xm_layers != nullptr) {
       a.parts = 4;
       for (int i = 1; i < 4; ++i) a.more[i - 1] = xm_layers[i];
     }
-    TP_TRY(launch_gemm(a, P + L.w_kv0, kCm, R, 2 * kC, kCm, plain_epilogue(bf(W.h_kv), 2 * kC, wf(L.b_kv0), 1), dev.sms, stream));
+    g[0] = GemmItem{a, P + L.w_kv0, kCm, R, 2 * kC, kCm, plain_epilogue(bf(W.h_kv), 2 * kC, wf(L.b_kv0), 1)};
+    g[1] = GemmItem{AOperand{bf(W.h_kv), 2 * kC, 0, 0}, P + L.w_k2, kC, R, kC, kC, plain_epilogue(bf(W.y_k), kC, wf(L.b_k2), 0)};
+    g[1].ep.stats_out = stats_k;
+    g[2] = GemmItem{AOperand{bf(W.h_kv) + kC, 2 * kC, 0, 0}, P + L.w_v2, kC, R, kC, kC, plain_epilogue(bf(W.y_v), kC, wf(L.b_v2), 0)};
+    g[2].ep.stats_out = stats_v;
+    g[3] = GemmItem{AOperand{bf(W.q), kC, 0, 0}, P + L.w_q, kC, Q, kC, kC, plain_epilogue(bf(W.y_q), kC, nullptr, 0)};
+    g[3].ep.stats_out = stats_q;
+    for (int i = 1; i <= 3; ++i) {
+      g[i].ep.stats_out_slots = kStatSlots;
+      g[i].stage = 1;
+    }
+    g[1].ep.wm_s = g[2].ep.wm_s = s;
+    g[1].dep = g[2].dep = 0;
+    g[3].dep = kDepFront;
+    g[4] = GemmItem{AOperand{bf(W.y_q), kC, 0, 0}, P + L.w_iq, kC, Q, kC, kC, plain_epilogue(bf(W.q_p), kC, wf(L.c_q), 0)};
+    g[4].ep.col_a = wf(L.wsum_q);
+    g[4].ep.stats_in = stats_q;
+    g[4].ep.stats_in_slots = kStatSlots;
+    g[4].ep.alpha = 0.08838834764831845f;   // 1/sqrt(head_dim = 128): torch MHA scales q after the in-projection
+    g[4].stage = 2;
+    g[4].dep = 3;
+    g[5] = GemmItem{AOperand{bf(W.y_k), kC, 0, 0}, P + L.w_ik, kC, R, kC, kC, plain_epilogue(nullptr, kC, nullptr, 0)};
+    g[5].kind = 1;
+    g[5].a2 = bf(W.y_v);
+    g[5].b2 = P + L.w_iv;
+    g[5].attn.qp = bf(W.q_p);
+    g[5].attn.ctx = bf(W.ctx);
+    g[5].attn.stats_k = stats_k;
+    g[5].attn.stats_v = stats_v;
+    g[5].attn.wsum_k = wf(L.wsum_k);
+    g[5].attn.cst_k = wf(L.c_k);
+    g[5].attn.wsum_v = wf(L.wsum_v);
+    g[5].attn.cst_v = wf(L.c_v);
+    g[5].attn.s = s;
+    g[5].attn.stats_slots = kStatSlots;
+    g[5].attn.ln_inv_dim = 1.0f / kC;
+    g[5].attn.ln_eps = 1e-6f;
+    g[5].stage = 3;
+    g[5].dep = 1;
+    g[5].dep2 = 2;
+    g[5].dep3 = 4;
+    g[6] = GemmItem{AOperand{bf(W.ctx), kC, 0, 0}, P + L.w_om, kC, Q, H, kC, plain_epilogue(bf(W.h_m), H, wf(L.b_om), 1)};
+    g[6].stage = 4;
+    g[6].dep = 5;
+    GemmEpilogue ep = plain_epilogue(out, H, wf(L.b_m2), 0);
+    if (out_crop_rows != 0 && out_crop_rows != Mq) {
+      if (out_crop_rows < Mq || out_crop_rows > 0x7fffffffll / H) return TP_ERR_INVALID_ARGUMENT;
+      ep.seg_len = Mq;
+      ep.seg_stride = static_cast<int>(out_crop_rows);
+    }
+    g[7] = GemmItem{AOperand{bf(W.h_m), H, 0, 0}, P + L.w_m2, H, Q, H, H, ep};
+    g[7].peer_c = peer_out;
+    g[7].n_peers = n_peers;
+    g[7].stage = 5;
+    g[7].dep = 6;
+    if (chain_feasible(g, 8, dev.sms, false)) return launch_chain(g, 8, flags, W.n_flags, &front, dev.sms, stream);
   }
+  // k' / v' have buffers of their own: in a chained launch [3] runs while other row blocks of [2] still read h_kv, so the
+  // round-1 trick of writing them over the dead h_kv buffer is no longer legal
+  __nv_bfloat16* k_p = bf(W.k_p);
+  __nv_bfloat16* v_p = bf(W.v_p);
   {
-    GemmItem g[3];
-    g[0] = GemmItem{AOperand{bf(W.h_kv), 2 * kC, 0, 0}, P + L.w_k2, kC, R, kC, kC, plain_epilogue(bf(W.y_k), kC, wf(L.b_k2), 0)};
-    g[0].ep.stats_out = stats_k;
-    g[0].ep.stats_out_slots = kStatSlots;
-    g[1] = GemmItem{AOperand{bf(W.h_kv) + kC, 2 * kC, 0, 0}, P + L.w_v2, kC, R, kC, kC, plain_epilogue(bf(W.y_v), kC, wf(L.b_v2), 0)};
-    g[1].ep.stats_out = stats_v;
+    GemmItem g[7];
+    AOperand a{xm, xm_width, 0, 0};
+    if (xm_crop_stride != static_cast<int64_t>(kTokens) * xm_width) a = AOperand{xm, xm_width, kTokens, xm_crop_stride};
+    if (xm_layers != nullptr) {
+      a.parts = 4;
+      for (int i = 1; i < 4; ++i) a.more[i - 1] = xm_layers[i];
+    }
+    g[0] = GemmItem{a, P + L.w_kv0, kCm, R, 2 * kC, kCm, plain_epilogue(bf(W.h_kv), 2 * kC, wf(L.b_kv0), 1)};
+    g[0].stage = 0;
+    g[1] = GemmItem{AOperand{bf(W.h_kv), 2 * kC, 0, 0}, P + L.w_k2, kC, R, kC, kC, plain_epilogue(bf(W.y_k), kC, wf(L.b_k2), 0)};
+    g[1].ep.stats_out = stats_k;
     g[1].ep.stats_out_slots = kStatSlots;
-    g[2] = GemmItem{AOperand{bf(W.q), kC, 0, 0}, P + L.w_q, kC, Q, kC, kC, plain_epilogue(bf(W.y_q), kC, nullptr, 0)};
-    g[2].ep.stats_out = stats_q;
+    g[2] = GemmItem{AOperand{bf(W.h_kv) + kC, 2 * kC, 0, 0}, P + L.w_v2, kC, R, kC, kC, plain_epilogue(bf(W.y_v), kC, wf(L.b_v2), 0)};
+    g[2].ep.stats_out = stats_v;
     g[2].ep.stats_out_slots = kStatSlots;
-    TP_TRY(launch_gemms(g, 3, dev.sms, stream));
-  }
-  // k' / v' are written over the dead h_kv buffer
-  __nv_bfloat16* k_p = bf(W.h_kv);
-  __nv_bfloat16* v_p = bf(W.h_kv) + static_cast<size_t>(R) * kC;
-  {
-    GemmItem g[3];
-    g[0] = GemmItem{AOperand{bf(W.y_k), kC, 0, 0}, P + L.w_ik, kC, R, kC, kC, plain_epilogue(k_p, kC, wf(L.c_k), 0)};
-    g[0].ep.col_a = wf(L.wsum_k);
-    g[0].ep.stats_in = stats_k;
-    g[0].ep.stats_in_slots = kStatSlots;
-    g[1] = GemmItem{AOperand{bf(W.y_v), kC, 0, 0}, P + L.w_iv, kC, R, kC, kC, plain_epilogue(v_p, kC, wf(L.c_v), 0)};
-    g[1].ep.col_a = wf(L.wsum_v);
-    g[1].ep.stats_in = stats_v;
-    g[1].ep.stats_in_slots = kStatSlots;
-    g[2] = GemmItem{AOperand{bf(W.y_q), kC, 0, 0}, P + L.w_iq, kC, Q, kC, kC, plain_epilogue(bf(W.q_p), kC, wf(L.c_q), 0)};
-    g[2].ep.col_a = wf(L.wsum_q);
-    g[2].ep.stats_in = stats_q;
-    g[2].ep.stats_in_slots = kStatSlots;
-    g[2].ep.alpha = 0.08838834764831845f;   // 1/sqrt(head_dim = 128): torch MHA scales q after the in-projection
-    TP_TRY(launch_gemms(g, 3, dev.sms, stream));
+    g[3] = GemmItem{AOperand{bf(W.q), kC, 0, 0}, P + L.w_q, kC, Q, kC, kC, plain_epilogue(bf(W.y_q), kC, nullptr, 0)};
+    g[3].ep.stats_out = stats_q;
+    g[3].ep.stats_out_slots = kStatSlots;
+    g[1].stage = g[2].stage = g[3].stage = 1;
+    g[1].dep = g[2].dep = 0;
+    g[3].dep = kDepFront;
+    g[4] = GemmItem{AOperand{bf(W.y_k), kC, 0, 0}, P + L.w_ik, kC, R, kC, kC, plain_epilogue(k_p, kC, wf(L.c_k), 0)};
+    g[4].ep.col_a = wf(L.wsum_k);
+    g[4].ep.stats_in = stats_k;
+    g[4].ep.stats_in_slots = kStatSlots;
+    g[5] = GemmItem{AOperand{bf(W.y_v), kC, 0, 0}, P + L.w_iv, kC, R, kC, kC, plain_epilogue(v_p, kC, wf(L.c_v), 0)};
+    g[5].ep.col_a = wf(L.wsum_v);
+    g[5].ep.stats_in = stats_v;
+    g[5].ep.stats_in_slots = kStatSlots;
+    g[6] = GemmItem{AOperand{bf(W.y_q), kC, 0, 0}, P + L.w_iq, kC, Q, kC, kC, plain_epilogue(bf(W.q_p), kC, wf(L.c_q), 0)};
+    g[6].ep.col_a = wf(L.wsum_q);
+    g[6].ep.stats_in = stats_q;
+    g[6].ep.stats_in_slots = kStatSlots;
+    g[6].ep.alpha = 0.08838834764831845f;   // 1/sqrt(head_dim = 128): torch MHA scales q after the in-projection
+    g[4].stage = g[5].stage = g[6].stage = 2;
+    g[4].dep = 1;
+    g[5].dep = 2;
+    g[6].dep = 3;
+    TP_TRY(launch_chain(g, 7, flags, flags_a + (Q + 255) / 256 + 1, &front, dev.sms, stream));
   }
   TP_TRY(launch_attn_s(s, bf(W.q_p), k_p, v_p, bf(W.ctx), Q, stream));
-  TP_TRY(launch_gemm(AOperand{bf(W.ctx), kC, 0, 0}, P + L.w_om, kC, Q, H, kC, plain_epilogue(bf(W.h_m), H, wf(L.b_om), 1), dev.sms, stream));
   {
+    GemmItem g[2];
+    g[0] = GemmItem{AOperand{bf(W.ctx), kC, 0, 0}, P + L.w_om, kC, Q, H, kC, plain_epilogue(bf(W.h_m), H, wf(L.b_om), 1)};
+    g[0].stage = 0;
     GemmEpilogue ep = plain_epilogue(out, H, wf(L.b_m2), 0);
     if (seg_row_offset != nullptr) {
       ep.seg_row_offset = reinterpret_cast<const long long*>(seg_row_offset);
@@ -668,10 +974,13 @@ int forward_impl(const void* packed, const void* x0, const void* xm, const void*
       ep.seg_len = Mq;
       ep.seg_stride = static_cast<int>(out_crop_rows);
     }
-    GemmItem it{AOperand{bf(W.h_m), H, 0, 0}, P + L.w_m2, H, Q, H, H, ep};
-    it.peer_c = peer_out;
-    it.n_peers = n_peers;
-    TP_TRY(launch_gemms(&it, 1, dev.sms, stream));
+    g[1] = GemmItem{AOperand{bf(W.h_m), H, 0, 0}, P + L.w_m2, H, Q, H, H, ep};
+    g[1].peer_c = peer_out;
+    g[1].n_peers = n_peers;
+    g[1].stage = 1;
+    g[1].dep = 0;
+    int* flags_b = flags + flags_a + (Q + 255) / 256 + 1;
+    TP_TRY(launch_chain(g, 2, flags_b, (Q + 255) / 256, nullptr, dev.sms, stream));
   }
   return TP_OK;
 }

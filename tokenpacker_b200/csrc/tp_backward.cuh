@@ -435,4 +435,20 @@ __global__ void __launch_bounds__(256) window_attn_bwd_stream_kernel(const __nv_
   for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(dqp + query * kC + i * 256 + lane * 8) = pack8(dq[i]);
 }
 
+// Split-K epilogue: out[i] = bf16(alpha * sum_s partial[s][i]), slices summed in fixed order (deterministic).  4 elements per thread.
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ partial, int splits, long long slice_elems,
+                                                            float alpha, __nv_bfloat16* __restrict__ out) {
+  const long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
+  if (i >= slice_elems) return;
+  float4 acc = __ldg(reinterpret_cast<const float4*>(partial + i));
+  for (int s = 1; s < splits; ++s) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(partial + s * slice_elems + i));
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+  uint2 o;
+  o.x = pack_bf16x2(acc.x * alpha, acc.y * alpha);
+  o.y = pack_bf16x2(acc.z * alpha, acc.w * alpha);
+  *reinterpret_cast<uint2*>(out + i) = o;
+}
+
 }  // namespace tp

@@ -16,9 +16,13 @@
 //
 // CTA = 384 threads, persistent over output tiles (default role layout):
 //   warps 0-7   epilogue: tcgen05.ld 32x32b (thread == output row), fused per-row / per-column math on the packed fp32
-//               pipe, swizzled shared-memory slabs -> TMA stores (direct 16-byte stores in the one-CTA kernels / row scatter)
-//   warp 9      TMEM allocator (2 accumulator buffers: the epilogue of tile i overlaps tile i+1's MMAs)
-//   warp 10     TMA producer   (warp-uniform loop, elect.sync around the issue): cp.async.bulk.tensor boxes, 128B swizzle, mbarrier ring
+//               pipe, swizzled shared-memory slabs (direct 16-byte stores in the one-CTA kernels / arbitrary row scatter)
+//   warps 8, 9  store warps of the pair kernel (one per column half): wait for a finished slab on an mbarrier, issue its TMA
+//               store(s), hand the buffer back, and — for GEMMs that other GEMMs of the same launch depend on — publish each
+//               finished tile to a global counter.  The epilogue warps never wait for a store.  Warp 9 also allocates TMEM
+//               (2 accumulator buffers: the epilogue of tile i overlaps tile i+1's MMAs)
+//   warp 10     TMA producer   (warp-uniform loop, elect.sync around the issue): cp.async.bulk.tensor boxes, 128B swizzle, mbarrier
+//               ring; spins on the producer GEMM's tile counter before the first load of a dependent tile
 //   warp 11     MMA issuer     (leader CTA only in pair mode): fp32 accumulators in TMEM
 //
 // Fused epilogue (all optional, selected at run time, warp-uniform branches):
@@ -55,6 +59,11 @@ struct GemmEpilogue {
   float ln_eps;
   float alpha;
   int gelu;
+  int wm_s;                // != 0: rows are tokens in raster order (24 x 24 per crop) and C is stored WINDOW-MAJOR for scale factor
+                           // wm_s: row (crop, hb, wb, hi, wi) of [crops * 576] — the s x s keys of a window become wm_s^2 consecutive
+                           // rows (divide_feature, builder.py:96-105, done by the store instead of five permute copies).  The row
+                           // statistics go to the permuted row too.  Pair kernel / TMA stores only; wm_s in {2, 4, 8}.
+  int out_f32;             // 1: C is float [M, ldc] (split-K partial sums of the wgrads): fp32 direct stores, no bf16 rounding
   long long* prof;         // TP_GEMM_PROFILE builds only: [grid][16] cycle counters (nullptr otherwise)
 };
 
@@ -78,20 +87,11 @@ constexpr int kGemmThreads = 384;
 // the single-lane TMA / MMA warps must never lose an issue slot to the (instruction-heavy) epilogue warps: they get
 // the HIGHEST ids.  Epilogue warp w reads TMEM lanes 32*(w % 4)..+31 (hardware restriction), so 8 epilogue warps =
 // 4 lane quarters x 2 column halves.
-#ifndef TP_ROLE_LAYOUT
-#define TP_ROLE_LAYOUT 1
-#endif
-#if TP_ROLE_LAYOUT == 1
 constexpr int kEpiWarp0 = 0;
 constexpr int kTmaWarp = 10;
 constexpr int kMmaWarp = 11;
 constexpr int kAllocWarp = 9;
-#else
-constexpr int kEpiWarp0 = 4;
-constexpr int kTmaWarp = 0;
-constexpr int kMmaWarp = 1;
-constexpr int kAllocWarp = 2;
-#endif
+constexpr int kStoreWarp0 = 8;      // pair kernel: warps 8 and 9 issue the TMA stores of column half 0 / 1 (role layout 1 only)
 constexpr int kNumEpiWarps = 8;
 constexpr int kEpiThreads = kNumEpiWarps * 32;
 constexpr int kEpiBarrierId = 1;
@@ -117,48 +117,55 @@ struct PeerStores {
 };
 
 struct OutStage {
-  uint8_t* buf;              // this half's 2 x 16 KiB staging buffers (nullptr: direct 16-byte global stores)
-  const CUtensorMap* tmap;   // C tensor map(s), box = 64 cols x 128 rows, SWIZZLE_128B  (3-D, box 64 x seg_box x 1, when seg_len != 0)
-  int seg_len;               // 0: plain 2-D output; else rows per segment of the 3-D (cols, row in segment, segment) map
-  int seg_box;               // box rows of the 3-D map = min(seg_len, 128)
-  int n_segs;
-  int n_maps;                // 1, or the number of peer maps (consecutive CUtensorMaps starting at tmap)
-  int row_tile0;             // first global row of this CTA's 128-row tile
-  int n_bufs;                // 2: slabs alternate buffers (one barrier per slab); 1: single buffer (two barriers per slab)
-  uint32_t barrier_id;       // named barrier shared by the 4 warps (128 threads) of this half
-  bool issuer;               // this thread issues (and tracks) the half's TMA stores
+  uint8_t* buf;              // this half's n_bufs x 16 KiB staging buffers (nullptr: direct 16-byte global stores)
+  uint64_t* full_bar;        // [n_bufs] slab written (count 4: one arrive per epilogue warp of the half) -> store warp
+  uint64_t* empty_bar;       // [n_bufs] slab's TMA store has finished reading the buffer (count 1, store warp) -> epilogue warps
+  int n_bufs;                // 2: slabs alternate buffers; 1: single buffer
+  uint32_t slab_seq;         // running slab number of this half (buffer = seq % n_bufs, mbarrier phase = seq / n_bufs)
 };
 constexpr int kOutSlabBytes = 128 * 128;   // 128 rows x 64 bf16
+
+// raster row (crop n, token row tr, token column tc) -> window-major row (crop n, window (hb, wb), key (hi, wi)) for windows of s x s
+__device__ __forceinline__ long long window_major_row(long long row, int s) {
+  const long long n = row / 576;
+  const int t = static_cast<int>(row - n * 576);
+  const int tr = t / 24, tc = t - tr * 24;
+  const int hb = tr / s, hi = tr - hb * s, wb = tc / s, wi = tc - wb * s;
+  return n * 576 + ((hb * (24 / s) + wb) * s + hi) * s + wi;
+}
+
+// (mean, rstd) of a LayerNorm row from its per-128-column (mean, M2) pairs, combined Chan-style in fixed order
+__device__ __forceinline__ void ln_row_stats(const float* stats, long long row, int slots, float inv_dim, float eps, float& mu, float& rstd) {
+  const float2* st = reinterpret_cast<const float2*>(stats) + row * slots;
+  float t1 = 0.f, m2 = 0.f;
+  for (int i = 0; i < slots; ++i) t1 = __fadd_rn(t1, st[i].x);
+  const float inv_slots = __frcp_rn(static_cast<float>(slots));
+  mu = __fmul_rn(t1, inv_slots);
+  float between = 0.f;
+  for (int i = 0; i < slots; ++i) {
+    const float2 v = st[i];
+    const float d = __fsub_rn(v.x, mu);
+    between = fmaf(d, d, between);
+    m2 = __fadd_rn(m2, v.y);
+  }
+  const float var = __fmul_rn(fmaf(between, __fmul_rn(inv_slots, __frcp_rn(inv_dim)), m2), inv_dim);
+  rstd = rsqrtf(__fadd_rn(var, eps));
+}
 
 template <int kTileN, typename ReleaseFn>
 __device__ __forceinline__ void epilogue_tile(const GemmEpilogue& ep, int M, int N, uint32_t tmem_acc, int row, int col_tile0,
                                               int quarter, int half, const float* s_col, const OutStage& out, ReleaseFn release,
-                                              [[maybe_unused]] long long* pc = nullptr) {
+                                              [[maybe_unused]] long long* pc = nullptr, long long c_extra = 0) {
   constexpr int kColsPerWarp = kTileN / 2;
   constexpr int kChunks = kColsPerWarp / 32;
   const bool ln_fold = ep.col_a != nullptr;
   const bool row_ok = row < M;
   float mu = 0.f, rstd = 1.f;
-  if (ln_fold && row_ok) {
-    // Row statistics arrive as one (mean_i, M2_i) pair per 128-column block (M2 = sum of squared deviations from the block's own
-    // mean) and are combined Chan-style in a fixed order: no E[y^2] - mu^2 cancellation when |mean| >> std, bitwise reproducible.
-    const float2* st = reinterpret_cast<const float2*>(ep.stats_in) + static_cast<long long>(row) * ep.stats_in_slots;
-    float t1 = 0.f, m2 = 0.f;
-    for (int i = 0; i < ep.stats_in_slots; ++i) t1 = __fadd_rn(t1, st[i].x);
-    const float inv_slots = __frcp_rn(static_cast<float>(ep.stats_in_slots));
-    mu = __fmul_rn(t1, inv_slots);
-    float between = 0.f;
-    for (int i = 0; i < ep.stats_in_slots; ++i) {
-      const float2 v = st[i];
-      const float d = __fsub_rn(v.x, mu);
-      between = fmaf(d, d, between);
-      m2 = __fadd_rn(m2, v.y);
-    }
-    // explicit intrinsics throughout the epilogue math: no FMA-contraction freedom for the compiler, so the one-CTA and
-    // CTA-pair instantiations (and any future one) produce the same bits for the same row
-    const float var = __fmul_rn(fmaf(between, __fmul_rn(inv_slots, __frcp_rn(ep.ln_inv_dim)), m2), ep.ln_inv_dim);
-    rstd = rsqrtf(__fadd_rn(var, ep.ln_eps));
-  }
+  // Row statistics arrive as one (mean_i, M2_i) pair per 128-column block (M2 = sum of squared deviations from the block's own
+  // mean) and are combined Chan-style in a fixed order: no E[y^2] - mu^2 cancellation when |mean| >> std, bitwise reproducible.
+  // (explicit intrinsics throughout the epilogue math: no FMA-contraction freedom for the compiler, so the one-CTA and CTA-pair
+  // instantiations produce the same bits for the same row)
+  if (ln_fold && row_ok) ln_row_stats(ep.stats_in, row, ep.stats_in_slots, ep.ln_inv_dim, ep.ln_eps, mu, rstd);
   long long dst_row = row;
   if (ep.seg_row_offset != nullptr && row_ok) {
     const int seg = row / ep.seg_len;
@@ -168,6 +175,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmEpilogue& ep, int M, int
     dst_row = static_cast<long long>(seg) * ep.seg_stride + (row - seg * ep.seg_len);
   }
   __nv_bfloat16* c_row = ep.c + dst_row * ep.ldc;
+  float* c_row32 = reinterpret_cast<float*>(ep.c) + c_extra + dst_row * ep.ldc;     // out_f32 only (c_extra: split-K slice)
   const uint32_t taddr = tmem_acc + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(half * kColsPerWarp);
   const uint32_t sa_addr = smem_u32(s_col + half * kColsPerWarp), sb_addr = smem_u32(s_col + kTileN + half * kColsPerWarp);
   const uint32_t out_addr = out.buf != nullptr ? smem_u32(out.buf) : 0u;
@@ -188,10 +196,13 @@ __device__ __forceinline__ void epilogue_tile(const GemmEpilogue& ep, int M, int
     if (chunk + 1 < kChunks) tmem_ld_32x32b_x32(taddr + static_cast<uint32_t>((chunk + 1) * 32), r[(chunk + 1) & 1]);
     else release();                                   // every TMEM read of this warp has landed in registers
     const int col0 = col_tile0 + half * kColsPerWarp + chunk * 32;
-    if (out.buf != nullptr && out.n_bufs == 1 && (chunk & 1) == 0) {
-      // single staging buffer: the previous slab's TMA store must have finished READING it before anyone overwrites it
-      if (out.issuer) bulk_wait_group_read<0>();
-      named_bar_sync(out.barrier_id, 128);
+    const uint32_t slab_q = out.slab_seq + static_cast<uint32_t>(chunk >> 1);
+    const uint32_t slab_buf = slab_q & static_cast<uint32_t>(out.n_bufs - 1);
+    if (out.buf != nullptr && (chunk & 1) == 0) {
+      // the TMA store that last used this staging buffer must have finished READING it (signalled by the store warp)
+      TP_PROF_T0();
+      mbar_wait(&out.empty_bar[slab_buf], ((slab_q >> (out.n_bufs - 1)) & 1u) ^ 1u);
+      TP_PROF_ADD(pc[2]);
     }
     if (col0 < N) {        // N is a multiple of 32 (checked on the host) -> whole chunk in or out
       // kSubPairs packed pairs (2 columns each) go through every step together: each run-time option is ONE warp-uniform branch
@@ -248,63 +259,174 @@ __device__ __forceinline__ void epilogue_tile(const GemmEpilogue& ep, int M, int
         }
         if (out.buf != nullptr) {
           // slab = 2 chunks; 16-byte piece index inside the 128-byte row, XOR-swizzled with (row & 7) like TMA's SWIZZLE_128B
-          const uint32_t row_base = out_addr + static_cast<uint32_t>(((chunk >> 1) & (out.n_bufs - 1)) * kOutSlabBytes + rloc * 128);
+          const uint32_t row_base = out_addr + static_cast<uint32_t>(slab_buf * kOutSlabBytes + rloc * 128);
 #pragma unroll
           for (int g = 0; g < kSubPairs / 4; ++g) {
             const int ci = (chunk & 1) * 4 + sub * (kSubPairs / 4) + g;
             sts_u4(row_base + static_cast<uint32_t>((ci ^ (rloc & 7)) << 4), pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
           }
         } else if (row_ok) {
+          if (ep.out_f32) {
 #pragma unroll
-          for (int g = 0; g < kSubPairs / 4; ++g)
-            *reinterpret_cast<uint4*>(c_row + col0 + sub * kSubPairs * 2 + g * 8) = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+            for (int g = 0; g < kSubPairs / 2; ++g) {
+              float4 f;
+              upk2(v[2 * g], f.x, f.y);
+              upk2(v[2 * g + 1], f.z, f.w);
+              *reinterpret_cast<float4*>(c_row32 + col0 + sub * kSubPairs * 2 + g * 4) = f;
+            }
+          } else {
+#pragma unroll
+            for (int g = 0; g < kSubPairs / 4; ++g)
+              *reinterpret_cast<uint4*>(c_row + col0 + sub * kSubPairs * 2 + g * 8) = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+          }
         }
+      }
+    }
+    if (chunk == kChunks - 1 && ep.stats_out != nullptr && row_ok) {
+      // statistics are final once the last chunk's values exist; written BEFORE the last slab is handed over so that the store
+      // warp's tile-done release (dependent GEMMs of the same launch read them) covers these stores too
+      const int slot = (col_tile0 + half * kColsPerWarp) / kColsPerWarp;
+      long long srow = row;
+      if (ep.wm_s != 0) srow = window_major_row(row, ep.wm_s);
+      if (slot < ep.stats_out_slots) {
+        // (mean, M2) of this 128-column block: mean = shift + s1/n, M2 = s2 - s1^2/n  (deviations from `shift` are O(std): no cancellation)
+        constexpr float inv_n = 1.0f / kColsPerWarp;
+        const float dm = __fmul_rn(s1, inv_n);
+        reinterpret_cast<float2*>(ep.stats_out)[srow * ep.stats_out_slots + slot] =
+            make_float2(__fadd_rn(shift, dm), fmaxf(fmaf(-s1, dm, s2), 0.f));
       }
     }
     if (out.buf != nullptr && (chunk & 1) == 1) {
-      // slab complete: publish to the async proxy, make sure the previous store of this half has drained its buffer
-      // (so the NEXT slab may overwrite it), then one thread issues the TMA store
-      {
-        TP_PROF_T0();
-        fence_proxy_async_smem();
-        TP_PROF_ADD(pc[1]);
-      }
-      {
-        TP_PROF_T0();
-        if (out.issuer && out.n_bufs == 2) bulk_wait_group_read<0>();
-        named_bar_sync(out.barrier_id, 128);
-        TP_PROF_ADD(pc[2]);
-      }
-      if (out.issuer) {
-        const int slab = chunk >> 1;
-        const uint8_t* src = out.buf + (slab & (out.n_bufs - 1)) * kOutSlabBytes;
-        const int col = col_tile0 + half * kColsPerWarp + slab * 64;
-        if (out.seg_len == 0) {
-          for (int p = 0; p < out.n_maps; ++p) tma_store_2d(out.tmap + p, src, col, out.row_tile0);
-        } else {
-          // Segmented output rows (global row g = seg * seg_len + r  ->  map coordinate (col, r, seg)): the slab's 128 rows are
-          // cut at segment boundaries and each piece leaves through the SAME fixed-size box.  A piece that starts before the slab
-          // or ends after it is positioned so that the surplus box rows fall outside [0, seg_len) of its segment, where TMA clips
-          // them (signed coordinates): src_row = clamp(a, 0, 128 - box), r0 = src_row - a, a = slab row of the segment's row 0.
-          // The 128B swizzle is a function of the absolute shared-memory address, so any 128-byte-aligned source row works.
-          int seg = out.row_tile0 / out.seg_len;
-          for (int a = seg * out.seg_len - out.row_tile0; a < kBlockM && seg < out.n_segs; a += out.seg_len, ++seg) {
-            const int src_row = min(max(a, 0), kBlockM - out.seg_box);
-            for (int p = 0; p < out.n_maps; ++p) tma_store_3d(out.tmap + p, src + src_row * 128, col, src_row - a, seg);
-          }
-        }
-        bulk_commit_group();
-      }
+      // slab complete: make the generic-proxy writes visible to the async proxy, then one arrive per warp hands it to the store warp
+      TP_PROF_T0();
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane_id() == 0) mbar_arrive(&out.full_bar[slab_buf]);
+      TP_PROF_ADD(pc[1]);
     }
   }
-  if (ep.stats_out != nullptr && row_ok) {
-    const int slot = (col_tile0 + half * kColsPerWarp) / kColsPerWarp;
-    if (slot < ep.stats_out_slots) {
-      // (mean, M2) of this 128-column block: mean = shift + s1/n, M2 = s2 - s1^2/n  (deviations from `shift` are O(std): no cancellation)
-      constexpr float inv_n = 1.0f / kColsPerWarp;
-      const float dm = __fmul_rn(s1, inv_n);
-      reinterpret_cast<float2*>(ep.stats_out)[static_cast<long long>(row) * ep.stats_out_slots + slot] =
-          make_float2(__fadd_rn(shift, dm), fmaxf(fmaf(-s1, dm, s2), 0.f));
+}
+
+// ------------------------------------------------------------------------------------------------
+// KV-attention tiles (problem kind 1): the MHA in-projections of the keys and values FUSED with the local-window attention core
+// (builder.py:122-130 == nn.MultiheadAttention, L = 1 query, S = s*s keys per window, 8 heads x 128).
+//   A tile = 256 window-major rows (CTA pair) x ONE head: the MMA warp runs two K=1024 GEMMs into the two 128-column halves of
+//   the accumulator buffer — k' = y_k . (gamma_k W_ik)^T and v' = y_v . (gamma_v W_iv)^T for this head — and the epilogue, thread ==
+//   key row, applies the folded LayerNorms, dots k' with the window's q' (already scaled by 1/sqrt 128), takes the softmax over
+//   the s*s consecutive lanes of the window with warp shuffles, scales v' and reduces it over the same lanes with a halving
+//   exchange, and writes the window's 128 context channels of this head.  k' and v' never exist in memory (fp32, unrounded, in
+//   registers): the [R,1024] x 2 round trip through HBM and the separate attention kernel are gone.
+// The two column halves of the epilogue (warps 0-3 / 4-7) each take 64 channels of the head: their partial scores meet in
+// shared memory (fixed order: half 0 + half 1).
+// ------------------------------------------------------------------------------------------------
+struct AttnParams {
+  const __nv_bfloat16* qp;      // [Q, 1024] q', row = window index (= query index), scaled
+  __nv_bfloat16* ctx;           // [Q, 1024]
+  const float* stats_k;         // [R, slots, 2] (window-major rows) per-block (mean, M2) of y_k / y_v
+  const float* stats_v;
+  const float* wsum_k;          // [1024] LayerNorm-fold column vectors of the two in-projections
+  const float* cst_k;
+  const float* wsum_v;
+  const float* cst_v;
+  int s;                        // scale factor: W = s*s consecutive rows per window (2 or 4)
+  int stats_slots;
+  float ln_inv_dim, ln_eps;
+  int* done_counter;            // ctx row blocks of 256 queries: counter[(m_blk * 256 / W) / 256] += 1 per (CTA, head)
+  // dependencies of a tile: the raster row blocks of y_k / y_v covering the crops it touches, and its queries' q' row block
+  const int* k_counter;
+  const int* v_counter;
+  int kv_target;
+  const int* q_counter;
+  int q_target;
+};
+
+__device__ __forceinline__ float bf16x2_get(const uint4& v, int i) {      // i in [0, 8)
+  const uint32_t w = i < 4 ? (i < 2 ? v.x : v.y) : (i < 6 ? v.z : v.w);
+  return (i & 1) ? bf16_hi(w) : bf16_lo(w);
+}
+
+template <typename ReleaseFn>
+__device__ __forceinline__ void attn_epilogue_tile(const AttnParams& at, int M, uint32_t tmem_acc, int row, int head, int quarter, int half,
+                                                   const float* s_vec, float* s_score, ReleaseFn release) {
+  const int W = at.s * at.s;
+  const bool row_ok = row < M;
+  const uint32_t lane = lane_id();
+  const int rloc = quarter * 32 + static_cast<int>(lane);
+  float mu_k = 0.f, rstd_k = 0.f, mu_v = 0.f, rstd_v = 0.f;
+  if (row_ok) {
+    ln_row_stats(at.stats_k, row, at.stats_slots, at.ln_inv_dim, at.ln_eps, mu_k, rstd_k);
+    ln_row_stats(at.stats_v, row, at.stats_slots, at.ln_inv_dim, at.ln_eps, mu_v, rstd_v);
+  }
+  const long long window = row / W;
+  const int col0 = head * 128 + half * 64;                  // first channel of this thread's 64
+  const float* wsum_k = s_vec + half * 64;                  // staged per tile: [wsum_k | cst_k | wsum_v | cst_v][128]
+  const float* cst_k = s_vec + 128 + half * 64;
+  const float* wsum_v = s_vec + 256 + half * 64;
+  const float* cst_v = s_vec + 384 + half * 64;
+  const uint32_t taddr_k = tmem_acc + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(half * 64);
+  const uint32_t taddr_v = taddr_k + 128u;
+
+  uint32_t r[2][32];
+  tmem_ld_32x32b_x32(taddr_k, r[0]);
+  float score = 0.f;
+#pragma unroll
+  for (int chunk = 0; chunk < 2; ++chunk) {
+    tmem_ld_wait();
+    tmem_ld_32x32b_x32(chunk == 0 ? taddr_k + 32u : taddr_v, r[(chunk + 1) & 1]);
+    uint4 q4[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      q4[i] = row_ok ? __ldg(reinterpret_cast<const uint4*>(at.qp + window * 1024 + col0 + chunk * 32) + i) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+    for (int c = 0; c < 32; ++c) {
+      const float kf = fmaf(rstd_k, fmaf(-mu_k, wsum_k[chunk * 32 + c], __uint_as_float(r[chunk & 1][c])), cst_k[chunk * 32 + c]);
+      score = fmaf(bf16x2_get(q4[c >> 3], c & 7), kf, score);
+    }
+  }
+  // the other column half holds the rest of the head's 128 channels: partial scores meet in shared memory
+  s_score[half * 128 + rloc] = score;
+  named_bar_sync(kEpiBarrierId, kEpiThreads);
+  score = __fadd_rn(s_score[rloc], s_score[128 + rloc]);
+  // softmax over the W keys of my window = W consecutive lanes (W divides 32, windows never straddle a warp)
+  float mx = score;
+  for (int off = 1; off < W; off <<= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+  const float e = __expf(score - mx);
+  float den = e;
+  for (int off = 1; off < W; off <<= 1) den += __shfl_xor_sync(0xffffffffu, den, off);
+  const float p = e * (1.0f / den);
+  // ctx = sum over the window's lanes of p * v': halving exchange — after log2(W) steps each lane holds 32 / W channels of the chunk
+#pragma unroll
+  for (int chunk = 0; chunk < 2; ++chunk) {
+    tmem_ld_wait();
+    if (chunk == 0) tmem_ld_32x32b_x32(taddr_v + 32u, r[1]);
+    else release();                                   // every TMEM read of this warp has landed in registers
+    float v[32];
+#pragma unroll
+    for (int c = 0; c < 32; ++c)
+      v[c] = p * fmaf(rstd_v, fmaf(-mu_v, wsum_v[chunk * 32 + c], __uint_as_float(r[chunk & 1][c])), cst_v[chunk * 32 + c]);
+    int first = 0;                                    // my live values cover channels [first, first + 32 >> steps) of the chunk
+#pragma unroll
+    for (int step = 0; step < 4; ++step) {
+      const int off = 1 << step;
+      const int hn = 16 >> step;                      // steps run as a prefix (off < W), so the live count before step k is 32 >> k
+      if (off < W) {
+        const bool up = (lane & off) != 0;            // upper lane of the pair keeps the upper half
+#pragma unroll
+        for (int i = 0; i < hn; ++i) {
+          const float send = up ? v[i] : v[i + hn];
+          const float keep = up ? v[i + hn] : v[i];
+          v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+        if (up) first += hn;
+      }
+    }
+    if (row_ok) {
+      __nv_bfloat16* dst = at.ctx + window * 1024 + col0 + chunk * 32 + first;
+      if (W == 4) {
+        *reinterpret_cast<uint4*>(dst) = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+      } else {                                        // W == 16: two channels per lane
+        *reinterpret_cast<uint32_t*>(dst) = pack_bf16x2(v[0], v[1]);
+      }
     }
   }
 }
@@ -462,7 +584,7 @@ tp_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tcgen05_fence_after();
       uint64_t* release_bar = &tmem_empty_bar[acc];
-      const OutStage no_stage{nullptr, nullptr, 0, 0, 0, 0, 0, 0, 0, false};
+      const OutStage no_stage{nullptr, nullptr, nullptr, 1, 0u};
       epilogue_tile<kBlockN>(ep, M, N, tmem_base + static_cast<uint32_t>(acc * kBlockN),
                              m_blk * kBlockM + quarter * 32 + static_cast<int>(lane), n_blk * kBlockN, quarter, half, s_col, no_stage, [&]() {
                                tcgen05_fence_before();
@@ -501,16 +623,21 @@ struct Gemm2Config {
   static constexpr int kTmemCols = 2 * kTileN;
   static constexpr int kOutBytes = 2 * kOutBufs * kOutSlabBytes; // [2 column halves][kOutBufs] output slabs for TMA stores
   static constexpr int kColStageBytes = 2 * 2 * kTileN * 4;
-  static constexpr int kBarrierBytes = (2 * kStages + 4) * 8 + 16;
-  static constexpr int kSmemBytes = kStages * kStageBytes + kOutBytes + kColStageBytes + kBarrierBytes + 1024;
+  static constexpr int kScoreBytes = 2 * kBlockM * 4;            // KV-attention tiles: partial scores of the two column halves
+  static constexpr int kBarrierBytes = (2 * kStages + 4 + 4 * kOutBufs) * 8 + 16;   // ring + accumulators + slab full/empty per half
+  static constexpr int kSmemBytes = kStages * kStageBytes + kOutBytes + kColStageBytes + kScoreBytes + kBarrierBytes + 1024;
 };
 
-constexpr int kMaxGroup = 3;
+constexpr int kMaxGroup = 8;
 
 constexpr int kMaxAParts = 4;
 
 struct GemmProblem {
   CUtensorMap tmap_a, tmap_b, tmap_c;
+  CUtensorMap tmap_a2, tmap_b2;              // kind 1: the value operands (tmap_a / tmap_b: the key operands)
+  int kind;              // 0: GEMM with the fused epilogue; 1: KV-attention tile (see attn_epilogue_tile)
+  int c_wm_s;            // != 0: tmap_c is the 5-D window-major map of GemmEpilogue::wm_s
+  AttnParams attn;
   CUtensorMap tmap_a_more[kMaxAParts - 1];   // A given as several tensors side by side along K (e.g. the four CLIP hidden states
                                              // that the reference concatenates, clip_encoder.py:28-44): part p covers k-blocks
                                              // [p * a_kblocks_per_part, (p+1) * a_kblocks_per_part)
@@ -522,20 +649,56 @@ struct GemmProblem {
   int use_tma_store;     // C through TMA stores (0 when rows are scattered to arbitrary segment offsets)
   int c_seg_len;         // != 0: tmap_c (and the peer maps) are 3-D (cols, row in segment, segment): uniform-stride segmented output
   int num_n_blocks;
-  int num_tiles;
+  int num_tiles;         // = tiles_mn * k_splits
   int num_k_blocks;
+  // split-K (wgrads whose output is a few tiles but whose contraction runs over every row of the batch): tile = (split, m, n),
+  // split s covers k-blocks [s * kb_per_split, (s+1) * kb_per_split) and writes its fp32 partial to slice s of C (ep.out_f32)
+  int k_splits;          // >= 1
+  int kb_per_split;
+  int tiles_mn;
+  long long c_split_stride;   // floats between consecutive split slices of C
+  // Dependencies between GEMMs of ONE launch (a chain of linears runs as a single persistent kernel: no ramp / drain / partial
+  // last wave per layer).  Tiles are numbered problem after problem and every CTA pair walks its tiles in increasing order, so a
+  // tile only ever waits for lower-numbered tiles: no deadlock as long as all pairs are co-resident (grid <= 74 pairs).
+  int* done_counter;     // != nullptr: [ceil(M/256)] tile counter of THIS problem's output row blocks, +1 per (CTA, column half)
+                         //             once that part of a tile is in global memory (bumped by the store warps)
+  const int* dep_counter;// != nullptr: the A operand's row block m_blk is ready when dep_counter[m_blk >> dep_shift] >= dep_target
+  int dep_target;        //             (= 4 * num_n_blocks of the producing problem: 2 CTAs x 2 column halves per tile)
+  int dep_shift;         //             0 for GEMM -> GEMM (same row blocks); 31 for a single launch-wide counter (front work)
+  int dep_span;          // != 0: the producer is a KV-attention problem: row block m_blk (256 queries) is complete after dep_per arrivals
+  int dep_src_blocks;    //       from each of its source tiles [m_blk * dep_span, min((m_blk + 1) * dep_span, dep_src_blocks))
+  int dep_per;
+  int peer_out;          // C of this problem goes to the PeerStores maps (fused all-gather) instead of tmap_c
   GemmEpilogue ep;
+};
+
+// Optional prologue work of a chained launch: the point queries (builder.py:117-118: bilinear 24x24 -> g x g, align_corners=False
+// == a fixed stencil per s x s window: the centre token for odd s, the mean of the centre 2x2 for even s; fp32, one bf16 rounding).
+// Done by the epilogue warps of every CTA BEFORE their first tile — that time is otherwise idle (the first accumulator of the
+// K=4096 GEMM takes ~33k cycles to appear), so the stencil costs nothing and needs no launch of its own.  Every CTA handles a
+// strided share of the (query, 8-channel vector) items and then bumps done_counter once; the GEMM that reads q waits for
+// gridDim.x arrivals.
+struct FrontWork {
+  const __nv_bfloat16* x0;   // nullptr: no front work in this launch
+  __nv_bfloat16* q;          // [n_queries, 1024]
+  long long crop_stride;     // elements between crops of x0
+  long long n_queries;
+  int s;                     // scale factor
+  int* done_counter;
 };
 
 struct GemmGroup {
   GemmProblem p[kMaxGroup];
   int count;
   int total_tiles;
+  FrontWork front;
 };
 
 struct TileRef {
   const GemmProblem* pr;
   int m_blk, n_blk;
+  int kb0, kb1;          // k-block range of this tile (the whole K unless the problem is split)
+  int split;
 };
 
 __device__ __forceinline__ TileRef decode_tile(const GemmGroup& g, int tile) {
@@ -546,8 +709,15 @@ __device__ __forceinline__ TileRef decode_tile(const GemmGroup& g, int tile) {
   }
   TileRef t;
   t.pr = &g.p[p];
+  t.split = 0;
+  if (t.pr->k_splits > 1) {
+    t.split = tile / t.pr->tiles_mn;
+    tile -= t.split * t.pr->tiles_mn;
+  }
   t.m_blk = tile / t.pr->num_n_blocks;
   t.n_blk = tile - t.m_blk * t.pr->num_n_blocks;
+  t.kb0 = t.split * t.pr->kb_per_split;
+  t.kb1 = t.kb0 + t.pr->kb_per_split < t.pr->num_k_blocks ? t.kb0 + t.pr->kb_per_split : t.pr->num_k_blocks;
   return t;
 }
 
@@ -562,11 +732,14 @@ tp_gemm2_kernel(const __grid_constant__ GemmGroup grp, const __grid_constant__ P
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* s_out = smem + kStages * Cfg::kStageBytes;                                  // 1 KiB aligned (swizzle atoms)
   float* s_col_base = reinterpret_cast<float*>(s_out + Cfg::kOutBytes);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_out + Cfg::kOutBytes + Cfg::kColStageBytes);
+  float* s_score = reinterpret_cast<float*>(s_out + Cfg::kOutBytes + Cfg::kColStageBytes);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_out + Cfg::kOutBytes + Cfg::kColStageBytes + Cfg::kScoreBytes);
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tmem_full_bar = empty_bar + kStages;
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;
-  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  uint64_t* slab_full_bar = tmem_empty_bar + 2;                 // [2 halves][kOutBufs]
+  uint64_t* slab_empty_bar = slab_full_bar + 2 * Cfg::kOutBufs; // [2 halves][kOutBufs]
+  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(slab_empty_bar + 2 * Cfg::kOutBufs);
 
   const int warp_idx = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
   const uint32_t lane = lane_id();
@@ -581,6 +754,10 @@ tp_gemm2_kernel(const __grid_constant__ GemmGroup grp, const __grid_constant__ P
       tma_prefetch_desc(&grp.p[i].tmap_a);
       for (int q = 1; q < grp.p[i].a_parts; ++q) tma_prefetch_desc(&grp.p[i].tmap_a_more[q - 1]);
       tma_prefetch_desc(&grp.p[i].tmap_b);
+      if (grp.p[i].kind == 1) {
+        tma_prefetch_desc(&grp.p[i].tmap_a2);
+        tma_prefetch_desc(&grp.p[i].tmap_b2);
+      }
       if (grp.p[i].use_tma_store) tma_prefetch_desc(&grp.p[i].tmap_c);
     }
   } else if (warp_idx == kMmaWarp && lane == 0) {
@@ -591,6 +768,10 @@ tp_gemm2_kernel(const __grid_constant__ GemmGroup grp, const __grid_constant__ P
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full_bar[i], 1);                   // multicast tcgen05.commit from the leader
       mbar_init(&tmem_empty_bar[i], 2 * kNumEpiWarps);   // epilogue warps of BOTH CTAs (waited on in the leader only)
+    }
+    for (int i = 0; i < 2 * Cfg::kOutBufs; ++i) {
+      mbar_init(&slab_full_bar[i], kNumEpiWarps / 2);    // one arrive per epilogue warp of the column half
+      mbar_init(&slab_empty_bar[i], 1);                  // the half's store warp
     }
     fence_barrier_init();
   } else if (warp_idx == kAllocWarp) {
@@ -618,6 +799,56 @@ tp_gemm2_kernel(const __grid_constant__ GemmGroup grp, const __grid_constant__ P
       const int row0 = t.m_blk * Cfg::kTileM + static_cast<int>(cta_rank) * kBlockM;          // my 128 rows of A
       const int brow0 = t.n_blk * kTileN + static_cast<int>(cta_rank) * (kTileN / 2);        // my half of the B tile
       // segmented A (3-D map, 64-row boxes): global row g -> (segment g / seg_rows, row g % seg_rows); hoisted per tile
+      if (pr.dep_counter != nullptr) {
+        // A's row block is written by an earlier problem of this launch: wait until all its tiles have been published (acquire),
+        // then order the TMA (async proxy) reads after the acquire
+        int target = pr.dep_target;
+        if (pr.dep_span != 0) {
+          const int lo = t.m_blk * pr.dep_span;
+          const int hi = lo + pr.dep_span < pr.dep_src_blocks ? lo + pr.dep_span : pr.dep_src_blocks;
+          target = (hi - lo) * pr.dep_per;
+        }
+        wait_counter_at_least(pr.dep_counter + (t.m_blk >> pr.dep_shift), target);
+        fence_proxy_async_all();
+      }
+      if (pr.kind == 1) {
+        // KV-attention tile: y_k . W_ik(head)^T, then y_v . W_iv(head)^T, through the same ring (B boxes of 64 rows per CTA)
+        const AttnParams& at = pr.attn;
+        if (at.k_counter != nullptr) {
+          // y_k / y_v were stored window-major by raster-ordered GEMMs of this launch: wait for every raster row block of the
+          // crops this tile touches, and for the q' row block of its windows
+          const long long r_lo = static_cast<long long>(t.m_blk) * Cfg::kTileM;
+          const long long r_hi = r_lo + Cfg::kTileM < pr.M ? r_lo + Cfg::kTileM : pr.M;
+          const int n_blocks = (pr.M + Cfg::kTileM - 1) / Cfg::kTileM;
+          int b_lo = static_cast<int>((r_lo / 576) * 576 / Cfg::kTileM);
+          int b_hi = static_cast<int>((((r_hi - 1) / 576 + 1) * 576 + Cfg::kTileM - 1) / Cfg::kTileM);
+          if (b_hi > n_blocks) b_hi = n_blocks;
+          for (int b = b_lo; b < b_hi; ++b) {
+            wait_counter_at_least(at.k_counter + b, at.kv_target);
+            wait_counter_at_least(at.v_counter + b, at.kv_target);
+          }
+          if (at.q_counter != nullptr) wait_counter_at_least(at.q_counter + ((r_lo / (at.s * at.s)) >> 8), at.q_target);
+          fence_proxy_async_all();
+        }
+        const int hrow0 = t.n_blk * 128 + static_cast<int>(cta_rank) * 64;      // my 64 weight rows of this head
+        for (int op = 0; op < 2; ++op) {
+          const CUtensorMap* ta = op == 0 ? &pr.tmap_a : &pr.tmap_a2;
+          const CUtensorMap* tb = op == 0 ? &pr.tmap_b : &pr.tmap_b2;
+          for (int kb = 0; kb < pr.num_k_blocks; ++kb) {
+            mbar_wait(&empty_bar[stage], phase ^ 1u);
+            if (elect_one()) {
+              uint8_t* sa = smem + stage * Cfg::kStageBytes;
+              if (is_leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * (Cfg::kABytes + Cfg::kBBytes / 2));
+              else mbar_arrive_cluster(&full_bar[stage], 0);
+              tma_load_2d_pair(sa, ta, &full_bar[stage], kb * kBlockK, row0);
+              tma_load_2d_pair(sa + Cfg::kABytes, tb, &full_bar[stage], kb * kBlockK, hrow0);
+            }
+            __syncwarp();
+            if (++stage == kStages) { stage = 0; phase ^= 1u; }
+          }
+        }
+        continue;
+      }
       int seg0 = 0, srow0 = 0, seg1 = 0, srow1 = 0;
       if (pr.a_seg_rows != 0) {
         seg0 = row0 / pr.a_seg_rows;
@@ -625,7 +856,7 @@ tp_gemm2_kernel(const __grid_constant__ GemmGroup grp, const __grid_constant__ P
         seg1 = (row0 + 64) / pr.a_seg_rows;
         srow1 = row0 + 64 - seg1 * pr.a_seg_rows;
       }
-      for (int kb = 0; kb < pr.num_k_blocks; ++kb) {
+      for (int kb = t.kb0; kb < t.kb1; ++kb) {
         {
           TP_PROF_T0();
           mbar_wait(&empty_bar[stage], phase ^ 1u);
@@ -675,8 +906,8 @@ tp_gemm2_kernel(const __grid_constant__ GemmGroup grp, const __grid_constant__ P
       [[maybe_unused]] long long w_full = 0, w_tmem = 0;
       [[maybe_unused]] const long long t_begin = clock64();
       for (int tile = pair_idx; tile < num_tiles; tile += num_pairs) {
-        const GemmProblem& mpr = *decode_tile(grp, tile).pr;
-        const int num_k_blocks = mpr.num_k_blocks;
+        const TileRef mt = decode_tile(grp, tile);
+        const GemmProblem& mpr = *mt.pr;
         const bool mn_major = mpr.ab_mn_major != 0;
         const uint32_t idesc = mn_major ? make_idesc_bf16_f32(Cfg::kTileM, kTileN, 1, 1) : make_idesc_bf16_f32(Cfg::kTileM, kTileN);
         {
@@ -686,7 +917,33 @@ tp_gemm2_kernel(const __grid_constant__ GemmGroup grp, const __grid_constant__ P
         }
         tcgen05_fence_after();
         const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * kTileN);
-        for (int kb = 0; kb < num_k_blocks; ++kb) {
+        if (mpr.kind == 1) {
+          // two M=256 x N=128 GEMMs into the two halves of the accumulator buffer (k' then v')
+          constexpr uint32_t idesc_kv = make_idesc_bf16_f32(Cfg::kTileM, 128);
+          for (int op = 0; op < 2; ++op) {
+            for (int kb = 0; kb < mpr.num_k_blocks; ++kb) {
+              mbar_wait(&full_bar[stage], phase);
+              tcgen05_fence_after();
+              if (elect_one()) {
+                const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
+                const uint64_t desc_a = make_smem_desc_kmajor_sw128(sa);
+                const uint64_t desc_b = make_smem_desc_kmajor_sw128(sa + Cfg::kABytes);
+#pragma unroll
+                for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+                  umma_bf16_pair(tmem_d + static_cast<uint32_t>(op * 128), desc_a + static_cast<uint64_t>(k * 2), desc_b + static_cast<uint64_t>(k * 2),
+                                 idesc_kv, static_cast<uint32_t>((kb | k) != 0));
+                }
+                umma_commit_pair(&empty_bar[stage], 0x3);
+                if (op == 1 && kb == mpr.num_k_blocks - 1) umma_commit_pair(&tmem_full_bar[acc], 0x3);
+              }
+              __syncwarp();
+              if (++stage == kStages) { stage = 0; phase ^= 1u; }
+            }
+          }
+          if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+          continue;
+        }
+        for (int kb = mt.kb0; kb < mt.kb1; ++kb) {
           {
             TP_PROF_T0();
             mbar_wait(&full_bar[stage], phase);              // both CTAs' boxes have landed
@@ -701,7 +958,7 @@ tp_gemm2_kernel(const __grid_constant__ GemmGroup grp, const __grid_constant__ P
 #pragma unroll
               for (int k = 0; k < kBlockK / kUmmaK; ++k) {
                 umma_bf16_pair(tmem_d, desc_a + static_cast<uint64_t>(k * 2), desc_b + static_cast<uint64_t>(k * 2), idesc,
-                               static_cast<uint32_t>((kb | k) != 0));
+                               static_cast<uint32_t>(((kb - mt.kb0) | k) != 0));
               }
             } else {
               // MN-major tiles: two 64-wide MN atoms 8 KiB apart per operand; one UMMA (K = 16) consumes two 8-row K groups = 2 KiB
@@ -710,11 +967,11 @@ tp_gemm2_kernel(const __grid_constant__ GemmGroup grp, const __grid_constant__ P
 #pragma unroll
               for (int k = 0; k < kBlockK / kUmmaK; ++k) {
                 umma_bf16_pair(tmem_d, desc_a + static_cast<uint64_t>(k * (2048 >> 4)), desc_b + static_cast<uint64_t>(k * (2048 >> 4)), idesc,
-                               static_cast<uint32_t>((kb | k) != 0));
+                               static_cast<uint32_t>(((kb - mt.kb0) | k) != 0));
               }
             }
             umma_commit_pair(&empty_bar[stage], 0x3);        // frees the slot in BOTH CTAs
-            if (kb == num_k_blocks - 1) umma_commit_pair(&tmem_full_bar[acc], 0x3);   // accumulator complete -> both epilogues
+            if (kb == mt.kb1 - 1) umma_commit_pair(&tmem_full_bar[acc], 0x3);   // accumulator complete -> both epilogues
           }
           __syncwarp();
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
@@ -737,13 +994,77 @@ tp_gemm2_kernel(const __grid_constant__ GemmGroup grp, const __grid_constant__ P
     const int epi_tid = e * 32 + static_cast<int>(lane);
     int acc = 0;
     uint32_t acc_phase = 0;
-    bool stored = false;
+    uint32_t slab_seq = 0;
     [[maybe_unused]] long long w_acc = 0, t_work = 0;
     [[maybe_unused]] long long pc[3] = {0, 0, 0};
+    if (grp.front.x0 != nullptr) {
+      // point queries: this CTA's share of the (query, 8-channel vector) items, 128 vectors per query
+      const FrontWork& fw = grp.front;
+      const int g = 24 / fw.s, mq = g * g;
+      const int lo = (fw.s & 1) ? (fw.s - 1) / 2 : fw.s / 2 - 1;          // first tap inside the window (row and column)
+      const long long items = fw.n_queries * 128;
+      for (long long idx = static_cast<long long>(blockIdx.x) * kEpiThreads + epi_tid; idx < items; idx += static_cast<long long>(gridDim.x) * kEpiThreads) {
+        const long long query = idx >> 7;
+        const int vec = static_cast<int>(idx & 127);
+        const long long n = query / mq;
+        const int m = static_cast<int>(query - n * mq);
+        const int hb = m / g, wb = m - hb * g;
+        const __nv_bfloat16* base = fw.x0 + n * fw.crop_stride + vec * 8 + static_cast<long long>((hb * fw.s + lo) * 24 + wb * fw.s + lo) * 1024;
+        uint4 o = __ldg(reinterpret_cast<const uint4*>(base));
+        if (!(fw.s & 1)) {
+          const uint4 b = __ldg(reinterpret_cast<const uint4*>(base + 1024)), c = __ldg(reinterpret_cast<const uint4*>(base + 24 * 1024)),
+                      d = __ldg(reinterpret_cast<const uint4*>(base + 25 * 1024));
+          // 0.25 * ((a + b) + (c + d)): the association of point_query_kernel (bit-identical; power-of-two scaling is exact)
+          auto mean4 = [](uint32_t a_, uint32_t b_, uint32_t c_, uint32_t d_) {
+            const float l = 0.25f * ((bf16_lo(a_) + bf16_lo(b_)) + (bf16_lo(c_) + bf16_lo(d_)));
+            const float h = 0.25f * ((bf16_hi(a_) + bf16_hi(b_)) + (bf16_hi(c_) + bf16_hi(d_)));
+            return pack_bf16x2(l, h);
+          };
+          o = make_uint4(mean4(o.x, b.x, c.x, d.x), mean4(o.y, b.y, c.y, d.y), mean4(o.z, b.z, c.z, d.z), mean4(o.w, b.w, c.w, d.w));
+        }
+        *reinterpret_cast<uint4*>(fw.q + query * 1024 + vec * 8) = o;
+      }
+      named_bar_sync(kEpiBarrierId, kEpiThreads);           // every epilogue thread's stores are issued ...
+      if (epi_tid == 0) {
+        __threadfence();                                     // ... and ordered (cumulatively) before the release below
+        red_release_gpu_add(fw.done_counter, 1);
+      }
+    }
     for (int tile = pair_idx; tile < num_tiles; tile += num_pairs) {
       const TileRef t = decode_tile(grp, tile);
       const GemmProblem& pr = *t.pr;
       float* s_col = s_col_base + acc * 2 * kTileN;
+      uint64_t* release_bar = &tmem_empty_bar[acc];
+      const int row_tile0 = t.m_blk * Cfg::kTileM + static_cast<int>(cta_rank) * kBlockM;
+      const int row = row_tile0 + quarter * 32 + static_cast<int>(lane);
+      if (pr.kind == 1) {
+        const AttnParams& at = pr.attn;
+        {   // this head's slices of the four LayerNorm-fold vectors: [wsum_k | cst_k | wsum_v | cst_v][128]
+          const int which = epi_tid >> 7, c = epi_tid & 127, col = t.n_blk * 128 + c;
+          s_col[epi_tid] = __ldg((which == 0 ? at.wsum_k : at.cst_k) + col);
+          s_col[256 + epi_tid] = __ldg((which == 0 ? at.wsum_v : at.cst_v) + col);
+          named_bar_sync(kEpiBarrierId, kEpiThreads);
+        }
+        mbar_wait(&tmem_full_bar[acc], acc_phase);
+        tcgen05_fence_after();
+        attn_epilogue_tile(at, pr.M, tmem_base + static_cast<uint32_t>(acc * kTileN), row, t.n_blk, quarter, half, s_col, s_score, [&]() {
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (is_leader) mbar_arrive(release_bar);
+            else mbar_arrive_cluster(release_bar, 0);
+          }
+        });
+        if (at.done_counter != nullptr) {
+          named_bar_sync(kEpiBarrierId, kEpiThreads);       // every epilogue thread's ctx stores are issued ...
+          if (epi_tid == 0) {
+            __threadfence();                                 // ... and ordered (cumulatively) before the release
+            red_release_gpu_add(at.done_counter + ((static_cast<long long>(t.m_blk) * Cfg::kTileM / (at.s * at.s)) >> 8), 1);
+          }
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        continue;
+      }
       stage_col_vectors<kTileN>(pr.ep, pr.N, t.n_blk * kTileN, s_col, epi_tid);
       {
         TP_PROF_T0();
@@ -752,14 +1073,9 @@ tp_gemm2_kernel(const __grid_constant__ GemmGroup grp, const __grid_constant__ P
       }
       TP_PROF_T0();
       tcgen05_fence_after();
-      uint64_t* release_bar = &tmem_empty_bar[acc];
-      const int row_tile0 = t.m_blk * Cfg::kTileM + static_cast<int>(cta_rank) * kBlockM;
-      const int row = row_tile0 + quarter * 32 + static_cast<int>(lane);
-      const OutStage out{pr.use_tma_store ? s_out + half * Cfg::kOutBufs * kOutSlabBytes : nullptr, peers.count > 0 ? &peers.m[0] : &pr.tmap_c,
-                         pr.c_seg_len, pr.c_seg_len < kBlockM ? pr.c_seg_len : kBlockM, pr.c_seg_len != 0 ? pr.M / pr.c_seg_len : 0,
-                         peers.count > 0 ? peers.count : 1, row_tile0, Cfg::kOutBufs, static_cast<uint32_t>(2 + half),
-                         quarter == 0 && lane == 0};
-      stored = stored || pr.use_tma_store;
+      const OutStage out{pr.use_tma_store ? s_out + half * Cfg::kOutBufs * kOutSlabBytes : nullptr, slab_full_bar + half * Cfg::kOutBufs,
+                         slab_empty_bar + half * Cfg::kOutBufs, Cfg::kOutBufs, slab_seq};
+      if (pr.use_tma_store) slab_seq += kTileN / 2 / 64;            // slabs per tile and column half
       epilogue_tile<kTileN>(pr.ep, pr.M, pr.N, tmem_base + static_cast<uint32_t>(acc * kTileN), row, t.n_blk * kTileN, quarter, half, s_col,
                             out, [&]() {
                               tcgen05_fence_before();
@@ -768,13 +1084,9 @@ tp_gemm2_kernel(const __grid_constant__ GemmGroup grp, const __grid_constant__ P
                                 if (is_leader) mbar_arrive(release_bar);
                                 else mbar_arrive_cluster(release_bar, 0);
                               }
-                            }, pc);
+                            }, pc, static_cast<long long>(t.split) * pr.c_split_stride);
       TP_PROF_ADD(t_work);
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
-    }
-    if (stored && quarter == 0 && lane == 0) {
-      bulk_wait_group<0>();                      // my half's last TMA stores have been performed
-      if (peers.count > 0) __threadfence_system();   // ... and are ordered before the cross-GPU barrier that follows the kernel
     }
 #ifdef TP_GEMM_PROFILE
     if (grp.p[0].ep.prof != nullptr && e == 0 && lane == 0) {
@@ -785,6 +1097,80 @@ tp_gemm2_kernel(const __grid_constant__ GemmGroup grp, const __grid_constant__ P
       grp.p[0].ep.prof[blockIdx.x * 16 + 10] = pc[2];          // ... in wait_group.read + named barrier
     }
 #endif
+  }
+
+  if (warp_idx == kStoreWarp0 || warp_idx == kStoreWarp0 + 1) {
+    // ======================================= store warps (both CTAs, one per column half) =========
+    // Walks the same tile sequence as the epilogue warps of its half.  Per slab: wait until the 4 epilogue warps have written
+    // it (mbarrier), issue the TMA store(s) — plain 2-D box, clipped 3-D boxes for segmented rows, one per peer GPU for the
+    // fused all-gather —, wait until the copy engine has READ the buffer and hand it back.  Per tile of a GEMM that others in
+    // this launch depend on: wait for the stores to be PERFORMED, then publish the tile (release) on its row block's counter.
+    const int half = warp_idx - kStoreWarp0;
+    uint64_t* full = slab_full_bar + half * Cfg::kOutBufs;
+    uint64_t* empty = slab_empty_bar + half * Cfg::kOutBufs;
+    uint32_t q = 0;
+    for (int tile = pair_idx; tile < num_tiles; tile += num_pairs) {
+      const TileRef t = decode_tile(grp, tile);
+      const GemmProblem& pr = *t.pr;
+      if (!pr.use_tma_store) continue;
+      const int row_tile0 = t.m_blk * Cfg::kTileM + static_cast<int>(cta_rank) * kBlockM;
+      const bool to_peers = pr.peer_out != 0 && peers.count > 0;
+      const CUtensorMap* maps = to_peers ? &peers.m[0] : &pr.tmap_c;
+      const int n_maps = to_peers ? peers.count : 1;
+      for (int slab = 0; slab < kTileN / 2 / 64; ++slab, ++q) {
+        const uint32_t buf = q & static_cast<uint32_t>(Cfg::kOutBufs - 1);
+        mbar_wait(&full[buf], (q >> (Cfg::kOutBufs - 1)) & 1u);
+        if (elect_one()) {
+          const uint8_t* src = s_out + (half * Cfg::kOutBufs + static_cast<int>(buf)) * kOutSlabBytes;
+          const int col = t.n_blk * kTileN + half * (kTileN / 2) + slab * 64;
+          if (pr.c_wm_s != 0) {
+            // Raster rows -> window-major rows: the slab is cut at token-row boundaries (24 tokens; crops are 24 token rows, so
+            // token row R24 = global row / 24 = (crop * g + hb) * s + hi) and each piece leaves through one (channel, wi, wb) box
+            // of the 5-D map at (hi, crop-and-hb); pieces cut by the slab edge are clipped along wb (slab edges fall on multiples
+            // of 8 tokens, a whole number of windows for s in {2, 4, 8}).
+            const int sf = pr.c_wm_s;
+            int r24 = row_tile0 / 24;
+            for (int a = r24 * 24 - row_tile0; a < kBlockM; a += 24, ++r24) {
+              const int src_row = min(max(a, 0), kBlockM - 24);
+              const int tok0 = src_row - a;                         // token offset inside the token row (may be negative)
+              tma_store_5d(maps, src + src_row * 128, col, 0, tok0 / sf, r24 % sf, r24 / sf);
+            }
+          } else if (pr.c_seg_len == 0) {
+            for (int p = 0; p < n_maps; ++p) tma_store_2d(maps + p, src, col, row_tile0);
+          } else {
+            // Segmented output rows (global row g = seg * seg_len + r  ->  map coordinate (col, r, seg)): the slab's 128 rows are
+            // cut at segment boundaries and each piece leaves through the SAME fixed-size box.  A piece that starts before the slab
+            // or ends after it is positioned so that the surplus box rows fall outside [0, seg_len) of its segment, where TMA clips
+            // them (signed coordinates): src_row = clamp(a, 0, 128 - box), r0 = src_row - a, a = slab row of the segment's row 0.
+            // The 128B swizzle is a function of the absolute shared-memory address, so any 128-byte-aligned source row works.
+            const int seg_box = pr.c_seg_len < kBlockM ? pr.c_seg_len : kBlockM;
+            const int n_segs = pr.M / pr.c_seg_len;
+            int seg = row_tile0 / pr.c_seg_len;
+            for (int a = seg * pr.c_seg_len - row_tile0; a < kBlockM && seg < n_segs; a += pr.c_seg_len, ++seg) {
+              const int src_row = min(max(a, 0), kBlockM - seg_box);
+              for (int p = 0; p < n_maps; ++p) tma_store_3d(maps + p, src + src_row * 128, col, src_row - a, seg);
+            }
+          }
+          bulk_commit_group();
+          bulk_wait_group_read<0>();               // the buffer has been read: the epilogue warps may overwrite it
+          mbar_arrive(&empty[buf]);
+        }
+        __syncwarp();
+      }
+      if (pr.done_counter != nullptr) {
+        if (elect_one()) {
+          bulk_wait_group<0>();                    // this CTA-half's part of the tile is in global memory ...
+          fence_proxy_async_all();                 // ... (async-proxy writes) ordered before the generic-proxy release below
+          red_release_gpu_add(pr.done_counter + t.m_blk, 1);
+        }
+        __syncwarp();
+      }
+    }
+    if (elect_one()) {
+      bulk_wait_group<0>();                        // my half's last TMA stores have been performed
+      if (peers.count > 0) __threadfence_system(); // ... and are ordered before the cross-GPU barrier that follows the kernel
+    }
+    __syncwarp();
   }
 
   tcgen05_fence_before();

@@ -141,6 +141,14 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* s
                "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
                : "memory");
 }
+// 5-D form, used to store rows that arrive in natural token order (24 x 24 raster per crop) in WINDOW-MAJOR order: the map views
+// the destination as (channel, wi, wb, hi, crop-and-hb) with strides that put the s x s tokens of a window next to each other.
+__device__ __forceinline__ void tma_store_5d(const CUtensorMap* m, const void* smem_src, int32_t c0, int32_t c1, int32_t c2, int32_t c3,
+                                             int32_t c4) {
+  asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];" ::"l"(reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+               : "memory");
+}
 __device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // wait until at most kPending of this thread's bulk groups still READ their shared-memory source
 template <int kPending>
@@ -347,6 +355,35 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar, uint16_t cta_mas
 // NEXT kernel's CTAs to be scheduled (they run their prologue, then block in their own wait).
 __device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void grid_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// ------------------------------------------------------------------------------------------------
+// Cross-CTA tile counters in global memory (dependencies between GEMMs of one persistent launch)
+// ------------------------------------------------------------------------------------------------
+// Orders async-proxy accesses (TMA loads / stores) with the generic-proxy ones around it, all state spaces.
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+__device__ __forceinline__ void red_release_gpu_add(int* p, int v) {
+  asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// Bounded like every other spin of the library: a protocol bug must trap, never hang the GPU.
+__device__ __forceinline__ void wait_counter_at_least(const int* p, int target) {
+  if (ld_acquire_gpu(p) >= target) return;
+  const long long t0 = clock64();
+  while (ld_acquire_gpu(p) < target) {
+    __nanosleep(64);
+    if (clock64() - t0 > TP_SPIN_LIMIT_CYCLES) {
+      printf("tokenpacker_b200: tile-counter wait timed out (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
+      __trap();
+    }
+  }
+}
 
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");

@@ -50,12 +50,14 @@ struct BwdLayout {
   size_t dzkv, dzkv_t, xm_t;
   size_t ln_part;        // f32 [3][kLnBlocks][2][1024]
   size_t col_part;       // f32 [kColChunks][max(H, 2048)]  column-sum partials (bias gradients)
+  size_t splitk;         // f32 [2][kWgradSplits][1024,1024]  split-K partial sums of the 1024x1024 wgrads that contract over R rows
   size_t total;
   long long Rp, Qp;
 };
 
 constexpr int kLnBlocks = 296;
 constexpr int kColChunks = 592;     // 4 CTAs per SM: each sums ~rows/592 rows of 1024 columns
+constexpr int kWgradSplits = 4;     // 16 output tiles x 4 K-slices = 64 tiles of R/4 rows instead of 16 tiles of R rows
 
 BwdLayout bwd_layout(long long n_crops, int s, int H) {
   const size_t R = static_cast<size_t>(n_crops) * kTokens;
@@ -83,6 +85,7 @@ BwdLayout bwd_layout(long long n_crops, int s, int H) {
   L.dzm_t = L.o_t = L.do_t = L.ctx_t = L.dqp_t = L.dkp_t = L.dvp_t = L.dyq_t = L.dyk_t = L.dyv_t = L.q_t = L.hkv_t = L.dzkv_t = L.xm_t = 0;   // unused (TN wgrad)
   L.ln_part = take(3ull * kLnBlocks * 2 * kC * 4);
   L.col_part = take(static_cast<size_t>(kColChunks) * (Hs > 2048 ? Hs : 2048) * 4);
+  L.splitk = take(2ull * kWgradSplits * kC * kC * 4);
   L.total = off;
   return L;
 }
@@ -271,6 +274,25 @@ int tp_backward(const tp_weights* w, const void* xm, int64_t xm_crop_stride, int
     *item = plain_item(wb(dy_t_off), ldt, wb(x_t_off), ldt, dw, ld_dw, n_out, n_in, rows, nullptr, alpha);
     return TP_OK;
   };
+  // The 1024x1024 wgrads that contract over all R = 576 N rows are 16 output tiles of 576 N / 64 k-blocks each: alone they leave
+  // 58 of 74 CTA pairs idle for the longest GEMM time of the step.  They run split-K (kWgradSplits fp32 partial slices, summed in
+  // fixed order by splitk_reduce_kernel) INSIDE the launch of the dgrads of the same stage, whose ~1300 tiles fill the machine.
+  float* splitk = reinterpret_cast<float*>(ws + B.splitk);
+  auto wgrad_split = [&](const void* dy, long long ld_dy, const void* x, long long ld_x, long long rows, int slot, GemmItem* item) -> bool {
+    if (rows < 64ll * kBlockK * kWgradSplits) return false;            // short contractions: not worth the partials
+    *item = GemmItem{AOperand{dy, ld_dy, 0, 0}, x, ld_x, kC, kC, rows, plain_epilogue(splitk + static_cast<size_t>(slot) * kWgradSplits * kC * kC, kC, nullptr, 0)};
+    item->tn = 1;
+    item->k_splits = kWgradSplits;
+    item->ep.out_f32 = 1;
+    return true;
+  };
+  auto wgrad_reduce = [&](int slot, float alpha, void* dw) -> int {
+    const long long elems = static_cast<long long>(kC) * kC;
+    splitk_reduce_kernel<<<static_cast<unsigned>((elems / 4 + 255) / 256), 256, 0, stream>>>(
+        splitk + static_cast<size_t>(slot) * kWgradSplits * kC * kC, kWgradSplits, elems, alpha, static_cast<__nv_bfloat16*>(dw));
+    TP_CUDA(cudaGetLastError()); ++g_launch_count;
+    return TP_OK;
+  };
   // bias gradient = column sums of dY (deterministic two-stage reduction: kColChunks row chunks, then a fixed-order sum)
   float* col_part = reinterpret_cast<float*>(ws + B.col_part);
   auto bias_grad = [&](const void* dy, long long ld_dy, long long rows, int cols, float scale, void* out) -> int {
@@ -333,15 +355,25 @@ int tp_backward(const tp_weights* w, const void* xm, int64_t xm_crop_stride, int
   TP_TRY(bias_grad(wb(B.dkp), kC, R, kC, 1.0f, d_in_b + kC));
   TP_TRY(bias_grad(wb(B.dvp), kC, R, kC, 1.0f, d_in_b + 2 * kC));
   {
-    GemmItem gi[3];
-    TP_TRY(wgrad(wb(B.dqp), kC, wb(B.lnq_t), kC, Q, kC, kC, d_in_w, kC, alpha_q, B.dqp_t, B.q_t, &gi[0]));
-    TP_TRY(wgrad(wb(B.dkp), kC, wb(B.lnk_t), kC, R, kC, kC, d_in_w + static_cast<size_t>(kC) * kC, kC, 1.0f, B.dkp_t, B.dyk_t, &gi[1]));
-    TP_TRY(wgrad(wb(B.dvp), kC, wb(B.lnv_t), kC, R, kC, kC, d_in_w + 2 * static_cast<size_t>(kC) * kC, kC, 1.0f, B.dvp_t, B.dyv_t, &gi[2]));
-    TP_TRY(launch_gemms(gi, 3, dev.sms, stream));
-    gi[0] = plain_item(wb(B.dqp), kC, wb(B.w_iqt), kC, wb(B.dqh), kC, Q, kC, kC, nullptr, alpha_q);   // d LN(y_q)
-    gi[1] = plain_item(wb(B.dkp), kC, wb(B.w_ikt), kC, wb(B.dkh), kC, R, kC, kC);
-    gi[2] = plain_item(wb(B.dvp), kC, wb(B.w_ivt), kC, wb(B.dvh), kC, R, kC, kC);
-    TP_TRY(launch_gemms(gi, 3, dev.sms, stream));
+    // one launch: the two long wgrads (split-K, first: longest tiles start earliest), the three dgrads, the short q wgrad
+    GemmItem gi[6];
+    int n = 0;
+    const bool sk = wgrad_split(wb(B.dkp), kC, wb(B.lnk_t), kC, R, 0, &gi[0]) && wgrad_split(wb(B.dvp), kC, wb(B.lnv_t), kC, R, 1, &gi[1]);
+    if (sk) {
+      n = 2;
+    } else {
+      TP_TRY(wgrad(wb(B.dkp), kC, wb(B.lnk_t), kC, R, kC, kC, d_in_w + static_cast<size_t>(kC) * kC, kC, 1.0f, B.dkp_t, B.dyk_t, &gi[n++]));
+      TP_TRY(wgrad(wb(B.dvp), kC, wb(B.lnv_t), kC, R, kC, kC, d_in_w + 2 * static_cast<size_t>(kC) * kC, kC, 1.0f, B.dvp_t, B.dyv_t, &gi[n++]));
+    }
+    gi[n++] = plain_item(wb(B.dkp), kC, wb(B.w_ikt), kC, wb(B.dkh), kC, R, kC, kC);                     // d LN(y_k)
+    gi[n++] = plain_item(wb(B.dvp), kC, wb(B.w_ivt), kC, wb(B.dvh), kC, R, kC, kC);
+    gi[n++] = plain_item(wb(B.dqp), kC, wb(B.w_iqt), kC, wb(B.dqh), kC, Q, kC, kC, nullptr, alpha_q);   // d LN(y_q)
+    TP_TRY(wgrad(wb(B.dqp), kC, wb(B.lnq_t), kC, Q, kC, kC, d_in_w, kC, alpha_q, B.dqp_t, B.q_t, &gi[n++]));
+    TP_TRY(launch_gemms(gi, n, dev.sms, stream));
+    if (sk) {
+      TP_TRY(wgrad_reduce(0, 1.0f, d_in_w + static_cast<size_t>(kC) * kC));
+      TP_TRY(wgrad_reduce(1, 1.0f, d_in_w + 2 * static_cast<size_t>(kC) * kC));
+    }
   }
   // ---- LayerNorms
   TP_TRY(launch_ln_bwd(wb(B.dqh), sb(S.y_q), stats_q, w->ln_q_w, wb(B.dyq), ln_part, Q, G(grads->ln_q_w), G(grads->ln_q_b), stream));
@@ -353,14 +385,23 @@ int tp_backward(const tp_weights* w, const void* xm, int64_t xm_crop_stride, int
   TP_TRY(bias_grad(wb(B.dyk), kC, R, kC, 1.0f, G(grads->k_proj_2_b)));
   TP_TRY(bias_grad(wb(B.dyv), kC, R, kC, 1.0f, G(grads->v_proj_2_b)));
   {
-    GemmItem gi[3];
-    TP_TRY(wgrad(wb(B.dyq), kC, sb(S.q), kC, Q, kC, kC, G(grads->q_proj_w), kC, 1.0f, B.dyq_t, B.q_t, &gi[0]));
-    TP_TRY(wgrad(wb(B.dyk), kC, sb(S.h_kv), 2 * kC, R, kC, kC, G(grads->k_proj_2_w), kC, 1.0f, B.dyk_t, B.hkv_t, &gi[1]));
-    TP_TRY(wgrad(wb(B.dyv), kC, sb(S.h_kv) + kC, 2 * kC, R, kC, kC, G(grads->v_proj_2_w), kC, 1.0f, B.dyv_t, B.hkv_t + static_cast<size_t>(kC) * Rp * 2, &gi[2]));
-    TP_TRY(launch_gemms(gi, 3, dev.sms, stream));
-    gi[0] = plain_item(wb(B.dyk), kC, wb(B.w_k2t), kC, wb(B.dzkv), 2 * kC, R, kC, kC);               // dh_k  -> dzkv[:, :1024]
-    gi[1] = plain_item(wb(B.dyv), kC, wb(B.w_v2t), kC, wb(B.dzkv) + kC, 2 * kC, R, kC, kC);          // dh_v  -> dzkv[:, 1024:]
-    TP_TRY(launch_gemms(gi, 2, dev.sms, stream));
+    GemmItem gi[5];
+    int n = 0;
+    const bool sk = wgrad_split(wb(B.dyk), kC, sb(S.h_kv), 2 * kC, R, 0, &gi[0]) && wgrad_split(wb(B.dyv), kC, sb(S.h_kv) + kC, 2 * kC, R, 1, &gi[1]);
+    if (sk) {
+      n = 2;
+    } else {
+      TP_TRY(wgrad(wb(B.dyk), kC, sb(S.h_kv), 2 * kC, R, kC, kC, G(grads->k_proj_2_w), kC, 1.0f, B.dyk_t, B.hkv_t, &gi[n++]));
+      TP_TRY(wgrad(wb(B.dyv), kC, sb(S.h_kv) + kC, 2 * kC, R, kC, kC, G(grads->v_proj_2_w), kC, 1.0f, B.dyv_t, B.hkv_t + static_cast<size_t>(kC) * Rp * 2, &gi[n++]));
+    }
+    gi[n++] = plain_item(wb(B.dyk), kC, wb(B.w_k2t), kC, wb(B.dzkv), 2 * kC, R, kC, kC);               // dh_k  -> dzkv[:, :1024]
+    gi[n++] = plain_item(wb(B.dyv), kC, wb(B.w_v2t), kC, wb(B.dzkv) + kC, 2 * kC, R, kC, kC);          // dh_v  -> dzkv[:, 1024:]
+    TP_TRY(wgrad(wb(B.dyq), kC, sb(S.q), kC, Q, kC, kC, G(grads->q_proj_w), kC, 1.0f, B.dyq_t, B.q_t, &gi[n++]));
+    TP_TRY(launch_gemms(gi, n, dev.sms, stream));
+    if (sk) {
+      TP_TRY(wgrad_reduce(0, 1.0f, G(grads->k_proj_2_w)));
+      TP_TRY(wgrad_reduce(1, 1.0f, G(grads->v_proj_2_w)));
+    }
   }
   TP_TRY(launch_gelu_bwd(wb(B.dzkv), sb(S.z_kv), static_cast<size_t>(R) * 2 * kC, stream));        // dz_kv
   // ---- k_proj_1.0 / v_proj_1.0:  z = xm W0^T + b   (no gradient to xm: the CLIP tower is frozen)
