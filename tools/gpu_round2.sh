@@ -1,35 +1,41 @@
 #!/bin/bash
-# Round-2 GPU visit (1 GPU): tests, smoke, bench, phase profile, ncu (launch list with DRAM bytes + full sets of the five GEMM
-# launches of one step), sanitizers.  Everything lands in gpurun_out/.
+# Round-2 GPU visit (1 GPU): tests (one process per file: a device-side trap cannot take the other files down), smoke, A/B of the
+# launch plans, the full bench line, phase profile, ncu launch list with DRAM bytes, sanitizers.  Everything lands in gpurun_out/.
 mkdir -p gpurun_out
-( timeout 1500 python -m pytest tests -q -m gpu -x 2>&1 | tail -40 ) > gpurun_out/pytest_gpu.log
-tail -5 gpurun_out/pytest_gpu.log
+for f in tests/test_*gpu*.py; do
+  n=$(basename $f .py)
+  ( timeout 900 python -m pytest $f -q -m gpu 2>&1 | tail -70 ) > gpurun_out/pytest_$n.log
+  echo "$n: $(tail -1 gpurun_out/pytest_$n.log)"
+done
 ( timeout 120 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3 ) | tee gpurun_out/smoke.log
+ab() {  # name, env...
+  name=$1; shift
+  ( env "$@" timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-e2e --no-extras 2>&1 | tail -1 | python -c "
+import sys, json
+try:
+    d = json.loads(sys.stdin.read()); print('$name', 'ms_per_step', round(d['ms_per_step'], 4), 'launches/step', d['gpu_launches'] / d['steps'], 'single_image_ms', d['configs0_single_image']['gpu_ms'])
+except Exception as e:
+    print('$name', 'FAILED', e)
+" ) | tee -a gpurun_out/ab.log
+}
+rm -f gpurun_out/ab.log
+ab fused_default X=1
+ab chain_nofuse TP_FUSE_ATTN=0
+ab plain_7_launches TP_FUSE_ATTN=0 TP_CHAIN=0
+ab fused_5stages TOKENPACKER_B200_LIB_OVERRIDE=$PWD/build_ab/s5.so
+ab nofuse_5stages TP_FUSE_ATTN=0 TOKENPACKER_B200_LIB_OVERRIDE=$PWD/build_ab/s5.so
 ( timeout 900 python bench.py --steps 20 --warmup 5 2>gpurun_out/bench.err | tail -1 ) > gpurun_out/bench_line.json
-cut -c1-1500 gpurun_out/bench_line.json
+cut -c1-400 gpurun_out/bench_line.json
 ( timeout 300 python tools/gemm_phase_profile.py 2>&1 ) > gpurun_out/phase_profile.log
 timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed,sm__cycles_elapsed.max \
-    --clock-control none -c 80 --csv --log-file gpurun_out/launches.csv \
+    --clock-control none -c 40 --csv --log-file gpurun_out/launches.csv \
     python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e --no-extras > gpurun_out/ncu_launches.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:tp_gemm2 -s 21 -c 5 -f -o gpurun_out/prof_step_gemms \
-    python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e --no-extras > gpurun_out/ncu_full.log 2>&1
-tail -2 gpurun_out/ncu_full.log
-ncu -i gpurun_out/prof_step_gemms.ncu-rep --page raw --csv > gpurun_out/prof_step_gemms.raw.csv 2>/dev/null
-( timeout 500 compute-sanitizer --tool memcheck python tools/sanitize_small.py 2>&1 | tail -5 ) | tee gpurun_out/memcheck.log
-( timeout 500 compute-sanitizer --tool synccheck python tools/sanitize_small.py 2>&1 | tail -5 ) | tee gpurun_out/synccheck.log
-( timeout 600 compute-sanitizer --tool racecheck python tools/sanitize_small.py 2>&1 | tail -12 ) | tee gpurun_out/racecheck.log
-# ---- A/B: the development build (store warps, chained persistent GEMM launches, front work, split-K wgrads) on the same box
-if [ -f build_ab/dev.so ]; then
-  export TOKENPACKER_B200_LIB_OVERRIDE=$PWD/build_ab/dev.so
-  ( timeout 1200 python -m pytest tests -q -m gpu -x 2>&1 | tail -40 ) > gpurun_out/pytest_dev.log
-  tail -5 gpurun_out/pytest_dev.log
-  ( timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline 2>gpurun_out/bench_dev.err | tail -1 ) > gpurun_out/bench_dev_line.json
-  cut -c1-700 gpurun_out/bench_dev_line.json
-  timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed \
-      --clock-control none -c 60 --csv --log-file gpurun_out/launches_dev.csv \
-      python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e --no-extras > gpurun_out/ncu_launches_dev.log 2>&1
-  ( TP_CHAIN=0 timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-e2e --no-extras 2>/dev/null | tail -1 | cut -c1-400 ) > gpurun_out/bench_dev_nochain.json
-  cat gpurun_out/bench_dev_nochain.json
-  unset TOKENPACKER_B200_LIB_OVERRIDE
-fi
+TP_FUSE_ATTN=0 TP_CHAIN=0 timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed,sm__cycles_elapsed.max \
+    --clock-control none -c 80 --csv --log-file gpurun_out/launches_plain.csv \
+    python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e --no-extras > gpurun_out/ncu_launches_plain.log 2>&1
+( timeout 500 compute-sanitizer --tool memcheck python tools/sanitize_small.py 2>&1 | head -60 ) > gpurun_out/memcheck.log
+tail -3 gpurun_out/memcheck.log
+( timeout 500 compute-sanitizer --tool synccheck python tools/sanitize_small.py 2>&1 | tail -8 ) | tee gpurun_out/synccheck.log
+( timeout 600 compute-sanitizer --tool racecheck python tools/sanitize_small.py 2>&1 | tail -30 ) > gpurun_out/racecheck.log
+tail -3 gpurun_out/racecheck.log
 ls -la gpurun_out | head -70
