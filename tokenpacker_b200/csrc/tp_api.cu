@@ -56,7 +56,7 @@ EncodeTiledFn encode_tiled_fn() {
 }
 
 // bf16 matrix [rows, cols] with row stride ld (elements); box = 64 columns x box_rows rows, 128-byte swizzle.
-int make_map_2d(CUtensorMap* map, const void* ptr, long long rows, long long cols, long long ld, int box_rows) {
+int make_map_2d(CUtensorMap* map, const void* ptr, long long rows, long long cols, long long ld, int box_rows, int box_cols = kBlockK) {
   EncodeTiledFn fn = encode_tiled_fn();
   if (fn == nullptr) {
     snprintf(g_last_cuda_error, sizeof(g_last_cuda_error), "cuTensorMapEncodeTiled entry point not found");
@@ -65,10 +65,10 @@ int make_map_2d(CUtensorMap* map, const void* ptr, long long rows, long long col
   if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0 || (ld * 2) % 16 != 0) return TP_ERR_INVALID_ARGUMENT;
   cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
   cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
-  cuuint32_t box[2] = {static_cast<cuuint32_t>(kBlockK), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows)};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, box_cols == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     snprintf(g_last_cuda_error, sizeof(g_last_cuda_error), "cuTensorMapEncodeTiled(2d) failed: %d", static_cast<int>(r));
@@ -79,7 +79,7 @@ int make_map_2d(CUtensorMap* map, const void* ptr, long long rows, long long col
 
 // bf16 tensor [segs, seg_rows, cols] with row stride ld and segment stride seg_stride (elements); box 64 x 64 x 1.
 int make_map_3d(CUtensorMap* map, const void* ptr, long long segs, long long seg_rows, long long cols, long long ld,
-                long long seg_stride, int box_rows = 64) {
+                long long seg_stride, int box_rows = 64, int box_cols = kBlockK) {
   EncodeTiledFn fn = encode_tiled_fn();
   if (fn == nullptr) {
     snprintf(g_last_cuda_error, sizeof(g_last_cuda_error), "cuTensorMapEncodeTiled entry point not found");
@@ -88,10 +88,10 @@ int make_map_3d(CUtensorMap* map, const void* ptr, long long segs, long long seg
   if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0 || (ld * 2) % 16 != 0 || (seg_stride * 2) % 16 != 0) return TP_ERR_INVALID_ARGUMENT;
   cuuint64_t dims[3] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(seg_rows), static_cast<cuuint64_t>(segs)};
   cuuint64_t strides[2] = {static_cast<cuuint64_t>(ld) * 2, static_cast<cuuint64_t>(seg_stride) * 2};
-  cuuint32_t box[3] = {static_cast<cuuint32_t>(kBlockK), static_cast<cuuint32_t>(box_rows), 1};
+  cuuint32_t box[3] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows), 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, box_cols == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     snprintf(g_last_cuda_error, sizeof(g_last_cuda_error), "cuTensorMapEncodeTiled(3d) failed: %d", static_cast<int>(r));
@@ -114,10 +114,10 @@ int make_map_wm(CUtensorMap* map, const void* ptr, long long rows, long long col
                         static_cast<cuuint64_t>(rows / 576 * g)};
   const cuuint64_t row_b = static_cast<cuuint64_t>(ld) * 2;
   cuuint64_t strides[4] = {row_b, row_b * s * s, row_b * s, row_b * s * s * g};
-  cuuint32_t box[5] = {static_cast<cuuint32_t>(kBlockK), static_cast<cuuint32_t>(s), static_cast<cuuint32_t>(g), 1, 1};
+  cuuint32_t box[5] = {static_cast<cuuint32_t>(kSlabCols), static_cast<cuuint32_t>(s), static_cast<cuuint32_t>(g), 1, 1};
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  kSlabCols == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     snprintf(g_last_cuda_error, sizeof(g_last_cuda_error), "cuTensorMapEncodeTiled(5d) failed: %d", static_cast<int>(r));
     return TP_ERR_CUDA;
@@ -306,9 +306,9 @@ int launch_gemm_pair_group(const GemmItem* items, int count, int sms, cudaStream
       if (it.ep.seg_len <= 0 || it.M % it.ep.seg_len != 0 || it.ep.seg_stride < it.ep.seg_len) return TP_ERR_INVALID_ARGUMENT;
       p.c_seg_len = it.ep.seg_len;
       TP_TRY(make_map_3d(&p.tmap_c, it.ep.c, it.M / it.ep.seg_len, it.ep.seg_len, it.N, it.ep.ldc, it.ep.seg_stride * it.ep.ldc,
-                         it.ep.seg_len < kBlockM ? it.ep.seg_len : kBlockM));
+                         it.ep.seg_len < kBlockM ? it.ep.seg_len : kBlockM, kSlabCols));
     } else {
-      TP_TRY(make_map_2d(&p.tmap_c, it.ep.c, it.M, it.N, it.ep.ldc, kBlockM));
+      TP_TRY(make_map_2d(&p.tmap_c, it.ep.c, it.M, it.N, it.ep.ldc, kBlockM, kSlabCols));
     }
     p.M = static_cast<int>(it.M);
     p.N = static_cast<int>(it.N);
@@ -352,9 +352,9 @@ int launch_gemm_pair_group(const GemmItem* items, int count, int sms, cudaStream
     for (int p = 0; p < it0.n_peers; ++p) {
       if (g.p[peer_item].c_seg_len != 0)
         TP_TRY(make_map_3d(&peers.m[p], it0.peer_c[p], it0.M / it0.ep.seg_len, it0.ep.seg_len, it0.N, it0.ep.ldc, it0.ep.seg_stride * it0.ep.ldc,
-                           it0.ep.seg_len < kBlockM ? it0.ep.seg_len : kBlockM));
+                           it0.ep.seg_len < kBlockM ? it0.ep.seg_len : kBlockM, kSlabCols));
       else
-        TP_TRY(make_map_2d(&peers.m[p], it0.peer_c[p], it0.M, it0.N, it0.ep.ldc, kBlockM));
+        TP_TRY(make_map_2d(&peers.m[p], it0.peer_c[p], it0.M, it0.N, it0.ep.ldc, kBlockM, kSlabCols));
     }
     peers.count = it0.n_peers;
   }

@@ -123,7 +123,17 @@ struct OutStage {
   int n_bufs;                // 2: slabs alternate buffers; 1: single buffer
   uint32_t slab_seq;         // running slab number of this half (buffer = seq % n_bufs, mbarrier phase = seq / n_bufs)
 };
-constexpr int kOutSlabBytes = 128 * 128;   // 128 rows x 64 bf16
+// Output slab = 128 rows x kSlabCols columns of bf16, in the TMA swizzle of that row width (64 columns: 128-byte rows,
+// SWIZZLE_128B; 32 columns: 64-byte rows, SWIZZLE_64B).  The narrow form halves the staging memory, which buys two more
+// stages of the operand ring (-DTP_SLAB_COLS=32 -DTP_PAIR_STAGES=6): the ring depth is what hides operand-fetch latency.
+#ifndef TP_SLAB_COLS
+#define TP_SLAB_COLS 64
+#endif
+constexpr int kSlabCols = TP_SLAB_COLS;
+static_assert(kSlabCols == 64 || kSlabCols == 32, "slab width: 64 (128B swizzle) or 32 (64B swizzle) columns");
+constexpr int kSlabRowBytes = kSlabCols * 2;
+constexpr int kChunksPerSlab = kSlabCols / 32;
+constexpr int kOutSlabBytes = 128 * kSlabRowBytes;
 
 // raster row (crop n, token row tr, token column tc) -> window-major row (crop n, window (hb, wb), key (hi, wi)) for windows of s x s
 __device__ __forceinline__ long long window_major_row(long long row, int s) {
@@ -196,9 +206,9 @@ __device__ __forceinline__ void epilogue_tile(const GemmEpilogue& ep, int M, int
     if (chunk + 1 < kChunks) tmem_ld_32x32b_x32(taddr + static_cast<uint32_t>((chunk + 1) * 32), r[(chunk + 1) & 1]);
     else release();                                   // every TMEM read of this warp has landed in registers
     const int col0 = col_tile0 + half * kColsPerWarp + chunk * 32;
-    const uint32_t slab_q = out.slab_seq + static_cast<uint32_t>(chunk >> 1);
+    const uint32_t slab_q = out.slab_seq + static_cast<uint32_t>(chunk / kChunksPerSlab);
     const uint32_t slab_buf = slab_q & static_cast<uint32_t>(out.n_bufs - 1);
-    if (out.buf != nullptr && (chunk & 1) == 0) {
+    if (out.buf != nullptr && (chunk % kChunksPerSlab) == 0) {
       // the TMA store that last used this staging buffer must have finished READING it (signalled by the store warp)
       TP_PROF_T0();
       mbar_wait(&out.empty_bar[slab_buf], ((slab_q >> (out.n_bufs - 1)) & 1u) ^ 1u);
@@ -258,12 +268,14 @@ __device__ __forceinline__ void epilogue_tile(const GemmEpilogue& ep, int M, int
           }
         }
         if (out.buf != nullptr) {
-          // slab = 2 chunks; 16-byte piece index inside the 128-byte row, XOR-swizzled with (row & 7) like TMA's SWIZZLE_128B
-          const uint32_t row_base = out_addr + static_cast<uint32_t>(slab_buf * kOutSlabBytes + rloc * 128);
+          // 16-byte piece index inside the slab row, XOR-swizzled like TMA does: 128-byte rows (SWIZZLE_128B) with (row & 7),
+          // 64-byte rows (SWIZZLE_64B) with ((row >> 1) & 3) — address bits [7,9/10) folded into bits [4,6/7)
+          const uint32_t row_base = out_addr + static_cast<uint32_t>(slab_buf * kOutSlabBytes + rloc * kSlabRowBytes);
+          const int swz = kSlabCols == 64 ? (rloc & 7) : ((rloc >> 1) & 3);
 #pragma unroll
           for (int g = 0; g < kSubPairs / 4; ++g) {
-            const int ci = (chunk & 1) * 4 + sub * (kSubPairs / 4) + g;
-            sts_u4(row_base + static_cast<uint32_t>((ci ^ (rloc & 7)) << 4), pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+            const int ci = (chunk % kChunksPerSlab) * 4 + sub * (kSubPairs / 4) + g;
+            sts_u4(row_base + static_cast<uint32_t>((ci ^ swz) << 4), pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
           }
         } else if (row_ok) {
           if (ep.out_f32) {
@@ -296,7 +308,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmEpilogue& ep, int M, int
             make_float2(__fadd_rn(shift, dm), fmaxf(fmaf(-s1, dm, s2), 0.f));
       }
     }
-    if (out.buf != nullptr && (chunk & 1) == 1) {
+    if (out.buf != nullptr && (chunk % kChunksPerSlab) == kChunksPerSlab - 1) {
       // slab complete: make the generic-proxy writes visible to the async proxy, then one arrive per warp hands it to the store warp
       TP_PROF_T0();
       fence_proxy_async_smem();
@@ -616,7 +628,7 @@ struct Gemm2Config {
 #define TP_PAIR_STAGES 4
 #endif
   static constexpr int kStages = TP_PAIR_STAGES;                 // 4: double-buffered output slabs; 5: single-buffered (smem budget)
-  static constexpr int kOutBufs = (kStages <= 4) ? 2 : 1;
+  static constexpr int kOutBufs = (kStages <= 4) ? 2 : 1;        // staging buffers per column half
   static constexpr int kABytes = kBlockM * kBlockK * 2;          // this CTA's 128 rows of A
   static constexpr int kBBytes = (kTileN / 2) * kBlockK * 2;     // this CTA's half of the B tile
   static constexpr int kStageBytes = kABytes + kBBytes;          // 32 KiB
@@ -1075,7 +1087,7 @@ tp_gemm2_kernel(const __grid_constant__ GemmGroup grp, const __grid_constant__ P
       tcgen05_fence_after();
       const OutStage out{pr.use_tma_store ? s_out + half * Cfg::kOutBufs * kOutSlabBytes : nullptr, slab_full_bar + half * Cfg::kOutBufs,
                          slab_empty_bar + half * Cfg::kOutBufs, Cfg::kOutBufs, slab_seq};
-      if (pr.use_tma_store) slab_seq += kTileN / 2 / 64;            // slabs per tile and column half
+      if (pr.use_tma_store) slab_seq += kTileN / 2 / kSlabCols;     // slabs per tile and column half
       epilogue_tile<kTileN>(pr.ep, pr.M, pr.N, tmem_base + static_cast<uint32_t>(acc * kTileN), row, t.n_blk * kTileN, quarter, half, s_col,
                             out, [&]() {
                               tcgen05_fence_before();
@@ -1117,12 +1129,12 @@ tp_gemm2_kernel(const __grid_constant__ GemmGroup grp, const __grid_constant__ P
       const bool to_peers = pr.peer_out != 0 && peers.count > 0;
       const CUtensorMap* maps = to_peers ? &peers.m[0] : &pr.tmap_c;
       const int n_maps = to_peers ? peers.count : 1;
-      for (int slab = 0; slab < kTileN / 2 / 64; ++slab, ++q) {
+      for (int slab = 0; slab < kTileN / 2 / kSlabCols; ++slab, ++q) {
         const uint32_t buf = q & static_cast<uint32_t>(Cfg::kOutBufs - 1);
         mbar_wait(&full[buf], (q >> (Cfg::kOutBufs - 1)) & 1u);
         if (elect_one()) {
           const uint8_t* src = s_out + (half * Cfg::kOutBufs + static_cast<int>(buf)) * kOutSlabBytes;
-          const int col = t.n_blk * kTileN + half * (kTileN / 2) + slab * 64;
+          const int col = t.n_blk * kTileN + half * (kTileN / 2) + slab * kSlabCols;
           if (pr.c_wm_s != 0) {
             // Raster rows -> window-major rows: the slab is cut at token-row boundaries (24 tokens; crops are 24 token rows, so
             // token row R24 = global row / 24 = (crop * g + hb) * s + hi) and each piece leaves through one (channel, wi, wb) box
@@ -1133,7 +1145,7 @@ tp_gemm2_kernel(const __grid_constant__ GemmGroup grp, const __grid_constant__ P
             for (int a = r24 * 24 - row_tile0; a < kBlockM; a += 24, ++r24) {
               const int src_row = min(max(a, 0), kBlockM - 24);
               const int tok0 = src_row - a;                         // token offset inside the token row (may be negative)
-              tma_store_5d(maps, src + src_row * 128, col, 0, tok0 / sf, r24 % sf, r24 / sf);
+              tma_store_5d(maps, src + src_row * kSlabRowBytes, col, 0, tok0 / sf, r24 % sf, r24 / sf);
             }
           } else if (pr.c_seg_len == 0) {
             for (int p = 0; p < n_maps; ++p) tma_store_2d(maps + p, src, col, row_tile0);
@@ -1148,7 +1160,7 @@ tp_gemm2_kernel(const __grid_constant__ GemmGroup grp, const __grid_constant__ P
             int seg = row_tile0 / pr.c_seg_len;
             for (int a = seg * pr.c_seg_len - row_tile0; a < kBlockM && seg < n_segs; a += pr.c_seg_len, ++seg) {
               const int src_row = min(max(a, 0), kBlockM - seg_box);
-              for (int p = 0; p < n_maps; ++p) tma_store_3d(maps + p, src + src_row * 128, col, src_row - a, seg);
+              for (int p = 0; p < n_maps; ++p) tma_store_3d(maps + p, src + src_row * kSlabRowBytes, col, src_row - a, seg);
             }
           }
           bulk_commit_group();
