@@ -101,7 +101,8 @@ int make_map_3d(CUtensorMap* map, const void* ptr, long long segs, long long seg
 }
 
 // Window-major destination of a raster-ordered [crops * 576, cols] bf16 matrix (scale factor s, g = 24 / s): dims
-// (channel, wi, wb, hi, crop-and-hb), box = 64 channels x s x g x 1 x 1 = one token row of 24 tokens.
+// (channel, wi, hi, wb, crop-and-hb) — ordered by increasing stride, as the tensor-map encoder wants —, box = 64 channels x s x 1 x
+// g x 1 = one token row of 24 tokens (hi has extent 1 in the box, so the box is traversed wi-then-wb: raster order).
 int make_map_wm(CUtensorMap* map, const void* ptr, long long rows, long long cols, long long ld, int s) {
   EncodeTiledFn fn = encode_tiled_fn();
   if (fn == nullptr) {
@@ -110,11 +111,11 @@ int make_map_wm(CUtensorMap* map, const void* ptr, long long rows, long long col
   }
   if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0 || (ld * 2) % 16 != 0 || rows % 576 != 0 || (s != 2 && s != 4 && s != 8)) return TP_ERR_INVALID_ARGUMENT;
   const int g = 24 / s;
-  cuuint64_t dims[5] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(s), static_cast<cuuint64_t>(g), static_cast<cuuint64_t>(s),
+  cuuint64_t dims[5] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(s), static_cast<cuuint64_t>(s), static_cast<cuuint64_t>(g),
                         static_cast<cuuint64_t>(rows / 576 * g)};
   const cuuint64_t row_b = static_cast<cuuint64_t>(ld) * 2;
-  cuuint64_t strides[4] = {row_b, row_b * s * s, row_b * s, row_b * s * s * g};
-  cuuint32_t box[5] = {static_cast<cuuint32_t>(kSlabCols), static_cast<cuuint32_t>(s), static_cast<cuuint32_t>(g), 1, 1};
+  cuuint64_t strides[4] = {row_b, row_b * s, row_b * s * s, row_b * s * s * g};
+  cuuint32_t box[5] = {static_cast<cuuint32_t>(kSlabCols), static_cast<cuuint32_t>(s), 1, static_cast<cuuint32_t>(g), 1};
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   kSlabCols == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

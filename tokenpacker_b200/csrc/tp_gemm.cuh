@@ -1137,7 +1137,7 @@ tp_gemm2_kernel(const __grid_constant__ GemmGroup grp, const __grid_constant__ P
           const int col = t.n_blk * kTileN + half * (kTileN / 2) + slab * kSlabCols;
           if (pr.c_wm_s != 0) {
             // Raster rows -> window-major rows: the slab is cut at token-row boundaries (24 tokens; crops are 24 token rows, so
-            // token row R24 = global row / 24 = (crop * g + hb) * s + hi) and each piece leaves through one (channel, wi, wb) box
+            // token row R24 = global row / 24 = (crop * g + hb) * s + hi) and each piece leaves through one (channel, wi, -, wb) box
             // of the 5-D map at (hi, crop-and-hb); pieces cut by the slab edge are clipped along wb (slab edges fall on multiples
             // of 8 tokens, a whole number of windows for s in {2, 4, 8}).
             const int sf = pr.c_wm_s;
@@ -1145,7 +1145,7 @@ tp_gemm2_kernel(const __grid_constant__ GemmGroup grp, const __grid_constant__ P
             for (int a = r24 * 24 - row_tile0; a < kBlockM; a += 24, ++r24) {
               const int src_row = min(max(a, 0), kBlockM - 24);
               const int tok0 = src_row - a;                         // token offset inside the token row (may be negative)
-              tma_store_5d(maps, src + src_row * kSlabRowBytes, col, 0, tok0 / sf, r24 % sf, r24 / sf);
+              tma_store_5d(maps, src + src_row * kSlabRowBytes, col, 0, r24 % sf, tok0 / sf, r24 / sf);    // (c, wi, hi, wb, crop-and-hb)
             }
           } else if (pr.c_seg_len == 0) {
             for (int p = 0; p < n_maps; ++p) tma_store_2d(maps + p, src, col, row_tile0);

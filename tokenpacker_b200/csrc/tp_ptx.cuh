@@ -142,7 +142,7 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* s
                : "memory");
 }
 // 5-D form, used to store rows that arrive in natural token order (24 x 24 raster per crop) in WINDOW-MAJOR order: the map views
-// the destination as (channel, wi, wb, hi, crop-and-hb) with strides that put the s x s tokens of a window next to each other.
+// the destination as (channel, wi, hi, wb, crop-and-hb) with strides that put the s x s tokens of a window next to each other.
 __device__ __forceinline__ void tma_store_5d(const CUtensorMap* m, const void* smem_src, int32_t c0, int32_t c1, int32_t c2, int32_t c3,
                                              int32_t c4) {
   asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];" ::"l"(reinterpret_cast<uint64_t>(m)),
