@@ -79,7 +79,7 @@ int make_map_2d(CUtensorMap* map, const void* ptr, long long rows, long long col
 
 // bf16 tensor [segs, seg_rows, cols] with row stride ld and segment stride seg_stride (elements); box 64 x 64 x 1.
 int make_map_3d(CUtensorMap* map, const void* ptr, long long segs, long long seg_rows, long long cols, long long ld,
-                long long seg_stride, int box_rows = 64, int box_cols = kBlockK) {
+                long long seg_stride, int box_rows = 64, int box_cols = kBlockK, bool swizzle = true) {
   EncodeTiledFn fn = encode_tiled_fn();
   if (fn == nullptr) {
     snprintf(g_last_cuda_error, sizeof(g_last_cuda_error), "cuTensorMapEncodeTiled entry point not found");
@@ -91,7 +91,7 @@ int make_map_3d(CUtensorMap* map, const void* ptr, long long segs, long long seg
   cuuint32_t box[3] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows), 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, box_cols == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, !swizzle ? CU_TENSOR_MAP_SWIZZLE_NONE : (box_cols == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     snprintf(g_last_cuda_error, sizeof(g_last_cuda_error), "cuTensorMapEncodeTiled(3d) failed: %d", static_cast<int>(r));
@@ -103,7 +103,7 @@ int make_map_3d(CUtensorMap* map, const void* ptr, long long segs, long long seg
 // Window-major destination of a raster-ordered [crops * 576, cols] bf16 matrix (scale factor s, g = 24 / s): dims
 // (channel, wi, hi, wb, crop-and-hb) — ordered by increasing stride, as the tensor-map encoder wants —, box = 64 channels x s x 1 x
 // g x 1 = one token row of 24 tokens (hi has extent 1 in the box, so the box is traversed wi-then-wb: raster order).
-int make_map_wm(CUtensorMap* map, const void* ptr, long long rows, long long cols, long long ld, int s) {
+int make_map_wm(CUtensorMap* map, const void* ptr, long long rows, long long cols, long long ld, int s, bool swizzle = true) {
   EncodeTiledFn fn = encode_tiled_fn();
   if (fn == nullptr) {
     snprintf(g_last_cuda_error, sizeof(g_last_cuda_error), "cuTensorMapEncodeTiled entry point not found");
@@ -118,7 +118,7 @@ int make_map_wm(CUtensorMap* map, const void* ptr, long long rows, long long col
   cuuint32_t box[5] = {static_cast<cuuint32_t>(kSlabCols), static_cast<cuuint32_t>(s), 1, static_cast<cuuint32_t>(g), 1};
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  kSlabCols == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  !swizzle ? CU_TENSOR_MAP_SWIZZLE_NONE : (kSlabCols == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B), CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     snprintf(g_last_cuda_error, sizeof(g_last_cuda_error), "cuTensorMapEncodeTiled(5d) failed: %d", static_cast<int>(r));
     return TP_ERR_CUDA;
@@ -299,15 +299,21 @@ int launch_gemm_pair_group(const GemmItem* items, int count, int sms, cudaStream
     // uniformly strided segments (the HD packed layout) stay on the TMA path through a 3-D (cols, row in segment, segment) map
     p.use_tma_store = (it.ep.seg_row_offset == nullptr && !it.ep.out_f32) ? 1 : 0;
     const bool c_segmented = p.use_tma_store && it.ep.seg_stride != 0 && it.ep.seg_stride != it.ep.seg_len;
+    // A/B aid (read per call): TP_SEG_NOSWIZZLE=1 builds the clipped-box maps (segmented rows, window-major rows) without
+    // swizzle; the epilogue then writes plain slab rows for those problems (bank-conflicted, but only their stores are affected)
+    const char* nsw_env = getenv("TP_SEG_NOSWIZZLE");
+    const bool noswz = nsw_env != nullptr && atoi(nsw_env) != 0;
     if (it.ep.wm_s != 0) {
       if (!p.use_tma_store || c_segmented || it.n_peers > 0) return TP_ERR_INVALID_ARGUMENT;
       p.c_wm_s = it.ep.wm_s;
-      TP_TRY(make_map_wm(&p.tmap_c, it.ep.c, it.M, it.N, it.ep.ldc, it.ep.wm_s));
+      p.c_noswz = noswz ? 1 : 0;
+      TP_TRY(make_map_wm(&p.tmap_c, it.ep.c, it.M, it.N, it.ep.ldc, it.ep.wm_s, !noswz));
     } else if (c_segmented) {
+      p.c_noswz = noswz ? 1 : 0;
       if (it.ep.seg_len <= 0 || it.M % it.ep.seg_len != 0 || it.ep.seg_stride < it.ep.seg_len) return TP_ERR_INVALID_ARGUMENT;
       p.c_seg_len = it.ep.seg_len;
       TP_TRY(make_map_3d(&p.tmap_c, it.ep.c, it.M / it.ep.seg_len, it.ep.seg_len, it.N, it.ep.ldc, it.ep.seg_stride * it.ep.ldc,
-                         it.ep.seg_len < kBlockM ? it.ep.seg_len : kBlockM, kSlabCols));
+                         it.ep.seg_len < kBlockM ? it.ep.seg_len : kBlockM, kSlabCols, !noswz));
     } else {
       TP_TRY(make_map_2d(&p.tmap_c, it.ep.c, it.M, it.N, it.ep.ldc, kBlockM, kSlabCols));
     }
@@ -353,7 +359,7 @@ int launch_gemm_pair_group(const GemmItem* items, int count, int sms, cudaStream
     for (int p = 0; p < it0.n_peers; ++p) {
       if (g.p[peer_item].c_seg_len != 0)
         TP_TRY(make_map_3d(&peers.m[p], it0.peer_c[p], it0.M / it0.ep.seg_len, it0.ep.seg_len, it0.N, it0.ep.ldc, it0.ep.seg_stride * it0.ep.ldc,
-                           it0.ep.seg_len < kBlockM ? it0.ep.seg_len : kBlockM, kSlabCols));
+                           it0.ep.seg_len < kBlockM ? it0.ep.seg_len : kBlockM, kSlabCols, g.p[peer_item].c_noswz == 0));
       else
         TP_TRY(make_map_2d(&peers.m[p], it0.peer_c[p], it0.M, it0.N, it0.ep.ldc, kBlockM, kSlabCols));
     }

@@ -122,6 +122,7 @@ struct OutStage {
   uint64_t* empty_bar;       // [n_bufs] slab's TMA store has finished reading the buffer (count 1, store warp) -> epilogue warps
   int n_bufs;                // 2: slabs alternate buffers; 1: single buffer
   uint32_t slab_seq;         // running slab number of this half (buffer = seq % n_bufs, mbarrier phase = seq / n_bufs)
+  bool swizzle;              // slab rows in the TMA swizzle of the row width (false: plain rows, for C maps built without swizzle)
 };
 // Output slab = 128 rows x kSlabCols columns of bf16, in the TMA swizzle of that row width (64 columns: 128-byte rows,
 // SWIZZLE_128B; 32 columns: 64-byte rows, SWIZZLE_64B).  The narrow form halves the staging memory, which buys two more
@@ -271,7 +272,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmEpilogue& ep, int M, int
           // 16-byte piece index inside the slab row, XOR-swizzled like TMA does: 128-byte rows (SWIZZLE_128B) with (row & 7),
           // 64-byte rows (SWIZZLE_64B) with ((row >> 1) & 3) — address bits [7,9/10) folded into bits [4,6/7)
           const uint32_t row_base = out_addr + static_cast<uint32_t>(slab_buf * kOutSlabBytes + rloc * kSlabRowBytes);
-          const int swz = kSlabCols == 64 ? (rloc & 7) : ((rloc >> 1) & 3);
+          const int swz = !out.swizzle ? 0 : (kSlabCols == 64 ? (rloc & 7) : ((rloc >> 1) & 3));
 #pragma unroll
           for (int g = 0; g < kSubPairs / 4; ++g) {
             const int ci = (chunk % kChunksPerSlab) * 4 + sub * (kSubPairs / 4) + g;
@@ -596,7 +597,7 @@ tp_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tcgen05_fence_after();
       uint64_t* release_bar = &tmem_empty_bar[acc];
-      const OutStage no_stage{nullptr, nullptr, nullptr, 1, 0u};
+      const OutStage no_stage{nullptr, nullptr, nullptr, 1, 0u, true};
       epilogue_tile<kBlockN>(ep, M, N, tmem_base + static_cast<uint32_t>(acc * kBlockN),
                              m_blk * kBlockM + quarter * 32 + static_cast<int>(lane), n_blk * kBlockN, quarter, half, s_col, no_stage, [&]() {
                                tcgen05_fence_before();
@@ -649,6 +650,7 @@ struct GemmProblem {
   CUtensorMap tmap_a2, tmap_b2;              // kind 1: the value operands (tmap_a / tmap_b: the key operands)
   int kind;              // 0: GEMM with the fused epilogue; 1: KV-attention tile (see attn_epilogue_tile)
   int c_wm_s;            // != 0: tmap_c is the 5-D window-major map of GemmEpilogue::wm_s
+  int c_noswz;           // 1: tmap_c (and the peer maps) were built WITHOUT swizzle: the epilogue writes plain slab rows
   AttnParams attn;
   CUtensorMap tmap_a_more[kMaxAParts - 1];   // A given as several tensors side by side along K (e.g. the four CLIP hidden states
                                              // that the reference concatenates, clip_encoder.py:28-44): part p covers k-blocks
@@ -1086,7 +1088,7 @@ tp_gemm2_kernel(const __grid_constant__ GemmGroup grp, const __grid_constant__ P
       TP_PROF_T0();
       tcgen05_fence_after();
       const OutStage out{pr.use_tma_store ? s_out + half * Cfg::kOutBufs * kOutSlabBytes : nullptr, slab_full_bar + half * Cfg::kOutBufs,
-                         slab_empty_bar + half * Cfg::kOutBufs, Cfg::kOutBufs, slab_seq};
+                         slab_empty_bar + half * Cfg::kOutBufs, Cfg::kOutBufs, slab_seq, pr.c_noswz == 0};
       if (pr.use_tma_store) slab_seq += kTileN / 2 / kSlabCols;     // slabs per tile and column half
       epilogue_tile<kTileN>(pr.ep, pr.M, pr.N, tmem_base + static_cast<uint32_t>(acc * kTileN), row, t.n_blk * kTileN, quarter, half, s_col,
                             out, [&]() {

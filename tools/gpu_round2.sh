@@ -2,6 +2,7 @@
 # Round-2 GPU visit (1 GPU): tests (one process per file: a device-side trap cannot take the other files down), smoke, A/B of the
 # launch plans, the full bench line, phase profile, ncu launch list with DRAM bytes, sanitizers.  Everything lands in gpurun_out/.
 mkdir -p gpurun_out
+( timeout 900 python tools/tma_store_probe.py 2>&1 ) | tee gpurun_out/tma_store_probe.log
 for f in tests/test_*gpu*.py; do
   n=$(basename $f .py)
   ( timeout 900 python -m pytest $f -q -m gpu 2>&1 | tail -70 ) > gpurun_out/pytest_$n.log
