@@ -20,15 +20,14 @@ except Exception as e:
 " ) | tee -a gpurun_out/ab.log
 }
 rm -f gpurun_out/ab.log
-ab fused_default X=1
+ab fused_default_5stages X=1
 ab chain_nofuse TP_FUSE_ATTN=0
 ab plain_7_launches TP_FUSE_ATTN=0 TP_CHAIN=0
-ab fused_5stages TOKENPACKER_B200_LIB_OVERRIDE=$PWD/build_ab/s5.so
-ab nofuse_5stages TP_FUSE_ATTN=0 TOKENPACKER_B200_LIB_OVERRIDE=$PWD/build_ab/s5.so
-ab fused_6stages_narrow_slabs TOKENPACKER_B200_LIB_OVERRIDE=$PWD/build_ab/s6.so
-ab nofuse_6stages_narrow_slabs TP_FUSE_ATTN=0 TOKENPACKER_B200_LIB_OVERRIDE=$PWD/build_ab/s6.so
-( TOKENPACKER_B200_LIB_OVERRIDE=$PWD/build_ab/s6.so timeout 600 python -m pytest tests/test_gemm_gpu.py tests/test_fullsize_gpu.py -q -m gpu 2>&1 | tail -30 ) > gpurun_out/pytest_s6.log
-echo "s6 variant tests: $(tail -1 gpurun_out/pytest_s6.log)"
+ab fused_4stages TOKENPACKER_B200_LIB_OVERRIDE=$PWD/build_ab/s4.so
+ab nofuse_4stages TP_FUSE_ATTN=0 TOKENPACKER_B200_LIB_OVERRIDE=$PWD/build_ab/s4.so
+ab fused_5stages_narrow_2bufs TOKENPACKER_B200_LIB_OVERRIDE=$PWD/build_ab/s5n2.so
+ab fused_6stages_narrow TOKENPACKER_B200_LIB_OVERRIDE=$PWD/build_ab/s6.so
+ab fused_noswizzle_segstores TP_SEG_NOSWIZZLE=1
 ( timeout 900 python bench.py --steps 20 --warmup 5 2>gpurun_out/bench.err | tail -1 ) > gpurun_out/bench_line.json
 cut -c1-400 gpurun_out/bench_line.json
 ( timeout 300 python tools/gemm_phase_profile.py 2>&1 ) > gpurun_out/phase_profile.log
