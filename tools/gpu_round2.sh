@@ -2,6 +2,7 @@
 # Round-2 GPU visit (1 GPU): tests (one process per file: a device-side trap cannot take the other files down), smoke, A/B of the
 # launch plans, the full bench line, phase profile, ncu launch list with DRAM bytes, sanitizers.  Everything lands in gpurun_out/.
 mkdir -p gpurun_out
+( timeout 900 python tools/tma_store_probe.py 2>&1 ) | tee gpurun_out/tma_store_probe.log
 for f in tests/test_*gpu*.py; do
   n=$(basename $f .py)
   ( timeout 900 python -m pytest $f -q -m gpu 2>&1 | tail -70 ) > gpurun_out/pytest_$n.log
@@ -24,6 +25,10 @@ ab chain_nofuse TP_FUSE_ATTN=0
 ab plain_7_launches TP_FUSE_ATTN=0 TP_CHAIN=0
 ab fused_5stages TOKENPACKER_B200_LIB_OVERRIDE=$PWD/build_ab/s5.so
 ab nofuse_5stages TP_FUSE_ATTN=0 TOKENPACKER_B200_LIB_OVERRIDE=$PWD/build_ab/s5.so
+ab fused_6stages_narrow_slabs TOKENPACKER_B200_LIB_OVERRIDE=$PWD/build_ab/s6.so
+ab nofuse_6stages_narrow_slabs TP_FUSE_ATTN=0 TOKENPACKER_B200_LIB_OVERRIDE=$PWD/build_ab/s6.so
+( TOKENPACKER_B200_LIB_OVERRIDE=$PWD/build_ab/s6.so timeout 600 python -m pytest tests/test_gemm_gpu.py tests/test_fullsize_gpu.py -q -m gpu 2>&1 | tail -30 ) > gpurun_out/pytest_s6.log
+echo "s6 variant tests: $(tail -1 gpurun_out/pytest_s6.log)"
 ( timeout 900 python bench.py --steps 20 --warmup 5 2>gpurun_out/bench.err | tail -1 ) > gpurun_out/bench_line.json
 cut -c1-400 gpurun_out/bench_line.json
 ( timeout 300 python tools/gemm_phase_profile.py 2>&1 ) > gpurun_out/phase_profile.log
