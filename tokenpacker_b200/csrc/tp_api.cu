@@ -102,8 +102,10 @@ int make_map_3d(CUtensorMap* map, const void* ptr, long long segs, long long seg
 
 // Window-major destination of a raster-ordered [crops * 576, cols] bf16 matrix (scale factor s, g = 24 / s): dims
 // (channel, wi, hi, wb, crop-and-hb) — ordered by increasing stride, as the tensor-map encoder wants —, box = 64 channels x s x 1 x
-// g x 1 = one token row of 24 tokens (hi has extent 1 in the box, so the box is traversed wi-then-wb: raster order).
-int make_map_wm(CUtensorMap* map, const void* ptr, long long rows, long long cols, long long ld, int s, bool swizzle = true) {
+// (box_tokens / s) x 1 = box_tokens consecutive tokens of one token row (hi has extent 1 in the box, so the box is traversed
+// wi-then-wb: raster order).  box_tokens in {8, 16, 24}: stores never stick out of the tensor (that faults), so each piece of a
+// slab uses the map of exactly its size.
+int make_map_wm(CUtensorMap* map, const void* ptr, long long rows, long long cols, long long ld, int s, int box_tokens, bool swizzle = true) {
   EncodeTiledFn fn = encode_tiled_fn();
   if (fn == nullptr) {
     snprintf(g_last_cuda_error, sizeof(g_last_cuda_error), "cuTensorMapEncodeTiled entry point not found");
@@ -115,7 +117,8 @@ int make_map_wm(CUtensorMap* map, const void* ptr, long long rows, long long col
                         static_cast<cuuint64_t>(rows / 576 * g)};
   const cuuint64_t row_b = static_cast<cuuint64_t>(ld) * 2;
   cuuint64_t strides[4] = {row_b, row_b * s, row_b * s * s, row_b * s * s * g};
-  cuuint32_t box[5] = {static_cast<cuuint32_t>(kSlabCols), static_cast<cuuint32_t>(s), 1, static_cast<cuuint32_t>(g), 1};
+  if (box_tokens % s != 0 || box_tokens > 24) return TP_ERR_INVALID_ARGUMENT;
+  cuuint32_t box[5] = {static_cast<cuuint32_t>(kSlabCols), static_cast<cuuint32_t>(s), 1, static_cast<cuuint32_t>(box_tokens / s), 1};
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   !swizzle ? CU_TENSOR_MAP_SWIZZLE_NONE : (kSlabCols == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B), CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -307,13 +310,22 @@ int launch_gemm_pair_group(const GemmItem* items, int count, int sms, cudaStream
       if (!p.use_tma_store || c_segmented || it.n_peers > 0) return TP_ERR_INVALID_ARGUMENT;
       p.c_wm_s = it.ep.wm_s;
       p.c_noswz = noswz ? 1 : 0;
-      TP_TRY(make_map_wm(&p.tmap_c, it.ep.c, it.M, it.N, it.ep.ldc, it.ep.wm_s, !noswz));
+      TP_TRY(make_map_wm(&p.tmap_c, it.ep.c, it.M, it.N, it.ep.ldc, it.ep.wm_s, 8, !noswz));
+      TP_TRY(make_map_wm(&p.tmap_cx[0], it.ep.c, it.M, it.N, it.ep.ldc, it.ep.wm_s, 16, !noswz));
+      TP_TRY(make_map_wm(&p.tmap_cx[1], it.ep.c, it.M, it.N, it.ep.ldc, it.ep.wm_s, 24, !noswz));
     } else if (c_segmented) {
       p.c_noswz = noswz ? 1 : 0;
       if (it.ep.seg_len <= 0 || it.M % it.ep.seg_len != 0 || it.ep.seg_stride < it.ep.seg_len) return TP_ERR_INVALID_ARGUMENT;
       p.c_seg_len = it.ep.seg_len;
-      TP_TRY(make_map_3d(&p.tmap_c, it.ep.c, it.M / it.ep.seg_len, it.ep.seg_len, it.N, it.ep.ldc, it.ep.seg_stride * it.ep.ldc,
-                         it.ep.seg_len < kBlockM ? it.ep.seg_len : kBlockM, kSlabCols, !noswz));
+      p.c_unit = 128;
+      while (it.ep.seg_len % p.c_unit != 0) p.c_unit >>= 1;          // gcd(seg_len, 128)
+      if (p.c_unit < 4) return TP_ERR_INVALID_ARGUMENT;             // (scale factors with < 4 tokens per crop keep the row-offset path)
+      for (int lvl = 0; lvl < kBoxLevels; ++lvl) {
+        int rows = p.c_unit << lvl;
+        if (rows > kBlockM || rows > it.ep.seg_len) rows = p.c_unit;  // level never used (pieces are at most min(seg_len, 128) rows)
+        TP_TRY(make_map_3d(lvl == 0 ? &p.tmap_c : &p.tmap_cx[lvl - 1], it.ep.c, it.M / it.ep.seg_len, it.ep.seg_len, it.N, it.ep.ldc,
+                           it.ep.seg_stride * it.ep.ldc, rows, kSlabCols, !noswz));
+      }
     } else {
       TP_TRY(make_map_2d(&p.tmap_c, it.ep.c, it.M, it.N, it.ep.ldc, kBlockM, kSlabCols));
     }
@@ -357,11 +369,16 @@ int launch_gemm_pair_group(const GemmItem* items, int count, int sms, cudaStream
     const GemmItem& it0 = items[peer_item];
     if (it0.n_peers > kMaxPeers || it0.ep.seg_row_offset != nullptr) return TP_ERR_INVALID_ARGUMENT;
     for (int p = 0; p < it0.n_peers; ++p) {
-      if (g.p[peer_item].c_seg_len != 0)
-        TP_TRY(make_map_3d(&peers.m[p], it0.peer_c[p], it0.M / it0.ep.seg_len, it0.ep.seg_len, it0.N, it0.ep.ldc, it0.ep.seg_stride * it0.ep.ldc,
-                           it0.ep.seg_len < kBlockM ? it0.ep.seg_len : kBlockM, kSlabCols, g.p[peer_item].c_noswz == 0));
-      else
-        TP_TRY(make_map_2d(&peers.m[p], it0.peer_c[p], it0.M, it0.N, it0.ep.ldc, kBlockM, kSlabCols));
+      if (g.p[peer_item].c_seg_len != 0) {
+        for (int lvl = 0; lvl < kBoxLevels; ++lvl) {
+          int rows = g.p[peer_item].c_unit << lvl;
+          if (rows > kBlockM || rows > it0.ep.seg_len) rows = g.p[peer_item].c_unit;
+          TP_TRY(make_map_3d(&peers.m[p][lvl], it0.peer_c[p], it0.M / it0.ep.seg_len, it0.ep.seg_len, it0.N, it0.ep.ldc,
+                             it0.ep.seg_stride * it0.ep.ldc, rows, kSlabCols, g.p[peer_item].c_noswz == 0));
+        }
+      } else {
+        TP_TRY(make_map_2d(&peers.m[p][0], it0.peer_c[p], it0.M, it0.N, it0.ep.ldc, kBlockM, kSlabCols));
+      }
     }
     peers.count = it0.n_peers;
   }

@@ -111,8 +111,9 @@ constexpr int kEpiBarrierId = 1;
 constexpr int kMaxPeers = 8;
 // Fused all-gather: tensor maps of the SAME output slot in every peer GPU's gathered buffer (peer-mapped over NVLink);
 // each finished slab is TMA-stored to all of them instead of to one local matrix.
+constexpr int kBoxLevels = 4;   // exact-size store boxes: rows = unit << level
 struct PeerStores {
-  CUtensorMap m[kMaxPeers];
+  CUtensorMap m[kMaxPeers][kBoxLevels];   // [peer][level]; plain (unsegmented) output uses level 0 only
   int count;                 // 0: ordinary local output through GemmProblem::tmap_c
 };
 
@@ -626,10 +627,16 @@ struct Gemm2Config {
   static constexpr int kTileM = 256;
   static constexpr int kTileN = 256;
 #ifndef TP_PAIR_STAGES
-#define TP_PAIR_STAGES 4
+#define TP_PAIR_STAGES 5
 #endif
-  static constexpr int kStages = TP_PAIR_STAGES;                 // 4: double-buffered output slabs; 5: single-buffered (smem budget)
-  static constexpr int kOutBufs = (kStages <= 4) ? 2 : 1;        // staging buffers per column half
+#ifndef TP_OUT_BUFS
+#define TP_OUT_BUFS ((TP_PAIR_STAGES <= 4) ? 2 : 1)
+#endif
+  // Ring depth is what hides the operand-fetch latency (measured on the configs[1] step, same box: 4 / 5 / 6 stages = 1.001 /
+  // 0.967 / 0.973 ms); since the store warps took the TMA stores off the epilogue warps' path one staging slab per column half is
+  // enough, which is what pays for the fifth stage.
+  static constexpr int kStages = TP_PAIR_STAGES;
+  static constexpr int kOutBufs = TP_OUT_BUFS;                   // staging buffers per column half (1 or 2)
   static constexpr int kABytes = kBlockM * kBlockK * 2;          // this CTA's 128 rows of A
   static constexpr int kBBytes = (kTileN / 2) * kBlockK * 2;     // this CTA's half of the B tile
   static constexpr int kStageBytes = kABytes + kBBytes;          // 32 KiB
@@ -647,6 +654,8 @@ constexpr int kMaxAParts = 4;
 
 struct GemmProblem {
   CUtensorMap tmap_a, tmap_b, tmap_c;
+  CUtensorMap tmap_cx[kBoxLevels - 1];       // further C maps of the segmented / window-major stores (see the store warps): boxes of
+                                             // c_unit << level rows (segmented) or 8 * (level + 1) tokens (window-major); level 0 = tmap_c
   CUtensorMap tmap_a2, tmap_b2;              // kind 1: the value operands (tmap_a / tmap_b: the key operands)
   int kind;              // 0: GEMM with the fused epilogue; 1: KV-attention tile (see attn_epilogue_tile)
   int c_wm_s;            // != 0: tmap_c is the 5-D window-major map of GemmEpilogue::wm_s
@@ -662,6 +671,7 @@ struct GemmProblem {
   int ab_mn_major;       // 1: BOTH operands are given as row-major [K, M] / [K, N] matrices (wgrad: C = A^T . B, contraction over rows)
   int use_tma_store;     // C through TMA stores (0 when rows are scattered to arbitrary segment offsets)
   int c_seg_len;         // != 0: tmap_c (and the peer maps) are 3-D (cols, row in segment, segment): uniform-stride segmented output
+  int c_unit;            //       gcd(c_seg_len, 128): every piece of a slab that belongs to one segment is a multiple of it
   int num_n_blocks;
   int num_tiles;         // = tiles_mn * k_splits
   int num_k_blocks;
@@ -1129,7 +1139,6 @@ tp_gemm2_kernel(const __grid_constant__ GemmGroup grp, const __grid_constant__ P
       if (!pr.use_tma_store) continue;
       const int row_tile0 = t.m_blk * Cfg::kTileM + static_cast<int>(cta_rank) * kBlockM;
       const bool to_peers = pr.peer_out != 0 && peers.count > 0;
-      const CUtensorMap* maps = to_peers ? &peers.m[0] : &pr.tmap_c;
       const int n_maps = to_peers ? peers.count : 1;
       for (int slab = 0; slab < kTileN / 2 / kSlabCols; ++slab, ++q) {
         const uint32_t buf = q & static_cast<uint32_t>(Cfg::kOutBufs - 1);
@@ -1137,32 +1146,40 @@ tp_gemm2_kernel(const __grid_constant__ GemmGroup grp, const __grid_constant__ P
         if (elect_one()) {
           const uint8_t* src = s_out + (half * Cfg::kOutBufs + static_cast<int>(buf)) * kOutSlabBytes;
           const int col = t.n_blk * kTileN + half * (kTileN / 2) + slab * kSlabCols;
+          // TMA stores must lie entirely inside the tensor (a box that sticks out of a segment faults: measured), so every piece of
+          // a slab goes out through boxes of EXACTLY its size: a few maps per destination with box heights unit << level.
           if (pr.c_wm_s != 0) {
             // Raster rows -> window-major rows: the slab is cut at token-row boundaries (24 tokens; crops are 24 token rows, so
-            // token row R24 = global row / 24 = (crop * g + hb) * s + hi) and each piece leaves through one (channel, wi, -, wb) box
-            // of the 5-D map at (hi, crop-and-hb); pieces cut by the slab edge are clipped along wb (slab edges fall on multiples
-            // of 8 tokens, a whole number of windows for s in {2, 4, 8}).
+            // token row R24 = global row / 24 = (crop * g + hb) * s + hi).  Slab edges fall on multiples of 8 tokens — a whole
+            // number of windows for s in {2, 4, 8} —, so a piece holds 8, 16 or 24 tokens: map (tokens / 8 - 1), a
+            // (channel, wi, -, wb) box of that many windows at (hi, crop-and-hb).
             const int sf = pr.c_wm_s;
+            const int n_r24 = pr.M / 24;
             int r24 = row_tile0 / 24;
-            for (int a = r24 * 24 - row_tile0; a < kBlockM; a += 24, ++r24) {
-              const int src_row = min(max(a, 0), kBlockM - 24);
-              const int tok0 = src_row - a;                         // token offset inside the token row (may be negative)
-              tma_store_5d(maps, src + src_row * kSlabRowBytes, col, 0, r24 % sf, tok0 / sf, r24 / sf);    // (c, wi, hi, wb, crop-and-hb)
+            for (int a = r24 * 24 - row_tile0; a < kBlockM && r24 < n_r24; a += 24, ++r24) {
+              const int lo = max(a, 0), hi = min(a + 24, kBlockM);
+              const int lvl = (hi - lo) / 8 - 1;
+              const CUtensorMap* mp = lvl == 0 ? &pr.tmap_c : &pr.tmap_cx[lvl - 1];
+              tma_store_5d(mp, src + lo * kSlabRowBytes, col, 0, r24 % sf, (lo - a) / sf, r24 / sf);    // (c, wi, hi, wb, crop-and-hb)
             }
           } else if (pr.c_seg_len == 0) {
-            for (int p = 0; p < n_maps; ++p) tma_store_2d(maps + p, src, col, row_tile0);
+            for (int p = 0; p < n_maps; ++p) tma_store_2d(to_peers ? &peers.m[p][0] : &pr.tmap_c, src, col, row_tile0);
           } else {
             // Segmented output rows (global row g = seg * seg_len + r  ->  map coordinate (col, r, seg)): the slab's 128 rows are
-            // cut at segment boundaries and each piece leaves through the SAME fixed-size box.  A piece that starts before the slab
-            // or ends after it is positioned so that the surplus box rows fall outside [0, seg_len) of its segment, where TMA clips
-            // them (signed coordinates): src_row = clamp(a, 0, 128 - box), r0 = src_row - a, a = slab row of the segment's row 0.
-            // The 128B swizzle is a function of the absolute shared-memory address, so any 128-byte-aligned source row works.
-            const int seg_box = pr.c_seg_len < kBlockM ? pr.c_seg_len : kBlockM;
+            // cut at segment boundaries; a piece of L = n * unit rows leaves as one box per set bit of n (largest first).
             const int n_segs = pr.M / pr.c_seg_len;
             int seg = row_tile0 / pr.c_seg_len;
             for (int a = seg * pr.c_seg_len - row_tile0; a < kBlockM && seg < n_segs; a += pr.c_seg_len, ++seg) {
-              const int src_row = min(max(a, 0), kBlockM - seg_box);
-              for (int p = 0; p < n_maps; ++p) tma_store_3d(maps + p, src + src_row * kSlabRowBytes, col, src_row - a, seg);
+              int lo = max(a, 0);
+              const int hi = min(a + pr.c_seg_len, kBlockM);
+              for (int lvl = kBoxLevels - 1; lvl >= 0; --lvl) {
+                const int rows = pr.c_unit << lvl;
+                while (hi - lo >= rows) {
+                  for (int p = 0; p < n_maps; ++p)
+                    tma_store_3d(to_peers ? &peers.m[p][lvl] : (lvl == 0 ? &pr.tmap_c : &pr.tmap_cx[lvl - 1]), src + lo * kSlabRowBytes, col, lo - a, seg);
+                  lo += rows;
+                }
+              }
             }
           }
           bulk_commit_group();
