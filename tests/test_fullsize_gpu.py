@@ -163,8 +163,10 @@ def test_packed_rows_pair_kernel_bit_exact(s, hidden, monkeypatch):
     assert torch.equal(packed, packed2), int((packed != packed2).any(-1).sum())
 
 
-def test_arbitrary_row_offsets_still_supported():
-    """tp_forward's seg_row_offset form (arbitrary destination rows, direct stores) is kept: scatter crops in REVERSE order."""
+def test_arbitrary_row_offsets_still_supported(monkeypatch):
+    """tp_forward's seg_row_offset form (arbitrary destination rows, direct stores) is kept: scatter crops in REVERSE order.
+    (That form runs the separate-kernel plan, so the dense reference is taken from the same plan: TP_FUSE_ATTN=0.)"""
+    monkeypatch.setenv("TP_FUSE_ATTN", "0")
     m, _ = _module(512, 4, seed=4)
     x0, xm = _inputs(5, 3)
     with torch.no_grad():
