@@ -244,7 +244,23 @@ int launch_gemm_t(const GemmItem& it, int sms, cudaStream_t stream) {
 }
 
 // Up to kMaxGroup independent problems in ONE launch of the CTA-pair kernel.
-int launch_gemm_pair_group(const GemmItem* items, int count, int sms, cudaStream_t stream, const FrontWork* front = nullptr) {
+// A tile schedule for a chained launch: segments (item, first row block, row blocks) in issue order; see TileSeg.
+struct SegPlan {
+  int n = 0;
+  int prob[kMaxSegs], m_lo[kMaxSegs], m_cnt[kMaxSegs];
+  bool add(int p, long long lo, long long hi, long long blocks) {
+    if (lo < 0) lo = 0;
+    if (hi > blocks) hi = blocks;
+    if (hi <= lo) return true;
+    if (n == kMaxSegs) return false;
+    prob[n] = p; m_lo[n] = static_cast<int>(lo); m_cnt[n] = static_cast<int>(hi - lo);
+    ++n;
+    return true;
+  }
+};
+
+int launch_gemm_pair_group(const GemmItem* items, int count, int sms, cudaStream_t stream, const FrontWork* front = nullptr,
+                           const SegPlan* plan = nullptr) {
   using Cfg = Gemm2Config;
   GemmGroup g;
   memset(&g, 0, sizeof(g));
@@ -257,15 +273,15 @@ int launch_gemm_pair_group(const GemmItem* items, int count, int sms, cudaStream
       if (it.N != kC || it.K != kC || it.a2 == nullptr || it.b2 == nullptr || (it.attn.s != 2 && it.attn.s != 4)) return TP_ERR_INVALID_ARGUMENT;
       TP_TRY(make_map_2d(&p.tmap_a, it.a.ptr, it.M, it.K, it.a.ld, kBlockM));
       TP_TRY(make_map_2d(&p.tmap_a2, it.a2, it.M, it.K, it.a.ld, kBlockM));
-      TP_TRY(make_map_2d(&p.tmap_b, it.b, it.N, it.K, it.ldb, 64));           // 64 of the head's 128 weight rows per CTA
-      TP_TRY(make_map_2d(&p.tmap_b2, it.b2, it.N, it.K, it.ldb, 64));
+      TP_TRY(make_map_2d(&p.tmap_b, it.b, it.N, it.K, it.ldb, Cfg::kTileN / 2));   // the head pair's 256 weight rows: 128 per CTA
+      TP_TRY(make_map_2d(&p.tmap_b2, it.b2, it.N, it.K, it.ldb, Cfg::kTileN / 2));
       p.kind = 1;
       p.attn = it.attn;
       p.a_parts = 1;
       p.M = static_cast<int>(it.M);
       p.N = static_cast<int>(it.N);
       p.K = static_cast<int>(it.K);
-      p.num_n_blocks = 8;                                                      // one tile column per head
+      p.num_n_blocks = 4;                                                      // one tile column per PAIR of heads
       p.num_k_blocks = static_cast<int>(it.K / kBlockK);
       p.tiles_mn = static_cast<int>((it.M + Cfg::kTileM - 1) / Cfg::kTileM) * p.num_n_blocks;
       p.k_splits = 1;
@@ -357,6 +373,21 @@ int launch_gemm_pair_group(const GemmItem* items, int count, int sms, cudaStream
   if (total > 0x7fffffffll) return TP_ERR_INVALID_ARGUMENT;
   g.total_tiles = static_cast<int>(total);
   if (front != nullptr) g.front = *front;
+  if (plan != nullptr && plan->n > 0) {
+    // the schedule must cover every row block of every problem exactly once (else fall back to stage order)
+    long long covered[kMaxGroup] = {0};
+    int t0 = 0;
+    bool ok = true;
+    for (int i = 0; i < plan->n && ok; ++i) {
+      const GemmProblem& pp = g.p[plan->prob[i]];
+      if (pp.k_splits != 1) ok = false;
+      g.segs[i] = TileSeg{plan->prob[i], plan->m_lo[i], t0, plan->m_cnt[i] * pp.num_n_blocks};
+      t0 += g.segs[i].n_tiles;
+      covered[plan->prob[i]] += plan->m_cnt[i];
+    }
+    for (int i = 0; i < count && ok; ++i) ok = covered[i] * g.p[i].num_n_blocks == g.p[i].num_tiles;
+    g.n_segs = (ok && t0 == g.total_tiles) ? plan->n : 0;
+  }
   PeerStores peers;
   memset(&peers, 0, sizeof(peers));
   int peer_item = -1;
@@ -493,7 +524,8 @@ bool chain_feasible(const GemmItem* items, int count, int sms, bool by_cost = tr
   return true;
 }
 
-int launch_chain(GemmItem* items, int count, int* flags, long long flag_capacity, const FrontWork* front, int sms, cudaStream_t stream) {
+int launch_chain(GemmItem* items, int count, int* flags, long long flag_capacity, const FrontWork* front, int sms, cudaStream_t stream,
+                 const SegPlan* plan = nullptr) {
   if (count <= 0 || count > kMaxGroup) return TP_ERR_INVALID_ARGUMENT;
   for (int i = 0; i < count; ++i) {
     const int deps[3] = {items[i].dep, items[i].dep2, items[i].dep3};
@@ -552,13 +584,13 @@ int launch_chain(GemmItem* items, int count, int* flags, long long flag_capacity
         it.dep_counter = counter_of(d);
         it.dep_span = items[d].attn.s * items[d].attn.s;                   // KV tiles per block of 256 queries
         it.dep_src_blocks = static_cast<int>((items[d].M + 255) / 256);
-        it.dep_per = 16;                                                   // 8 heads x 2 CTAs per KV tile
+        it.dep_per = 8;                                                    // 4 head pairs x 2 CTAs per KV row block
       } else if (d >= 0) {
         it.dep_counter = counter_of(d);
         it.dep_target = gemm_target(d);
       }
     }
-    return launch_gemm_pair_group(items, count, sms, stream, front != nullptr ? &fw : nullptr);
+    return launch_gemm_pair_group(items, count, sms, stream, front != nullptr ? &fw : nullptr, plan);
   }
   for (int i = 0; i < count; ++i)
     if (items[i].kind == 1 || items[i].ep.wm_s != 0) return TP_ERR_INVALID_ARGUMENT;      // fused-attention items exist only inside a chain
@@ -937,7 +969,29 @@ int forward_impl(const void* packed, const void* x0, const void* xm, const void*
     g[7].n_peers = n_peers;
     g[7].stage = 5;
     g[7].dep = 6;
-    if (chain_feasible(g, 8, dev.sms, false)) return launch_chain(g, 8, flags, W.n_flags, &front, dev.sms, stream);
+    if (chain_feasible(g, 8, dev.sms, false)) {
+      // Tile schedule: a software wavefront over groups of GR row blocks of the key/value side (= GQ blocks of 256 queries).
+      // Super-step j issues [1] for group j, [2]k/v for group j-1, the KV-attention tiles of group j-2, [4] for the queries of group
+      // j-3 and [5] for those of group j-4: every consumer runs one super-step (~60k cycles) behind its producer — its inputs are
+      // still in L2 — and each CTA pair alternates K=4096 tiles with the epilogue-heavy K=1024 ones.  The short query chain
+      // ([2]q, [3]q) goes first.  TP_SCHEDULE=0: stage after stage.
+      const char* sch_env = getenv("TP_SCHEDULE");
+      SegPlan plan;
+      if (sch_env == nullptr || atoi(sch_env) != 0) {
+        const long long nbR = (R + 255) / 256, nbQ = (Q + 255) / 256;
+        const int Wn = s * s;
+        long long GR = Wn > 8 ? Wn : 8;
+        while ((nbR + GR - 1) / GR > 48) GR *= 2;
+        const long long GQ = GR / Wn, NG = (nbR + GR - 1) / GR;
+        bool ok = plan.add(0, 0, GR, nbR) && plan.add(3, 0, nbQ, nbQ) && plan.add(4, 0, nbQ, nbQ);
+        for (long long j = 1; j <= NG + 4 && ok; ++j)
+          ok = plan.add(0, j * GR, (j + 1) * GR, nbR) && plan.add(1, (j - 1) * GR, j * GR, nbR) && plan.add(2, (j - 1) * GR, j * GR, nbR) &&
+               plan.add(5, (j - 2) * GR, (j - 1) * GR, nbR) && plan.add(6, (j - 3) * GQ, (j - 2) * GQ, nbQ) &&
+               plan.add(7, (j - 4) * GQ, (j - 3) * GQ, nbQ);
+        if (!ok) plan.n = 0;
+      }
+      return launch_chain(g, 8, flags, W.n_flags, &front, dev.sms, stream, &plan);
+    }
   }
   // k' / v' have buffers of their own: in a chained launch [3] runs while other row blocks of [2] still read h_kv, so the
   // round-1 trick of writing them over the dead h_kv buffer is no longer legal

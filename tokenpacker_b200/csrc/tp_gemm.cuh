@@ -324,14 +324,15 @@ __device__ __forceinline__ void epilogue_tile(const GemmEpilogue& ep, int M, int
 // ------------------------------------------------------------------------------------------------
 // KV-attention tiles (problem kind 1): the MHA in-projections of the keys and values FUSED with the local-window attention core
 // (builder.py:122-130 == nn.MultiheadAttention, L = 1 query, S = s*s keys per window, 8 heads x 128).
-//   A tile = 256 window-major rows (CTA pair) x ONE head: the MMA warp runs two K=1024 GEMMs into the two 128-column halves of
-//   the accumulator buffer — k' = y_k . (gamma_k W_ik)^T and v' = y_v . (gamma_v W_iv)^T for this head — and the epilogue, thread ==
-//   key row, applies the folded LayerNorms, dots k' with the window's q' (already scaled by 1/sqrt 128), takes the softmax over
-//   the s*s consecutive lanes of the window with warp shuffles, scales v' and reduces it over the same lanes with a halving
-//   exchange, and writes the window's 128 context channels of this head.  k' and v' never exist in memory (fp32, unrounded, in
+//   A tile = 256 window-major rows (CTA pair) x TWO heads, in two accumulator phases of the ordinary 256 x 256 x K pipeline:
+//     phase K: k' = y_k . (gamma_k W_ik)^T for the two heads  -> epilogue: folded LayerNorm, dot with the window's q' (already scaled
+//              by 1/sqrt 128), softmax over the s*s consecutive lanes of the window (warp shuffles)  -> p stays in a register
+//     phase V: v' = y_v . (gamma_v W_iv)^T                     -> epilogue: folded LayerNorm, p * v', halving exchange over the window's
+//              lanes, store the window's 128 context channels of the head
+//   The two phases use the two TMEM accumulator buffers alternately, so the MMAs of phase V run under the score epilogue and the
+//   next tile's phase K under the P.V epilogue: the tensor pipe sees the same back-to-back 256-wide k-loops as a plain GEMM.
+//   Thread == key row; column half (warps 0-3 / 4-7) == head of the pair.  k' and v' never exist in memory (fp32, unrounded, in
 //   registers): the [R,1024] x 2 round trip through HBM and the separate attention kernel are gone.
-// The two column halves of the epilogue (warps 0-3 / 4-7) each take 64 channels of the head: their partial scores meet in
-// shared memory (fixed order: half 0 + half 1).
 // ------------------------------------------------------------------------------------------------
 struct AttnParams {
   const __nv_bfloat16* qp;      // [Q, 1024] q', row = window index (= query index), scaled
@@ -345,7 +346,7 @@ struct AttnParams {
   int s;                        // scale factor: W = s*s consecutive rows per window (2 or 4)
   int stats_slots;
   float ln_inv_dim, ln_eps;
-  int* done_counter;            // ctx row blocks of 256 queries: counter[(m_blk * 256 / W) / 256] += 1 per (CTA, head)
+  int* done_counter;            // ctx row blocks of 256 queries: counter[(m_blk * 256 / W) / 256] += 1 per (CTA, head pair)
   // dependencies of a tile: the raster row blocks of y_k / y_v covering the crops it touches, and its queries' q' row block
   const int* k_counter;
   const int* v_counter;
@@ -359,65 +360,70 @@ __device__ __forceinline__ float bf16x2_get(const uint4& v, int i) {      // i i
   return (i & 1) ? bf16_hi(w) : bf16_lo(w);
 }
 
+// Phase K epilogue: returns this row's softmax weight p for head `head`.  s_vec: [wsum | cst][256] of the tile's two heads.
 template <typename ReleaseFn>
-__device__ __forceinline__ void attn_epilogue_tile(const AttnParams& at, int M, uint32_t tmem_acc, int row, int head, int quarter, int half,
-                                                   const float* s_vec, float* s_score, ReleaseFn release) {
+__device__ __forceinline__ float attn_scores(const AttnParams& at, int M, uint32_t tmem_acc, int row, int head, int quarter, int half,
+                                             const float* s_vec, ReleaseFn release) {
   const int W = at.s * at.s;
   const bool row_ok = row < M;
-  const uint32_t lane = lane_id();
-  const int rloc = quarter * 32 + static_cast<int>(lane);
-  float mu_k = 0.f, rstd_k = 0.f, mu_v = 0.f, rstd_v = 0.f;
-  if (row_ok) {
-    ln_row_stats(at.stats_k, row, at.stats_slots, at.ln_inv_dim, at.ln_eps, mu_k, rstd_k);
-    ln_row_stats(at.stats_v, row, at.stats_slots, at.ln_inv_dim, at.ln_eps, mu_v, rstd_v);
-  }
+  float mu = 0.f, rstd = 0.f;
+  if (row_ok) ln_row_stats(at.stats_k, row, at.stats_slots, at.ln_inv_dim, at.ln_eps, mu, rstd);
   const long long window = row / W;
-  const int col0 = head * 128 + half * 64;                  // first channel of this thread's 64
-  const float* wsum_k = s_vec + half * 64;                  // staged per tile: [wsum_k | cst_k | wsum_v | cst_v][128]
-  const float* cst_k = s_vec + 128 + half * 64;
-  const float* wsum_v = s_vec + 256 + half * 64;
-  const float* cst_v = s_vec + 384 + half * 64;
-  const uint32_t taddr_k = tmem_acc + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(half * 64);
-  const uint32_t taddr_v = taddr_k + 128u;
-
+  const float* wsum = s_vec + half * 128;
+  const float* cst = s_vec + 256 + half * 128;
+  const uint32_t taddr = tmem_acc + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(half * 128);
+  const uint4* qrow = reinterpret_cast<const uint4*>(at.qp + window * 1024 + head * 128);
   uint32_t r[2][32];
-  tmem_ld_32x32b_x32(taddr_k, r[0]);
+  tmem_ld_32x32b_x32(taddr, r[0]);
   float score = 0.f;
 #pragma unroll
-  for (int chunk = 0; chunk < 2; ++chunk) {
+  for (int chunk = 0; chunk < 4; ++chunk) {
     tmem_ld_wait();
-    tmem_ld_32x32b_x32(chunk == 0 ? taddr_k + 32u : taddr_v, r[(chunk + 1) & 1]);
+    if (chunk + 1 < 4) tmem_ld_32x32b_x32(taddr + static_cast<uint32_t>((chunk + 1) * 32), r[(chunk + 1) & 1]);
+    else release();                                   // every TMEM read of this warp has landed in registers
     uint4 q4[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
-      q4[i] = row_ok ? __ldg(reinterpret_cast<const uint4*>(at.qp + window * 1024 + col0 + chunk * 32) + i) : make_uint4(0u, 0u, 0u, 0u);
+    for (int i = 0; i < 4; ++i) q4[i] = row_ok ? __ldg(qrow + chunk * 4 + i) : make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
     for (int c = 0; c < 32; ++c) {
-      const float kf = fmaf(rstd_k, fmaf(-mu_k, wsum_k[chunk * 32 + c], __uint_as_float(r[chunk & 1][c])), cst_k[chunk * 32 + c]);
+      const float kf = fmaf(rstd, fmaf(-mu, wsum[chunk * 32 + c], __uint_as_float(r[chunk & 1][c])), cst[chunk * 32 + c]);
       score = fmaf(bf16x2_get(q4[c >> 3], c & 7), kf, score);
     }
   }
-  // the other column half holds the rest of the head's 128 channels: partial scores meet in shared memory
-  s_score[half * 128 + rloc] = score;
-  named_bar_sync(kEpiBarrierId, kEpiThreads);
-  score = __fadd_rn(s_score[rloc], s_score[128 + rloc]);
   // softmax over the W keys of my window = W consecutive lanes (W divides 32, windows never straddle a warp)
   float mx = score;
   for (int off = 1; off < W; off <<= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
   const float e = __expf(score - mx);
   float den = e;
   for (int off = 1; off < W; off <<= 1) den += __shfl_xor_sync(0xffffffffu, den, off);
-  const float p = e * (1.0f / den);
-  // ctx = sum over the window's lanes of p * v': halving exchange — after log2(W) steps each lane holds 32 / W channels of the chunk
+  return e * (1.0f / den);
+}
+
+// Phase V epilogue: ctx = sum over the window's lanes of p * v'.  Halving exchange: after log2(W) steps each lane holds 32 / W
+// channels of the chunk.
+template <typename ReleaseFn>
+__device__ __forceinline__ void attn_pv(const AttnParams& at, int M, uint32_t tmem_acc, int row, int head, int quarter, int half, float p,
+                                        const float* s_vec, ReleaseFn release) {
+  const int W = at.s * at.s;
+  const bool row_ok = row < M;
+  const uint32_t lane = lane_id();
+  float mu = 0.f, rstd = 0.f;
+  if (row_ok) ln_row_stats(at.stats_v, row, at.stats_slots, at.ln_inv_dim, at.ln_eps, mu, rstd);
+  const long long window = row / W;
+  const float* wsum = s_vec + half * 128;
+  const float* cst = s_vec + 256 + half * 128;
+  const uint32_t taddr = tmem_acc + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(half * 128);
+  uint32_t r[2][32];
+  tmem_ld_32x32b_x32(taddr, r[0]);
 #pragma unroll
-  for (int chunk = 0; chunk < 2; ++chunk) {
+  for (int chunk = 0; chunk < 4; ++chunk) {
     tmem_ld_wait();
-    if (chunk == 0) tmem_ld_32x32b_x32(taddr_v + 32u, r[1]);
-    else release();                                   // every TMEM read of this warp has landed in registers
+    if (chunk + 1 < 4) tmem_ld_32x32b_x32(taddr + static_cast<uint32_t>((chunk + 1) * 32), r[(chunk + 1) & 1]);
+    else release();
     float v[32];
 #pragma unroll
     for (int c = 0; c < 32; ++c)
-      v[c] = p * fmaf(rstd_v, fmaf(-mu_v, wsum_v[chunk * 32 + c], __uint_as_float(r[chunk & 1][c])), cst_v[chunk * 32 + c]);
+      v[c] = p * fmaf(rstd, fmaf(-mu, wsum[chunk * 32 + c], __uint_as_float(r[chunk & 1][c])), cst[chunk * 32 + c]);
     int first = 0;                                    // my live values cover channels [first, first + 32 >> steps) of the chunk
 #pragma unroll
     for (int step = 0; step < 4; ++step) {
@@ -435,7 +441,7 @@ __device__ __forceinline__ void attn_epilogue_tile(const AttnParams& at, int M, 
       }
     }
     if (row_ok) {
-      __nv_bfloat16* dst = at.ctx + window * 1024 + col0 + chunk * 32 + first;
+      __nv_bfloat16* dst = at.ctx + window * 1024 + head * 128 + chunk * 32 + first;
       if (W == 4) {
         *reinterpret_cast<uint4*>(dst) = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
       } else {                                        // W == 16: two channels per lane
@@ -643,9 +649,8 @@ struct Gemm2Config {
   static constexpr int kTmemCols = 2 * kTileN;
   static constexpr int kOutBytes = 2 * kOutBufs * kOutSlabBytes; // [2 column halves][kOutBufs] output slabs for TMA stores
   static constexpr int kColStageBytes = 2 * 2 * kTileN * 4;
-  static constexpr int kScoreBytes = 2 * kBlockM * 4;            // KV-attention tiles: partial scores of the two column halves
   static constexpr int kBarrierBytes = (2 * kStages + 4 + 4 * kOutBufs) * 8 + 16;   // ring + accumulators + slab full/empty per half
-  static constexpr int kSmemBytes = kStages * kStageBytes + kOutBytes + kColStageBytes + kScoreBytes + kBarrierBytes + 1024;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kOutBytes + kColStageBytes + kBarrierBytes + 1024;
 };
 
 constexpr int kMaxGroup = 8;
@@ -711,11 +716,27 @@ struct FrontWork {
   int* done_counter;
 };
 
+// Optional tile schedule of a chained launch: instead of "stage after stage", the tile numbers run through SEGMENTS (problem,
+// first row block, number of row blocks) in the order the host lists them.  The fused forward interleaves the stages by groups of
+// row blocks with a fixed lag between producer and consumer stages (a software wavefront): intermediates are consumed while they
+// are still in L2, and epilogue-heavy tiles (GELU, attention) alternate with K=4096 tiles on every CTA pair, so neither the
+// tensor pipe nor the epilogue warps idle through a whole stage.  Any order in which every tile's producers have lower tile
+// numbers is deadlock-free.
+struct TileSeg {
+  int prob;       // index into GemmGroup::p
+  int m_lo;       // first 256-row block
+  int tile0;      // first tile number of the segment
+  int n_tiles;    // row blocks x n-blocks of the problem
+};
+constexpr int kMaxSegs = 384;
+
 struct GemmGroup {
   GemmProblem p[kMaxGroup];
   int count;
   int total_tiles;
   FrontWork front;
+  int n_segs;                 // 0: tiles are numbered problem after problem
+  TileSeg segs[kMaxSegs];
 };
 
 struct TileRef {
@@ -725,7 +746,22 @@ struct TileRef {
   int split;
 };
 
-__device__ __forceinline__ TileRef decode_tile(const GemmGroup& g, int tile) {
+__device__ __forceinline__ TileRef decode_tile(const GemmGroup& g, int tile, int& cursor) {
+  if (g.n_segs != 0) {
+    // scheduled launch: every role walks its tiles in increasing order, so the segment cursor only moves forward
+    while (tile >= g.segs[cursor].tile0 + g.segs[cursor].n_tiles) ++cursor;
+    const TileSeg& sg = g.segs[cursor];
+    TileRef t;
+    t.pr = &g.p[sg.prob];
+    const int local = tile - sg.tile0;
+    const int mm = local / t.pr->num_n_blocks;
+    t.m_blk = sg.m_lo + mm;
+    t.n_blk = local - mm * t.pr->num_n_blocks;
+    t.split = 0;
+    t.kb0 = 0;
+    t.kb1 = t.pr->num_k_blocks;
+    return t;
+  }
   int p = 0;
   while (p + 1 < g.count && tile >= g.p[p].num_tiles) {
     tile -= g.p[p].num_tiles;
@@ -756,8 +792,7 @@ tp_gemm2_kernel(const __grid_constant__ GemmGroup grp, const __grid_constant__ P
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* s_out = smem + kStages * Cfg::kStageBytes;                                  // 1 KiB aligned (swizzle atoms)
   float* s_col_base = reinterpret_cast<float*>(s_out + Cfg::kOutBytes);
-  float* s_score = reinterpret_cast<float*>(s_out + Cfg::kOutBytes + Cfg::kColStageBytes);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_out + Cfg::kOutBytes + Cfg::kColStageBytes + Cfg::kScoreBytes);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_out + Cfg::kOutBytes + Cfg::kColStageBytes);
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tmem_full_bar = empty_bar + kStages;
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;
@@ -813,12 +848,12 @@ tp_gemm2_kernel(const __grid_constant__ GemmGroup grp, const __grid_constant__ P
   if (warp_idx == kTmaWarp) {
     // ======================================= TMA producer (both CTAs) ============================
     // Whole warp runs the loop (uniform control flow); one elected lane issues the arrive + TMA instructions.
-    int stage = 0;
+    int stage = 0, cursor = 0;
     uint32_t phase = 0;
     [[maybe_unused]] long long w_empty = 0;
     [[maybe_unused]] const long long t_begin = clock64();
     for (int tile = pair_idx; tile < num_tiles; tile += num_pairs) {
-      const TileRef t = decode_tile(grp, tile);
+      const TileRef t = decode_tile(grp, tile, cursor);
       const GemmProblem& pr = *t.pr;
       const int row0 = t.m_blk * Cfg::kTileM + static_cast<int>(cta_rank) * kBlockM;          // my 128 rows of A
       const int brow0 = t.n_blk * kTileN + static_cast<int>(cta_rank) * (kTileN / 2);        // my half of the B tile
@@ -836,7 +871,7 @@ tp_gemm2_kernel(const __grid_constant__ GemmGroup grp, const __grid_constant__ P
         fence_proxy_async_all();
       }
       if (pr.kind == 1) {
-        // KV-attention tile: y_k . W_ik(head)^T, then y_v . W_iv(head)^T, through the same ring (B boxes of 64 rows per CTA)
+        // KV-attention tile: y_k . W_ik(head pair)^T, then y_v . W_iv(head pair)^T, through the same ring
         const AttnParams& at = pr.attn;
         if (at.k_counter != nullptr) {
           // y_k / y_v were stored window-major by raster-ordered GEMMs of this launch: wait for every raster row block of the
@@ -854,18 +889,17 @@ tp_gemm2_kernel(const __grid_constant__ GemmGroup grp, const __grid_constant__ P
           if (at.q_counter != nullptr) wait_counter_at_least(at.q_counter + ((r_lo / (at.s * at.s)) >> 8), at.q_target);
           fence_proxy_async_all();
         }
-        const int hrow0 = t.n_blk * 128 + static_cast<int>(cta_rank) * 64;      // my 64 weight rows of this head
-        for (int op = 0; op < 2; ++op) {
+        for (int op = 0; op < 2; ++op) {            // phase K, then phase V: two ordinary 256-wide k-loops (brow0: my half of the head pair's weight rows)
           const CUtensorMap* ta = op == 0 ? &pr.tmap_a : &pr.tmap_a2;
           const CUtensorMap* tb = op == 0 ? &pr.tmap_b : &pr.tmap_b2;
           for (int kb = 0; kb < pr.num_k_blocks; ++kb) {
             mbar_wait(&empty_bar[stage], phase ^ 1u);
             if (elect_one()) {
               uint8_t* sa = smem + stage * Cfg::kStageBytes;
-              if (is_leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * (Cfg::kABytes + Cfg::kBBytes / 2));
+              if (is_leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
               else mbar_arrive_cluster(&full_bar[stage], 0);
               tma_load_2d_pair(sa, ta, &full_bar[stage], kb * kBlockK, row0);
-              tma_load_2d_pair(sa + Cfg::kABytes, tb, &full_bar[stage], kb * kBlockK, hrow0);
+              tma_load_2d_pair(sa + Cfg::kABytes, tb, &full_bar[stage], kb * kBlockK, brow0);
             }
             __syncwarp();
             if (++stage == kStages) { stage = 0; phase ^= 1u; }
@@ -923,14 +957,14 @@ tp_gemm2_kernel(const __grid_constant__ GemmGroup grp, const __grid_constant__ P
   } else if (warp_idx == kMmaWarp) {
     // ======================================= MMA issuer (leader CTA only) ========================
     if (is_leader) {
-      int stage = 0;
+      int stage = 0, cursor = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
       [[maybe_unused]] long long w_full = 0, w_tmem = 0;
       [[maybe_unused]] const long long t_begin = clock64();
       for (int tile = pair_idx; tile < num_tiles; tile += num_pairs) {
-        const TileRef mt = decode_tile(grp, tile);
+        const TileRef mt = decode_tile(grp, tile, cursor);
         const GemmProblem& mpr = *mt.pr;
         const bool mn_major = mpr.ab_mn_major != 0;
         const uint32_t idesc = mn_major ? make_idesc_bf16_f32(Cfg::kTileM, kTileN, 1, 1) : make_idesc_bf16_f32(Cfg::kTileM, kTileN);
@@ -942,9 +976,15 @@ tp_gemm2_kernel(const __grid_constant__ GemmGroup grp, const __grid_constant__ P
         tcgen05_fence_after();
         const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * kTileN);
         if (mpr.kind == 1) {
-          // two M=256 x N=128 GEMMs into the two halves of the accumulator buffer (k' then v')
-          constexpr uint32_t idesc_kv = make_idesc_bf16_f32(Cfg::kTileM, 128);
+          // phase K into this accumulator buffer, phase V into the other one: two ordinary 256 x 256 k-loops, each handed to the
+          // epilogue on its own (the wait on tmem_empty above covered phase K's buffer)
+          constexpr uint32_t idesc_kv = make_idesc_bf16_f32(Cfg::kTileM, kTileN);
           for (int op = 0; op < 2; ++op) {
+            if (op == 1) {
+              mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1u);
+              tcgen05_fence_after();
+            }
+            const uint32_t tmem_kv = tmem_base + static_cast<uint32_t>(acc * kTileN);
             for (int kb = 0; kb < mpr.num_k_blocks; ++kb) {
               mbar_wait(&full_bar[stage], phase);
               tcgen05_fence_after();
@@ -954,17 +994,17 @@ tp_gemm2_kernel(const __grid_constant__ GemmGroup grp, const __grid_constant__ P
                 const uint64_t desc_b = make_smem_desc_kmajor_sw128(sa + Cfg::kABytes);
 #pragma unroll
                 for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-                  umma_bf16_pair(tmem_d + static_cast<uint32_t>(op * 128), desc_a + static_cast<uint64_t>(k * 2), desc_b + static_cast<uint64_t>(k * 2),
-                                 idesc_kv, static_cast<uint32_t>((kb | k) != 0));
+                  umma_bf16_pair(tmem_kv, desc_a + static_cast<uint64_t>(k * 2), desc_b + static_cast<uint64_t>(k * 2), idesc_kv,
+                                 static_cast<uint32_t>((kb | k) != 0));
                 }
                 umma_commit_pair(&empty_bar[stage], 0x3);
-                if (op == 1 && kb == mpr.num_k_blocks - 1) umma_commit_pair(&tmem_full_bar[acc], 0x3);
+                if (kb == mpr.num_k_blocks - 1) umma_commit_pair(&tmem_full_bar[acc], 0x3);
               }
               __syncwarp();
               if (++stage == kStages) { stage = 0; phase ^= 1u; }
             }
+            if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
           }
-          if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
           continue;
         }
         for (int kb = mt.kb0; kb < mt.kb1; ++kb) {
@@ -1016,7 +1056,7 @@ tp_gemm2_kernel(const __grid_constant__ GemmGroup grp, const __grid_constant__ P
     const int quarter = warp_idx & 3;
     const int half = e >> 2;
     const int epi_tid = e * 32 + static_cast<int>(lane);
-    int acc = 0;
+    int acc = 0, cursor = 0;
     uint32_t acc_phase = 0;
     uint32_t slab_seq = 0;
     [[maybe_unused]] long long w_acc = 0, t_work = 0;
@@ -1055,7 +1095,7 @@ tp_gemm2_kernel(const __grid_constant__ GemmGroup grp, const __grid_constant__ P
       }
     }
     for (int tile = pair_idx; tile < num_tiles; tile += num_pairs) {
-      const TileRef t = decode_tile(grp, tile);
+      const TileRef t = decode_tile(grp, tile, cursor);
       const GemmProblem& pr = *t.pr;
       float* s_col = s_col_base + acc * 2 * kTileN;
       uint64_t* release_bar = &tmem_empty_bar[acc];
@@ -1063,22 +1103,32 @@ tp_gemm2_kernel(const __grid_constant__ GemmGroup grp, const __grid_constant__ P
       const int row = row_tile0 + quarter * 32 + static_cast<int>(lane);
       if (pr.kind == 1) {
         const AttnParams& at = pr.attn;
-        {   // this head's slices of the four LayerNorm-fold vectors: [wsum_k | cst_k | wsum_v | cst_v][128]
-          const int which = epi_tid >> 7, c = epi_tid & 127, col = t.n_blk * 128 + c;
-          s_col[epi_tid] = __ldg((which == 0 ? at.wsum_k : at.cst_k) + col);
-          s_col[256 + epi_tid] = __ldg((which == 0 ? at.wsum_v : at.cst_v) + col);
-          named_bar_sync(kEpiBarrierId, kEpiThreads);
-        }
-        mbar_wait(&tmem_full_bar[acc], acc_phase);
-        tcgen05_fence_after();
-        attn_epilogue_tile(at, pr.M, tmem_base + static_cast<uint32_t>(acc * kTileN), row, t.n_blk, quarter, half, s_col, s_score, [&]() {
+        const int head = t.n_blk * 2 + half;                 // column half == head of the tile's pair
+        auto release_acc = [&](uint64_t* bar) {
           tcgen05_fence_before();
           __syncwarp();
           if (lane == 0) {
-            if (is_leader) mbar_arrive(release_bar);
-            else mbar_arrive_cluster(release_bar, 0);
+            if (is_leader) mbar_arrive(bar);
+            else mbar_arrive_cluster(bar, 0);
           }
-        });
+        };
+        GemmEpilogue vec;                                    // only col_a / col_b are read by the staging helper
+        vec.col_a = at.wsum_k;
+        vec.col_b = at.cst_k;
+        stage_col_vectors<kTileN>(vec, pr.N, t.n_blk * kTileN, s_col, epi_tid);
+        mbar_wait(&tmem_full_bar[acc], acc_phase);
+        tcgen05_fence_after();
+        const float p = attn_scores(at, pr.M, tmem_base + static_cast<uint32_t>(acc * kTileN), row, head, quarter, half, s_col,
+                                    [&]() { release_acc(release_bar); });
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        float* s_col_v = s_col_base + acc * 2 * kTileN;
+        vec.col_a = at.wsum_v;
+        vec.col_b = at.cst_v;
+        stage_col_vectors<kTileN>(vec, pr.N, t.n_blk * kTileN, s_col_v, epi_tid);
+        mbar_wait(&tmem_full_bar[acc], acc_phase);
+        tcgen05_fence_after();
+        uint64_t* release_v = &tmem_empty_bar[acc];
+        attn_pv(at, pr.M, tmem_base + static_cast<uint32_t>(acc * kTileN), row, head, quarter, half, p, s_col_v, [&]() { release_acc(release_v); });
         if (at.done_counter != nullptr) {
           named_bar_sync(kEpiBarrierId, kEpiThreads);       // every epilogue thread's ctx stores are issued ...
           if (epi_tid == 0) {
@@ -1133,8 +1183,9 @@ tp_gemm2_kernel(const __grid_constant__ GemmGroup grp, const __grid_constant__ P
     uint64_t* full = slab_full_bar + half * Cfg::kOutBufs;
     uint64_t* empty = slab_empty_bar + half * Cfg::kOutBufs;
     uint32_t q = 0;
+    int cursor = 0;
     for (int tile = pair_idx; tile < num_tiles; tile += num_pairs) {
-      const TileRef t = decode_tile(grp, tile);
+      const TileRef t = decode_tile(grp, tile, cursor);
       const GemmProblem& pr = *t.pr;
       if (!pr.use_tma_store) continue;
       const int row_tile0 = t.m_blk * Cfg::kTileM + static_cast<int>(cta_rank) * kBlockM;

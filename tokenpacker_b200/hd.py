@@ -72,6 +72,24 @@ def hd_tile(image: torch.Tensor, patch_num: int = 9):
     return crops, hb, wb
 
 
+_STAGING: dict = {}
+
+
+def _staging(device, nbytes: int):
+    """Pinned host + device byte buffers for the batched tiling plan, one pair per device, grown on demand.  (Calls on one device
+    are expected from one stream at a time, like every other entry point of the package.)"""
+    key = str(device)
+    st = _STAGING.get(key)
+    if st is None or st["host"].numel() < nbytes:
+        cap = max(1 << 16, 1 << (nbytes - 1).bit_length())
+        with torch.cuda.device(device):
+            st = {"host": torch.empty(cap, dtype=torch.uint8).pin_memory(), "dev": torch.empty(cap, dtype=torch.uint8, device=device),
+                  "event": torch.cuda.Event()}
+            st["event"].record(torch.cuda.current_stream(device))
+        _STAGING[key] = st
+    return st
+
+
 def hd_tile_batch(images, patch_num: int = 9):
     """The tiling block for a whole batch in ONE launch (the collator cats the crops of a batch, train.py:797-800).
 
@@ -99,19 +117,25 @@ def hd_tile_batch(images, patch_num: int = 9):
     hb, wb = (C.c_int * b)(), (C.c_int * b)()
     nc = C.c_int64(0)
     check(lib.tp_hd_tile_batch_plan(hs, ws, ptrs, b, int(patch_num), None, None, hb, wb, C.byref(nc)), "tp_hd_tile_batch_plan")
-    table = torch.empty((max(nc.value, 1), 3), dtype=torch.int32)
-    desc = (_lib.TpHdImage * b)()
-    check(lib.tp_hd_tile_batch_plan(hs, ws, ptrs, b, int(patch_num), desc, C.cast(table.data_ptr(), C.POINTER(C.c_int32)), hb, wb,
+    # plan tables (image descriptors + crop table) go through ONE pinned staging buffer and ONE asynchronous copy per call
+    desc_bytes = C.sizeof(_lib.TpHdImage) * b
+    table_off = (desc_bytes + 15) // 16 * 16
+    total_bytes = table_off + max(nc.value, 1) * 12
+    st = _staging(device, total_bytes)
+    st["event"].synchronize()                     # the previous call's copy has left the pinned buffer
+    host = st["host"]
+    desc = (_lib.TpHdImage * b).from_address(host.data_ptr())
+    check(lib.tp_hd_tile_batch_plan(hs, ws, ptrs, b, int(patch_num), desc, C.cast(host.data_ptr() + table_off, C.POINTER(C.c_int32)), hb, wb,
                                     C.byref(nc)), "tp_hd_tile_batch_plan")
-    desc_t = torch.frombuffer(bytearray(bytes(desc)), dtype=torch.uint8)
     with torch.cuda.device(device):
-        desc_d = desc_t.to(device)
-        table_d = table.to(device)
+        dev = st["dev"]
+        dev[:total_bytes].copy_(host[:total_bytes], non_blocking=True)
+        st["event"].record(torch.cuda.current_stream(device))
         crops = torch.empty((nc.value, 3, BLOCK, BLOCK), dtype=torch.float32, device=device)
         stream = torch.cuda.current_stream(device).cuda_stream
-        check(lib.tp_hd_tile_batch(desc_d.data_ptr(), table_d.data_ptr(), nc.value, crops.data_ptr(), stream), "tp_hd_tile_batch")
-        # the sources and tables must outlive the asynchronous launch: tie them to the stream
-        for t in imgs + [desc_d, table_d]:
+        check(lib.tp_hd_tile_batch(dev.data_ptr(), dev.data_ptr() + table_off, nc.value, crops.data_ptr(), stream), "tp_hd_tile_batch")
+        # the source images must outlive the asynchronous launch: tie them to the stream
+        for t in imgs:
             t.record_stream(torch.cuda.current_stream(device))
     return crops, list(hb), list(wb)
 
