@@ -20,14 +20,11 @@ except Exception as e:
 " ) | tee -a gpurun_out/ab.log
 }
 rm -f gpurun_out/ab.log
-ab fused_default_5stages X=1
+ab fused_scheduled_default X=1
+ab fused_stage_order TP_SCHEDULE=0
 ab chain_nofuse TP_FUSE_ATTN=0
 ab plain_7_launches TP_FUSE_ATTN=0 TP_CHAIN=0
-ab fused_4stages TOKENPACKER_B200_LIB_OVERRIDE=$PWD/build_ab/s4.so
-ab nofuse_4stages TP_FUSE_ATTN=0 TOKENPACKER_B200_LIB_OVERRIDE=$PWD/build_ab/s4.so
-ab fused_5stages_narrow_2bufs TOKENPACKER_B200_LIB_OVERRIDE=$PWD/build_ab/s5n2.so
-ab fused_6stages_narrow TOKENPACKER_B200_LIB_OVERRIDE=$PWD/build_ab/s6.so
-ab fused_noswizzle_segstores TP_SEG_NOSWIZZLE=1
+ab fused_scheduled_4stages TOKENPACKER_B200_LIB_OVERRIDE=$PWD/build_ab/s4.so
 ( timeout 900 python bench.py --steps 20 --warmup 5 2>gpurun_out/bench.err | tail -1 ) > gpurun_out/bench_line.json
 cut -c1-400 gpurun_out/bench_line.json
 ( timeout 300 python tools/gemm_phase_profile.py 2>&1 ) > gpurun_out/phase_profile.log
