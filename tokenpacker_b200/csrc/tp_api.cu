@@ -970,15 +970,23 @@ int forward_impl(const void* packed, const void* x0, const void* xm, const void*
     g[7].stage = 5;
     g[7].dep = 6;
     if (chain_feasible(g, 8, dev.sms, false)) {
-      // Tile schedule: a software wavefront over groups of GR row blocks of the key/value side (= GQ blocks of 256 queries).
-      // Super-step j issues [1] for group j, [2]k/v for group j-1, the KV-attention tiles of group j-2, [4] for the queries of group
-      // j-3 and [5] for those of group j-4: every consumer runs one super-step (~60k cycles) behind its producer — its inputs are
-      // still in L2 — and each CTA pair alternates K=4096 tiles with the epilogue-heavy K=1024 ones.  The short query chain
-      // ([2]q, [3]q) goes first.  TP_SCHEDULE=0: stage after stage.
+      // Tile schedule (TP_SCHEDULE, read per call; default 0 = stage after stage).
+      //   1: [4] and [5] interleaved row block by row block ([5] five row blocks behind): the GELU epilogue of [4] (longer than its
+      //      K=1024 MMAs) then overlaps the K=4096 MMAs of [5] on every CTA pair instead of stalling the tensor pipe for a whole stage.
+      //   2: full software wavefront over groups of row blocks ([1] for group j, [2]k/v for j-1, KV-attention for j-2, [4] for j-3,
+      //      [5] for j-4).  MEASURED NEGATIVE: all 73 MB of weights plus the streaming activations thrash the 126 MB L2 (DRAM reads
+      //      0.8 -> 2.0 GB per step, 0.986 -> 1.114 ms); kept as an experiment.
       const char* sch_env = getenv("TP_SCHEDULE");
+      const int sch = sch_env != nullptr ? atoi(sch_env) : 0;
       SegPlan plan;
-      if (sch_env == nullptr || atoi(sch_env) != 0) {
-        const long long nbR = (R + 255) / 256, nbQ = (Q + 255) / 256;
+      const long long nbR = (R + 255) / 256, nbQ = (Q + 255) / 256;
+      if (sch == 1) {
+        bool ok = true;
+        for (int i = 0; i < 6 && ok; ++i) ok = plan.add(i, 0, i == 3 || i == 4 ? nbQ : nbR, i == 3 || i == 4 ? nbQ : nbR);
+        const long long lag = 5;
+        for (long long j = 0; j < nbQ + lag && ok; ++j) ok = plan.add(6, j, j + 1, nbQ) && plan.add(7, j - lag, j - lag + 1, nbQ);
+        if (!ok) plan.n = 0;
+      } else if (sch == 2) {
         const int Wn = s * s;
         long long GR = Wn > 8 ? Wn : 8;
         while ((nbR + GR - 1) / GR > 48) GR *= 2;
