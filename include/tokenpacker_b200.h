@@ -182,6 +182,7 @@ typedef struct tp_hd_image {
   int32_t h_r, w_r;
   int32_t h_t, w_t;
   int64_t crop0;
+  float sy, sx, ty, tx;   /* bilinear scales (source extent / resized extent) of the main canvas and of the thumbnail */
 } tp_hd_image;
 TP_API int tp_hd_tile_batch_plan(const int64_t* h, const int64_t* w, const void* const* images, int64_t n_images, int patch_num,
                                  tp_hd_image* images_host, int32_t* crop_table_host, int* h_block, int* w_block, int64_t* n_crops);

@@ -45,7 +45,8 @@ class TpWeights(C.Structure):
 class TpHdImage(C.Structure):
     """tp_hd_image: one row of the batched tiling plan."""
     _fields_ = [("image", C.c_void_p), ("h", C.c_int32), ("w", C.c_int32), ("hb", C.c_int32), ("wb", C.c_int32),
-                ("h_r", C.c_int32), ("w_r", C.c_int32), ("h_t", C.c_int32), ("w_t", C.c_int32), ("crop0", C.c_int64)]
+                ("h_r", C.c_int32), ("w_r", C.c_int32), ("h_t", C.c_int32), ("w_t", C.c_int32), ("crop0", C.c_int64),
+                ("sy", C.c_float), ("sx", C.c_float), ("ty", C.c_float), ("tx", C.c_float)]
 
 
 # name -> (restype, argtypes); kept as data so tests can check the header and the binding agree

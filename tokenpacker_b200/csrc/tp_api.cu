@@ -1379,6 +1379,11 @@ int tp_hd_tile_batch_plan(const int64_t* h, const int64_t* w, const void* const*
       im.h = static_cast<int>(h[b]); im.w = static_cast<int>(w[b]); im.hb = hb; im.wb = wb;
       im.h_r = h_r; im.w_r = w_r; im.h_t = hb * wb > 1 ? h_t : 0; im.w_t = hb * wb > 1 ? w_t : 0;
       im.crop0 = crop;
+      // ATen derives the bilinear scale from the sizes as ONE float division; done here once per image instead of per pixel
+      im.sy = static_cast<float>(im.h) / static_cast<float>(h_r);
+      im.sx = static_cast<float>(im.w) / static_cast<float>(w_r);
+      im.ty = im.h_t > 0 ? static_cast<float>(kBlockPx * hb) / static_cast<float>(im.h_t) : 1.f;
+      im.tx = im.w_t > 0 ? static_cast<float>(kBlockPx * wb) / static_cast<float>(im.w_t) : 1.f;
     }
     for (int i = 0; i < hb; ++i)
       for (int j = 0; j < wb; ++j, ++crop)

@@ -291,8 +291,14 @@ struct LinearTap {
 };
 
 // ATen upsample_bilinear2d, align_corners=False, scales derived from sizes: src = (in/out)*(dst+0.5)-0.5 clamped at 0.
+__device__ __forceinline__ LinearTap linear_tap_scaled(int dst, int in_size, float scale);
+
 __device__ __forceinline__ LinearTap linear_tap(int dst, int in_size, int out_size) {
-  const float scale = static_cast<float>(in_size) / static_cast<float>(out_size);
+  return linear_tap_scaled(dst, in_size, static_cast<float>(in_size) / static_cast<float>(out_size));
+}
+
+// same with the scale (in_size / out_size as one IEEE float division) supplied by the caller
+__device__ __forceinline__ LinearTap linear_tap_scaled(int dst, int in_size, float scale) {
   float src = __fmaf_rn(scale, static_cast<float>(dst) + 0.5f, -0.5f);   // ONE fused multiply-add, like ATen's CPU kernel (see oracle/hd_oracle.py)
   src = fmaxf(src, 0.f);
   LinearTap t;
@@ -366,11 +372,13 @@ struct HdImage {            // mirrors tp_hd_image (include/tokenpacker_b200.h)
   int h_r, w_r;             // resized content of the main canvas
   int h_t, w_t;             // resized content of the thumbnail (0 when hb*wb == 1)
   long long crop0;          // index of this image's first crop in the batch output
+  float sy, sx;             // h / h_r, w / w_r as float divisions (ATen's scale), computed once per image on the host
+  float ty, tx;             // (336 hb) / h_t, (336 wb) / w_t
 };
 
 __device__ __forceinline__ float hd_canvas_value(const HdImage& im, const float* __restrict__ plane, int Y, int X) {
   if (Y >= im.h_r || X >= im.w_r) return 0.f;
-  const LinearTap ty = linear_tap(Y, im.h, im.h_r), tx = linear_tap(X, im.w, im.w_r);
+  const LinearTap ty = linear_tap_scaled(Y, im.h, im.sy), tx = linear_tap_scaled(X, im.w, im.sx);
   const float* r0 = plane + static_cast<long long>(ty.i0) * im.w;
   const float* r1 = plane + static_cast<long long>(ty.i1) * im.w;
   return bilerp(__ldg(r0 + tx.i0), __ldg(r0 + tx.i1), __ldg(r1 + tx.i0), __ldg(r1 + tx.i1), ty, tx);
@@ -393,8 +401,23 @@ __global__ void __launch_bounds__(256) hd_tile_batch_kernel(const HdImage* __res
   float v[4];
   if (cj >= 0) {
     const int Y = ci * kBlockPx + y;
+    if (Y >= im.h_r) {
+      v[0] = v[1] = v[2] = v[3] = 0.f;
+    } else {
+      const LinearTap ty = linear_tap_scaled(Y, im.h, im.sy);          // one row tap for the thread's four pixels
+      const float* r0 = plane + static_cast<long long>(ty.i0) * im.w;
+      const float* r1 = plane + static_cast<long long>(ty.i1) * im.w;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) v[k] = hd_canvas_value(im, plane, Y, cj * kBlockPx + xv * 4 + k);
+      for (int k = 0; k < 4; ++k) {
+        const int X = cj * kBlockPx + xv * 4 + k;
+        float out = 0.f;
+        if (X < im.w_r) {
+          const LinearTap tx = linear_tap_scaled(X, im.w, im.sx);
+          out = bilerp(__ldg(r0 + tx.i0), __ldg(r0 + tx.i1), __ldg(r1 + tx.i0), __ldg(r1 + tx.i1), ty, tx);
+        }
+        v[k] = out;
+      }
+    }
   } else {
     const int ch_h = im.hb * kBlockPx, ch_w = im.wb * kBlockPx;
 #pragma unroll
@@ -402,7 +425,7 @@ __global__ void __launch_bounds__(256) hd_tile_batch_kernel(const HdImage* __res
       const int x = xv * 4 + k;
       float out = 0.f;
       if (y < im.h_t && x < im.w_t) {
-        const LinearTap ty = linear_tap(y, ch_h, im.h_t), tx = linear_tap(x, ch_w, im.w_t);
+        const LinearTap ty = linear_tap_scaled(y, ch_h, im.ty), tx = linear_tap_scaled(x, ch_w, im.tx);
         out = bilerp(hd_canvas_value(im, plane, ty.i0, tx.i0), hd_canvas_value(im, plane, ty.i0, tx.i1),
                      hd_canvas_value(im, plane, ty.i1, tx.i0), hd_canvas_value(im, plane, ty.i1, tx.i1), ty, tx);
       }
