@@ -20,11 +20,10 @@ except Exception as e:
 " ) | tee -a gpurun_out/ab.log
 }
 rm -f gpurun_out/ab.log
-ab fused_scheduled_default X=1
-ab fused_stage_order TP_SCHEDULE=0
+ab fused_default X=1
+ab fused_mlp_interleave TP_SCHEDULE=1
 ab chain_nofuse TP_FUSE_ATTN=0
 ab plain_7_launches TP_FUSE_ATTN=0 TP_CHAIN=0
-ab fused_scheduled_4stages TOKENPACKER_B200_LIB_OVERRIDE=$PWD/build_ab/s4.so
 ( timeout 900 python bench.py --steps 20 --warmup 5 2>gpurun_out/bench.err | tail -1 ) > gpurun_out/bench_line.json
 cut -c1-400 gpurun_out/bench_line.json
 ( timeout 300 python tools/gemm_phase_profile.py 2>&1 ) > gpurun_out/phase_profile.log
@@ -34,6 +33,12 @@ timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__byte
 TP_FUSE_ATTN=0 TP_CHAIN=0 timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed,sm__cycles_elapsed.max \
     --clock-control none -c 80 --csv --log-file gpurun_out/launches_plain.csv \
     python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e --no-extras > gpurun_out/ncu_launches_plain.log 2>&1
+timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed \
+    --clock-control none -c 160 --csv --log-file gpurun_out/launches_train.csv \
+    python bench.py --workload train --steps 3 > gpurun_out/ncu_launches_train.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:tp_gemm2 -s 5 -c 1 -f -o gpurun_out/prof_fused_forward \
+    python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e --no-extras > gpurun_out/ncu_full.log 2>&1
+ncu -i gpurun_out/prof_fused_forward.ncu-rep --page raw --csv > gpurun_out/prof_fused_forward.raw.csv 2>/dev/null
 ( timeout 500 compute-sanitizer --tool memcheck python tools/sanitize_small.py 2>&1 | head -60 ) > gpurun_out/memcheck.log
 tail -3 gpurun_out/memcheck.log
 ( timeout 500 compute-sanitizer --tool synccheck python tools/sanitize_small.py 2>&1 | tail -8 ) | tee gpurun_out/synccheck.log
