@@ -17,6 +17,10 @@ except Exception as e:
     print("bench line missing:", e)
     print(open("gpurun_out/bench_${N}gpu.err").read()[-3000:])
 PY
+# NVLink evidence for the fused exchange: per-link data counters of GPU 0 before / after the configs[4] run (60 fused + 60 NCCL steps)
+nvidia-smi nvlink -gt d -i 0 > gpurun_out/nvlink_before_${N}gpu.txt 2>&1
 ( timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 \
     bench.py --gpus $N --workload hd5 --steps 50 --warmup 10 2>>gpurun_out/bench_${N}gpu.err | tail -1 ) > gpurun_out/hd5_${N}gpu.json
+nvidia-smi nvlink -gt d -i 0 > gpurun_out/nvlink_after_${N}gpu.txt 2>&1
 cut -c1-1500 gpurun_out/hd5_${N}gpu.json
+head -12 gpurun_out/nvlink_after_${N}gpu.txt
