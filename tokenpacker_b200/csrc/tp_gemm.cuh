@@ -453,7 +453,9 @@ __device__ __forceinline__ void attn_pv(const AttnParams& at, int M, uint32_t tm
 
 // Stage this tile's slices of col_a / col_b into shared memory (coalesced), then sync the 256 epilogue threads.
 template <int kTileN>
-__device__ __forceinline__ void stage_col_vectors(const GemmEpilogue& ep, int N, int col_tile0, float* s_col, int epi_tid) {
+__device__ __forceinline__ void stage_col_vectors(const GemmEpilogue& ep, int N, int col_tile0, float* s_col, int epi_tid,
+                                                  bool single_buffer = false) {
+  if (single_buffer) named_bar_sync(kEpiBarrierId, kEpiThreads);      // everyone is done reading the previous tile's vectors
   for (int c = epi_tid; c < kTileN; c += kEpiThreads) {
     const int col = col_tile0 + c;
     const bool ok = col < N;
@@ -636,7 +638,7 @@ struct Gemm2Config {
 #define TP_PAIR_STAGES 5
 #endif
 #ifndef TP_OUT_BUFS
-#define TP_OUT_BUFS ((TP_PAIR_STAGES <= 4) ? 2 : 1)
+#define TP_OUT_BUFS ((TP_PAIR_STAGES <= 5 || TP_SLAB_COLS == 32) ? 2 : 1)
 #endif
   // Ring depth is what hides the operand-fetch latency (measured on the configs[1] step, same box: 4 / 5 / 6 stages = 1.001 /
   // 0.967 / 0.973 ms); since the store warps took the TMA stores off the epilogue warps' path one staging slab per column half is
@@ -648,9 +650,12 @@ struct Gemm2Config {
   static constexpr int kStageBytes = kABytes + kBBytes;          // 32 KiB
   static constexpr int kTmemCols = 2 * kTileN;
   static constexpr int kOutBytes = 2 * kOutBufs * kOutSlabBytes; // [2 column halves][kOutBufs] output slabs for TMA stores
-  static constexpr int kColStageBytes = 2 * 2 * kTileN * 4;
+  static constexpr int kColStageBytes = 2 * kTileN * 4;          // [col_a | col_b][kTileN] floats, ONE buffer (barrier before it is rewritten)
   static constexpr int kBarrierBytes = (2 * kStages + 4 + 4 * kOutBufs) * 8 + 16;   // ring + accumulators + slab full/empty per half
-  static constexpr int kSmemBytes = kStages * kStageBytes + kOutBytes + kColStageBytes + kBarrierBytes + 1024;
+  // 5 stages x 32 KiB + 4 x 16 KiB slabs + 2 KiB + barriers = 226.2 KiB of the 227 KiB an SM offers: the dynamic shared memory is
+  // declared 1024-byte aligned (no alignment slack), and the per-column vectors are single-buffered
+  static constexpr int kSmemBytes = kStages * kStageBytes + kOutBytes + kColStageBytes + kBarrierBytes;
+  static_assert(kSmemBytes <= 232448, "shared memory budget of an sm_100 SM (227 KiB)");
 };
 
 constexpr int kMaxGroup = 8;
@@ -787,9 +792,8 @@ tp_gemm2_kernel(const __grid_constant__ GemmGroup grp, const __grid_constant__ P
   constexpr int kStages = Cfg::kStages;
   constexpr int kTileN = Cfg::kTileN;
 
-  extern __shared__ uint8_t smem_raw[];
-  // the dynamic smem base has the same offset in both CTAs of the pair, so this alignment fix-up is identical too
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  extern __shared__ __align__(1024) uint8_t smem_raw[];     // 1 KiB aligned: swizzle atoms of the operand tiles and output slabs
+  uint8_t* smem = smem_raw;
   uint8_t* s_out = smem + kStages * Cfg::kStageBytes;                                  // 1 KiB aligned (swizzle atoms)
   float* s_col_base = reinterpret_cast<float*>(s_out + Cfg::kOutBytes);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_out + Cfg::kOutBytes + Cfg::kColStageBytes);
@@ -1097,7 +1101,7 @@ tp_gemm2_kernel(const __grid_constant__ GemmGroup grp, const __grid_constant__ P
     for (int tile = pair_idx; tile < num_tiles; tile += num_pairs) {
       const TileRef t = decode_tile(grp, tile, cursor);
       const GemmProblem& pr = *t.pr;
-      float* s_col = s_col_base + acc * 2 * kTileN;
+      float* s_col = s_col_base;
       uint64_t* release_bar = &tmem_empty_bar[acc];
       const int row_tile0 = t.m_blk * Cfg::kTileM + static_cast<int>(cta_rank) * kBlockM;
       const int row = row_tile0 + quarter * 32 + static_cast<int>(lane);
@@ -1115,16 +1119,16 @@ tp_gemm2_kernel(const __grid_constant__ GemmGroup grp, const __grid_constant__ P
         GemmEpilogue vec;                                    // only col_a / col_b are read by the staging helper
         vec.col_a = at.wsum_k;
         vec.col_b = at.cst_k;
-        stage_col_vectors<kTileN>(vec, pr.N, t.n_blk * kTileN, s_col, epi_tid);
+        stage_col_vectors<kTileN>(vec, pr.N, t.n_blk * kTileN, s_col, epi_tid, true);
         mbar_wait(&tmem_full_bar[acc], acc_phase);
         tcgen05_fence_after();
         const float p = attn_scores(at, pr.M, tmem_base + static_cast<uint32_t>(acc * kTileN), row, head, quarter, half, s_col,
                                     [&]() { release_acc(release_bar); });
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
-        float* s_col_v = s_col_base + acc * 2 * kTileN;
+        float* s_col_v = s_col_base;
         vec.col_a = at.wsum_v;
         vec.col_b = at.cst_v;
-        stage_col_vectors<kTileN>(vec, pr.N, t.n_blk * kTileN, s_col_v, epi_tid);
+        stage_col_vectors<kTileN>(vec, pr.N, t.n_blk * kTileN, s_col_v, epi_tid, true);
         mbar_wait(&tmem_full_bar[acc], acc_phase);
         tcgen05_fence_after();
         uint64_t* release_v = &tmem_empty_bar[acc];
@@ -1139,7 +1143,7 @@ tp_gemm2_kernel(const __grid_constant__ GemmGroup grp, const __grid_constant__ P
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
         continue;
       }
-      stage_col_vectors<kTileN>(pr.ep, pr.N, t.n_blk * kTileN, s_col, epi_tid);
+      stage_col_vectors<kTileN>(pr.ep, pr.N, t.n_blk * kTileN, s_col, epi_tid, true);
       {
         TP_PROF_T0();
         mbar_wait(&tmem_full_bar[acc], acc_phase);
