@@ -129,6 +129,25 @@ def _gather(table, vis, hidden, src, out):
     check(lib.tp_gather_rows(table.data_ptr(), vis.data_ptr(), hidden, src.data_ptr(), src.numel(), out.data_ptr(), stream), "tp_gather_rows")
 
 
+_TABLE_CACHE: dict = {}
+
+
+def _bf16_table(embed_weight: torch.Tensor) -> torch.Tensor:
+    """bf16 view of the embedding table for the inference splice.  A bf16 table (every released recipe) is used in place; an fp16 /
+    fp32 table would otherwise be re-cast on every call (0.5 GB for a 32k x 4096 fp32 table), so its bf16 copy is cached, keyed like
+    the packed projector weights on (data_ptr, _version, dtype, shape).  Writes through a ``.data`` alias are not seen: inference only
+    (the training path goes through _SpliceFunction, which casts per call)."""
+    w = embed_weight.detach()
+    if w.dtype == torch.bfloat16:
+        return w.contiguous()
+    key = (w.data_ptr(), embed_weight._version, w.dtype, tuple(w.shape), str(w.device))
+    hit = _TABLE_CACHE.get("t")
+    if hit is None or hit[0] != key:
+        hit = (key, w.to(torch.bfloat16).contiguous())
+        _TABLE_CACHE["t"] = hit
+    return hit[1]
+
+
 class _SpliceFunction(torch.autograd.Function):
     """out[i] = table[src[i]] | visual[-src[i]-2] | 0.  Every visual row is placed at most once, so its gradient is again a
     gather (inverse index, tp_gather_rows); table rows can repeat, so their gradient is an index_add over the text positions."""
@@ -197,7 +216,7 @@ def splice_multimodal(input_ids: torch.Tensor, embed_weight: torch.Tensor, visua
         out = _SpliceFunction.apply(embed_weight, visual_rows, src, torch.from_numpy(inv).to(device), torch.from_numpy(text_pos).to(device),
                                     torch.from_numpy(src_np[text_pos]).to(device), (B, plan.lmax, hidden))
     else:
-        table = embed_weight.detach().to(torch.bfloat16).contiguous()
+        table = _bf16_table(embed_weight)
         vis = visual_rows.detach().to(torch.bfloat16).contiguous()
         out = torch.empty((B, plan.lmax, hidden), dtype=torch.bfloat16, device=device)
         with torch.cuda.device(device):
