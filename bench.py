@@ -309,6 +309,16 @@ def hd5_measure(steps, warmup, rank, world, dev, dist, verify=True):
                 "exchange": "fused: the last GEMM's TMA stores write each crop's rows into the packed sequence of EVERY rank (peer-mapped "
                             "symmetric memory over NVLink), one symmetric-memory barrier, no assembly pass; nccl: all_gather_into_tensor + "
                             "scatter/fill assembly on every rank"})
+    # where the fused step's time goes: this rank's share of the compute alone (packed rows of its own crops only), and the
+    # cross-rank barrier alone
+    lo_r, hi_r = shard_bounds(total, world, rank)
+    n_local = hi_r - lo_r
+    ms_local, _, _ = timed(lambda: model.forward_packed((x0, xm), [1] * n_local, [1] * n_local, sep, ret))
+    buf, hdl = fused._buffers((int(cu[-1]), hidden), dev)
+    ms_bar, _, _ = timed(lambda: hdl.barrier(channel=0))
+    rec.update({"rank_local_compute_ms": ms_local, "symm_barrier_ms": ms_bar,
+                "note": "rank_local_compute_ms = this rank's 1/N of the crops through forward_packed into a local buffer (max over ranks); "
+                        "fused_peer_store_ms - rank_local_compute_ms = exchange + barrier + separator fill not hidden under compute"})
     # every rank checks that both exchanges gave it the same packed sequences
     same = torch.tensor([1 if torch.equal(packed_f, packed_n) else 0], device=dev)
     dist.all_reduce(same, op=dist.ReduceOp.MIN)
