@@ -134,12 +134,25 @@ __global__ void colsum_partial_kernel(const __nv_bfloat16* __restrict__ in, long
   for (int j = 0; j < 8; ++j) partial[static_cast<long long>(blockIdx.y) * cols + c0 + j] = acc[j];
 }
 
-__global__ void colsum_reduce_kernel(const float* __restrict__ partial, int n_chunks, int cols, float scale, __nv_bfloat16* __restrict__ out) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= cols) return;
+// Second stage: out[c] = scale * sum_i partial[i][c].  Block = 32 columns x 16 chunk lanes: every thread sums chunks ty, ty+16, ...
+// (independent loads), the 16 lane sums are added in fixed order — deterministic, and ~10x faster than one thread walking all
+// chunks of a column with dependent loads (45 us per call at 592 chunks: 10 calls were 11 % of the training step).
+constexpr int kReduceLanes = 16;
+__global__ void __launch_bounds__(32 * kReduceLanes) colsum_reduce_kernel(const float* __restrict__ partial, int n_chunks, int cols, float scale,
+                                                                          __nv_bfloat16* __restrict__ out) {
+  __shared__ float s_sum[kReduceLanes][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
   float a = 0.f;
-  for (int i = 0; i < n_chunks; ++i) a += partial[static_cast<long long>(i) * cols + c];
-  out[c] = __float2bfloat16_rn(a * scale);
+  if (c < cols)
+    for (int i = threadIdx.y; i < n_chunks; i += kReduceLanes) a += partial[static_cast<long long>(i) * cols + c];
+  s_sum[threadIdx.y][threadIdx.x] = a;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < cols) {
+    float t = 0.f;
+#pragma unroll
+    for (int j = 0; j < kReduceLanes; ++j) t += s_sum[j][threadIdx.x];
+    out[c] = __float2bfloat16_rn(t * scale);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -216,17 +229,28 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const __nv_bfloat16* __rest
 }
 
 // dgamma / dbeta = sum over CTAs of the partials (fixed order -> deterministic); one thread per column
-__global__ void ln_param_reduce_kernel(const float* __restrict__ partial, int n_blocks, __nv_bfloat16* __restrict__ dgamma,
-                                       __nv_bfloat16* __restrict__ dbeta) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= kC) return;
+__global__ void __launch_bounds__(32 * kReduceLanes) ln_param_reduce_kernel(const float* __restrict__ partial, int n_blocks,
+                                                                            __nv_bfloat16* __restrict__ dgamma, __nv_bfloat16* __restrict__ dbeta) {
+  __shared__ float s_a[kReduceLanes][33], s_b[kReduceLanes][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;        // kC is a multiple of 32
   float a = 0.f, b = 0.f;
-  for (int i = 0; i < n_blocks; ++i) {
+  for (int i = threadIdx.y; i < n_blocks; i += kReduceLanes) {
     a += partial[(static_cast<long long>(i) * 2 + 0) * kC + c];
     b += partial[(static_cast<long long>(i) * 2 + 1) * kC + c];
   }
-  dgamma[c] = __float2bfloat16_rn(a);
-  dbeta[c] = __float2bfloat16_rn(b);
+  s_a[threadIdx.y][threadIdx.x] = a;
+  s_b[threadIdx.y][threadIdx.x] = b;
+  __syncthreads();
+  if (threadIdx.y == 0) {
+    float ta = 0.f, tb = 0.f;
+#pragma unroll
+    for (int j = 0; j < kReduceLanes; ++j) {
+      ta += s_a[j][threadIdx.x];
+      tb += s_b[j][threadIdx.x];
+    }
+    dgamma[c] = __float2bfloat16_rn(ta);
+    dbeta[c] = __float2bfloat16_rn(tb);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------

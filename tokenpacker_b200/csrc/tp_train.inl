@@ -119,7 +119,7 @@ int launch_ln_bwd(const void* g, const void* y, const float* stats, const void* 
   ln_bwd_kernel<<<kLnBlocks, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(g), static_cast<const __nv_bfloat16*>(y), stats,
                                                static_cast<const __nv_bfloat16*>(gamma), static_cast<__nv_bfloat16*>(dy), partial, rows);
   TP_CUDA(cudaGetLastError()); ++g_launch_count;
-  ln_param_reduce_kernel<<<kC / 256, 256, 0, stream>>>(partial, kLnBlocks, static_cast<__nv_bfloat16*>(dgamma),
+  ln_param_reduce_kernel<<<kC / 32, dim3(32, kReduceLanes), 0, stream>>>(partial, kLnBlocks, static_cast<__nv_bfloat16*>(dgamma),
                                                        static_cast<__nv_bfloat16*>(dbeta));
   TP_CUDA(cudaGetLastError()); ++g_launch_count;
   return TP_OK;
@@ -301,7 +301,7 @@ int tp_backward(const tp_weights* w, const void* xm, int64_t xm_crop_stride, int
     colsum_partial_kernel<<<dim3((cols + 1023) / 1024, chunks), 128, 0, stream>>>(static_cast<const __nv_bfloat16*>(dy), ld_dy, rows, cols,
                                                                                   chunks, col_part);
     TP_CUDA(cudaGetLastError()); ++g_launch_count;
-    colsum_reduce_kernel<<<(cols + 255) / 256, 256, 0, stream>>>(col_part, chunks, cols, scale, static_cast<__nv_bfloat16*>(out));
+    colsum_reduce_kernel<<<(cols + 31) / 32, dim3(32, kReduceLanes), 0, stream>>>(col_part, chunks, cols, scale, static_cast<__nv_bfloat16*>(out));
     TP_CUDA(cudaGetLastError()); ++g_launch_count;
     return TP_OK;
   };
