@@ -153,6 +153,7 @@ class TokenPackerB200(nn.Module):
         self._packed = None
         self._packed_key = None
         self._keepalive = None
+        self._param_list = None
         self._warned_dtype = False
         self.register_load_state_dict_post_hook(lambda module, incompatible: module.invalidate_packed())
 
@@ -172,8 +173,13 @@ class TokenPackerB200(nn.Module):
     # derived weight cache
     # ------------------------------------------------------------------------------------------------------------
     def _raw_params(self):
-        sd = dict(self.named_parameters())
-        return [sd[key] for _, key in _lib.WEIGHT_FIELDS]
+        # the 23 nn.Parameter objects in tp_weights order; looked up once (walking named_parameters() costs more host time than
+        # a single-image forward takes on the GPU) and again after anything that may have replaced them (invalidate_packed)
+        params = self._param_list
+        if params is None:
+            sd = dict(self.named_parameters())
+            params = self._param_list = [sd[key] for _, key in _lib.WEIGHT_FIELDS]
+        return params
 
     def invalidate_packed(self):
         """Drop the derived weight cache.  Called automatically by load_state_dict, .to() / .cuda() / .half() (``_apply``),
@@ -181,6 +187,7 @@ class TokenPackerB200(nn.Module):
         ``.data`` alias outside of training (such writes change neither ``data_ptr`` nor ``_version``, so no cache key sees them)."""
         self._packed = None
         self._packed_key = None
+        self._param_list = None
 
     def _apply(self, fn, *args, **kwargs):
         self.invalidate_packed()
@@ -229,7 +236,7 @@ class TokenPackerB200(nn.Module):
             raise ValueError(f"expected feat [N,576,1024] and feat_multi [N,576,4096], got {tuple(x0.shape)} {tuple(xm.shape)}")
         if not (x0.is_cuda and xm.is_cuda):
             raise RuntimeError("tokenpacker_b200 has no CPU path: inputs must be CUDA tensors on a B200")
-        if not self._warned_dtype and (x0.dtype != torch.bfloat16 or next(self.parameters()).dtype != torch.bfloat16):
+        if not self._warned_dtype and (x0.dtype != torch.bfloat16 or self._raw_params()[0].dtype != torch.bfloat16):
             self._warned_dtype = True
             warnings.warn("tokenpacker_b200 computes with bf16 storage and fp32 accumulation: fp16 / fp32 inputs and parameters are cast to "
                           "bf16 at the boundary and the result is cast back (every released TokenPacker recipe runs bf16; an fp16 or "
@@ -249,7 +256,7 @@ class TokenPackerB200(nn.Module):
         with torch.cuda.device(device):
             x0b, s0 = self._as_crop_strided(x0.to(torch.bfloat16), 1024)
             xmb, sm = self._as_crop_strided(xm.to(torch.bfloat16), 4096)
-            if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            if torch.is_grad_enabled() and any(p.requires_grad for p in self._raw_params()):
                 # training: same output, intermediates kept, gradients for every parameter (tp_forward_train / tp_backward)
                 out = _ProjectorFunction.apply(self, x0b, s0, xmb, sm, *self._raw_params())
             else:
