@@ -1026,6 +1026,7 @@ int forward_impl(const void* packed, const void* x0, const void* xm, const void*
       // Tile schedule (TP_SCHEDULE, read per call; default 0 = stage after stage).
       //   1: [4] and [5] interleaved row block by row block ([5] five row blocks behind): the GELU epilogue of [4] (longer than its
       //      K=1024 MMAs) then overlaps the K=4096 MMAs of [5] on every CTA pair instead of stalling the tensor pipe for a whole stage.
+      //   3: see below (wavefront over the last three stages only; for the fused all-gather).
       //   2: full software wavefront over groups of row blocks ([1] for group j, [2]k/v for j-1, KV-attention for j-2, [4] for j-3,
       //      [5] for j-4).  MEASURED NEGATIVE: all 73 MB of weights plus the streaming activations thrash the 126 MB L2 (DRAM reads
       //      0.8 -> 2.0 GB per step, 0.986 -> 1.114 ms); kept as an experiment.
@@ -1038,6 +1039,19 @@ int forward_impl(const void* packed, const void* x0, const void* xm, const void*
         for (int i = 0; i < 6 && ok; ++i) ok = plan.add(i, 0, i == 3 || i == 4 ? nbQ : nbR, i == 3 || i == 4 ? nbQ : nbR);
         const long long lag = 5;
         for (long long j = 0; j < nbQ + lag && ok; ++j) ok = plan.add(6, j, j + 1, nbQ) && plan.add(7, j - lag, j - lag + 1, nbQ);
+        if (!ok) plan.n = 0;
+      } else if (sch == 3) {
+        // stages [1] [2] [3]q in order, then a wavefront over blocks of 256 queries: KV-attention tiles of block j, [4] of block j-1,
+        // [5] of block j-2.  Meant for the fused all-gather: [5]'s peer stores start flowing during the attention stage instead of
+        // all at the end, so the NVLink transfer (7/8 of the packed output per rank) hides under compute.
+        const int Wn = s * s;
+        long long GR = Wn;
+        while ((nbR + GR - 1) / GR > 100) GR *= 2;
+        const long long GQ = GR / Wn, NG = (nbR + GR - 1) / GR;
+        bool ok = true;
+        for (int i = 0; i < 5 && ok; ++i) ok = plan.add(i, 0, i == 3 || i == 4 ? nbQ : nbR, i == 3 || i == 4 ? nbQ : nbR);
+        for (long long j = 0; j <= NG + 2 && ok; ++j)
+          ok = plan.add(5, j * GR, (j + 1) * GR, nbR) && plan.add(6, (j - 1) * GQ, j * GQ, nbQ) && plan.add(7, (j - 2) * GQ, (j - 1) * GQ, nbQ);
         if (!ok) plan.n = 0;
       } else if (sch == 2) {
         const int Wn = s * s;
