@@ -21,9 +21,8 @@ except Exception as e:
 }
 rm -f gpurun_out/ab.log
 ab fused_default X=1
-ab fused_mlp_interleave TP_SCHEDULE=1
+ab fused_schedule3 TP_SCHEDULE=3
 ab chain_nofuse TP_FUSE_ATTN=0
-ab fused_single_slab_per_half TOKENPACKER_B200_LIB_OVERRIDE=$PWD/build_ab/b1.so
 ab plain_7_launches TP_FUSE_ATTN=0 TP_CHAIN=0
 ( timeout 900 python bench.py --steps 20 --warmup 5 2>gpurun_out/bench.err | tail -1 ) > gpurun_out/bench_line.json
 cut -c1-400 gpurun_out/bench_line.json
