@@ -430,6 +430,7 @@ def hd_tile_measure(dev, peaks):
     ws = torch.randint(224, 1345, (32,), generator=g).tolist()
     gg = torch.Generator(device=dev).manual_seed(3)
     imgs = [torch.randn(3, h, w, device=dev, generator=gg) for h, w in zip(hs, ws)]
+    from tokenpacker_b200._lib import lib, check
     for _ in range(3):
         crops, hb, wb = hd_tile_batch(imgs, 9)
     torch.cuda.synchronize()
@@ -440,10 +441,25 @@ def hd_tile_measure(dev, peaks):
         crops, hb, wb = hd_tile_batch(imgs, 9)
     e1.record()
     torch.cuda.synchronize()
+    ms_call = e0.elapsed_time(e1) / reps
+    # the kernel on its own: the same launch re-issued through the C ABI with the tables already on the device
+    crops, hb, wb, (tables, table_off, n_crops) = hd_tile_batch(imgs, 9, _return_launch=True)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    for _ in range(3):
+        check(lib.tp_hd_tile_batch(tables.data_ptr(), tables.data_ptr() + table_off, n_crops, crops.data_ptr(), stream), "tp_hd_tile_batch")
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(reps):
+        check(lib.tp_hd_tile_batch(tables.data_ptr(), tables.data_ptr() + table_off, n_crops, crops.data_ptr(), stream), "tp_hd_tile_batch")
+    e1.record()
+    torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
     bytes_alg = sum(3 * h * w * 4 for h, w in zip(hs, ws)) + crops.numel() * 4
     return {"what": "hd_tile_batch: 32 images (seeded sizes 224..1344), patch_num=9 -> %d crops [3,336,336] fp32, one launch, thumbnails fused" % crops.shape[0],
-            "ms": ms, "includes": "host plan + two small H2D table uploads + the launch (the public call)", "algorithmic_bytes": bytes_alg,
+            "ms": ms, "ms_public_call": ms_call,
+            "includes": "ms: the tp_hd_tile_batch launch alone (tables resident); ms_public_call: hd_tile_batch() incl. the host plan for 32 images and "
+                        "its one asynchronous table upload (host-bound at this batch size)",
+            "algorithmic_bytes": bytes_alg,
             "achieved_gbs": bytes_alg / (ms * 1e-3) / 1e9, "peak_gbs": peaks["hbm_gbs"], "frac": bytes_alg / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"]}
 
 

@@ -90,7 +90,7 @@ def _staging(device, nbytes: int):
     return st
 
 
-def hd_tile_batch(images, patch_num: int = 9):
+def hd_tile_batch(images, patch_num: int = 9, _return_launch: bool = False):
     """The tiling block for a whole batch in ONE launch (the collator cats the crops of a batch, train.py:797-800).
 
     images: sequence of float32 CUDA tensors [3,h,w] or [1,3,h,w] (already normalised), sizes may differ.
@@ -137,6 +137,9 @@ def hd_tile_batch(images, patch_num: int = 9):
         # the source images must outlive the asynchronous launch: tie them to the stream
         for t in imgs:
             t.record_stream(torch.cuda.current_stream(device))
+    if _return_launch:
+        # benchmark hook: (device tables, table offset, crop count) so that the kernel can be re-launched and timed on its own
+        return crops, list(hb), list(wb), (dev, table_off, nc.value)
     return crops, list(hb), list(wb)
 
 
