@@ -1027,6 +1027,7 @@ int forward_impl(const void* packed, const void* x0, const void* xm, const void*
       //   1: [4] and [5] interleaved row block by row block ([5] five row blocks behind): the GELU epilogue of [4] (longer than its
       //      K=1024 MMAs) then overlaps the K=4096 MMAs of [5] on every CTA pair instead of stalling the tensor pipe for a whole stage.
       //   3: see below (wavefront over the last three stages only; for the fused all-gather).
+      //   4, 6: the batch as 2 / 4 sub-batches, each through all stages in turn (for the fused all-gather).
       //   2: full software wavefront over groups of row blocks ([1] for group j, [2]k/v for j-1, KV-attention for j-2, [4] for j-3,
       //      [5] for j-4).  MEASURED NEGATIVE: all 73 MB of weights plus the streaming activations thrash the 126 MB L2 (DRAM reads
       //      0.8 -> 2.0 GB per step, 0.986 -> 1.114 ms); kept as an experiment.
@@ -1052,6 +1053,24 @@ int forward_impl(const void* packed, const void* x0, const void* xm, const void*
         for (int i = 0; i < 5 && ok; ++i) ok = plan.add(i, 0, i == 3 || i == 4 ? nbQ : nbR, i == 3 || i == 4 ? nbQ : nbR);
         for (long long j = 0; j <= NG + 2 && ok; ++j)
           ok = plan.add(5, j * GR, (j + 1) * GR, nbR) && plan.add(6, (j - 1) * GQ, j * GQ, nbQ) && plan.add(7, (j - 2) * GQ, (j - 1) * GQ, nbQ);
+        if (!ok) plan.n = 0;
+      } else if (sch >= 4) {
+        // sub-batches: the batch is cut into (sch - 2) groups of query blocks; ALL stages of group g run (stage after stage) before
+        // group g+1 starts.  For the fused all-gather: the peer stores of group g's [5] tiles travel over NVLink while group g+1
+        // computes, so only the last group's share of the exchange is exposed.  The [1] / [2] ranges of a group reach 3 row blocks
+        // past its KV-attention range (a crop that straddles the group boundary needs its keys from both sides).
+        const int Wn = s * s;
+        const long long nsub = sch - 2;
+        const long long GQ = (nbQ + nsub - 1) / nsub > 0 ? (nbQ + nsub - 1) / nsub : 1, GR = GQ * Wn, NG = (nbQ + GQ - 1) / GQ;
+        bool ok = true;
+        for (long long gidx = 0; gidx < NG && ok; ++gidx) {
+          const bool last = gidx == NG - 1;
+          const long long r_lo = gidx == 0 ? 0 : gidx * GR + 3, r_hi = last ? nbR : (gidx + 1) * GR + 3;
+          const long long q_lo = gidx * GQ, q_hi = last ? nbQ : (gidx + 1) * GQ;
+          ok = plan.add(0, r_lo, r_hi, nbR) && plan.add(1, r_lo, r_hi, nbR) && plan.add(2, r_lo, r_hi, nbR) && plan.add(3, q_lo, q_hi, nbQ) &&
+               plan.add(4, q_lo, q_hi, nbQ) && plan.add(5, gidx * GR, last ? nbR : (gidx + 1) * GR, nbR) && plan.add(6, q_lo, q_hi, nbQ) &&
+               plan.add(7, q_lo, q_hi, nbQ);
+        }
         if (!ok) plan.n = 0;
       } else if (sch == 2) {
         const int Wn = s * s;
