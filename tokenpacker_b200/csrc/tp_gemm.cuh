@@ -862,6 +862,28 @@ tp_gemm2_kernel(const __grid_constant__ GemmGroup grp, const __grid_constant__ P
       const int row0 = t.m_blk * Cfg::kTileM + static_cast<int>(cta_rank) * kBlockM;          // my 128 rows of A
       const int brow0 = t.n_blk * kTileN + static_cast<int>(cta_rank) * (kTileN / 2);        // my half of the B tile
       // segmented A (3-D map, 64-row boxes): global row g -> (segment g / seg_rows, row g % seg_rows); hoisted per tile
+#ifdef TP_PREFETCH_NEXT
+      // EXPERIMENT: L2 prefetch of the A operand of this pair's NEXT tile when that tile is a short-K one (its operand fetches are
+      // latency bound: 16 k-blocks do not amortise a cold start).  One burst of <= 16 (32 for KV tiles) prefetch instructions per tile.
+      {
+        const int next = tile + num_pairs;
+        if (next < num_tiles) {
+          int cur2 = cursor;
+          const TileRef tn = decode_tile(grp, next, cur2);
+          const GemmProblem& pn = *tn.pr;
+          if (pn.num_k_blocks <= 16 && pn.ab_mn_major == 0 && pn.a_seg_rows == 0 && pn.a_parts == 1) {
+            const int rown = tn.m_blk * Cfg::kTileM + static_cast<int>(cta_rank) * kBlockM;
+            if (elect_one()) {
+              for (int kb = 0; kb < pn.num_k_blocks; ++kb) {
+                tma_prefetch_l2_2d(&pn.tmap_a, kb * kBlockK, rown);
+                if (pn.kind == 1) tma_prefetch_l2_2d(&pn.tmap_a2, kb * kBlockK, rown);
+              }
+            }
+            __syncwarp();
+          }
+        }
+      }
+#endif
       if (pr.dep_counter != nullptr) {
         // A's row block is written by an earlier problem of this launch: wait until all its tiles have been published (acquire),
         // then order the TMA (async proxy) reads after the acquire
