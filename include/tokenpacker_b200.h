@@ -154,6 +154,11 @@ TP_API int tp_gemm_bf16(const void* a, int64_t lda, const void* b, int64_t ldb, 
 TP_API int tp_gemm_tn_bf16(const void* a, int64_t lda, const void* b, int64_t ldb, void* c, int64_t ldc, int64_t m, int64_t n,
                            int64_t k, float alpha, void* stream);
 
+/* The dgrad form:  C[M,N] = alpha * A . B  with A the usual row-major [M, K] and B given as a row-major [K, N] matrix (a weight
+ * as stored, [out, in]): B reaches the tensor cores as MN-major tiles — no transposed copy of the weight.  Needs N % 256 == 0. */
+TP_API int tp_gemm_nn_bf16(const void* a, int64_t lda, const void* b, int64_t ldb, void* c, int64_t ldc, int64_t m, int64_t n,
+                           int64_t k, float alpha, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------------------
  * TokenPacker-HD front end.
  * ------------------------------------------------------------------------------------------------------------- */

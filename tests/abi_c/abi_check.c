@@ -17,7 +17,8 @@ int main(void) {
       (const void*)&tp_gemm_tn_bf16,      (const void*)&tp_hd_grid,           (const void*)&tp_hd_fit,
       (const void*)&tp_hd_tile,           (const void*)&tp_hd_plan,           (const void*)&tp_hd_scatter_crops,
       (const void*)&tp_gather_rows,       (const void*)&tp_hd_fill_separators, (const void*)&tp_forward_packed,
-      (const void*)&tp_launch_count,      (const void*)&tp_hd_tile_batch_plan, (const void*)&tp_hd_tile_batch};
+      (const void*)&tp_launch_count,      (const void*)&tp_hd_tile_batch_plan, (const void*)&tp_hd_tile_batch,
+      (const void*)&tp_gemm_nn_bf16};
   size_t i;
   for (i = 0; i < sizeof(entry) / sizeof(entry[0]); ++i)
     if (entry[i] == NULL) return 2;

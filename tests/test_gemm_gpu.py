@@ -86,3 +86,23 @@ def test_gemm_tn_exact_small_integers():
     a = torch.randint(-3, 4, (640, 512), device="cuda", generator=g).to(torch.bfloat16)
     b = torch.randint(-3, 4, (640, 256), device="cuda", generator=g).to(torch.bfloat16)
     assert torch.equal(gemm_tn_bf16(a, b), (a.float().t() @ b.float()).to(torch.bfloat16))
+
+
+@pytest.mark.parametrize("m,n,k", [(256, 256, 64), (512, 1024, 1024), (1000, 1024, 4096), (9216, 4096, 4096), (300, 256, 200)])
+def test_gemm_nn_dgrad_form(m, n, k):
+    """C = A B with B a row-major [K,N] matrix (a weight as stored): K-major A tiles, MN-major B tiles, no transposed copy (dgrad)."""
+    from tokenpacker_b200.kernels import gemm_nn_bf16
+    g = torch.Generator(device="cuda").manual_seed(m + n + k + 1)
+    a = torch.randn(m, k, device="cuda", generator=g).to(torch.bfloat16)
+    b = (torch.randn(k, n, device="cuda", generator=g) * 0.05).to(torch.bfloat16)
+    out = gemm_nn_bf16(a, b, alpha=0.5)
+    ref = 0.5 * (a.float() @ b.float())
+    _assert_close(out, ref)
+
+
+def test_gemm_nn_exact_small_integers():
+    from tokenpacker_b200.kernels import gemm_nn_bf16
+    g = torch.Generator(device="cuda").manual_seed(4)
+    a = torch.randint(-3, 4, (384, 640), device="cuda", generator=g).to(torch.bfloat16)
+    b = torch.randint(-3, 4, (640, 512), device="cuda", generator=g).to(torch.bfloat16)
+    assert torch.equal(gemm_nn_bf16(a, b), (a.float() @ b.float()).to(torch.bfloat16))

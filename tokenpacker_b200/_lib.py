@@ -78,6 +78,8 @@ SIGNATURES = {
                                C.c_int64, C.c_void_p, C.c_int, C.c_float, C.c_void_p]),
     "tp_gemm_tn_bf16": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
                                   C.c_float, C.c_void_p]),
+    "tp_gemm_nn_bf16": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
+                                  C.c_float, C.c_void_p]),
     "tp_hd_grid": (C.c_int, [C.c_int64, C.c_int64, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "tp_hd_fit": (C.c_int, [C.c_int64, C.c_int64, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
                             C.POINTER(C.c_int), C.POINTER(C.c_int)]),

@@ -184,11 +184,14 @@ struct GemmItem {
   void* const* peer_c = nullptr;   // fused all-gather: the same output slot in every peer's gathered buffer
   int n_peers = 0;
   int tn = 0;                      // 1: C[M,N] = A^T . B with A given as [K, M] (ld = a.ld) and B as [K, N] (ld = ldb), both row-major
+                                   // 2: C[M,N] = A . B with A the usual [M, K] and B given as [K, N] row-major (dgrad with the weight as stored)
   // kind 1 (KV-attention, pair kernel only): a / b = y_k (window-major rows) and the gamma-folded W_ik; a2 / b2 = y_v and W_iv;
   // M = rows of y_k, N = K = 1024; attn holds everything else; dep / dep2 / dep3 = the producers of y_k, y_v and q'
   int kind = 0;
   const void* a2 = nullptr;
   const void* b2 = nullptr;
+  void* c_pre = nullptr;           // ep.dual: destination of the pre-activation copy [M, N], row stride ld_pre
+  long long ld_pre = 0;
   AttnParams attn = {};
   int dep2 = -1, dep3 = -1;
   int k_splits = 1;                // > 1: split-K; ep.c must then be a float buffer [k_splits][M, ldc] (ep.out_f32 = 1, pair kernel only)
@@ -299,11 +302,17 @@ int launch_gemm_pair_group(const GemmItem* items, int count, int sms, cudaStream
       total += p.num_tiles;
       continue;
     }
-    if (it.tn) {
+    if (it.tn == 1) {
       // row-major [K, M] / [K, N] operands: box = 64 MN-elements x 64 K-rows
       TP_TRY(make_map_2d(&p.tmap_a, it.a.ptr, it.K, it.M, it.a.ld, 64));
       TP_TRY(make_map_2d(&p.tmap_b, it.b, it.K, it.N, it.ldb, 64));
       p.ab_mn_major = 1;
+    } else if (it.tn == 2) {
+      // C = A . B with B row-major [K, N]: the usual A boxes, B as 64 N-elements x 64 K-rows boxes
+      if (it.a.parts > 1) return TP_ERR_INVALID_ARGUMENT;
+      TP_TRY(make_a_map(&p.tmap_a, it.a, it.M, it.K));
+      TP_TRY(make_map_2d(&p.tmap_b, it.b, it.K, it.N, it.ldb, 64));
+      p.ab_mn_major = 2;
     } else if (it.a.parts > 1) {
       if (it.a.parts > kMaxAParts || it.K % (it.a.parts * kBlockK) != 0) return TP_ERR_INVALID_ARGUMENT;
       const long long kp = it.K / it.a.parts;
@@ -352,6 +361,13 @@ int launch_gemm_pair_group(const GemmItem* items, int count, int sms, cudaStream
       }
     } else {
       TP_TRY(make_map_2d(&p.tmap_c, it.ep.c, it.M, it.N, it.ep.ldc, kBlockM, kSlabCols));
+    }
+    if (it.ep.dual) {
+      // pre-activation copy: plain TMA-store output only, and the two staging buffers of a half must exist (z and GELU(z) slabs side by side)
+      if (!p.use_tma_store || c_segmented || it.ep.wm_s != 0 || it.n_peers > 0 || !it.ep.gelu || it.c_pre == nullptr || Cfg::kOutBufs != 2 ||
+          kSlabCols != 64 || it.k_splits > 1)
+        return TP_ERR_INVALID_ARGUMENT;
+      TP_TRY(make_map_2d(&p.tmap_cx[0], it.c_pre, it.M, it.N, it.ld_pre, kBlockM, kSlabCols));
     }
     p.M = static_cast<int>(it.M);
     p.N = static_cast<int>(it.N);
@@ -449,7 +465,7 @@ int launch_gemm_pair_group(const GemmItem* items, int count, int sms, cudaStream
 // Returns 0 pair, 1 one-CTA 256, 2 one-CTA 128, or -1 (invalid).
 int choose_kernel(const GemmItem& it, int count, int sms, int mode) {
   const bool pair_ok = (it.N % 256 == 0) && sms >= 2;
-  const bool pair_only = it.n_peers > 0 || it.tn || it.a.parts > 1 || it.k_splits > 1 || it.ep.out_f32 || it.kind == 1 || it.ep.wm_s != 0;   // pair-kernel-only features
+  const bool pair_only = it.n_peers > 0 || it.tn || it.ep.dual || it.a.parts > 1 || it.k_splits > 1 || it.ep.out_f32 || it.kind == 1 || it.ep.wm_s != 0;   // pair-kernel-only features
   if (pair_only && !pair_ok) return -1;
   const bool needs_256 = it.ep.stats_out != nullptr;                        // statistics slots assume 256-column tiles
   // Estimated tensor-pipe cycles of each candidate = waves x k-blocks x cycles per k-block.  Large problems always land
@@ -1328,6 +1344,17 @@ int tp_gemm_tn_bf16(const void* a, int64_t lda, const void* b, int64_t ldb, void
   GemmItem it{AOperand{a, lda, 0, 0}, b, ldb, m, n, k, plain_epilogue(c, ldc, nullptr, 0)};
   it.ep.alpha = alpha;
   it.tn = 1;
+  return launch_gemms(&it, 1, dev.sms, static_cast<cudaStream_t>(stream));
+}
+
+int tp_gemm_nn_bf16(const void* a, int64_t lda, const void* b, int64_t ldb, void* c, int64_t ldc, int64_t m, int64_t n, int64_t k,
+                    float alpha, void* stream) {
+  if (a == nullptr || b == nullptr || c == nullptr) return TP_ERR_INVALID_ARGUMENT;
+  DeviceInfo dev;
+  TP_TRY(device_info(&dev));
+  GemmItem it{AOperand{a, lda, 0, 0}, b, ldb, m, n, k, plain_epilogue(c, ldc, nullptr, 0)};
+  it.ep.alpha = alpha;
+  it.tn = 2;
   return launch_gemms(&it, 1, dev.sms, static_cast<cudaStream_t>(stream));
 }
 

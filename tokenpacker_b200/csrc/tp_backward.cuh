@@ -82,16 +82,43 @@ __global__ void gelu_fwd_kernel(const __nv_bfloat16* __restrict__ z, __nv_bfloat
   reinterpret_cast<uint4*>(h)[i] = pack8(f);
 }
 
-// dz = dh * GELU'(z), in place over dh
-__global__ void gelu_bwd_kernel(__nv_bfloat16* __restrict__ dh, const __nv_bfloat16* __restrict__ z, long long n8) {
-  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= n8) return;
-  float g[8], zz[8];
-  unpack8(reinterpret_cast<const uint4*>(dh)[i], g);
-  unpack8(__ldg(reinterpret_cast<const uint4*>(z) + i), zz);
+// dz = dh * GELU'(z) in place over dh, FUSED with the first stage of the bias gradient that follows it (column sums of dz): the
+// thread layout of colsum_partial_kernel (8 columns per thread, a chunk of rows per CTA row), so dz is never re-read.  The sums
+// are taken over the ROUNDED values that were stored, in row order: the same bits as colsum_partial_kernel over the stored dz.
+// grid = (ceil(cols / 1024), n_chunks), 128 threads; dh and z share the row stride ld.
+__global__ void __launch_bounds__(128) gelu_bwd_colsum_kernel(__nv_bfloat16* __restrict__ dh, const __nv_bfloat16* __restrict__ z, long long ld,
+                                                              long long rows, int cols, int n_chunks, float* __restrict__ partial) {
+  const int c0 = (blockIdx.x * 128 + threadIdx.x) * 8;
+  if (c0 >= cols) return;
+  const long long per = (rows + n_chunks - 1) / n_chunks;
+  const long long r0 = per * blockIdx.y, r1 = min(rows, r0 + per);
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  auto one = [&](const uint4& gv, const uint4& zv, long long r) {
+    float g[8], zz[8];
+    unpack8(gv, g);
+    unpack8(zv, zz);
 #pragma unroll
-  for (int j = 0; j < 8; ++j) g[j] *= gelu_grad(zz[j]);
-  reinterpret_cast<uint4*>(dh)[i] = pack8(g);
+    for (int j = 0; j < 8; ++j) g[j] *= gelu_grad(zz[j]);
+    const uint4 o = pack8(g);
+    *reinterpret_cast<uint4*>(dh + r * ld + c0) = o;
+    unpack8(o, g);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] += g[j];
+  };
+  long long r = r0;
+  for (; r + 4 <= r1; r += 4) {          // four rows of loads in flight before the first (aliasing) store
+    uint4 gv[4], zv[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      gv[u] = *reinterpret_cast<const uint4*>(dh + (r + u) * ld + c0);
+      zv[u] = __ldg(reinterpret_cast<const uint4*>(z + (r + u) * ld + c0));
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) one(gv[u], zv[u], r + u);
+  }
+  for (; r < r1; ++r) one(*reinterpret_cast<const uint4*>(dh + r * ld + c0), __ldg(reinterpret_cast<const uint4*>(z + r * ld + c0)), r);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) partial[static_cast<long long>(blockIdx.y) * cols + c0 + j] = acc[j];
 }
 
 // LayerNorm output  out[r,:] = (y[r,:] - mu_r) rstd_r gamma + beta  (bf16; one warp per row): B operand of the in-projection wgrad
@@ -134,17 +161,17 @@ __global__ void colsum_partial_kernel(const __nv_bfloat16* __restrict__ in, long
   for (int j = 0; j < 8; ++j) partial[static_cast<long long>(blockIdx.y) * cols + c0 + j] = acc[j];
 }
 
-// Second stage: out[c] = scale * sum_i partial[i][c].  Block = 32 columns x 16 chunk lanes: every thread sums chunks ty, ty+16, ...
+// Second stage: out[c] = scale * sum_i partial[i][c] (partial rows ld_part floats apart).  Block = 32 columns x 16 chunk lanes: every thread sums chunks ty, ty+16, ...
 // (independent loads), the 16 lane sums are added in fixed order — deterministic, and ~10x faster than one thread walking all
 // chunks of a column with dependent loads (45 us per call at 592 chunks: 10 calls were 11 % of the training step).
 constexpr int kReduceLanes = 16;
-__global__ void __launch_bounds__(32 * kReduceLanes) colsum_reduce_kernel(const float* __restrict__ partial, int n_chunks, int cols, float scale,
-                                                                          __nv_bfloat16* __restrict__ out) {
+__global__ void __launch_bounds__(32 * kReduceLanes) colsum_reduce_kernel(const float* __restrict__ partial, int n_chunks, int cols, int ld_part,
+                                                                          float scale, __nv_bfloat16* __restrict__ out) {
   __shared__ float s_sum[kReduceLanes][33];
   const int c = blockIdx.x * 32 + threadIdx.x;
   float a = 0.f;
   if (c < cols)
-    for (int i = threadIdx.y; i < n_chunks; i += kReduceLanes) a += partial[static_cast<long long>(i) * cols + c];
+    for (int i = threadIdx.y; i < n_chunks; i += kReduceLanes) a += partial[static_cast<long long>(i) * ld_part + c];
   s_sum[threadIdx.y][threadIdx.x] = a;
   __syncthreads();
   if (threadIdx.y == 0 && c < cols) {
@@ -159,21 +186,22 @@ __global__ void __launch_bounds__(32 * kReduceLanes) colsum_reduce_kernel(const 
 // LayerNorm backward (eps 1e-6, 1024 wide).  g = dL/d(LN output) [rows,1024], y = LN input, stats = its partial sums.
 //   yhat = (y - mu) rstd;  gg = gamma * g;  dy = rstd (gg - mean(gg) - yhat mean(gg yhat))
 // One warp per row (lane owns 4 x 8 channels), rows strided over the grid; per-CTA column partials of
-// dgamma = sum_r g yhat and dbeta = sum_r g are written to partial[blockIdx][2][1024] (fp32) for ln_param_reduce_kernel.
+// dgamma = sum_r g yhat, dbeta = sum_r g and sum_r dy (the bias gradient of the linear layer that feeds this LayerNorm, summed over
+// the ROUNDED dy that is stored) are written to partial[blockIdx][3][1024] (fp32) for ln_param_reduce_kernel.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) ln_bwd_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* __restrict__ y,
                                                      const float* __restrict__ stats, const __nv_bfloat16* __restrict__ gamma,
                                                      __nv_bfloat16* __restrict__ dy, float* __restrict__ partial, long long rows) {
-  __shared__ float s_part[8][2][kC / 4];   // staged in 4 passes of 256 columns to keep smem small
+  __shared__ float s_part[8][3][kC / 4];   // staged in 4 passes of 256 columns to keep smem small
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float gam[4][8];
 #pragma unroll
   for (int i = 0; i < 4; ++i) unpack8(__ldg(reinterpret_cast<const uint4*>(gamma + i * 256 + lane * 8)), gam[i]);
-  float dg[4][8], db[4][8];
+  float dg[4][8], db[4][8], ds[4][8];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) dg[i][j] = db[i][j] = 0.f;
+    for (int j = 0; j < 8; ++j) dg[i][j] = db[i][j] = ds[i][j] = 0.f;
   for (long long row = static_cast<long long>(blockIdx.x) * 8 + warp; row < rows; row += static_cast<long long>(gridDim.x) * 8) {
     float mu, rstd;
     row_mean_rstd(stats, row, mu, rstd);
@@ -205,7 +233,11 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const __nv_bfloat16* __rest
       float o[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) o[j] = rstd * (gam[i][j] * gv[i][j] - c1 - yh[i][j] * c2);
-      *reinterpret_cast<uint4*>(dy + row * kC + i * 256 + lane * 8) = pack8(o);
+      const uint4 pk = pack8(o);
+      *reinterpret_cast<uint4*>(dy + row * kC + i * 256 + lane * 8) = pk;
+      unpack8(pk, o);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) ds[i][j] += o[j];
     }
   }
   // cross-warp reduction of the column partials, 256 columns (one channel block i) at a time
@@ -215,41 +247,47 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const __nv_bfloat16* __rest
     for (int j = 0; j < 8; ++j) {
       s_part[warp][0][lane * 8 + j] = dg[i][j];
       s_part[warp][1][lane * 8 + j] = db[i][j];
+      s_part[warp][2][lane * 8 + j] = ds[i][j];
     }
     __syncthreads();
-    for (int idx = threadIdx.x; idx < 2 * 256; idx += blockDim.x) {
+    for (int idx = threadIdx.x; idx < 3 * 256; idx += blockDim.x) {
       const int which = idx >> 8, c = idx & 255;
       float acc = 0.f;
 #pragma unroll
       for (int w = 0; w < 8; ++w) acc += s_part[w][which][c];
-      partial[(static_cast<long long>(blockIdx.x) * 2 + which) * kC + i * 256 + c] = acc;
+      partial[(static_cast<long long>(blockIdx.x) * 3 + which) * kC + i * 256 + c] = acc;
     }
     __syncthreads();
   }
 }
 
-// dgamma / dbeta = sum over CTAs of the partials (fixed order -> deterministic); one thread per column
+// dgamma / dbeta / dbias = sum over CTAs of the partials (fixed order -> deterministic); dbias (the column sums of dy) may be nullptr
 __global__ void __launch_bounds__(32 * kReduceLanes) ln_param_reduce_kernel(const float* __restrict__ partial, int n_blocks,
-                                                                            __nv_bfloat16* __restrict__ dgamma, __nv_bfloat16* __restrict__ dbeta) {
-  __shared__ float s_a[kReduceLanes][33], s_b[kReduceLanes][33];
+                                                                            __nv_bfloat16* __restrict__ dgamma, __nv_bfloat16* __restrict__ dbeta,
+                                                                            __nv_bfloat16* __restrict__ dbias) {
+  __shared__ float s_a[kReduceLanes][33], s_b[kReduceLanes][33], s_c[kReduceLanes][33];
   const int c = blockIdx.x * 32 + threadIdx.x;        // kC is a multiple of 32
-  float a = 0.f, b = 0.f;
+  float a = 0.f, b = 0.f, d = 0.f;
   for (int i = threadIdx.y; i < n_blocks; i += kReduceLanes) {
-    a += partial[(static_cast<long long>(i) * 2 + 0) * kC + c];
-    b += partial[(static_cast<long long>(i) * 2 + 1) * kC + c];
+    a += partial[(static_cast<long long>(i) * 3 + 0) * kC + c];
+    b += partial[(static_cast<long long>(i) * 3 + 1) * kC + c];
+    d += partial[(static_cast<long long>(i) * 3 + 2) * kC + c];
   }
   s_a[threadIdx.y][threadIdx.x] = a;
   s_b[threadIdx.y][threadIdx.x] = b;
+  s_c[threadIdx.y][threadIdx.x] = d;
   __syncthreads();
   if (threadIdx.y == 0) {
-    float ta = 0.f, tb = 0.f;
+    float ta = 0.f, tb = 0.f, tc = 0.f;
 #pragma unroll
     for (int j = 0; j < kReduceLanes; ++j) {
       ta += s_a[j][threadIdx.x];
       tb += s_b[j][threadIdx.x];
+      tc += s_c[j][threadIdx.x];
     }
     dgamma[c] = __float2bfloat16_rn(ta);
     dbeta[c] = __float2bfloat16_rn(tb);
+    if (dbias != nullptr) dbias[c] = __float2bfloat16_rn(tc);
   }
 }
 

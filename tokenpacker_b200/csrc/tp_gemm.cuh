@@ -64,6 +64,9 @@ struct GemmEpilogue {
                            // rows (divide_feature, builder.py:96-105, done by the store instead of five permute copies).  The row
                            // statistics go to the permuted row too.  Pair kernel / TMA stores only; wm_s in {2, 4, 8}.
   int out_f32;             // 1: C is float [M, ldc] (split-K partial sums of the wgrads): fp32 direct stores, no bf16 rounding
+  int dual;                // 1 (with gelu): the bf16-rounded PRE-activation (after bias / LN fold, before GELU and alpha) is stored too,
+                           // through GemmProblem::tmap_cx[0] (the training forward keeps z for GELU'(z); builder.py:66-75 under autograd).
+                           // Pair kernel, plain (unsegmented) TMA-store output, two 64-column staging buffers per half.
   long long* prof;         // TP_GEMM_PROFILE builds only: [grid][16] cycle counters (nullptr otherwise)
 };
 
@@ -208,11 +211,15 @@ __device__ __forceinline__ void epilogue_tile(const GemmEpilogue& ep, int M, int
     if (chunk + 1 < kChunks) tmem_ld_32x32b_x32(taddr + static_cast<uint32_t>((chunk + 1) * 32), r[(chunk + 1) & 1]);
     else release();                                   // every TMEM read of this warp has landed in registers
     const int col0 = col_tile0 + half * kColsPerWarp + chunk * 32;
-    const uint32_t slab_q = out.slab_seq + static_cast<uint32_t>(chunk / kChunksPerSlab);
+    // dual output: every 64-column slab exists twice — pre-activation (even slab number, buffer 0) and activation (odd, buffer 1)
+    const bool dual = ep.dual != 0 && out.buf != nullptr;
+    const uint32_t slab_pre = out.slab_seq + 2u * static_cast<uint32_t>(chunk / kChunksPerSlab);
+    const uint32_t slab_q = dual ? slab_pre + 1u : out.slab_seq + static_cast<uint32_t>(chunk / kChunksPerSlab);
     const uint32_t slab_buf = slab_q & static_cast<uint32_t>(out.n_bufs - 1);
     if (out.buf != nullptr && (chunk % kChunksPerSlab) == 0) {
       // the TMA store that last used this staging buffer must have finished READING it (signalled by the store warp)
       TP_PROF_T0();
+      if (dual) mbar_wait(&out.empty_bar[slab_pre & 1u], ((slab_pre >> 1) & 1u) ^ 1u);
       mbar_wait(&out.empty_bar[slab_buf], ((slab_q >> (out.n_bufs - 1)) & 1u) ^ 1u);
       TP_PROF_ADD(pc[2]);
     }
@@ -243,6 +250,22 @@ __device__ __forceinline__ void epilogue_tile(const GemmEpilogue& ep, int M, int
             const float4 b = lds_f4(sb4 + q * 16);
             v[2 * q] = add2(v[2 * q], pk2(b.x, b.y));
             v[2 * q + 1] = add2(v[2 * q + 1], pk2(b.z, b.w));
+          }
+        }
+        if (dual) {        // the pre-activation slab (same swizzled position in the other staging buffer)
+          const uint32_t row_pre = out_addr + static_cast<uint32_t>((slab_pre & 1u) * kOutSlabBytes + rloc * kSlabRowBytes);
+          const int swz_pre = !out.swizzle ? 0 : (kSlabCols == 64 ? (rloc & 7) : ((rloc >> 1) & 3));
+#pragma unroll
+          for (int g = 0; g < kSubPairs / 4; ++g) {
+            uint32_t w[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float lo, hi;
+              upk2(v[4 * g + j], lo, hi);
+              w[j] = pack_bf16x2(lo, hi);
+            }
+            const int ci = (chunk % kChunksPerSlab) * 4 + sub * (kSubPairs / 4) + g;
+            sts_u4(row_pre + static_cast<uint32_t>((ci ^ swz_pre) << 4), w[0], w[1], w[2], w[3]);
           }
         }
         if (ep.gelu) {
@@ -315,7 +338,10 @@ __device__ __forceinline__ void epilogue_tile(const GemmEpilogue& ep, int M, int
       TP_PROF_T0();
       fence_proxy_async_smem();
       __syncwarp();
-      if (lane_id() == 0) mbar_arrive(&out.full_bar[slab_buf]);
+      if (lane_id() == 0) {
+        if (dual) mbar_arrive(&out.full_bar[slab_pre & 1u]);
+        mbar_arrive(&out.full_bar[slab_buf]);
+      }
       TP_PROF_ADD(pc[1]);
     }
   }
@@ -679,6 +705,7 @@ struct GemmProblem {
   int M, N, K;
   int a_seg_rows;        // 0: plain 2-D A; else rows per segment of the 3-D (crop-strided) A map
   int ab_mn_major;       // 1: BOTH operands are given as row-major [K, M] / [K, N] matrices (wgrad: C = A^T . B, contraction over rows)
+                         // 2: only B is ([K, N] row-major: dgrad C = A . B with the weight as stored); A is the usual K-major [M, K]
   int use_tma_store;     // C through TMA stores (0 when rows are scattered to arbitrary segment offsets)
   int c_seg_len;         // != 0: tmap_c (and the peer maps) are 3-D (cols, row in segment, segment): uniform-stride segmented output
   int c_unit;            //       gcd(c_seg_len, 128): every piece of a slab that belongs to one segment is a multiple of it
@@ -862,28 +889,6 @@ tp_gemm2_kernel(const __grid_constant__ GemmGroup grp, const __grid_constant__ P
       const int row0 = t.m_blk * Cfg::kTileM + static_cast<int>(cta_rank) * kBlockM;          // my 128 rows of A
       const int brow0 = t.n_blk * kTileN + static_cast<int>(cta_rank) * (kTileN / 2);        // my half of the B tile
       // segmented A (3-D map, 64-row boxes): global row g -> (segment g / seg_rows, row g % seg_rows); hoisted per tile
-#ifdef TP_PREFETCH_NEXT
-      // EXPERIMENT: L2 prefetch of the A operand of this pair's NEXT tile when that tile is a short-K one (its operand fetches are
-      // latency bound: 16 k-blocks do not amortise a cold start).  One burst of <= 16 (32 for KV tiles) prefetch instructions per tile.
-      {
-        const int next = tile + num_pairs;
-        if (next < num_tiles) {
-          int cur2 = cursor;
-          const TileRef tn = decode_tile(grp, next, cur2);
-          const GemmProblem& pn = *tn.pr;
-          if (pn.num_k_blocks <= 16 && pn.ab_mn_major == 0 && pn.a_seg_rows == 0 && pn.a_parts == 1) {
-            const int rown = tn.m_blk * Cfg::kTileM + static_cast<int>(cta_rank) * kBlockM;
-            if (elect_one()) {
-              for (int kb = 0; kb < pn.num_k_blocks; ++kb) {
-                tma_prefetch_l2_2d(&pn.tmap_a, kb * kBlockK, rown);
-                if (pn.kind == 1) tma_prefetch_l2_2d(&pn.tmap_a2, kb * kBlockK, rown);
-              }
-            }
-            __syncwarp();
-          }
-        }
-      }
-#endif
       if (pr.dep_counter != nullptr) {
         // A's row block is written by an earlier problem of this launch: wait until all its tiles have been published (acquire),
         // then order the TMA (async proxy) reads after the acquire
@@ -951,12 +956,10 @@ tp_gemm2_kernel(const __grid_constant__ GemmGroup grp, const __grid_constant__ P
           uint8_t* sb = sa + Cfg::kABytes;
           if (is_leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
           else mbar_arrive_cluster(&full_bar[stage], 0);
-          if (pr.ab_mn_major) {
+          if (pr.ab_mn_major == 1) {
             // boxes of [64 K-rows x 64 MN-elements]: coordinates (mn, k); two MN atoms per operand per CTA
             tma_load_2d_pair(sa, &pr.tmap_a, &full_bar[stage], row0, kb * kBlockK);
             tma_load_2d_pair(sa + Cfg::kABytes / 2, &pr.tmap_a, &full_bar[stage], row0 + 64, kb * kBlockK);
-            tma_load_2d_pair(sb, &pr.tmap_b, &full_bar[stage], brow0, kb * kBlockK);
-            tma_load_2d_pair(sb + Cfg::kBBytes / 2, &pr.tmap_b, &full_bar[stage], brow0 + 64, kb * kBlockK);
           } else {
             const int part = pr.a_parts > 1 ? kb / pr.a_kblocks_per_part : 0;
             const CUtensorMap* ta = part == 0 ? &pr.tmap_a : &pr.tmap_a_more[part - 1];
@@ -968,7 +971,12 @@ tp_gemm2_kernel(const __grid_constant__ GemmGroup grp, const __grid_constant__ P
               tma_load_3d_pair(sa + Cfg::kABytes / 2, ta, &full_bar[stage], ka, srow1, seg1);
             }
           }
-          if (!pr.ab_mn_major) tma_load_2d_pair(sb, &pr.tmap_b, &full_bar[stage], kb * kBlockK, brow0);
+          if (pr.ab_mn_major == 0) {
+            tma_load_2d_pair(sb, &pr.tmap_b, &full_bar[stage], kb * kBlockK, brow0);
+          } else {                                       // 1 (TN) and 2 (NN): B is a row-major [K, N] matrix
+            tma_load_2d_pair(sb, &pr.tmap_b, &full_bar[stage], brow0, kb * kBlockK);
+            tma_load_2d_pair(sb + Cfg::kBBytes / 2, &pr.tmap_b, &full_bar[stage], brow0 + 64, kb * kBlockK);
+          }
         }
         __syncwarp();
         if (++stage == kStages) { stage = 0; phase ^= 1u; }
@@ -992,8 +1000,9 @@ tp_gemm2_kernel(const __grid_constant__ GemmGroup grp, const __grid_constant__ P
       for (int tile = pair_idx; tile < num_tiles; tile += num_pairs) {
         const TileRef mt = decode_tile(grp, tile, cursor);
         const GemmProblem& mpr = *mt.pr;
-        const bool mn_major = mpr.ab_mn_major != 0;
-        const uint32_t idesc = mn_major ? make_idesc_bf16_f32(Cfg::kTileM, kTileN, 1, 1) : make_idesc_bf16_f32(Cfg::kTileM, kTileN);
+        const int mn_major = mpr.ab_mn_major;
+        const uint32_t idesc = mn_major == 1 ? make_idesc_bf16_f32(Cfg::kTileM, kTileN, 1, 1)
+                             : mn_major == 2 ? make_idesc_bf16_f32(Cfg::kTileM, kTileN, 0, 1) : make_idesc_bf16_f32(Cfg::kTileM, kTileN);
         {
           TP_PROF_T0();
           mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1u);   // both epilogues have drained this accumulator buffer
@@ -1042,7 +1051,16 @@ tp_gemm2_kernel(const __grid_constant__ GemmGroup grp, const __grid_constant__ P
           tcgen05_fence_after();
           if (elect_one()) {
             const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
-            if (!mn_major) {
+            if (mn_major == 2) {
+              // NN (dgrad: B = the weight as stored, row-major [K, N]): K-major A tile, MN-major B tile
+              const uint64_t desc_a = make_smem_desc_kmajor_sw128(sa);
+              const uint64_t desc_b = make_smem_desc_mnmajor_sw128(sa + Cfg::kABytes, Cfg::kBBytes / 2);
+#pragma unroll
+              for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+                umma_bf16_pair(tmem_d, desc_a + static_cast<uint64_t>(k * 2), desc_b + static_cast<uint64_t>(k * (2048 >> 4)), idesc,
+                               static_cast<uint32_t>(((kb - mt.kb0) | k) != 0));
+              }
+            } else if (!mn_major) {
               const uint64_t desc_a = make_smem_desc_kmajor_sw128(sa);
               const uint64_t desc_b = make_smem_desc_kmajor_sw128(sa + Cfg::kABytes);
 #pragma unroll
@@ -1175,7 +1193,7 @@ tp_gemm2_kernel(const __grid_constant__ GemmGroup grp, const __grid_constant__ P
       tcgen05_fence_after();
       const OutStage out{pr.use_tma_store ? s_out + half * Cfg::kOutBufs * kOutSlabBytes : nullptr, slab_full_bar + half * Cfg::kOutBufs,
                          slab_empty_bar + half * Cfg::kOutBufs, Cfg::kOutBufs, slab_seq, pr.c_noswz == 0};
-      if (pr.use_tma_store) slab_seq += kTileN / 2 / kSlabCols;     // slabs per tile and column half
+      if (pr.use_tma_store) slab_seq += (kTileN / 2 / kSlabCols) * (pr.ep.dual ? 2 : 1);     // slabs per tile and column half
       epilogue_tile<kTileN>(pr.ep, pr.M, pr.N, tmem_base + static_cast<uint32_t>(acc * kTileN), row, t.n_blk * kTileN, quarter, half, s_col,
                             out, [&]() {
                               tcgen05_fence_before();
@@ -1217,12 +1235,13 @@ tp_gemm2_kernel(const __grid_constant__ GemmGroup grp, const __grid_constant__ P
       const int row_tile0 = t.m_blk * Cfg::kTileM + static_cast<int>(cta_rank) * kBlockM;
       const bool to_peers = pr.peer_out != 0 && peers.count > 0;
       const int n_maps = to_peers ? peers.count : 1;
-      for (int slab = 0; slab < kTileN / 2 / kSlabCols; ++slab, ++q) {
+      const int dual = pr.ep.dual != 0 ? 1 : 0;     // every column slab twice: pre-activation (tmap_cx[0]) then activation (tmap_c)
+      for (int slab = 0; slab < (kTileN / 2 / kSlabCols) << dual; ++slab, ++q) {
         const uint32_t buf = q & static_cast<uint32_t>(Cfg::kOutBufs - 1);
         mbar_wait(&full[buf], (q >> (Cfg::kOutBufs - 1)) & 1u);
         if (elect_one()) {
           const uint8_t* src = s_out + (half * Cfg::kOutBufs + static_cast<int>(buf)) * kOutSlabBytes;
-          const int col = t.n_blk * kTileN + half * (kTileN / 2) + slab * kSlabCols;
+          const int col = t.n_blk * kTileN + half * (kTileN / 2) + (slab >> dual) * kSlabCols;
           // TMA stores must lie entirely inside the tensor (a box that sticks out of a segment faults: measured), so every piece of
           // a slab goes out through boxes of EXACTLY its size: a few maps per destination with box heights unit << level.
           if (pr.c_wm_s != 0) {
@@ -1240,7 +1259,9 @@ tp_gemm2_kernel(const __grid_constant__ GemmGroup grp, const __grid_constant__ P
               tma_store_5d(mp, src + lo * kSlabRowBytes, col, 0, r24 % sf, (lo - a) / sf, r24 / sf);    // (c, wi, hi, wb, crop-and-hb)
             }
           } else if (pr.c_seg_len == 0) {
-            for (int p = 0; p < n_maps; ++p) tma_store_2d(to_peers ? &peers.m[p][0] : &pr.tmap_c, src, col, row_tile0);
+            if (dual && (slab & 1) == 0) tma_store_2d(&pr.tmap_cx[0], src, col, row_tile0);
+            else
+              for (int p = 0; p < n_maps; ++p) tma_store_2d(to_peers ? &peers.m[p][0] : &pr.tmap_c, src, col, row_tile0);
           } else {
             // Segmented output rows (global row g = seg * seg_len + r  ->  map coordinate (col, r, seg)): the slab's 128 rows are
             // cut at segment boundaries; a piece of L = n * unit rows leaves as one box per set bit of n (largest first).

@@ -3,9 +3,9 @@
 //
 // The reference trains this module (it is the only trainable module of stage 1 and is trained in stage 2:
 // llava/train/train.py:950-958, scripts/v1_5/pretrain*.sh), through PyTorch autograd over builder.py:107-137.  Here:
-//   forward_train = the inference launch plan without the out_proj fold and with GELU as a separate pass, so that the
-//                   pre-activations z exist in memory (GELU'(z) needs z; GELU(z) is not invertible);
-//   backward      = dgrad GEMMs (dY . W, B operand = transposed weight), wgrad GEMMs in the TN form of the pair kernel
+//   forward_train = the inference launch plan without the out_proj fold, and with the pre-activations z of the two GELUs kept in
+//                   memory (GELU'(z) needs z; GELU(z) is not invertible): k/v_proj.0's epilogue stores z and GELU(z) together;
+//   backward      = dgrad GEMMs in the NN form of the pair kernel (dY . W, the weight read as stored), wgrad GEMMs in the TN form
 //                   (dW = dY^T . X straight from the row-major activations: MN-major UMMA tiles, contraction over rows),
 //                   LayerNorm / GELU / window-attention backward kernels, bias gradients as deterministic column sums.
 // Gradients w.r.t. the CLIP features are not produced (the tower is frozen in every released recipe; the Python layer raises
@@ -48,7 +48,7 @@ struct BwdLayout {
   size_t dqp, dkp, dvp, dqp_t, dkp_t, dvp_t, lnq_t, lnk_t, lnv_t;
   size_t dqh, dkh, dvh, dyq, dyk, dyv, dyq_t, dyk_t, dyv_t, q_t, hkv_t;
   size_t dzkv, dzkv_t, xm_t;
-  size_t ln_part;        // f32 [3][kLnBlocks][2][1024]
+  size_t ln_part;        // f32 [3][kLnBlocks][3][1024]
   size_t col_part;       // f32 [kColChunks][max(H, 2048)]  column-sum partials (bias gradients)
   size_t splitk;         // f32 [2][kWgradSplits][1024,1024]  split-K partial sums of the 1024x1024 wgrads that contract over R rows
   size_t total;
@@ -83,7 +83,7 @@ BwdLayout bwd_layout(long long n_crops, int s, int H) {
   L.dyq = take(Q * kC * 2); L.dyk = take(R * kC * 2); L.dyv = take(R * kC * 2);
   L.dzkv = take(R * 2 * kC * 2);
   L.dzm_t = L.o_t = L.do_t = L.ctx_t = L.dqp_t = L.dkp_t = L.dvp_t = L.dyq_t = L.dyk_t = L.dyv_t = L.q_t = L.hkv_t = L.dzkv_t = L.xm_t = 0;   // unused (TN wgrad)
-  L.ln_part = take(3ull * kLnBlocks * 2 * kC * 4);
+  L.ln_part = take(3ull * kLnBlocks * 3 * kC * 4);
   L.col_part = take(static_cast<size_t>(kColChunks) * (Hs > 2048 ? Hs : 2048) * 4);
   L.splitk = take(2ull * kWgradSplits * kC * kC * 4);
   L.total = off;
@@ -106,21 +106,13 @@ int launch_gelu_fwd(const void* z, void* h, size_t elems, cudaStream_t stream) {
   return TP_OK;
 }
 
-int launch_gelu_bwd(void* dh, const void* z, size_t elems, cudaStream_t stream) {
-  const long long n8 = static_cast<long long>(elems / 8);
-  gelu_bwd_kernel<<<static_cast<unsigned>((n8 + 255) / 256), 256, 0, stream>>>(static_cast<__nv_bfloat16*>(dh),
-                                                                                static_cast<const __nv_bfloat16*>(z), n8);
-  TP_CUDA(cudaGetLastError()); ++g_launch_count;
-  return TP_OK;
-}
-
 int launch_ln_bwd(const void* g, const void* y, const float* stats, const void* gamma, void* dy, float* partial, long long rows,
-                  void* dgamma, void* dbeta, cudaStream_t stream) {
+                  void* dgamma, void* dbeta, void* dbias, cudaStream_t stream) {
   ln_bwd_kernel<<<kLnBlocks, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(g), static_cast<const __nv_bfloat16*>(y), stats,
                                                static_cast<const __nv_bfloat16*>(gamma), static_cast<__nv_bfloat16*>(dy), partial, rows);
   TP_CUDA(cudaGetLastError()); ++g_launch_count;
   ln_param_reduce_kernel<<<kC / 32, dim3(32, kReduceLanes), 0, stream>>>(partial, kLnBlocks, static_cast<__nv_bfloat16*>(dgamma),
-                                                       static_cast<__nv_bfloat16*>(dbeta));
+                                                       static_cast<__nv_bfloat16*>(dbeta), static_cast<__nv_bfloat16*>(dbias));
   TP_CUDA(cudaGetLastError()); ++g_launch_count;
   return TP_OK;
 }
@@ -171,6 +163,10 @@ int tp_forward_train(const void* packed, const void* x0, const void* xm, int64_t
   float* stats_v = stats_k + 2 * kStatSlots * R;
   float* stats_q = stats_v + 2 * kStatSlots * R;
 
+  // GELU stages: bit 0 = k/v_proj.0, bit 1 = mlp.0 store z and GELU(z) from one epilogue (else a GEMM that stores z + an elementwise
+  // GELU pass).  TP_TRAIN_DUAL overrides (A/B aid, read per call); the dual store needs the two-slab staging of the default build.
+  int dual_mask = (Gemm2Config::kOutBufs == 2 && kSlabCols == 64 && dev.sms >= 2) ? 1 : 0;
+  if (const char* e = getenv("TP_TRAIN_DUAL")) dual_mask = (Gemm2Config::kOutBufs == 2 && kSlabCols == 64 && dev.sms >= 2) ? atoi(e) : 0;
   {
     const __nv_bfloat16* x0p = static_cast<const __nv_bfloat16*>(x0);
     TP_TRY(launch_front_s(s, x0p, x0_crop_stride, bf(S.q), Q, stream));
@@ -178,8 +174,17 @@ int tp_forward_train(const void* packed, const void* x0, const void* xm, int64_t
   {
     AOperand a{xm, kCm, 0, 0};
     if (xm_crop_stride != static_cast<int64_t>(kTokens) * kCm) a = AOperand{xm, kCm, kTokens, xm_crop_stride};
-    TP_TRY(launch_gemm(a, P + L.w_kv0, kCm, R, 2 * kC, kCm, plain_epilogue(bf(S.z_kv), 2 * kC, wf(L.b_kv0), 0), dev.sms, stream));
-    TP_TRY(launch_gelu_fwd(bf(S.z_kv), bf(S.h_kv), static_cast<size_t>(R) * 2 * kC, stream));
+    if (dual_mask & 1) {
+      // one pass: the epilogue stores the rounded pre-activation z (kept for GELU'(z)) AND GELU(z)
+      GemmItem it{a, P + L.w_kv0, kCm, R, 2 * kC, kCm, plain_epilogue(bf(S.h_kv), 2 * kC, wf(L.b_kv0), 1)};
+      it.ep.dual = 1;
+      it.c_pre = bf(S.z_kv);
+      it.ld_pre = 2 * kC;
+      TP_TRY(launch_gemms(&it, 1, dev.sms, stream));
+    } else {
+      TP_TRY(launch_gemm(a, P + L.w_kv0, kCm, R, 2 * kC, kCm, plain_epilogue(bf(S.z_kv), 2 * kC, wf(L.b_kv0), 0), dev.sms, stream));
+      TP_TRY(launch_gelu_fwd(bf(S.z_kv), bf(S.h_kv), static_cast<size_t>(R) * 2 * kC, stream));
+    }
   }
   {
     GemmItem gi[3];
@@ -204,8 +209,16 @@ int tp_forward_train(const void* packed, const void* x0, const void* xm, int64_t
   }
   TP_TRY(launch_attn_s(s, bf(S.q_p), bf(S.k_p), bf(S.v_p), bf(S.ctx), Q, stream));
   TP_TRY(launch_gemm(AOperand{bf(S.ctx), kC, 0, 0}, P + L.w_o, kC, Q, kC, kC, plain_epilogue(bf(S.o), kC, wf(L.b_o), 0), dev.sms, stream));
-  TP_TRY(launch_gemm(AOperand{bf(S.o), kC, 0, 0}, P + L.w_m0, kC, Q, H, kC, plain_epilogue(bf(S.z_m), H, wf(L.b_m0), 0), dev.sms, stream));
-  TP_TRY(launch_gelu_fwd(bf(S.z_m), bf(S.h_m), static_cast<size_t>(Q) * H, stream));
+  if ((dual_mask & 2) && H % 256 == 0) {
+    GemmItem it{AOperand{bf(S.o), kC, 0, 0}, P + L.w_m0, kC, Q, H, kC, plain_epilogue(bf(S.h_m), H, wf(L.b_m0), 1)};
+    it.ep.dual = 1;
+    it.c_pre = bf(S.z_m);
+    it.ld_pre = H;
+    TP_TRY(launch_gemms(&it, 1, dev.sms, stream));
+  } else {
+    TP_TRY(launch_gemm(AOperand{bf(S.o), kC, 0, 0}, P + L.w_m0, kC, Q, H, kC, plain_epilogue(bf(S.z_m), H, wf(L.b_m0), 0), dev.sms, stream));
+    TP_TRY(launch_gelu_fwd(bf(S.z_m), bf(S.h_m), static_cast<size_t>(Q) * H, stream));
+  }
   TP_TRY(launch_gemm(AOperand{bf(S.h_m), H, 0, 0}, P + L.w_m2, H, Q, H, H, plain_epilogue(out, H, wf(L.b_m2), 0), dev.sms, stream));
   return TP_OK;
 }
@@ -247,15 +260,19 @@ int tp_backward(const tp_weights* w, const void* xm, int64_t xm_crop_stride, int
   auto G = [&](const void* p) { return const_cast<void*>(p); };
   const float alpha_q = 0.08838834764831845f;
 
-  // transposed weights: B operands of the dgrad GEMMs (dX = dY . W  ==  dY . (W^T)^T in the kernel's A.B^T form)
-  TP_TRY(launch_transpose(w->mlp_2_w, H, wb(B.w_m2t), H, H, H, stream));
-  TP_TRY(launch_transpose(w->mlp_0_w, kC, wb(B.w_m0t), H, H, kC, stream));
-  TP_TRY(launch_transpose(w->out_proj_w, kC, wb(B.w_ot), kC, kC, kC, stream));
-  TP_TRY(launch_transpose(in_w, kC, wb(B.w_iqt), kC, kC, kC, stream));
-  TP_TRY(launch_transpose(in_w + static_cast<size_t>(kC) * kC, kC, wb(B.w_ikt), kC, kC, kC, stream));
-  TP_TRY(launch_transpose(in_w + 2 * static_cast<size_t>(kC) * kC, kC, wb(B.w_ivt), kC, kC, kC, stream));
-  TP_TRY(launch_transpose(w->k_proj_2_w, kC, wb(B.w_k2t), kC, kC, kC, stream));
-  TP_TRY(launch_transpose(w->v_proj_2_w, kC, wb(B.w_v2t), kC, kC, kC, stream));
+  // dgrad  dX[rows, n_in] = alpha * dY[rows, n_out] . W[n_out, n_in]: the NN form of the pair kernel reads the weight as stored (MN-major
+  // B tiles).  Fallback for n_in not a multiple of 256 (mlp.2 at tiny hidden sizes): a transposed copy + the ordinary NT form.
+  auto dgrad = [&](const void* dy, long long ld_dy, const void* wt, long long ld_w, void* dx, long long ld_dx, long long rows, int n_in,
+                   int n_out, float alpha, size_t wt_off, GemmItem* item) -> int {
+    if (n_in % 256 == 0) {
+      *item = plain_item(dy, ld_dy, wt, ld_w, dx, ld_dx, rows, n_in, n_out, nullptr, alpha);
+      item->tn = 2;
+      return TP_OK;
+    }
+    TP_TRY(launch_transpose(wt, ld_w, wb(wt_off), n_out, n_out, n_in, stream));
+    *item = plain_item(dy, ld_dy, wb(wt_off), n_out, dx, ld_dx, rows, n_in, n_out, nullptr, alpha);
+    return TP_OK;
+  };
 
   // wgrad  dW[n_out, n_in] = alpha * dY^T X  (dY: [rows, n_out], X: [rows, n_in], both as stored).  Normal case: the TN form of
   // the pair kernel reads both operands in place (MN-major UMMA tiles).  Fallback for n_in not a multiple of 256 (tiny hidden
@@ -301,8 +318,24 @@ int tp_backward(const tp_weights* w, const void* xm, int64_t xm_crop_stride, int
     colsum_partial_kernel<<<dim3((cols + 1023) / 1024, chunks), 128, 0, stream>>>(static_cast<const __nv_bfloat16*>(dy), ld_dy, rows, cols,
                                                                                   chunks, col_part);
     TP_CUDA(cudaGetLastError()); ++g_launch_count;
-    colsum_reduce_kernel<<<(cols + 31) / 32, dim3(32, kReduceLanes), 0, stream>>>(col_part, chunks, cols, scale, static_cast<__nv_bfloat16*>(out));
+    colsum_reduce_kernel<<<(cols + 31) / 32, dim3(32, kReduceLanes), 0, stream>>>(col_part, chunks, cols, cols, scale, static_cast<__nv_bfloat16*>(out));
     TP_CUDA(cudaGetLastError()); ++g_launch_count;
+    return TP_OK;
+  };
+  // dz = dh GELU'(z) in place + bias gradient(s) = column sums of dz; out_hi != nullptr: columns [cols/2, cols) go to out_hi
+  auto gelu_bwd_bias = [&](__nv_bfloat16* dh, const __nv_bfloat16* z, long long ld, long long rows, int cols, void* out, void* out_hi) -> int {
+    if (cols > (H > 2048 ? H : 2048) || cols % 8 != 0) return TP_ERR_INVALID_ARGUMENT;
+    const int chunks = static_cast<int>(rows < kColChunks ? rows : kColChunks);
+    gelu_bwd_colsum_kernel<<<dim3((cols + 1023) / 1024, chunks), 128, 0, stream>>>(dh, z, ld, rows, cols, chunks, col_part);
+    TP_CUDA(cudaGetLastError()); ++g_launch_count;
+    const int n_out = out_hi != nullptr ? cols / 2 : cols;
+    colsum_reduce_kernel<<<(n_out + 31) / 32, dim3(32, kReduceLanes), 0, stream>>>(col_part, chunks, n_out, cols, 1.0f, static_cast<__nv_bfloat16*>(out));
+    TP_CUDA(cudaGetLastError()); ++g_launch_count;
+    if (out_hi != nullptr) {
+      colsum_reduce_kernel<<<(n_out + 31) / 32, dim3(32, kReduceLanes), 0, stream>>>(col_part + n_out, chunks, n_out, cols, 1.0f,
+                                                                                      static_cast<__nv_bfloat16*>(out_hi));
+      TP_CUDA(cudaGetLastError()); ++g_launch_count;
+    }
     return TP_OK;
   };
   auto ln_apply = [&](const __nv_bfloat16* y, const float* stats, const void* gamma, const void* beta, __nv_bfloat16* out, long long rows) -> int {
@@ -317,16 +350,15 @@ int tp_backward(const tp_weights* w, const void* xm, int64_t xm_crop_stride, int
   {
     GemmItem gi[2];
     TP_TRY(wgrad(grad_out, H, sb(S.h_m), H, Q, H, H, G(grads->mlp_2_w), H, 1.0f, B.g_t, B.hm_t, &gi[0]));      // dW_m2 = G^T h_m
-    gi[1] = plain_item(grad_out, H, wb(B.w_m2t), H, wb(B.dzm), H, Q, H, H);                                    // dh_m = G W_m2
+    TP_TRY(dgrad(grad_out, H, w->mlp_2_w, H, wb(B.dzm), H, Q, H, H, 1.0f, B.w_m2t, &gi[1]));                    // dh_m = G W_m2
     TP_TRY(launch_gemms(gi, 2, dev.sms, stream));
   }
-  TP_TRY(launch_gelu_bwd(wb(B.dzm), sb(S.z_m), static_cast<size_t>(Q) * H, stream));                          // dz_m
-  // ---- mlp.0:  z_m = o W_m0^T + b
-  TP_TRY(bias_grad(wb(B.dzm), H, Q, H, 1.0f, G(grads->mlp_0_b)));
+  // ---- mlp.0:  z_m = o W_m0^T + b   (dz_m = dh_m GELU'(z_m) and the column sums of dz_m in one pass)
+  TP_TRY(gelu_bwd_bias(wb(B.dzm), sb(S.z_m), H, Q, H, G(grads->mlp_0_b), nullptr));
   {
     GemmItem gi[2];
     TP_TRY(wgrad(wb(B.dzm), H, sb(S.o), kC, Q, H, kC, G(grads->mlp_0_w), kC, 1.0f, B.dzm_t, B.o_t, &gi[0]));   // dW_m0 = dz_m^T o
-    gi[1] = plain_item(wb(B.dzm), H, wb(B.w_m0t), H, wb(B.d_o), kC, Q, kC, H);                                 // do = dz_m W_m0
+    TP_TRY(dgrad(wb(B.dzm), H, w->mlp_0_w, kC, wb(B.d_o), kC, Q, kC, H, 1.0f, B.w_m0t, &gi[1]));               // do = dz_m W_m0
     TP_TRY(launch_gemms(gi, 2, dev.sms, stream));
   }
   // ---- out_proj:  o = ctx W_o^T + b
@@ -334,7 +366,7 @@ int tp_backward(const tp_weights* w, const void* xm, int64_t xm_crop_stride, int
   {
     GemmItem gi[2];
     TP_TRY(wgrad(wb(B.d_o), kC, sb(S.ctx), kC, Q, kC, kC, G(grads->out_proj_w), kC, 1.0f, B.do_t, B.ctx_t, &gi[0]));   // dW_o = do^T ctx
-    gi[1] = plain_item(wb(B.d_o), kC, wb(B.w_ot), kC, wb(B.dctx), kC, Q, kC, kC);                               // dctx = do W_o
+    TP_TRY(dgrad(wb(B.d_o), kC, w->out_proj_w, kC, wb(B.dctx), kC, Q, kC, kC, 1.0f, B.w_ot, &gi[1]));           // dctx = do W_o
     TP_TRY(launch_gemms(gi, 2, dev.sms, stream));
   }
   // ---- window attention
@@ -365,9 +397,9 @@ int tp_backward(const tp_weights* w, const void* xm, int64_t xm_crop_stride, int
       TP_TRY(wgrad(wb(B.dkp), kC, wb(B.lnk_t), kC, R, kC, kC, d_in_w + static_cast<size_t>(kC) * kC, kC, 1.0f, B.dkp_t, B.dyk_t, &gi[n++]));
       TP_TRY(wgrad(wb(B.dvp), kC, wb(B.lnv_t), kC, R, kC, kC, d_in_w + 2 * static_cast<size_t>(kC) * kC, kC, 1.0f, B.dvp_t, B.dyv_t, &gi[n++]));
     }
-    gi[n++] = plain_item(wb(B.dkp), kC, wb(B.w_ikt), kC, wb(B.dkh), kC, R, kC, kC);                     // d LN(y_k)
-    gi[n++] = plain_item(wb(B.dvp), kC, wb(B.w_ivt), kC, wb(B.dvh), kC, R, kC, kC);
-    gi[n++] = plain_item(wb(B.dqp), kC, wb(B.w_iqt), kC, wb(B.dqh), kC, Q, kC, kC, nullptr, alpha_q);   // d LN(y_q)
+    TP_TRY(dgrad(wb(B.dkp), kC, in_w + static_cast<size_t>(kC) * kC, kC, wb(B.dkh), kC, R, kC, kC, 1.0f, B.w_ikt, &gi[n++]));      // d LN(y_k)
+    TP_TRY(dgrad(wb(B.dvp), kC, in_w + 2 * static_cast<size_t>(kC) * kC, kC, wb(B.dvh), kC, R, kC, kC, 1.0f, B.w_ivt, &gi[n++]));
+    TP_TRY(dgrad(wb(B.dqp), kC, in_w, kC, wb(B.dqh), kC, Q, kC, kC, alpha_q, B.w_iqt, &gi[n++]));                                 // d LN(y_q)
     TP_TRY(wgrad(wb(B.dqp), kC, wb(B.lnq_t), kC, Q, kC, kC, d_in_w, kC, alpha_q, B.dqp_t, B.q_t, &gi[n++]));
     TP_TRY(launch_gemms(gi, n, dev.sms, stream));
     if (sk) {
@@ -376,14 +408,13 @@ int tp_backward(const tp_weights* w, const void* xm, int64_t xm_crop_stride, int
     }
   }
   // ---- LayerNorms
-  TP_TRY(launch_ln_bwd(wb(B.dqh), sb(S.y_q), stats_q, w->ln_q_w, wb(B.dyq), ln_part, Q, G(grads->ln_q_w), G(grads->ln_q_b), stream));
-  TP_TRY(launch_ln_bwd(wb(B.dkh), sb(S.y_k), stats_k, w->ln_k_w, wb(B.dyk), ln_part + 2ll * kLnBlocks * kC, R, G(grads->ln_k_w),
-                       G(grads->ln_k_b), stream));
-  TP_TRY(launch_ln_bwd(wb(B.dvh), sb(S.y_v), stats_v, w->ln_v_w, wb(B.dyv), ln_part + 4ll * kLnBlocks * kC, R, G(grads->ln_v_w),
-                       G(grads->ln_v_b), stream));
-  // ---- q_proj_1 (no bias), k_proj_1.2, v_proj_1.2
-  TP_TRY(bias_grad(wb(B.dyk), kC, R, kC, 1.0f, G(grads->k_proj_2_b)));
-  TP_TRY(bias_grad(wb(B.dyv), kC, R, kC, 1.0f, G(grads->v_proj_2_b)));
+  // (the column sums of dy_k / dy_v = the bias gradients of k_proj_1.2 / v_proj_1.2 come out of the same pass; q_proj_1 has no bias)
+  TP_TRY(launch_ln_bwd(wb(B.dqh), sb(S.y_q), stats_q, w->ln_q_w, wb(B.dyq), ln_part, Q, G(grads->ln_q_w), G(grads->ln_q_b), nullptr, stream));
+  TP_TRY(launch_ln_bwd(wb(B.dkh), sb(S.y_k), stats_k, w->ln_k_w, wb(B.dyk), ln_part + 3ll * kLnBlocks * kC, R, G(grads->ln_k_w),
+                       G(grads->ln_k_b), G(grads->k_proj_2_b), stream));
+  TP_TRY(launch_ln_bwd(wb(B.dvh), sb(S.y_v), stats_v, w->ln_v_w, wb(B.dyv), ln_part + 6ll * kLnBlocks * kC, R, G(grads->ln_v_w),
+                       G(grads->ln_v_b), G(grads->v_proj_2_b), stream));
+  // ---- q_proj_1, k_proj_1.2, v_proj_1.2
   {
     GemmItem gi[5];
     int n = 0;
@@ -394,8 +425,8 @@ int tp_backward(const tp_weights* w, const void* xm, int64_t xm_crop_stride, int
       TP_TRY(wgrad(wb(B.dyk), kC, sb(S.h_kv), 2 * kC, R, kC, kC, G(grads->k_proj_2_w), kC, 1.0f, B.dyk_t, B.hkv_t, &gi[n++]));
       TP_TRY(wgrad(wb(B.dyv), kC, sb(S.h_kv) + kC, 2 * kC, R, kC, kC, G(grads->v_proj_2_w), kC, 1.0f, B.dyv_t, B.hkv_t + static_cast<size_t>(kC) * Rp * 2, &gi[n++]));
     }
-    gi[n++] = plain_item(wb(B.dyk), kC, wb(B.w_k2t), kC, wb(B.dzkv), 2 * kC, R, kC, kC);               // dh_k  -> dzkv[:, :1024]
-    gi[n++] = plain_item(wb(B.dyv), kC, wb(B.w_v2t), kC, wb(B.dzkv) + kC, 2 * kC, R, kC, kC);          // dh_v  -> dzkv[:, 1024:]
+    TP_TRY(dgrad(wb(B.dyk), kC, w->k_proj_2_w, kC, wb(B.dzkv), 2 * kC, R, kC, kC, 1.0f, B.w_k2t, &gi[n++]));        // dh_k  -> dzkv[:, :1024]
+    TP_TRY(dgrad(wb(B.dyv), kC, w->v_proj_2_w, kC, wb(B.dzkv) + kC, 2 * kC, R, kC, kC, 1.0f, B.w_v2t, &gi[n++]));   // dh_v  -> dzkv[:, 1024:]
     TP_TRY(wgrad(wb(B.dyq), kC, sb(S.q), kC, Q, kC, kC, G(grads->q_proj_w), kC, 1.0f, B.dyq_t, B.q_t, &gi[n++]));
     TP_TRY(launch_gemms(gi, n, dev.sms, stream));
     if (sk) {
@@ -403,10 +434,8 @@ int tp_backward(const tp_weights* w, const void* xm, int64_t xm_crop_stride, int
       TP_TRY(wgrad_reduce(1, 1.0f, G(grads->v_proj_2_w)));
     }
   }
-  TP_TRY(launch_gelu_bwd(wb(B.dzkv), sb(S.z_kv), static_cast<size_t>(R) * 2 * kC, stream));        // dz_kv
   // ---- k_proj_1.0 / v_proj_1.0:  z = xm W0^T + b   (no gradient to xm: the CLIP tower is frozen)
-  TP_TRY(bias_grad(wb(B.dzkv), 2 * kC, R, kC, 1.0f, G(grads->k_proj_0_b)));
-  TP_TRY(bias_grad(wb(B.dzkv) + kC, 2 * kC, R, kC, 1.0f, G(grads->v_proj_0_b)));
+  TP_TRY(gelu_bwd_bias(wb(B.dzkv), sb(S.z_kv), 2 * kC, R, 2 * kC, G(grads->k_proj_0_b), G(grads->v_proj_0_b)));     // dz_kv + both bias gradients
   {
     GemmItem gi[2];
     TP_TRY(wgrad(wb(B.dzkv), 2 * kC, xm, kCm, R, kC, kCm, G(grads->k_proj_0_w), kCm, 1.0f, B.dzkv_t, B.xm_t, &gi[0]));
