@@ -136,7 +136,12 @@ TP_API int tp_forward_host(const void* packed, const void* x0_host, const void* 
  * ------------------------------------------------------------------------------------------------------------- */
 TP_API size_t tp_train_saved_bytes(int64_t n_crops, int scale_factor, int hidden);
 TP_API size_t tp_backward_workspace_bytes(int64_t n_crops, int scale_factor, int hidden);
-TP_API int tp_forward_train(const void* packed, const void* x0, const void* xm, int64_t n_crops, int64_t x0_crop_stride,
+/* ``w`` NULL: every weight matrix is read from ``packed`` (a full tp_pack_weights buffer).  ``w`` non-NULL: the matrices that need no
+ * transformation (k/v_proj.2, q_proj, out_proj, mlp.0, mlp.2) are read from the live parameters IN PLACE and ``packed`` only has to hold
+ * what tp_pack_weights_train writes (fp32 biases, the LayerNorm-folded in-projections, the concatenated k/v_proj.0): a training step
+ * repacks every forward (the optimizer moved the weights), so the 50 MB of copies and the inference-only out_proj fold are skipped. */
+TP_API int tp_pack_weights_train(const tp_weights* w, int hidden, void* packed, size_t packed_bytes, void* stream);
+TP_API int tp_forward_train(const tp_weights* w, const void* packed, const void* x0, const void* xm, int64_t n_crops, int64_t x0_crop_stride,
                             int64_t xm_crop_stride, int scale_factor, int hidden, void* out, void* saved, size_t saved_bytes,
                             void* stream);
 TP_API int tp_backward(const tp_weights* w, const void* xm, int64_t xm_crop_stride, int64_t n_crops, int scale_factor, int hidden,

@@ -18,7 +18,7 @@ int main(void) {
       (const void*)&tp_hd_tile,           (const void*)&tp_hd_plan,           (const void*)&tp_hd_scatter_crops,
       (const void*)&tp_gather_rows,       (const void*)&tp_hd_fill_separators, (const void*)&tp_forward_packed,
       (const void*)&tp_launch_count,      (const void*)&tp_hd_tile_batch_plan, (const void*)&tp_hd_tile_batch,
-      (const void*)&tp_gemm_nn_bf16};
+      (const void*)&tp_gemm_nn_bf16,      (const void*)&tp_pack_weights_train};
   size_t i;
   for (i = 0; i < sizeof(entry) / sizeof(entry[0]); ++i)
     if (entry[i] == NULL) return 2;

@@ -70,7 +70,8 @@ SIGNATURES = {
                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int64, C.c_void_p]),
     "tp_train_saved_bytes": (C.c_size_t, [C.c_int64, C.c_int, C.c_int]),
     "tp_backward_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int, C.c_int]),
-    "tp_forward_train": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_void_p,
+    "tp_pack_weights_train": (C.c_int, [C.POINTER(TpWeights), C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "tp_forward_train": (C.c_int, [C.POINTER(TpWeights), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_void_p,
                                    C.c_void_p, C.c_size_t, C.c_void_p]),
     "tp_backward": (C.c_int, [C.POINTER(TpWeights), C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                               C.POINTER(TpWeights), C.c_void_p, C.c_size_t, C.c_void_p]),

@@ -864,6 +864,48 @@ int tp_pack_weights(const tp_weights* w, int hidden, void* packed, size_t packed
   return TP_OK;
 }
 
+int tp_pack_weights_train(const tp_weights* w, int hidden, void* packed, size_t packed_bytes, void* stream_) {
+  if (w == nullptr || packed == nullptr || !valid_hidden(hidden)) return TP_ERR_INVALID_ARGUMENT;
+  const void* const* fields = reinterpret_cast<const void* const*>(w);
+  for (size_t i = 0; i < sizeof(tp_weights) / sizeof(void*); ++i)
+    if (fields[i] == nullptr) return TP_ERR_INVALID_ARGUMENT;
+  const PackedLayout L = packed_layout(hidden);
+  if (packed_bytes < L.total) return TP_ERR_WORKSPACE_TOO_SMALL;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  uint8_t* P = static_cast<uint8_t*>(packed);
+  // k/v_proj.0 side by side: ONE GEMM of N = 2048 reads every row block of the 4096-wide features once
+  const size_t kv0 = static_cast<size_t>(kC) * kCm * 2;
+  TP_CUDA(cudaMemcpyAsync(P + L.w_kv0, w->k_proj_0_w, kv0, cudaMemcpyDeviceToDevice, stream));
+  TP_CUDA(cudaMemcpyAsync(P + L.w_kv0 + kv0, w->v_proj_0_w, kv0, cudaMemcpyDeviceToDevice, stream));
+  CastSegs segs;
+  auto seg = [&](int i, const void* src, size_t off, int n) {
+    segs.s[i] = CastSeg{static_cast<const __nv_bfloat16*>(src), reinterpret_cast<float*>(P + off), n};
+  };
+  seg(0, w->k_proj_0_b, L.b_kv0, kC);
+  seg(1, w->v_proj_0_b, L.b_kv0 + kC * 4, kC);
+  seg(2, w->k_proj_2_b, L.b_k2, kC);
+  seg(3, w->v_proj_2_b, L.b_v2, kC);
+  seg(4, w->out_proj_b, L.b_o, kC);
+  seg(5, w->mlp_0_b, L.b_m0, hidden);
+  seg(6, w->mlp_2_b, L.b_m2, hidden);
+  bf16_to_f32_multi_kernel<<<dim3(4, 7), 256, 0, stream>>>(segs);
+  TP_CUDA(cudaGetLastError()); ++g_launch_count;
+  const __nv_bfloat16* in_w = static_cast<const __nv_bfloat16*>(w->in_proj_w);
+  const __nv_bfloat16* in_b = static_cast<const __nv_bfloat16*>(w->in_proj_b);
+  auto fold = [&](size_t w_off, size_t wsum_off, size_t c_off, const void* wsrc, const void* bsrc, const void* gamma, const void* beta) {
+    fold_layernorm_kernel<<<(kC * 32 + 255) / 256, 256, 0, stream>>>(
+        static_cast<const __nv_bfloat16*>(wsrc), static_cast<const __nv_bfloat16*>(bsrc), static_cast<const __nv_bfloat16*>(gamma),
+        static_cast<const __nv_bfloat16*>(beta), reinterpret_cast<__nv_bfloat16*>(P + w_off), reinterpret_cast<float*>(P + wsum_off),
+        reinterpret_cast<float*>(P + c_off), kC, kC);
+    ++g_launch_count;
+    return cudaGetLastError();
+  };
+  TP_CUDA(fold(L.w_iq, L.wsum_q, L.c_q, in_w, in_b, w->ln_q_w, w->ln_q_b));
+  TP_CUDA(fold(L.w_ik, L.wsum_k, L.c_k, in_w + static_cast<size_t>(kC) * kC, in_b + kC, w->ln_k_w, w->ln_k_b));
+  TP_CUDA(fold(L.w_iv, L.wsum_v, L.c_v, in_w + 2 * static_cast<size_t>(kC) * kC, in_b + 2 * kC, w->ln_v_w, w->ln_v_b));
+  return TP_OK;
+}
+
 size_t tp_workspace_bytes(int64_t n_crops, int scale_factor, int hidden) {
   if (n_crops <= 0 || scale_factor <= 0 || kGrid % scale_factor != 0 || !valid_hidden(hidden)) return 0;
   return work_layout(n_crops, scale_factor, hidden).total;

@@ -229,6 +229,14 @@ __global__ void bf16_to_f32_kernel(const __nv_bfloat16* __restrict__ src, float*
   if (i < n) dst[i] = __bfloat162float(src[i]);
 }
 
+// Several bf16 -> fp32 vectors in one launch (the biases of a training-step repack): blockIdx.y = segment
+struct CastSeg { const __nv_bfloat16* src; float* dst; int n; };
+struct CastSegs { CastSeg s[8]; };
+__global__ void bf16_to_f32_multi_kernel(CastSegs segs) {
+  const CastSeg g = segs.s[blockIdx.y];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < g.n; i += gridDim.x * blockDim.x) g.dst[i] = __bfloat162float(g.src[i]);
+}
+
 // LayerNorm folded into the following linear (one warp per output feature o):
 //   LN(y) W^T + b = rstd * ( y (gamma.W)^T - mu * rowsum(gamma.W) ) + ( W beta + b )
 //   w_out[o,:] = bf16(W[o,:] * gamma),  wsum[o] = sum_i w_out[o,i] (of the ROUNDED values),  cst[o] = W[o,:].beta + b[o]

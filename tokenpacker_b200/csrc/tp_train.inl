@@ -4,7 +4,7 @@
 // The reference trains this module (it is the only trainable module of stage 1 and is trained in stage 2:
 // llava/train/train.py:950-958, scripts/v1_5/pretrain*.sh), through PyTorch autograd over builder.py:107-137.  Here:
 //   forward_train = the inference launch plan without the out_proj fold, and with the pre-activations z of the two GELUs kept in
-//                   memory (GELU'(z) needs z; GELU(z) is not invertible): k/v_proj.0's epilogue stores z and GELU(z) together;
+//                   memory (GELU'(z) needs z; GELU(z) is not invertible): the epilogues of k/v_proj.0 and mlp.0 store z and GELU(z) together;
 //   backward      = dgrad GEMMs in the NN form of the pair kernel (dY . W, the weight read as stored), wgrad GEMMs in the TN form
 //                   (dW = dY^T . X straight from the row-major activations: MN-major UMMA tiles, contraction over rows),
 //                   LayerNorm / GELU / window-attention backward kernels, bias gradients as deterministic column sums.
@@ -138,7 +138,7 @@ size_t tp_backward_workspace_bytes(int64_t n_crops, int scale_factor, int hidden
   return bwd_layout(n_crops, scale_factor, hidden).total;
 }
 
-int tp_forward_train(const void* packed, const void* x0, const void* xm, int64_t n_crops, int64_t x0_crop_stride, int64_t xm_crop_stride,
+int tp_forward_train(const tp_weights* w, const void* packed, const void* x0, const void* xm, int64_t n_crops, int64_t x0_crop_stride, int64_t xm_crop_stride,
                      int scale_factor, int hidden, void* out, void* saved, size_t saved_bytes, void* stream_) {
   if (scale_factor <= 0 || kGrid % scale_factor != 0) return TP_ERR_BAD_SCALE_FACTOR;
   if (packed == nullptr || x0 == nullptr || xm == nullptr || out == nullptr || saved == nullptr || n_crops <= 0 || !valid_hidden(hidden))
@@ -159,13 +159,22 @@ int tp_forward_train(const void* packed, const void* x0, const void* xm, int64_t
   uint8_t* sv = static_cast<uint8_t*>(saved);
   auto wf = [&](size_t off) { return reinterpret_cast<const float*>(P + off); };
   auto bf = [&](size_t off) { return reinterpret_cast<__nv_bfloat16*>(sv + off); };
+  // weight matrices that need no transformation: the live parameters in place (w given), else their copies in the packed buffer
+  const void* W_k2 = w != nullptr ? w->k_proj_2_w : P + L.w_k2;
+  const void* W_v2 = w != nullptr ? w->v_proj_2_w : P + L.w_v2;
+  const void* W_q = w != nullptr ? w->q_proj_w : P + L.w_q;
+  const void* W_o = w != nullptr ? w->out_proj_w : P + L.w_o;
+  const void* W_m0 = w != nullptr ? w->mlp_0_w : P + L.w_m0;
+  const void* W_m2 = w != nullptr ? w->mlp_2_w : P + L.w_m2;
+  if (w != nullptr && (W_k2 == nullptr || W_v2 == nullptr || W_q == nullptr || W_o == nullptr || W_m0 == nullptr || W_m2 == nullptr))
+    return TP_ERR_INVALID_ARGUMENT;
   float* stats_k = reinterpret_cast<float*>(sv + S.stats);
   float* stats_v = stats_k + 2 * kStatSlots * R;
   float* stats_q = stats_v + 2 * kStatSlots * R;
 
   // GELU stages: bit 0 = k/v_proj.0, bit 1 = mlp.0 store z and GELU(z) from one epilogue (else a GEMM that stores z + an elementwise
   // GELU pass).  TP_TRAIN_DUAL overrides (A/B aid, read per call); the dual store needs the two-slab staging of the default build.
-  int dual_mask = (Gemm2Config::kOutBufs == 2 && kSlabCols == 64 && dev.sms >= 2) ? 1 : 0;
+  int dual_mask = (Gemm2Config::kOutBufs == 2 && kSlabCols == 64 && dev.sms >= 2) ? 3 : 0;
   if (const char* e = getenv("TP_TRAIN_DUAL")) dual_mask = (Gemm2Config::kOutBufs == 2 && kSlabCols == 64 && dev.sms >= 2) ? atoi(e) : 0;
   {
     const __nv_bfloat16* x0p = static_cast<const __nv_bfloat16*>(x0);
@@ -188,11 +197,11 @@ int tp_forward_train(const void* packed, const void* x0, const void* xm, int64_t
   }
   {
     GemmItem gi[3];
-    gi[0] = GemmItem{AOperand{bf(S.h_kv), 2 * kC, 0, 0}, P + L.w_k2, kC, R, kC, kC, plain_epilogue(bf(S.y_k), kC, wf(L.b_k2), 0)};
+    gi[0] = GemmItem{AOperand{bf(S.h_kv), 2 * kC, 0, 0}, W_k2, kC, R, kC, kC, plain_epilogue(bf(S.y_k), kC, wf(L.b_k2), 0)};
     gi[0].ep.stats_out = stats_k; gi[0].ep.stats_out_slots = kStatSlots;
-    gi[1] = GemmItem{AOperand{bf(S.h_kv) + kC, 2 * kC, 0, 0}, P + L.w_v2, kC, R, kC, kC, plain_epilogue(bf(S.y_v), kC, wf(L.b_v2), 0)};
+    gi[1] = GemmItem{AOperand{bf(S.h_kv) + kC, 2 * kC, 0, 0}, W_v2, kC, R, kC, kC, plain_epilogue(bf(S.y_v), kC, wf(L.b_v2), 0)};
     gi[1].ep.stats_out = stats_v; gi[1].ep.stats_out_slots = kStatSlots;
-    gi[2] = GemmItem{AOperand{bf(S.q), kC, 0, 0}, P + L.w_q, kC, Q, kC, kC, plain_epilogue(bf(S.y_q), kC, nullptr, 0)};
+    gi[2] = GemmItem{AOperand{bf(S.q), kC, 0, 0}, W_q, kC, Q, kC, kC, plain_epilogue(bf(S.y_q), kC, nullptr, 0)};
     gi[2].ep.stats_out = stats_q; gi[2].ep.stats_out_slots = kStatSlots;
     TP_TRY(launch_gemms(gi, 3, dev.sms, stream));
   }
@@ -208,18 +217,18 @@ int tp_forward_train(const void* packed, const void* x0, const void* xm, int64_t
     TP_TRY(launch_gemms(gi, 3, dev.sms, stream));
   }
   TP_TRY(launch_attn_s(s, bf(S.q_p), bf(S.k_p), bf(S.v_p), bf(S.ctx), Q, stream));
-  TP_TRY(launch_gemm(AOperand{bf(S.ctx), kC, 0, 0}, P + L.w_o, kC, Q, kC, kC, plain_epilogue(bf(S.o), kC, wf(L.b_o), 0), dev.sms, stream));
+  TP_TRY(launch_gemm(AOperand{bf(S.ctx), kC, 0, 0}, W_o, kC, Q, kC, kC, plain_epilogue(bf(S.o), kC, wf(L.b_o), 0), dev.sms, stream));
   if ((dual_mask & 2) && H % 256 == 0) {
-    GemmItem it{AOperand{bf(S.o), kC, 0, 0}, P + L.w_m0, kC, Q, H, kC, plain_epilogue(bf(S.h_m), H, wf(L.b_m0), 1)};
+    GemmItem it{AOperand{bf(S.o), kC, 0, 0}, W_m0, kC, Q, H, kC, plain_epilogue(bf(S.h_m), H, wf(L.b_m0), 1)};
     it.ep.dual = 1;
     it.c_pre = bf(S.z_m);
     it.ld_pre = H;
     TP_TRY(launch_gemms(&it, 1, dev.sms, stream));
   } else {
-    TP_TRY(launch_gemm(AOperand{bf(S.o), kC, 0, 0}, P + L.w_m0, kC, Q, H, kC, plain_epilogue(bf(S.z_m), H, wf(L.b_m0), 0), dev.sms, stream));
+    TP_TRY(launch_gemm(AOperand{bf(S.o), kC, 0, 0}, W_m0, kC, Q, H, kC, plain_epilogue(bf(S.z_m), H, wf(L.b_m0), 0), dev.sms, stream));
     TP_TRY(launch_gelu_fwd(bf(S.z_m), bf(S.h_m), static_cast<size_t>(Q) * H, stream));
   }
-  TP_TRY(launch_gemm(AOperand{bf(S.h_m), H, 0, 0}, P + L.w_m2, H, Q, H, H, plain_epilogue(out, H, wf(L.b_m2), 0), dev.sms, stream));
+  TP_TRY(launch_gemm(AOperand{bf(S.h_m), H, 0, 0}, W_m2, H, Q, H, H, plain_epilogue(out, H, wf(L.b_m2), 0), dev.sms, stream));
   return TP_OK;
 }
 

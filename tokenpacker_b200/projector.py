@@ -49,17 +49,24 @@ class _ProjectorFunction(torch.autograd.Function):
         # training: ALWAYS repack from the live parameters.  Optimizers that update through a ``.data`` alias (DeepSpeed ZeRO-2's
         # bit16 flat buffer: every reference recipe, scripts/v1_5/*.sh) change neither data_ptr nor _version, so no key can tell
         # that the weights moved; they change every step anyway and the pack is small next to forward + backward.
-        packed = module._packed_weights(device, fresh=True)
+        # The matrices that need no transformation are read from the (bf16) parameters in place; only the fp32 biases, the
+        # LayerNorm-folded in-projections and the k/v_proj.0 concatenation are rebuilt (tp_pack_weights_train).
+        bf = [p.detach().to(device=device, dtype=torch.bfloat16).contiguous() for p in params]
+        w_struct = _lib.TpWeights(*[t.data_ptr() for t in bf])
+        stream = torch.cuda.current_stream(device).cuda_stream
+        pbytes = lib.tp_packed_bytes(module.hidden_size)
+        packed = torch.empty(pbytes, dtype=torch.uint8, device=device)
+        check(lib.tp_pack_weights_train(C.byref(w_struct), module.hidden_size, packed.data_ptr(), pbytes, stream), "tp_pack_weights_train")
+        module._packed = module._packed_key = None           # whatever the inference path cached predates this step's weights
         out = torch.empty((n, module.num_queries, module.hidden_size), dtype=torch.bfloat16, device=device)
         nbytes = lib.tp_train_saved_bytes(n, module.scale_factor, module.hidden_size)
         saved = torch.empty(nbytes, dtype=torch.uint8, device=device)
-        stream = torch.cuda.current_stream(device).cuda_stream
-        check(lib.tp_forward_train(packed.data_ptr(), x0b.data_ptr(), xmb.data_ptr(), n, s0, sm, module.scale_factor,
+        check(lib.tp_forward_train(C.byref(w_struct), packed.data_ptr(), x0b.data_ptr(), xmb.data_ptr(), n, s0, sm, module.scale_factor,
                                    module.hidden_size, out.data_ptr(), saved.data_ptr(), nbytes, stream), "tp_forward_train")
         ctx.module = module
         ctx.saved = saved
         ctx.xm = xmb if xmb.is_contiguous() else xmb.contiguous()
-        ctx.weights_bf16 = list(module._keepalive)           # bf16 parameter snapshots this forward used
+        ctx.weights_bf16 = bf                                # the parameters this forward read (bf16; aliases of the live ones when they are bf16)
         ctx.param_meta = [(p.dtype, p.requires_grad) for p in params]
         return out
 
