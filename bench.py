@@ -371,7 +371,11 @@ def train_measure(model, x0, xm, steps=10):
     for p in model.parameters():
         p.requires_grad_(True)
 
+    params = list(model.parameters())
+
     def step():
+        for p in params:                 # what optimizer.zero_grad(set_to_none=True) (the default) does every training step: without
+            p.grad = None                # it autograd ACCUMULATES into the old gradients (23 extra elementwise launches per step)
         out = model((x0, xm))
         out.backward(go)
         return out
@@ -400,6 +404,8 @@ def train_measure(model, x0, xm, steps=10):
         pd = {k: v.detach().clone().requires_grad_(True) for k, v in model.state_dict().items()}
 
         def estep():
+            for v in pd.values():
+                v.grad = None
             o = torch_port.forward(pd, x0, xm, SCALE)
             o.backward(go)
         for _ in range(2):
