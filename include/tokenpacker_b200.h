@@ -45,7 +45,7 @@ TP_API const char* tp_strerror(int status);
 TP_API int tp_abi_version(void);
 /* Name of the last failing CUDA call on this thread ("" if none); diagnostic only. */
 TP_API const char* tp_last_cuda_error(void);
-/* Number of kernels this library has launched from the calling host thread so far (diagnostic: the benchmark's gpu_launches). */
+/* Number of kernels this library has launched so far, over all host threads of the process (diagnostic: the benchmark's gpu_launches). */
 TP_API uint64_t tp_launch_count(void);
 
 /* ---------------------------------------------------------------------------------------------------------------

@@ -109,6 +109,10 @@ def test_argument_errors_are_status_codes_not_crashes():
     # null pointers
     assert lib.tp_forward(None, None, None, 1, 576 * 1024, 576 * 4096, 2, 4096, None, None, None, 0, None) == _lib.TP_ERR_INVALID_ARGUMENT
     assert lib.tp_pack_weights(None, 4096, None, 0, None) == _lib.TP_ERR_INVALID_ARGUMENT
+    assert lib.tp_pack_weights_train(None, 4096, None, 0, None) == _lib.TP_ERR_INVALID_ARGUMENT
+    assert lib.tp_forward_train(None, None, None, None, 1, 0, 0, 2, 4096, None, None, 0, None) == _lib.TP_ERR_INVALID_ARGUMENT
+    assert lib.tp_forward_train(None, None, None, None, 1, 0, 0, 5, 4096, None, None, 0, None) == _lib.TP_ERR_BAD_SCALE_FACTOR
+    assert lib.tp_gemm_nn_bf16(None, 0, None, 0, None, 0, 256, 256, 64, 1.0, None) == _lib.TP_ERR_INVALID_ARGUMENT
     hb, wb = C.c_int(0), C.c_int(0)
     assert lib.tp_hd_grid(100, 100, 7, 336, C.byref(hb), C.byref(wb)) == _lib.TP_ERR_BAD_PATCH_NUM
     assert lib.tp_hd_grid(0, 100, 9, 336, C.byref(hb), C.byref(wb)) == _lib.TP_ERR_INVALID_ARGUMENT

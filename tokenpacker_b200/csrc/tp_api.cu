@@ -2,6 +2,7 @@
 // encoding, workspace carving and kernel launches on the caller's stream.  No allocation, no synchronisation
 // (except tp_forward_host), no global mutable state.
 #include <limits.h>
+#include <atomic>
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -17,7 +18,7 @@ namespace {
 using namespace tp;
 
 thread_local char g_last_cuda_error[256] = "";
-thread_local unsigned long long g_launch_count = 0;   // kernels launched from this host thread (tp_launch_count, diagnostic)
+std::atomic<unsigned long long> g_launch_count{0};   // kernels launched by this library, all host threads (autograd runs backward on its own thread)
 
 #define TP_CUDA(call)                                                                                        \
   do {                                                                                                       \
@@ -798,7 +799,7 @@ int tp_abi_version(void) { return TP_ABI_VERSION; }
 
 const char* tp_last_cuda_error(void) { return g_last_cuda_error; }
 
-uint64_t tp_launch_count(void) { return g_launch_count; }
+uint64_t tp_launch_count(void) { return g_launch_count.load(std::memory_order_relaxed); }
 
 size_t tp_packed_bytes(int hidden) { return valid_hidden(hidden) ? packed_layout(hidden).total : 0; }
 
