@@ -1,13 +1,10 @@
 #!/bin/bash
-# Round-2 GPU visit (1 GPU): tests (one process per file: a device-side trap cannot take the other files down), smoke, A/B of the
+# Round-2 GPU visit (1 GPU): the GPU suite as the driver runs it (one process, -x), smoke, A/B of the
 # launch plans, the full bench line, phase profile, ncu launch list with DRAM bytes, sanitizers.  Everything lands in gpurun_out/.
 mkdir -p gpurun_out
+( timeout 1500 python -m pytest tests -x -q -m gpu 2>&1 | tail -15 ) > gpurun_out/pytest_driver_style.log
+tail -2 gpurun_out/pytest_driver_style.log
 ( timeout 900 python tools/tma_store_probe.py 2>&1 ) | tee gpurun_out/tma_store_probe.log
-for f in tests/test_*gpu*.py; do
-  n=$(basename $f .py)
-  ( timeout 900 python -m pytest $f -q -m gpu 2>&1 | tail -70 ) > gpurun_out/pytest_$n.log
-  echo "$n: $(tail -1 gpurun_out/pytest_$n.log)"
-done
 ( timeout 120 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3 ) | tee gpurun_out/smoke.log
 ab() {  # name, env...
   name=$1; shift
@@ -21,11 +18,12 @@ except Exception as e:
 }
 rm -f gpurun_out/ab.log
 ab fused_default X=1
-ab fused_schedule3 TP_SCHEDULE=3
 ab chain_nofuse TP_FUSE_ATTN=0
 ab plain_7_launches TP_FUSE_ATTN=0 TP_CHAIN=0
 ( timeout 900 python bench.py --steps 20 --warmup 5 2>gpurun_out/bench.err | tail -1 ) > gpurun_out/bench_line.json
 cut -c1-400 gpurun_out/bench_line.json
+( timeout 900 python bench.py --impl reference --steps 3 --warmup 1 2>gpurun_out/bench_ref.err | tail -1 ) > gpurun_out/bench_ref_line.json
+cut -c1-300 gpurun_out/bench_ref_line.json
 ( timeout 300 python tools/gemm_phase_profile.py 2>&1 ) > gpurun_out/phase_profile.log
 timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed,sm__cycles_elapsed.max \
     --clock-control none -c 40 --csv --log-file gpurun_out/launches.csv \
@@ -34,7 +32,7 @@ TP_FUSE_ATTN=0 TP_CHAIN=0 timeout 600 ncu --metrics gpu__time_duration.sum,dram_
     --clock-control none -c 80 --csv --log-file gpurun_out/launches_plain.csv \
     python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e --no-extras > gpurun_out/ncu_launches_plain.log 2>&1
 timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed \
-    --clock-control none -c 160 --csv --log-file gpurun_out/launches_train.csv \
+    --clock-control none -s 150 -c 150 --csv --log-file gpurun_out/launches_train.csv \
     python bench.py --workload train --steps 3 > gpurun_out/ncu_launches_train.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:tp_gemm2 -s 5 -c 1 -f -o gpurun_out/prof_fused_forward \
     python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e --no-extras > gpurun_out/ncu_full.log 2>&1
