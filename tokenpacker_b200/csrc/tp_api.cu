@@ -80,7 +80,7 @@ int make_map_2d(CUtensorMap* map, const void* ptr, long long rows, long long col
 
 // bf16 tensor [segs, seg_rows, cols] with row stride ld and segment stride seg_stride (elements); box 64 x 64 x 1.
 int make_map_3d(CUtensorMap* map, const void* ptr, long long segs, long long seg_rows, long long cols, long long ld,
-                long long seg_stride, int box_rows = 64, int box_cols = kBlockK, bool swizzle = true) {
+                long long seg_stride, int box_rows = 64, int box_cols = kBlockK, bool swizzle = true, int box_segs = 1) {
   EncodeTiledFn fn = encode_tiled_fn();
   if (fn == nullptr) {
     snprintf(g_last_cuda_error, sizeof(g_last_cuda_error), "cuTensorMapEncodeTiled entry point not found");
@@ -89,7 +89,7 @@ int make_map_3d(CUtensorMap* map, const void* ptr, long long segs, long long seg
   if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0 || (ld * 2) % 16 != 0 || (seg_stride * 2) % 16 != 0) return TP_ERR_INVALID_ARGUMENT;
   cuuint64_t dims[3] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(seg_rows), static_cast<cuuint64_t>(segs)};
   cuuint64_t strides[2] = {static_cast<cuuint64_t>(ld) * 2, static_cast<cuuint64_t>(seg_stride) * 2};
-  cuuint32_t box[3] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows), 1};
+  cuuint32_t box[3] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows), static_cast<cuuint32_t>(box_segs)};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, !swizzle ? CU_TENSOR_MAP_SWIZZLE_NONE : (box_cols == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -416,27 +416,69 @@ int launch_gemm_pair_group(const GemmItem* items, int count, int sms, cudaStream
   PeerStores peers;
   memset(&peers, 0, sizeof(peers));
   int peer_item = -1;
+  // The destination maps of the launch: the peers of a fused all-gather, or — for a segmented (packed-row) output that stays on this
+  // GPU — the local buffer as the one "destination" (same store path, including the whole-segment boxes).
   for (int i = 0; i < count; ++i)
-    if (items[i].n_peers > 0) {
-      if (peer_item >= 0) return TP_ERR_INVALID_ARGUMENT;      // one set of peer maps per launch
+    if (items[i].n_peers > 0 || g.p[i].c_seg_len != 0) {
+      if (peer_item >= 0) return TP_ERR_INVALID_ARGUMENT;      // one set of destination maps per launch
       peer_item = i;
     }
   if (peer_item >= 0) {
     const GemmItem& it0 = items[peer_item];
-    if (it0.n_peers > kMaxPeers || it0.ep.seg_row_offset != nullptr) return TP_ERR_INVALID_ARGUMENT;
-    for (int p = 0; p < it0.n_peers; ++p) {
-      if (g.p[peer_item].c_seg_len != 0) {
+    const GemmProblem& p0 = g.p[peer_item];
+    void* const local_dst[1] = {it0.ep.c};
+    void* const* dst = it0.n_peers > 0 ? it0.peer_c : local_dst;
+    const int n_dst = it0.n_peers > 0 ? it0.n_peers : 1;
+    if (n_dst > kMaxPeers || it0.ep.seg_row_offset != nullptr) return TP_ERR_INVALID_ARGUMENT;
+    const bool whole = p0.c_seg_len != 0 && p0.c_seg_len <= kBlockM;
+    if (p0.c_seg_len != 0) {
+      // worst number of store pieces one 128-row slab is cut into (slab starts fall on multiples of unit inside a segment): the store
+      // warp has 96 job slots per slab (pieces x destinations)
+      int worst = 0;
+      for (int a0 = 0; a0 > -p0.c_seg_len; a0 -= p0.c_unit) {
+        int pieces = 0, a = a0;
+        while (a < kBlockM) {
+          if (whole && a >= 0 && a + p0.c_seg_len <= kBlockM) {
+            int k = 1;
+            while (k < kWholeLevels && a + (k + 1) * p0.c_seg_len <= kBlockM) ++k;
+            ++pieces;
+            a += k * p0.c_seg_len;
+            continue;
+          }
+          int len = (a + p0.c_seg_len < kBlockM ? a + p0.c_seg_len : kBlockM) - (a > 0 ? a : 0);
+          for (int lvl = kBoxLevels - 1; lvl >= 0; --lvl)
+            while (len >= (p0.c_unit << lvl)) { ++pieces; len -= p0.c_unit << lvl; }
+          a += p0.c_seg_len;
+        }
+        if (pieces > worst) worst = pieces;
+      }
+      if (worst * n_dst > 96) return TP_ERR_INVALID_ARGUMENT;
+    }
+    for (int p = 0; p < n_dst; ++p) {
+      if (p0.c_seg_len != 0) {
+        const long long n_segs = it0.M / it0.ep.seg_len;
         for (int lvl = 0; lvl < kBoxLevels; ++lvl) {
-          int rows = g.p[peer_item].c_unit << lvl;
-          if (rows > kBlockM || rows > it0.ep.seg_len) rows = g.p[peer_item].c_unit;
-          TP_TRY(make_map_3d(&peers.m[p][lvl], it0.peer_c[p], it0.M / it0.ep.seg_len, it0.ep.seg_len, it0.N, it0.ep.ldc,
-                             it0.ep.seg_stride * it0.ep.ldc, rows, kSlabCols, g.p[peer_item].c_noswz == 0));
+          int rows = p0.c_unit << lvl;
+          if (rows > kBlockM || rows > it0.ep.seg_len) rows = p0.c_unit;
+          TP_TRY(make_map_3d(&peers.m[p][lvl], dst[p], n_segs, it0.ep.seg_len, it0.N, it0.ep.ldc,
+                             it0.ep.seg_stride * it0.ep.ldc, rows, kSlabCols, p0.c_noswz == 0));
+        }
+        for (int k = 1; k <= kWholeLevels; ++k) {
+          // k whole segments; a level that can never be used (k segments do not fit a slab, or there are fewer segments) repeats k = 1
+          const int kk = (whole && k * it0.ep.seg_len <= kBlockM && k <= n_segs) ? k : 1;
+          if (whole)
+            TP_TRY(make_map_3d(&peers.m[p][kBoxLevels + k - 1], dst[p], n_segs, it0.ep.seg_len, it0.N, it0.ep.ldc,
+                               it0.ep.seg_stride * it0.ep.ldc, it0.ep.seg_len, kSlabCols, p0.c_noswz == 0, kk));
+          else
+            peers.m[p][kBoxLevels + k - 1] = peers.m[p][0];
         }
       } else {
-        TP_TRY(make_map_2d(&peers.m[p][0], it0.peer_c[p], it0.M, it0.N, it0.ep.ldc, kBlockM, kSlabCols));
+        TP_TRY(make_map_2d(&peers.m[p][0], dst[p], it0.M, it0.N, it0.ep.ldc, kBlockM, kSlabCols));
       }
     }
-    peers.count = it0.n_peers;
+    peers.count = n_dst;
+    peers.whole = whole ? 1 : 0;
+    g.p[peer_item].peer_out = 1;
   }
   {
     static thread_local unsigned attr_done = 0;

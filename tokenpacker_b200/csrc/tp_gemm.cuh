@@ -115,9 +115,11 @@ constexpr int kMaxPeers = 8;
 // Fused all-gather: tensor maps of the SAME output slot in every peer GPU's gathered buffer (peer-mapped over NVLink);
 // each finished slab is TMA-stored to all of them instead of to one local matrix.
 constexpr int kBoxLevels = 4;   // exact-size store boxes: rows = unit << level
+constexpr int kWholeLevels = 3; // ... and boxes of 1, 2 or 3 WHOLE segments (crops that lie entirely inside a 128-row slab)
 struct PeerStores {
-  CUtensorMap m[kMaxPeers][kBoxLevels];   // [peer][level]; plain (unsegmented) output uses level 0 only
+  CUtensorMap m[kMaxPeers][kBoxLevels + kWholeLevels];   // [destination][level]; plain (unsegmented) output uses level 0 only
   int count;                 // 0: ordinary local output through GemmProblem::tmap_c
+  int whole;                 // 1: the whole-segment maps m[.][kBoxLevels + k - 1] (k segments) are valid (seg_len <= 128)
 };
 
 struct OutStage {
@@ -1239,66 +1241,104 @@ tp_gemm2_kernel(const __grid_constant__ GemmGroup grp, const __grid_constant__ P
       for (int slab = 0; slab < (kTileN / 2 / kSlabCols) << dual; ++slab, ++q) {
         const uint32_t buf = q & static_cast<uint32_t>(Cfg::kOutBufs - 1);
         mbar_wait(&full[buf], (q >> (Cfg::kOutBufs - 1)) & 1u);
-        if (elect_one()) {
+        {
+          // Every TMA store of this slab is a JOB; lane l issues jobs l, l + 32, ...  All lanes walk the same (cheap) enumeration of the
+          // slab's pieces and keep the parameters of their own jobs, then issue them together: the up to ~64 stores of a packed-row
+          // slab that goes to eight GPUs leave the warp in two or three instructions instead of one lane issuing them one by one.
           const uint8_t* src = s_out + (half * Cfg::kOutBufs + static_cast<int>(buf)) * kOutSlabBytes;
           const int col = t.n_blk * kTileN + half * (kTileN / 2) + (slab >> dual) * kSlabCols;
+          constexpr int kJobsPerLane = 3;                  // 96 jobs per slab at most (host-checked: pieces x destinations)
+          const CUtensorMap* jmap[kJobsPerLane];
+          int jlo[kJobsPerLane], jc1[kJobsPerLane], jc2[kJobsPerLane], jc3[kJobsPerLane], jc4[kJobsPerLane];
+#pragma unroll
+          for (int k = 0; k < kJobsPerLane; ++k) jmap[k] = nullptr;
+          int job = 0;
+          auto add = [&](const CUtensorMap* mp, int lo, int c1, int c2, int c3, int c4) {
+#pragma unroll
+            for (int k = 0; k < kJobsPerLane; ++k)
+              if (job == static_cast<int>(lane) + 32 * k) { jmap[k] = mp; jlo[k] = lo; jc1[k] = c1; jc2[k] = c2; jc3[k] = c3; jc4[k] = c4; }
+            ++job;
+          };
           // TMA stores must lie entirely inside the tensor (a box that sticks out of a segment faults: measured), so every piece of
           // a slab goes out through boxes of EXACTLY its size: a few maps per destination with box heights unit << level.
+          int kind = 2;                                    // dimensionality of this problem's stores: 2, 3 or 5
           if (pr.c_wm_s != 0) {
             // Raster rows -> window-major rows: the slab is cut at token-row boundaries (24 tokens; crops are 24 token rows, so
             // token row R24 = global row / 24 = (crop * g + hb) * s + hi).  Slab edges fall on multiples of 8 tokens — a whole
             // number of windows for s in {2, 4, 8} —, so a piece holds 8, 16 or 24 tokens: map (tokens / 8 - 1), a
             // (channel, wi, -, wb) box of that many windows at (hi, crop-and-hb).
+            kind = 5;
             const int sf = pr.c_wm_s;
             const int n_r24 = pr.M / 24;
             int r24 = row_tile0 / 24;
             for (int a = r24 * 24 - row_tile0; a < kBlockM && r24 < n_r24; a += 24, ++r24) {
               const int lo = max(a, 0), hi = min(a + 24, kBlockM);
               const int lvl = (hi - lo) / 8 - 1;
-              const CUtensorMap* mp = lvl == 0 ? &pr.tmap_c : &pr.tmap_cx[lvl - 1];
-              tma_store_5d(mp, src + lo * kSlabRowBytes, col, 0, r24 % sf, (lo - a) / sf, r24 / sf);    // (c, wi, hi, wb, crop-and-hb)
+              add(lvl == 0 ? &pr.tmap_c : &pr.tmap_cx[lvl - 1], lo, 0, r24 % sf, (lo - a) / sf, r24 / sf);    // (c, wi, hi, wb, crop-and-hb)
             }
           } else if (pr.c_seg_len == 0) {
-            if (dual && (slab & 1) == 0) tma_store_2d(&pr.tmap_cx[0], src, col, row_tile0);
+            if (dual && (slab & 1) == 0) add(&pr.tmap_cx[0], 0, row_tile0, 0, 0, 0);
             else
-              for (int p = 0; p < n_maps; ++p) tma_store_2d(to_peers ? &peers.m[p][0] : &pr.tmap_c, src, col, row_tile0);
+              for (int p = 0; p < n_maps; ++p) add(to_peers ? &peers.m[p][0] : &pr.tmap_c, 0, row_tile0, 0, 0, 0);
           } else {
             // Segmented output rows (global row g = seg * seg_len + r  ->  map coordinate (col, r, seg)): the slab's 128 rows are
-            // cut at segment boundaries; a piece of L = n * unit rows leaves as one box per set bit of n (largest first).
+            // cut at segment boundaries.  Runs of up to 3 WHOLE segments leave as one (cols, seg_len, k) box per destination; a
+            // partial piece of L = n * unit rows leaves as one box per set bit of n (largest first).
+            kind = 3;
             const int n_segs = pr.M / pr.c_seg_len;
+            const bool whole_ok = to_peers && peers.whole != 0;
             int seg = row_tile0 / pr.c_seg_len;
-            for (int a = seg * pr.c_seg_len - row_tile0; a < kBlockM && seg < n_segs; a += pr.c_seg_len, ++seg) {
+            int a = seg * pr.c_seg_len - row_tile0;
+            while (a < kBlockM && seg < n_segs) {
+              if (whole_ok && a >= 0 && a + pr.c_seg_len <= kBlockM) {
+                int k = 1;
+                while (k < kWholeLevels && a + (k + 1) * pr.c_seg_len <= kBlockM && seg + k < n_segs) ++k;
+                for (int p = 0; p < n_maps; ++p) add(&peers.m[p][kBoxLevels + k - 1], a, 0, seg, 0, 0);
+                a += k * pr.c_seg_len;
+                seg += k;
+                continue;
+              }
               int lo = max(a, 0);
               const int hi = min(a + pr.c_seg_len, kBlockM);
               for (int lvl = kBoxLevels - 1; lvl >= 0; --lvl) {
                 const int rows = pr.c_unit << lvl;
                 while (hi - lo >= rows) {
                   for (int p = 0; p < n_maps; ++p)
-                    tma_store_3d(to_peers ? &peers.m[p][lvl] : (lvl == 0 ? &pr.tmap_c : &pr.tmap_cx[lvl - 1]), src + lo * kSlabRowBytes, col, lo - a, seg);
+                    add(to_peers ? &peers.m[p][lvl] : (lvl == 0 ? &pr.tmap_c : &pr.tmap_cx[lvl - 1]), lo, lo - a, seg, 0, 0);
                   lo += rows;
                 }
               }
+              a += pr.c_seg_len;
+              ++seg;
+            }
+          }
+          if (job > 32 * kJobsPerLane) __trap();       // cannot happen: the host rejects shapes whose worst slab needs more jobs
+#pragma unroll
+          for (int k = 0; k < kJobsPerLane; ++k) {
+            if (jmap[k] != nullptr) {
+              const uint8_t* from = src + jlo[k] * kSlabRowBytes;
+              if (kind == 2) tma_store_2d(jmap[k], from, col, jc1[k]);
+              else if (kind == 3) tma_store_3d(jmap[k], from, col, jc1[k], jc2[k]);
+              else tma_store_5d(jmap[k], from, col, jc1[k], jc2[k], jc3[k], jc4[k]);
             }
           }
           bulk_commit_group();
-          bulk_wait_group_read<0>();               // the buffer has been read: the epilogue warps may overwrite it
-          mbar_arrive(&empty[buf]);
+          bulk_wait_group_read<0>();               // this lane's stores have read the buffer ...
+          __syncwarp();                            // ... and so have everybody else's: the epilogue warps may overwrite it
+          if (lane == 0) mbar_arrive(&empty[buf]);
         }
         __syncwarp();
       }
       if (pr.done_counter != nullptr) {
-        if (elect_one()) {
-          bulk_wait_group<0>();                    // this CTA-half's part of the tile is in global memory ...
-          fence_proxy_async_all();                 // ... (async-proxy writes) ordered before the generic-proxy release below
-          red_release_gpu_add(pr.done_counter + t.m_blk, 1);
-        }
+        bulk_wait_group<0>();                      // every lane: its stores of this CTA-half's part of the tile are in global memory ...
+        fence_proxy_async_all();                   // ... (async-proxy writes) ordered before the generic-proxy release below
+        __syncwarp();
+        if (lane == 0) red_release_gpu_add(pr.done_counter + t.m_blk, 1);
         __syncwarp();
       }
     }
-    if (elect_one()) {
-      bulk_wait_group<0>();                        // my half's last TMA stores have been performed
-      if (peers.count > 0) __threadfence_system(); // ... and are ordered before the cross-GPU barrier that follows the kernel
-    }
+    bulk_wait_group<0>();                          // my half's last TMA stores have been performed
+    if (peers.count > 0) __threadfence_system();   // ... and are ordered before the cross-GPU barrier that follows the kernel
     __syncwarp();
   }
 

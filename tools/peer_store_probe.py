@@ -30,8 +30,11 @@ def main():
             torch.cuda.synchronize()
             res.setdefault(n_dst, []).append(round(e0.elapsed_time(e1) / 40, 4))
         same = all(torch.equal(bufs[0], b) for b in bufs[1:])
+        dense = m((x0, xm))                                   # [32, M, H]: the packed rows must hold exactly these bits
+        rows = bufs[0].view(n_total, mq + 1, hidden)[64:64 + n_local, :mq]
+        same = same and torch.equal(rows, dense)
     print(json.dumps({"workload": "32 crops, s=4, H=4096 into packed rows (crop stride 37) of n local destinations", "ms_by_destinations": res,
-                      "all_destinations_equal": same, "TP_SCHEDULE": os.environ.get("TP_SCHEDULE", "0")}))
+                      "all_destinations_equal_and_match_dense_forward": same, "TP_SCHEDULE": os.environ.get("TP_SCHEDULE", "0")}))
 
 if __name__ == "__main__":
     main()
