@@ -1606,9 +1606,9 @@ int tp_hd_tile_batch(const tp_hd_image* images_dev, const int32_t* crop_table_de
   if (images_dev == nullptr || crop_table_dev == nullptr || crops == nullptr || n_crops < 0) return TP_ERR_INVALID_ARGUMENT;
   if (n_crops == 0) return TP_OK;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  const long long total = n_crops * (kBlockPx / kHdRows) * (kBlockPx / 4);      // a thread: 4 pixels x kHdRows rows x 3 channels
-  hd_tile_batch_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(reinterpret_cast<const HdImage*>(images_dev), crop_table_dev,
-                                                                                       n_crops, crops);
+  const long long blocks = n_crops * (kBlockPx / kHdRows);          // a CTA: kHdRows rows of one crop, one thread per pixel column, 3 channels
+  if (blocks > 0x7fffffffll) return TP_ERR_INVALID_ARGUMENT;
+  hd_tile_batch_kernel<<<static_cast<unsigned>(blocks), kBlockPx, 0, stream>>>(reinterpret_cast<const HdImage*>(images_dev), crop_table_dev, n_crops, crops);
   TP_CUDA(cudaGetLastError()); ++g_launch_count;
   return TP_OK;
 }

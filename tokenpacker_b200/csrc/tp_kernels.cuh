@@ -393,46 +393,37 @@ __device__ __forceinline__ float hd_canvas_value(const HdImage& im, const float*
 }
 
 // crop_table[c] = (image index, grid row, grid column); grid column -1 marks the image's thumbnail.
-// A thread produces 4 consecutive pixels x kHdRows rows x 3 channels of one crop: the column taps (the bulk of the arithmetic: the
-// first version of this kernel was issue-bound at 70 % of the issue slots, 18 % of DRAM) are computed once and reused by the 12
-// (row, channel) pairs; the tap arithmetic itself is unchanged, so the bits are.
-constexpr int kHdRows = 4;                                     // 336 = 84 x 4
-__global__ void __launch_bounds__(256) hd_tile_batch_kernel(const HdImage* __restrict__ images, const int* __restrict__ crop_table,
-                                                            long long n_crops, float* __restrict__ crops) {
-  constexpr int kVecPerRow = kBlockPx / 4;                     // 84 float4 per crop row
-  constexpr int kRowGroups = kBlockPx / kHdRows;               // 84
-  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (idx >= n_crops * kRowGroups * kVecPerRow) return;
-  const int within = static_cast<int>(idx % (kRowGroups * kVecPerRow));
-  const long long crop = idx / (kRowGroups * kVecPerRow);
-  const int xv = within % kVecPerRow, y0 = (within / kVecPerRow) * kHdRows;
+// One CTA = kHdRows rows of one crop; thread = one pixel COLUMN: its column tap is computed once and reused by the kHdRows x 3 (row,
+// channel) pairs, and the lanes of a warp read neighbouring source pixels (a warp's load touches 4-6 sectors; with 4 pixels per
+// thread it was 16 sectors of which 6.5 bytes each were used, and the kernel sat at 18 % of DRAM waiting for L1).  Scalar stores of
+// 32 consecutive floats per warp.  The tap arithmetic is unchanged, so the bits are.
+constexpr int kHdRows = 8;                                     // 336 = 42 x 8
+__global__ void __launch_bounds__(kBlockPx) hd_tile_batch_kernel(const HdImage* __restrict__ images, const int* __restrict__ crop_table,
+                                                                 long long n_crops, float* __restrict__ crops) {
+  constexpr int kRowGroups = kBlockPx / kHdRows;
+  const long long crop = blockIdx.x / kRowGroups;
+  const int y0 = static_cast<int>(blockIdx.x % kRowGroups) * kHdRows;
+  const int x = threadIdx.x;
+  if (crop >= n_crops) return;
   const int img = crop_table[crop * 3], ci = crop_table[crop * 3 + 1], cj = crop_table[crop * 3 + 2];
   const HdImage im = images[img];
   const long long plane_sz = static_cast<long long>(im.h) * im.w;
-  float* out_base = crops + (crop * 3 * kBlockPx + y0) * kBlockPx + xv * 4;       // channel stride 336 * 336, row stride 336
+  float* out_base = crops + (crop * 3 * kBlockPx + y0) * kBlockPx + x;            // channel stride 336 * 336, row stride 336
   if (cj >= 0) {
-    LinearTap tx[4];
-    bool okx[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int X = cj * kBlockPx + xv * 4 + k;
-      okx[k] = X < im.w_r;
-      tx[k] = linear_tap_scaled(okx[k] ? X : 0, im.w, im.sx);
-    }
-#pragma unroll
+    const int X = cj * kBlockPx + x;
+    const bool okx = X < im.w_r;
+    const LinearTap tx = linear_tap_scaled(okx ? X : 0, im.w, im.sx);
+#pragma unroll 2
     for (int r = 0; r < kHdRows; ++r) {
       const int Y = ci * kBlockPx + y0 + r;
-      const bool oky = Y < im.h_r;
-      const LinearTap ty = linear_tap_scaled(oky ? Y : 0, im.h, im.sy);
+      const bool ok = okx && Y < im.h_r;
+      const LinearTap ty = linear_tap_scaled(ok ? Y : 0, im.h, im.sy);
       const float* r0 = im.image + static_cast<long long>(ty.i0) * im.w;
       const float* r1 = im.image + static_cast<long long>(ty.i1) * im.w;
 #pragma unroll
       for (int ch = 0; ch < 3; ++ch) {
-        float v[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          v[k] = (oky && okx[k]) ? bilerp(__ldg(r0 + tx[k].i0), __ldg(r0 + tx[k].i1), __ldg(r1 + tx[k].i0), __ldg(r1 + tx[k].i1), ty, tx[k]) : 0.f;
-        *reinterpret_cast<float4*>(out_base + (static_cast<long long>(ch) * kBlockPx + r) * kBlockPx) = make_float4(v[0], v[1], v[2], v[3]);
+        out_base[(static_cast<long long>(ch) * kBlockPx + r) * kBlockPx] =
+            ok ? bilerp(__ldg(r0 + tx.i0), __ldg(r0 + tx.i1), __ldg(r1 + tx.i0), __ldg(r1 + tx.i1), ty, tx) : 0.f;
         r0 += plane_sz;
         r1 += plane_sz;
       }
@@ -440,23 +431,16 @@ __global__ void __launch_bounds__(256) hd_tile_batch_kernel(const HdImage* __res
   } else {
     // thumbnail: resized from the PADDED canvas; a canvas tap = the main crops' arithmetic at that canvas pixel (zero outside the content)
     const int ch_h = im.hb * kBlockPx, ch_w = im.wb * kBlockPx;
-    LinearTap cx[4], sx0[4], sx1[4];                 // canvas column taps and the source taps of their two canvas columns
-    bool okx[4], okx0[4], okx1[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int x = xv * 4 + k;
-      okx[k] = x < im.w_t;
-      cx[k] = linear_tap_scaled(okx[k] ? x : 0, ch_w, im.tx);
-      okx0[k] = cx[k].i0 < im.w_r;
-      okx1[k] = cx[k].i1 < im.w_r;
-      sx0[k] = linear_tap_scaled(okx0[k] ? cx[k].i0 : 0, im.w, im.sx);
-      sx1[k] = linear_tap_scaled(okx1[k] ? cx[k].i1 : 0, im.w, im.sx);
-    }
-#pragma unroll
+    const bool okx = x < im.w_t;
+    const LinearTap cx = linear_tap_scaled(okx ? x : 0, ch_w, im.tx);                 // canvas column tap ...
+    const bool okx0 = cx.i0 < im.w_r, okx1 = cx.i1 < im.w_r;
+    const LinearTap sx0 = linear_tap_scaled(okx0 ? cx.i0 : 0, im.w, im.sx);           // ... and the source taps of its two canvas columns
+    const LinearTap sx1 = linear_tap_scaled(okx1 ? cx.i1 : 0, im.w, im.sx);
+#pragma unroll 2
     for (int r = 0; r < kHdRows; ++r) {
       const int y = y0 + r;
-      const bool oky = y < im.h_t;
-      const LinearTap cy = linear_tap_scaled(oky ? y : 0, ch_h, im.ty);
+      const bool ok = okx && y < im.h_t;
+      const LinearTap cy = linear_tap_scaled(ok ? y : 0, ch_h, im.ty);
       const bool oky0 = cy.i0 < im.h_r, oky1 = cy.i1 < im.h_r;
       const LinearTap sy0 = linear_tap_scaled(oky0 ? cy.i0 : 0, im.h, im.sy), sy1 = linear_tap_scaled(oky1 ? cy.i1 : 0, im.h, im.sy);
       const float* a0 = im.image + static_cast<long long>(sy0.i0) * im.w;   // source rows of canvas row cy.i0
@@ -465,20 +449,15 @@ __global__ void __launch_bounds__(256) hd_tile_batch_kernel(const HdImage* __res
       const float* b1 = im.image + static_cast<long long>(sy1.i1) * im.w;
 #pragma unroll
       for (int ch = 0; ch < 3; ++ch) {
-        float v[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          float o = 0.f;
-          if (oky && okx[k]) {
-            auto canvas = [&](const float* q0, const float* q1, const LinearTap& sy, bool rowok, const LinearTap& sx, bool colok) {
-              return (rowok && colok) ? bilerp(__ldg(q0 + sx.i0), __ldg(q0 + sx.i1), __ldg(q1 + sx.i0), __ldg(q1 + sx.i1), sy, sx) : 0.f;
-            };
-            o = bilerp(canvas(a0, a1, sy0, oky0, sx0[k], okx0[k]), canvas(a0, a1, sy0, oky0, sx1[k], okx1[k]),
-                       canvas(b0, b1, sy1, oky1, sx0[k], okx0[k]), canvas(b0, b1, sy1, oky1, sx1[k], okx1[k]), cy, cx[k]);
-          }
-          v[k] = o;
+        float o = 0.f;
+        if (ok) {
+          auto canvas = [&](const float* q0, const float* q1, const LinearTap& sy, bool rowok, const LinearTap& sx, bool colok) {
+            return (rowok && colok) ? bilerp(__ldg(q0 + sx.i0), __ldg(q0 + sx.i1), __ldg(q1 + sx.i0), __ldg(q1 + sx.i1), sy, sx) : 0.f;
+          };
+          o = bilerp(canvas(a0, a1, sy0, oky0, sx0, okx0), canvas(a0, a1, sy0, oky0, sx1, okx1),
+                     canvas(b0, b1, sy1, oky1, sx0, okx0), canvas(b0, b1, sy1, oky1, sx1, okx1), cy, cx);
         }
-        *reinterpret_cast<float4*>(out_base + (static_cast<long long>(ch) * kBlockPx + r) * kBlockPx) = make_float4(v[0], v[1], v[2], v[3]);
+        out_base[(static_cast<long long>(ch) * kBlockPx + r) * kBlockPx] = o;
         a0 += plane_sz; a1 += plane_sz; b0 += plane_sz; b1 += plane_sz;
       }
     }
