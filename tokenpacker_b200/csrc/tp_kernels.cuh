@@ -397,11 +397,9 @@ __device__ __forceinline__ float hd_canvas_value(const HdImage& im, const float*
 // channel) pairs, and the lanes of a warp read neighbouring source pixels (a warp's load touches 4-6 sectors; with 4 pixels per
 // thread it was 16 sectors of which 6.5 bytes each were used, and the kernel sat at 18 % of DRAM waiting for L1).  Scalar stores of
 // 32 consecutive floats per warp.  The tap arithmetic is unchanged, so the bits are.
-constexpr int kHdRows = 4;                                     // 336 = 84 x 4
-constexpr int kHdWindow = 3840;                                // floats per channel of the staged source window (3 x 15 KB static smem)
+constexpr int kHdRows = 8;                                     // 336 = 42 x 8
 __global__ void __launch_bounds__(kBlockPx) hd_tile_batch_kernel(const HdImage* __restrict__ images, const int* __restrict__ crop_table,
                                                                  long long n_crops, float* __restrict__ crops) {
-  __shared__ float s_win[3][kHdWindow];
   constexpr int kRowGroups = kBlockPx / kHdRows;
   const long long crop = blockIdx.x / kRowGroups;
   const int y0 = static_cast<int>(blockIdx.x % kRowGroups) * kHdRows;
@@ -415,51 +413,19 @@ __global__ void __launch_bounds__(kBlockPx) hd_tile_batch_kernel(const HdImage* 
     const int X = cj * kBlockPx + x;
     const bool okx = X < im.w_r;
     const LinearTap tx = linear_tap_scaled(okx ? X : 0, im.w, im.sx);
-    // The source window of this CTA (rows of its kHdRows output rows x columns of its 336 output columns, all three channels) is
-    // staged in shared memory with coalesced row reads — every source pixel is fetched once per CTA instead of once per tap —
-    // when it fits (input / output scale up to ~1.5); larger windows and CTAs outside the content read global memory directly.
-    const int Yf = ci * kBlockPx + y0, Xf = cj * kBlockPx;
-    int wy0 = 0, wx0 = 0, wrows = 0, wcols = 0;
-    if (Yf < im.h_r && Xf < im.w_r) {                          // (uniform over the CTA)
-      const int Yl = min(Yf + kHdRows - 1, im.h_r - 1), Xl = min(Xf + kBlockPx - 1, im.w_r - 1);
-      wy0 = linear_tap_scaled(Yf, im.h, im.sy).i0;
-      wx0 = linear_tap_scaled(Xf, im.w, im.sx).i0;
-      wrows = linear_tap_scaled(Yl, im.h, im.sy).i1 - wy0 + 1;
-      wcols = linear_tap_scaled(Xl, im.w, im.sx).i1 - wx0 + 1;
-    }
-    const bool staged = wrows > 0 && wrows * wcols <= kHdWindow;
-    if (staged) {
-      for (int ch = 0; ch < 3; ++ch) {
-        const float* src = im.image + ch * plane_sz + static_cast<long long>(wy0) * im.w + wx0;
-        for (int r = 0; r < wrows; ++r)
-          for (int c = x; c < wcols; c += kBlockPx) s_win[ch][r * wcols + c] = __ldg(src + static_cast<long long>(r) * im.w + c);
-      }
-      __syncthreads();
-    }
 #pragma unroll 2
     for (int r = 0; r < kHdRows; ++r) {
       const int Y = ci * kBlockPx + y0 + r;
       const bool ok = okx && Y < im.h_r;
       const LinearTap ty = linear_tap_scaled(ok ? Y : 0, im.h, im.sy);
-      if (staged) {
-        // window-relative indices; pixels outside the content read element 0 (always inside the window) and store 0
-        const int q0 = ok ? (ty.i0 - wy0) * wcols : 0, q1 = ok ? (ty.i1 - wy0) * wcols : 0;
-        const int c0 = ok ? tx.i0 - wx0 : 0, c1 = ok ? tx.i1 - wx0 : 0;
+      const float* r0 = im.image + static_cast<long long>(ty.i0) * im.w;
+      const float* r1 = im.image + static_cast<long long>(ty.i1) * im.w;
 #pragma unroll
-        for (int ch = 0; ch < 3; ++ch) {
-          const float v = bilerp(s_win[ch][q0 + c0], s_win[ch][q0 + c1], s_win[ch][q1 + c0], s_win[ch][q1 + c1], ty, tx);
-          out_base[(static_cast<long long>(ch) * kBlockPx + r) * kBlockPx] = ok ? v : 0.f;
-        }
-      } else {
-        const float* r0 = im.image + static_cast<long long>(ty.i0) * im.w;
-        const float* r1 = im.image + static_cast<long long>(ty.i1) * im.w;
-#pragma unroll
-        for (int ch = 0; ch < 3; ++ch) {
-          out_base[(static_cast<long long>(ch) * kBlockPx + r) * kBlockPx] =
-              ok ? bilerp(__ldg(r0 + tx.i0), __ldg(r0 + tx.i1), __ldg(r1 + tx.i0), __ldg(r1 + tx.i1), ty, tx) : 0.f;
-          r0 += plane_sz;
-          r1 += plane_sz;
-        }
+      for (int ch = 0; ch < 3; ++ch) {
+        out_base[(static_cast<long long>(ch) * kBlockPx + r) * kBlockPx] =
+            ok ? bilerp(__ldg(r0 + tx.i0), __ldg(r0 + tx.i1), __ldg(r1 + tx.i0), __ldg(r1 + tx.i1), ty, tx) : 0.f;
+        r0 += plane_sz;
+        r1 += plane_sz;
       }
     }
   } else {
