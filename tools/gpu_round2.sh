@@ -37,6 +37,9 @@ timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__byte
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:tp_gemm2 -s 5 -c 1 -f -o gpurun_out/prof_fused_forward \
     python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e --no-extras > gpurun_out/ncu_full.log 2>&1
 ncu -i gpurun_out/prof_fused_forward.ncu-rep --page raw --csv > gpurun_out/prof_fused_forward.raw.csv 2>/dev/null
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:hd_tile_batch -c 1 -f -o gpurun_out/prof_hd_tile \
+    python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/ncu_hd_tile.log 2>&1
+ncu -i gpurun_out/prof_hd_tile.ncu-rep --page raw --csv > gpurun_out/prof_hd_tile.raw.csv 2>/dev/null
 ( timeout 500 compute-sanitizer --tool memcheck python tools/sanitize_small.py 2>&1 | head -60 ) > gpurun_out/memcheck.log
 tail -3 gpurun_out/memcheck.log
 ( timeout 500 compute-sanitizer --tool synccheck python tools/sanitize_small.py 2>&1 | tail -8 ) | tee gpurun_out/synccheck.log
