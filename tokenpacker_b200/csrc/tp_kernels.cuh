@@ -397,7 +397,15 @@ __device__ __forceinline__ float hd_canvas_value(const HdImage& im, const float*
 // channel) pairs, and the lanes of a warp read neighbouring source pixels (a warp's load touches 4-6 sectors; with 4 pixels per
 // thread it was 16 sectors of which 6.5 bytes each were used, and the kernel sat at 18 % of DRAM waiting for L1).  Scalar stores of
 // 32 consecutive floats per warp.  The tap arithmetic is unchanged, so the bits are.
-constexpr int kHdRows = 8;                                     // 336 = 42 x 8
+#ifndef TP_HD_ROWS
+#define TP_HD_ROWS 8
+#endif
+#ifndef TP_HD_UNROLL
+#define TP_HD_UNROLL 2
+#endif
+constexpr int kHdRows = TP_HD_ROWS;                            // rows per thread; 336 = 42 x 8
+constexpr int kHdUnroll = TP_HD_UNROLL;                        // rows in flight per thread (loads of the next row issue under the math of this one)
+static_assert(kBlockPx % kHdRows == 0, "rows per CTA must divide the crop height");
 __global__ void __launch_bounds__(kBlockPx) hd_tile_batch_kernel(const HdImage* __restrict__ images, const int* __restrict__ crop_table,
                                                                  long long n_crops, float* __restrict__ crops) {
   constexpr int kRowGroups = kBlockPx / kHdRows;
@@ -413,7 +421,7 @@ __global__ void __launch_bounds__(kBlockPx) hd_tile_batch_kernel(const HdImage* 
     const int X = cj * kBlockPx + x;
     const bool okx = X < im.w_r;
     const LinearTap tx = linear_tap_scaled(okx ? X : 0, im.w, im.sx);
-#pragma unroll 2
+#pragma unroll kHdUnroll
     for (int r = 0; r < kHdRows; ++r) {
       const int Y = ci * kBlockPx + y0 + r;
       const bool ok = okx && Y < im.h_r;
@@ -436,7 +444,7 @@ __global__ void __launch_bounds__(kBlockPx) hd_tile_batch_kernel(const HdImage* 
     const bool okx0 = cx.i0 < im.w_r, okx1 = cx.i1 < im.w_r;
     const LinearTap sx0 = linear_tap_scaled(okx0 ? cx.i0 : 0, im.w, im.sx);           // ... and the source taps of its two canvas columns
     const LinearTap sx1 = linear_tap_scaled(okx1 ? cx.i1 : 0, im.w, im.sx);
-#pragma unroll 2
+#pragma unroll kHdUnroll
     for (int r = 0; r < kHdRows; ++r) {
       const int y = y0 + r;
       const bool ok = okx && y < im.h_t;
