@@ -43,7 +43,7 @@ SavedLayout saved_layout(long long n_crops, int s, int H) {
 }
 
 struct BwdLayout {
-  size_t w_m2t, w_m0t, w_ot, w_iqt, w_ikt, w_ivt, w_k2t, w_v2t;   // transposed weights (dgrad B operands)
+  size_t w_m2t, w_m0t, w_ot, w_iqt, w_ikt, w_ivt, w_k2t, w_v2t;   // transposed weight (dgrad fallback: only w_m2t is ever allocated)
   size_t g_t, hm_t, dzm, dzm_t, o_t, d_o, do_t, ctx_t, dctx;
   size_t dqp, dkp, dvp, dqp_t, dkp_t, dvp_t, lnq_t, lnk_t, lnv_t;
   size_t dqh, dkh, dvh, dyq, dyk, dyv, dyq_t, dyk_t, dyv_t, q_t, hkv_t;
@@ -69,9 +69,10 @@ BwdLayout bwd_layout(long long n_crops, int s, int H) {
   const size_t Qp = L.Qp, Hs = H;
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 1024); return o; };
-  const size_t mat = static_cast<size_t>(kC) * kC * 2;
-  L.w_m2t = take(Hs * Hs * 2); L.w_m0t = take(kC * Hs * 2); L.w_ot = take(mat);
-  L.w_iqt = take(mat); L.w_ikt = take(mat); L.w_ivt = take(mat); L.w_k2t = take(mat); L.w_v2t = take(mat);
+  // transposed weight copies: only the dgrad fallback needs one (n_in % 256 != 0 = mlp.2 at tiny hidden sizes); every other dgrad reads
+  // the weight as stored (NN form)
+  L.w_m2t = take((H % 256 != 0) ? Hs * Hs * 2 : 0);
+  L.w_m0t = L.w_ot = L.w_iqt = L.w_ikt = L.w_ivt = L.w_k2t = L.w_v2t = 0;
   // scratch for the transposing wgrad fallback: only mlp.2's weight gradient with hidden % 256 != 0 ever takes it
   const size_t fb = (H % 256 != 0) ? Hs * Qp * 2 : 0;
   L.g_t = take(fb); L.hm_t = take(fb);
