@@ -69,3 +69,40 @@ def test_training_forward_equals_inference_forward_closely_and_step_changes_outp
     with torch.no_grad():
         after = m((x0, xm))                      # weight cache must notice the in-place update
     assert after.float().pow(2).mean() < inf.float().pow(2).mean()
+
+
+@pytest.mark.parametrize("hidden", [256, 4096])
+def test_train_forward_in_place_weights_equal_packed_copies(hidden):
+    """tp_forward_train reads the untransformed weight matrices either from the live parameters (w given + tp_pack_weights_train)
+    or from their copies in a full tp_pack_weights buffer (w NULL): same kernels on the same bits, so the outputs are identical."""
+    import ctypes as C
+    from tokenpacker_b200 import TokenPackerB200, _lib
+    lib = _lib.lib
+    s, n = 2, 3
+    params = {k: tpo.round_bf16(v) for k, v in tpo.make_params(hidden, seed=77).items()}
+    m = TokenPackerB200(hidden_size=hidden, scale_factor=s)
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in params.items()})
+    m = m.to("cuda", torch.bfloat16)
+    x0, xm = tpo.make_inputs(n, seed=78)
+    x0 = torch.from_numpy(tpo.round_bf16(x0)).cuda().bfloat16().contiguous()
+    xm = torch.from_numpy(tpo.round_bf16(xm)).cuda().bfloat16().contiguous()
+    bf = [p.detach().contiguous() for p in m._raw_params()]
+    w = _lib.TpWeights(*[t.data_ptr() for t in bf])
+    stream = torch.cuda.current_stream().cuda_stream
+    pbytes = lib.tp_packed_bytes(hidden)
+    sbytes = lib.tp_train_saved_bytes(n, s, hidden)
+    outs = []
+    for in_place in (False, True):
+        packed = torch.zeros(pbytes, dtype=torch.uint8, device="cuda")
+        saved = torch.empty(sbytes, dtype=torch.uint8, device="cuda")
+        out = torch.empty(n, m.num_queries, hidden, dtype=torch.bfloat16, device="cuda")
+        pack = lib.tp_pack_weights_train if in_place else lib.tp_pack_weights
+        _lib.check(pack(C.byref(w), hidden, packed.data_ptr(), pbytes, stream), "pack")
+        _lib.check(lib.tp_forward_train(C.byref(w) if in_place else None, packed.data_ptr(), x0.data_ptr(), xm.data_ptr(), n, 576 * 1024, 576 * 4096,
+                                        s, hidden, out.data_ptr(), saved.data_ptr(), sbytes, stream), "tp_forward_train")
+        outs.append(out)
+    torch.cuda.synchronize()
+    assert torch.equal(outs[0], outs[1])
+    with torch.no_grad():
+        inf = m.eval()((x0, xm))
+    assert (outs[1].float() - inf.float()).abs().max().item() < 1e-2
